@@ -1,0 +1,70 @@
+"""Synthetic NMPC batches for the USV collision-avoidance benchmark.
+
+Seeded and numpy-only so that tests, bench.py and the CPU baseline all see identical inputs.
+The ranges are the survey's; nothing here touches the GPU.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+U_REF = 0.9
+DT = 0.05
+
+# BASELINE.json configs: (N, K, batch, num_steps)
+CONFIGS = {
+    1: dict(N=20, K=3, B=1, num_steps=1),
+    2: dict(N=40, K=5, B=4096, num_steps=4),
+    3: dict(N=40, K=20, B=4096, num_steps=4),
+    4: dict(N=100, K=5, B=16384, num_steps=4),
+    5: dict(N=40, K=5, B=131072, num_steps=4),
+}
+
+
+@dataclass
+class Batch:
+    x0: np.ndarray      # [B, 6]
+    p: np.ndarray       # [B, 2K]   obstacle centres (ox_1, oy_1, ...), constant over the horizon
+    lh: np.ndarray      # [B, K]    obstacle radii = lower bound of the distance constraint
+    yref: np.ndarray    # [B, 8]
+    yref_e: np.ndarray  # [B, 6]
+
+
+def make_batch(config_id: int, B: int = None, N: int = None, K: int = None, seed: int = None) -> Batch:
+    cfg = CONFIGS[config_id]
+    B = cfg["B"] if B is None else B
+    N = cfg["N"] if N is None else N
+    K = cfg["K"] if K is None else K
+    rng = np.random.default_rng(1234 + config_id if seed is None else seed)
+    if config_id == 5:
+        # Monte-Carlo disturbance scenarios: 128 base scenes x draws of x0 += N(0, diag(...)^2)
+        nbase = min(128, B)
+        base = _scenes(rng, nbase, N, K)
+        reps = -(-B // nbase)
+        idx = np.tile(np.arange(nbase), reps)[:B]
+        sig = np.array([0.05, 0.05, 0.02, 0.05, 0.01, 0.02])
+        x0 = base.x0[idx] + rng.standard_normal((B, 6)) * sig
+        return Batch(x0, base.p[idx].copy(), base.lh[idx].copy(), base.yref[idx].copy(), base.yref_e[idx].copy())
+    return _scenes(rng, B, N, K)
+
+
+def _scenes(rng, B, N, K) -> Batch:
+    x0 = np.stack([np.zeros(B), rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), rng.uniform(0.4, 1.0, B),
+                   rng.uniform(-0.02, 0.02, B), rng.uniform(-0.05, 0.05, B)], axis=1)
+    span = U_REF * DT * N
+    yref = np.zeros((B, 8))
+    yref[:, 0] = x0[:, 0] + span * 1.5
+    yref[:, 3] = U_REF
+    p = np.zeros((B, 2 * K))
+    lh = np.zeros((B, K))
+    for k in range(K):
+        todo = np.ones(B, dtype=bool)
+        while todo.any():
+            n = int(todo.sum())
+            ox = rng.uniform(1.0, 1.0 + span * 1.2, n)
+            oy = rng.uniform(-2.5, 2.5, n)
+            r = rng.uniform(0.3, 0.9, n)
+            ok = np.hypot(ox - x0[todo, 0], oy - x0[todo, 1]) >= r + 0.3
+            ids = np.flatnonzero(todo)[ok]
+            p[ids, 2 * k], p[ids, 2 * k + 1], lh[ids, k] = ox[ok], oy[ok], r[ok]
+            todo[ids] = False
+    return Batch(x0, p, lh, yref, yref[:, :6].copy())

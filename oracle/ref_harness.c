@@ -161,6 +161,7 @@ typedef struct
     int calls;
     long ipm_iters;   /* sum of HPIPM iterations since last reset */
     long lq_calls;    /* LQ fallbacks since last reset */
+    long solve_calls; /* solve-only Riccati sweeps (corrector, centering, refinement) since last reset */
     /* captured (flat, per stage, column-major dense) */
     int N, got;
     int nx[128], nu[128], nb[128], ng[128];
@@ -230,6 +231,16 @@ void d_ocp_qp_fact_lq_solve_kkt_step(struct d_ocp_qp *qp, struct d_ocp_qp_sol *q
                         struct d_ocp_qp_ipm_ws *) = NULL;
     if (!real) real = dlsym(RTLD_NEXT, "d_ocp_qp_fact_lq_solve_kkt_step");
     g_tap.lq_calls++;
+    real(qp, qp_sol, arg, ws);
+}
+
+void d_ocp_qp_solve_kkt_step(struct d_ocp_qp *qp, struct d_ocp_qp_sol *qp_sol, struct d_ocp_qp_ipm_arg *arg,
+                             struct d_ocp_qp_ipm_ws *ws)
+{
+    static void (*real)(struct d_ocp_qp *, struct d_ocp_qp_sol *, struct d_ocp_qp_ipm_arg *,
+                        struct d_ocp_qp_ipm_ws *) = NULL;
+    if (!real) real = dlsym(RTLD_NEXT, "d_ocp_qp_solve_kkt_step");
+    g_tap.solve_calls++;
     real(qp, qp_sol, arg, ws);
 }
 
@@ -479,7 +490,7 @@ void usvref_free(void *h)
  *   set(0,lbx/ubx,x0); per stage set yref, p, lh; solve; get.
  * p: (N+1) x np when p_per_stage else np (broadcast); lh: N x K or K; yref: N x ny or ny.
  * xinit/uinit/piinit may be NULL (-> x_k = x0, u = 0, pi = 0: the cold start of SURVEY 8d).
- * stats[8] = {status, sqp_iter, qp_iter_total, res_stat, res_eq, res_ineq, res_comp, lq_calls}. */
+ * stats[9] = {status, sqp_iter, qp_iter_total, res_stat, res_eq, res_ineq, res_comp, lq_calls, solve_calls}. */
 int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, const double *lh, int lh_per_stage,
                  const double *yref, int yref_per_stage, const double *yref_e, const double *xinit,
                  const double *uinit, const double *piinit, double *x_out, double *u_out, double *pi_out,
@@ -513,7 +524,7 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
             ocp_nlp_out_set(c->config, c->dims, c->out, i, "pi", (void *) (piinit ? piinit + i * nx : zeros));
         }
     }
-    g_tap.ipm_iters = 0; g_tap.lq_calls = 0; g_tap.calls = 0; g_tap.got = 0;
+    g_tap.ipm_iters = 0; g_tap.lq_calls = 0; g_tap.solve_calls = 0; g_tap.calls = 0; g_tap.got = 0;
     int status = ocp_nlp_solve(c->solver, c->in, c->out);
     int sqp_iter = 0;
     ocp_nlp_get(c->config, c->solver, "sqp_iter", &sqp_iter);
@@ -545,7 +556,7 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
     if (stats)
     {
         stats[0] = status; stats[1] = sqp_iter; stats[2] = (double) g_tap.ipm_iters;
-        stats[3] = r[0]; stats[4] = r[1]; stats[5] = r[2]; stats[6] = r[3]; stats[7] = (double) g_tap.lq_calls;
+        stats[3] = r[0]; stats[4] = r[1]; stats[5] = r[2]; stats[6] = r[3]; stats[7] = (double) g_tap.lq_calls; stats[8] = (double) g_tap.solve_calls;
     }
     return status;
 }
@@ -586,7 +597,7 @@ static double now_s(void)
 /* Batch of B independent instances over `nthreads` host threads, one solver context per thread
  * (the reference is single-threaded per solver; this is "one solver instance per core",
  * BASELINE.md section 3).  Instance-major inputs: x0[B,nx], p[B,(N+1|1),np], lh[B,(N|1),K],
- * yref[B,(N|1),ny], yref_e[B,nye].  Outputs x[B,N+1,nx], u[B,N,nu], stats[B,8].
+ * yref[B,(N|1),ny], yref_e[B,nye].  Outputs x[B,N+1,nx], u[B,N,nu], stats[B,9].
  * Returns wall seconds spent in the solve loop (context creation excluded). */
 typedef struct
 {
@@ -608,7 +619,7 @@ static void *batch_worker(void *arg)
         usvref_solve(j->ctx, j->x0 + (long) i * j->nx, j->p + i * j->sp, j->p_per_stage, j->lh + i * j->slh,
                      j->lh_per_stage, j->yref + i * j->sy, j->yref_per_stage, j->yref_e + (long) i * j->nx, NULL, NULL,
                      NULL, j->x_out + (long) i * (j->N + 1) * j->nx, j->u_out + (long) i * j->N * j->nu, NULL, NULL,
-                     NULL, j->stats + (long) i * 8);
+                     NULL, j->stats + (long) i * 9);
     }
     return NULL;
 }

@@ -1,0 +1,78 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference stack (oracle/_ref, built by oracle/Makefile
+from /root/reference).  Run here (the reference does not exist on the GPU box):
+
+    make -C oracle ref && python tests/make_golden.py
+
+Fixtures:
+  usv_cfg{1,2,3}_solve.npz  inputs + reference outputs (x, u, status, sqp_iter, qp_iter, res) of full SQP solves
+  usv_cfg1_rti.npz          one SQP_RTI step (known answer 2 of SURVEY.md appendix B)
+  usv_cfg2_qp.npz           QPs captured at HPIPM's door (after x0 elimination) with HPIPM's solution and
+                            iteration count, for QP-level parity of the IPM/Riccati kernels
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+import refharness as rh  # noqa: E402
+from mpc_collisionavoidance_b200.workloads import CONFIGS, make_batch  # noqa: E402
+
+G = os.path.join(HERE, "golden")
+
+
+def solve_fixture(cfg_id, B, name):
+    c = CONFIGS[cfg_id]
+    b = make_batch(cfg_id, B=B)
+    P = rh.RefProblem(N=c["N"], K=c["K"], num_steps=c["num_steps"])
+    o = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=8)
+    np.savez_compressed(os.path.join(G, name), cfg_id=cfg_id, N=c["N"], K=c["K"], num_steps=c["num_steps"], x0=b.x0, p=b.p,
+                        lh=b.lh, yref=b.yref, yref_e=b.yref_e, x=o["x"], u=o["u"], status=o["status"],
+                        sqp_iter=o["sqp_iter"], qp_iter=o["qp_iter"], res=o["res"])
+    print(name, "status", np.bincount(o["status"]), "sqp_iter", o["sqp_iter"])
+
+
+def known_answer_fixture():
+    x0 = np.array([0, 0, 0, 0.7, 0, 0.0]); p = np.array([2.0, 0.2, 3.5, -0.6, 5.0, 0.5]); lh = np.full(3, 0.8)
+    yref = np.array([6, 0, 0, 1, 0, 0, 0, 0.0])
+    out = {}
+    for nlp_type, tag in ((0, "sqp"), (1, "rti")):
+        s = rh.RefSolver(rh.RefProblem(N=20, K=3, num_steps=1, nlp_type=nlp_type))
+        o = s.solve(x0, p, lh, yref, yref[:6])
+        for k in ("x", "u", "pi", "lam", "t", "res"):
+            out[f"{tag}_{k}"] = o[k]
+        out[f"{tag}_stat"] = np.array([o["status"], o["sqp_iter"], o["qp_iter"]])
+    np.savez_compressed(os.path.join(G, "usv_cfg1_known_answer.npz"), x0=x0, p=p, lh=lh, yref=yref, **out)
+    print("known answer", out["sqp_stat"], out["rti_stat"])
+
+
+def qp_fixture():
+    c = CONFIGS[2]
+    b = make_batch(2, B=4)
+    P = rh.RefProblem(N=c["N"], K=c["K"], num_steps=c["num_steps"])
+    s = rh.RefSolver(P)
+    qps = {}
+    n = 0
+    for i in range(4):
+        for want in (0, 2, 6):
+            _, buf = s.solve_capture_qp(want, b.x0[i], b.p[i], b.lh[i], b.yref[i], b.yref_e[i])
+            if not buf["got"]:
+                continue
+            for k in ("BAbt", "b", "RSQrq", "rqz", "DCt", "d", "idxb", "ux", "pi", "lam", "t", "dims"):
+                qps[f"q{n}_{k}"] = buf[k]
+            qps[f"q{n}_info"] = np.array([buf["iter"], buf["status"]])
+            n += 1
+    np.savez_compressed(os.path.join(G, "usv_cfg2_qp.npz"), n=n, **qps)
+    print("qp fixtures", n, [int(qps[f"q{i}_info"][0]) for i in range(n)])
+
+
+if __name__ == "__main__":
+    assert rh.available(), "build oracle/_ref first: make -C oracle ref"
+    known_answer_fixture()
+    solve_fixture(1, 16, "usv_cfg1_solve.npz")
+    solve_fixture(2, 32, "usv_cfg2_solve.npz")
+    solve_fixture(3, 8, "usv_cfg3_solve.npz")
+    qp_fixture()

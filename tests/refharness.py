@@ -80,12 +80,12 @@ class RefSolver:
         if lh is None:
             lh = np.zeros(1)
         x = np.zeros((N + 1, nx)); u = np.zeros((N, nu)); pi = np.zeros((N, nx))
-        lam = np.zeros((N + 1, 2 * P.nbm)); t = np.zeros((N + 1, 2 * P.nbm)); stats = np.zeros(8)
+        lam = np.zeros((N + 1, 2 * P.nbm)); t = np.zeros((N + 1, 2 * P.nbm)); stats = np.zeros(9)
         self.lib.usvref_solve(self.h, _d(x0), _d(p), int(p.ndim > 1), _d(lh), int(lh.ndim > 1), _d(yref),
                               int(yref.ndim > 1), _d(yref_e), _d(xinit), _d(uinit), _d(piinit), _d(x), _d(u), _d(pi),
                               _d(lam), _d(t), _d(stats))
         return dict(x=x, u=u, pi=pi, lam=lam, t=t, status=int(stats[0]), sqp_iter=int(stats[1]),
-                    qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]))
+                    qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]), solve_calls=int(stats[8]))
 
     def solve_capture_qp(self, want, *args, **kw):
         """Solve while capturing the `want`-th QP HPIPM sees (after x0 elimination)."""
@@ -113,10 +113,10 @@ def solve_batch(prob: RefProblem, x0, p, lh, yref, yref_e, nthreads=1):
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, p, lh, yref, yref_e = map(c, (x0, p, lh, yref, yref_e))
     B = x0.shape[0]
-    x = np.zeros((B, prob.N + 1, prob.nx)); u = np.zeros((B, prob.N, prob.nu)); stats = np.zeros((B, 8))
+    x = np.zeros((B, prob.N + 1, prob.nx)); u = np.zeros((B, prob.N, prob.nu)); stats = np.zeros((B, 9))
     secs = lib.usvref_solve_batch(_i(prob.icfg), _d(prob.dcfg), _d(prob.W), _d(prob.We), _d(prob.lbu), _d(prob.ubu),
                                   _i(prob.idxbx), _d(prob.lbx), _d(prob.ubx), B, _d(x0), _d(p), int(p.ndim > 2),
                                   _d(lh), int(lh.ndim > 2), _d(yref), int(yref.ndim > 2), _d(yref_e), _d(x), _d(u),
                                   _d(stats), nthreads)
     return dict(x=x, u=u, status=stats[:, 0].astype(int), sqp_iter=stats[:, 1].astype(int),
-                qp_iter=stats[:, 2].astype(int), res=stats[:, 3:7], lq_calls=stats[:, 7].astype(int), seconds=secs)
+                qp_iter=stats[:, 2].astype(int), res=stats[:, 3:7], lq_calls=stats[:, 7].astype(int), solve_calls=stats[:, 8].astype(int), seconds=secs)

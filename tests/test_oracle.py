@@ -1,0 +1,133 @@
+"""Pins the C restatement (oracle/usv_oracle.c) against
+  * the reference's own golden vectors (pendulum OCP JSONs copied from
+    AC/examples/acados_python/tests/test_data/pendulum_ocp_formulations/, tolerance of the reference's own test
+    test_ocp_setting.py:320-333: ||.||_2 <= 50 * 1e-8),
+  * fixtures generated from the unmodified reference stack by tests/make_golden.py,
+  * and, when oracle/_ref is present (this container; it also travels to the GPU box), the live reference stack.
+CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracleport as op
+import refharness as rh
+from mpc_collisionavoidance_b200.workloads import make_batch
+
+
+def usv_problem(f, **kw):
+    return rh.RefProblem(N=int(f["N"]), K=int(f["K"]), num_steps=int(f["num_steps"]), **kw)
+
+
+def test_model_known_answer():
+    # SURVEY.md appendix B, known answer 1
+    o = op.OracleSolver(rh.RefProblem(N=1, K=0, num_steps=1))
+    x = np.array([0.3, -0.2, 0.4, 0.8, 0.03, -0.12]); u = np.array([12.0, -7.0])
+    f_expected = np.array([0.725166244933049, 0.339166503667007, -0.12, -0.338512620155039, -0.280721908526256,
+                           0.593043699226245])
+    # a single explicit-Euler step of length dt recovers f: use num_stages=1
+    P = rh.RefProblem(N=1, K=0, num_steps=1, num_stages=1, dt=1e-3)
+    xn, A, B = op.OracleSolver(P).integrate(x, u)
+    np.testing.assert_allclose((xn - x) / 1e-3, f_expected, rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_sensitivities_match_finite_differences(model):
+    rng = np.random.default_rng(0)
+    P = rh.RefProblem(N=1, K=0, num_steps=4, dt=0.05) if model == 0 else rh.RefProblem(
+        model=1, N=1, K=0, num_steps=5, num_stages=2, W=np.eye(5), We=np.eye(4), lbu=[-80.0], ubu=[80.0])
+    o = op.OracleSolver(P)
+    for _ in range(5):
+        if model == 0:
+            x = np.array([0, 0, rng.uniform(-1, 1), rng.uniform(0.3, 1.2), rng.uniform(-0.05, 0.05), rng.uniform(-0.3, 0.3)])
+            u = rng.uniform(-20, 30, 2)
+        else:
+            x = rng.uniform(-1, 1, 4); u = rng.uniform(-10, 10, 1)
+        xn, A, B = o.integrate(x, u)
+        h = 1e-6
+        for j in range(P.nx):
+            e = np.zeros(P.nx); e[j] = h
+            fd = (o.integrate(x + e, u)[0] - o.integrate(x - e, u)[0]) / (2 * h)
+            np.testing.assert_allclose(A[:, j], fd, rtol=2e-6, atol=2e-7)
+        for j in range(P.nu):
+            e = np.zeros(P.nu); e[j] = h
+            fd = (o.integrate(x, u + e)[0] - o.integrate(x, u - e)[0]) / (2 * h)
+            np.testing.assert_allclose(B[:, j], fd, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("nlp_type,name", [(0, "SQP"), (1, "SQP_RTI")])
+def test_pendulum_reference_golden(golden_dir, nlp_type, name):
+    N = 20
+    P = rh.RefProblem(model=1, N=N, K=0, num_steps=5, num_stages=2, nlp_type=nlp_type, max_iter=200, cond_N=10, tol=1e-8,
+                      W=np.diag([2e3, 2e3, 2e-2, 2e-2, 2e-2]), We=np.diag([2e3, 2e3, 2e-2, 2e-2]), lbu=[-80.0], ubu=[80.0])
+    x0 = np.array([0, np.pi, 0, 0.0])
+    xinit = np.stack([np.zeros(N + 1), np.arange(np.pi, -np.pi / N, -np.pi / N), np.zeros(N + 1), np.zeros(N + 1)], 1)
+    r = op.OracleSolver(P).solve(x0, None, None, np.zeros(5), np.zeros(4), xinit=xinit, uinit=np.zeros((N, 1)),
+                                 piinit=np.ones((N, 4)))
+    g = json.load(open(os.path.join(golden_dir, f"pendulum_LS_LS_PCHPIPM_ERK_{name}_GN.json")))
+    assert r["status"] == 0
+    tol = 50 * 1e-8
+    assert np.linalg.norm(np.array(g["simX"]) - r["x"]) <= tol
+    assert np.linalg.norm(np.array(g["simU"]) - r["u"]) <= tol
+
+
+def test_known_answer_sqp_and_rti(golden_dir):
+    f = np.load(os.path.join(golden_dir, "usv_cfg1_known_answer.npz"))
+    for nlp_type, tag in ((0, "sqp"), (1, "rti")):
+        o = op.OracleSolver(rh.RefProblem(N=20, K=3, num_steps=1, nlp_type=nlp_type))
+        r = o.solve(f["x0"], f["p"], f["lh"], f["yref"], f["yref"][:6])
+        assert [r["status"], r["sqp_iter"], r["qp_iter"]] == list(f[f"{tag}_stat"])
+        for k in ("x", "u", "pi", "lam", "t"):
+            np.testing.assert_allclose(r[k], f[f"{tag}_{k}"], rtol=1e-9, atol=1e-9, err_msg=f"{tag} {k}")
+        np.testing.assert_allclose(r["res"], f[f"{tag}_res"], rtol=1e-5, atol=1e-13)
+    # the survey's printed values (known answer 2)
+    np.testing.assert_allclose(f["sqp_u"][0], [34.999998898613, 34.999998672745], atol=1e-11)
+    np.testing.assert_allclose(f["sqp_x"][-1], [1.171342216362, 0.024350327791, 0.063249336072, 1.065410430798,
+                                                -0.012462310315, 0.055944608712], atol=1e-11)
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_full_solve_matches_reference_fixture(golden_dir, cfg):
+    f = np.load(os.path.join(golden_dir, f"usv_cfg{cfg}_solve.npz"))
+    P = usv_problem(f)
+    r = op.solve_batch(P, f["x0"], f["p"], f["lh"], f["yref"], f["yref_e"], nthreads=4)
+    np.testing.assert_array_equal(r["status"], f["status"])
+    np.testing.assert_array_equal(r["sqp_iter"], f["sqp_iter"])
+    np.testing.assert_array_equal(r["qp_iter"], f["qp_iter"])
+    ok = f["status"] == 0
+    assert ok.sum() >= len(ok) - 2
+    for k in ("x", "u"):
+        d = np.abs(r[k] - f[k]).reshape(len(ok), -1).max(1)
+        scale = np.maximum(1.0, np.abs(f[k]).reshape(len(ok), -1).max(1))
+        assert (d[ok] <= 1e-6 * scale[ok]).all(), (k, d[ok].max())
+    assert (r["res"][ok] < 1e-6).all()
+
+
+def test_qp_level_matches_hpipm_fixture(golden_dir):
+    f = np.load(os.path.join(golden_dir, "usv_cfg2_qp.npz"))
+    for i in range(int(f["n"])):
+        buf = {k: f[f"q{i}_{k}"] for k in ("BAbt", "b", "RSQrq", "rqz", "DCt", "d", "idxb", "ux", "pi", "lam", "t", "dims")}
+        it, st = f[f"q{i}_info"]
+        q = op.qp_solve(buf)
+        assert (q["iter"], q["status"]) == (it, st)
+        # the QP itself is only solved to 1e-6 (SQP forwards its tolerance); round-off differences between two
+        # implementations are amplified by Gamma = lam/t ~ 1e10 in the last iterations, hence 1e-6 not 1e-12
+        np.testing.assert_allclose(q["ux"], buf["ux"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(q["pi"], buf["pi"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(q["lam"], buf["lam"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(q["t"], buf["t"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built (needs /root/reference: make -C oracle ref)")
+def test_live_reference_stack_agrees():
+    b = make_batch(2, B=24, seed=777)
+    P = rh.RefProblem(N=40, K=5, num_steps=4)
+    a = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=4)
+    c = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=4)
+    np.testing.assert_array_equal(a["status"], c["status"])
+    np.testing.assert_array_equal(a["sqp_iter"], c["sqp_iter"])
+    np.testing.assert_array_equal(a["qp_iter"], c["qp_iter"])
+    ok = a["status"] == 0
+    assert np.abs(a["x"][ok] - c["x"][ok]).max() < 1e-6
+    assert np.abs(a["u"][ok] - c["u"][ok]).max() < 1e-5
