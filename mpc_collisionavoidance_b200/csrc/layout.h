@@ -1,0 +1,102 @@
+// layout.h -- kernel parameter block and the HBM layout of one NMPC instance's working set.
+// Shared by the CUDA C-ABI (usvmpc_api.cu), the kernel (nmpc_kernel.cuh) and the CPU warp emulator
+// used by the tests.
+//
+// Every instance owns one contiguous block of `ws_stride` doubles.  Inside it each field is an array
+// [stage][dim] (stage-major) so that the warp that owns the instance streams whole stage rows with
+// unit stride; `Field{off, stride}` gives the offset of stage 0 and the stage pitch, both in doubles
+// and both multiples of 2 (16 B).
+//
+// Row layouts of the inequality vectors (one "side" = lower or upper; the upper side follows the
+// lower side at +ncq / +ncz):
+//   IPM / QP level  (ncq = nbu + nbx + K): [ u boxes | x boxes (idxbx) | h rows ]
+//   NLP level       (ncz = nbu + NX  + K): [ u boxes | x boxes: NX slots (stage 0 holds the x0
+//                                            embedding, stages 1..N-1 use the first nbx) | h rows ]
+#pragma once
+
+namespace usvmpc {
+
+constexpr int KMAX = 32;     // max obstacles per stage
+constexpr int NBXMAX = 8;
+constexpr int NBUMAX = 4;
+constexpr int NSTAT = 12;    // per-instance statistics record (doubles)
+// stats: 0 status, 1 sqp_iter, 2 qp_iter (total), 3..6 res_stat/eq/ineq/comp, 7 reserved,
+//        8 solve-only Riccati sweeps, 9 last QP status, 10 last QP iterations, 11 reserved
+
+struct Field { int off, stride; };
+
+struct Layout {
+    // NLP iterate (persists between solves = warm start, like nlp_out in the reference)
+    Field zux, zpi, zlam, zt, zfun;
+    // QP data written by the linearisation
+    Field BAt, b, rq, gxy, d;
+    // IPM iterate, step, residuals, factor
+    Field ux, pi, lam, t, dux, dpi, dlam, dt, rg, rb, rd, rmc, L, Pb;
+    // iterative refinement scratch
+    Field dux2, dpi2, dlam2, dt2, rg2, rb2, rd2, rm2;
+    long total;
+};
+
+struct Params {
+    int B, N, K, num_steps, num_stages, nlp_type, max_iter, qp_iter_max, nbx, nbu;
+    int idxbx[NBXMAX];
+    int p_per_stage, lh_per_stage, yref_per_stage, cold_start;
+    int ncq, ncz;
+    double dt, tol[4], uh;
+    double lbu[NBUMAX], ubu[NBUMAX], lbx[NBXMAX], ubx[NBXMAX];
+    const double* cst;      // [W (NY*NY col-major) | W_e (NX*NX col-major)]
+    const double* x0;       // [B][NX]
+    const double* p;        // [B][N+1][2K] or [B][2K]
+    const double* lh;       // [B][N][K]   or [B][K]
+    const double* yref;     // [B][N][NY]  or [B][NY]
+    const double* yref_e;   // [B][NX]
+    double* ws;             // [B][ws_stride]
+    long ws_stride;
+    double* stats;          // [B][NSTAT]
+    Layout lay;
+};
+
+inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
+
+// Compute the per-instance layout.  nx/nu are the model dimensions.
+inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
+{
+    Layout L;
+    const int N1 = N + 1, nv = nx + nu;
+    const int sv = round_up(nv, 2), sx = round_up(nx, 2);
+    const int ncq = nbu + nbx + K, ncz = nbu + nx + K;
+    const int scq = round_up(2 * ncq, 2), scz = round_up(2 * ncz, 2);
+    const int sBA = round_up(nv * nx, 2), sg = round_up(2 * K, 2) > 0 ? round_up(2 * K, 2) : 2;
+    const int sL = round_up((nv + 1) * nv, 2);
+    long o = 0;
+    auto put = [&](Field& f, int stride) { f.off = (int) o; f.stride = stride; o += (long) stride * N1; };
+    put(L.zux, sv); put(L.zpi, sx); put(L.zlam, scz); put(L.zt, scz); put(L.zfun, scz);
+    put(L.BAt, sBA); put(L.b, sx); put(L.rq, sv); put(L.gxy, sg); put(L.d, scq);
+    put(L.ux, sv); put(L.pi, sx); put(L.lam, scq); put(L.t, scq);
+    put(L.dux, sv); put(L.dpi, sx); put(L.dlam, scq); put(L.dt, scq);
+    put(L.rg, sv); put(L.rb, sx); put(L.rd, scq); put(L.rmc, scq); put(L.L, sL); put(L.Pb, sx);
+    put(L.dux2, sv); put(L.dpi2, sx); put(L.dlam2, scq); put(L.dt2, scq);
+    put(L.rg2, sv); put(L.rb2, sx); put(L.rd2, scq); put(L.rm2, scq);
+    L.total = (o + 15) / 16 * 16;  // 128-byte multiple
+    return L;
+}
+
+// per-warp shared-memory scratch (doubles) used by nmpc_kernel.cuh
+inline int warp_smem_doubles(int nx, int nu, int K)
+{
+    const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
+    int n = 0;
+    n += 2 * nv * nv;          // Hs, Hes
+    n += nv * nv + nx * nx;    // Ws, Wes
+    n += nv * nx;              // sBA
+    n += nx * nx + nx;         // sLn, slx
+    n += (nv + 1) * nx;        // sAL
+    n += 2 * ncq2;             // sG, sg
+    n += (nv + 1) * nv;        // sL
+    n += 2 * nv + 2 * nx;      // sz, sq, sx1, sx2
+    n += 2 * (K > 0 ? K : 1);  // sgxy
+    n += ncq2 + 8;             // srow + misc
+    return (n + 1) / 2 * 2;
+}
+
+}  // namespace usvmpc

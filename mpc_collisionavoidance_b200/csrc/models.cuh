@@ -1,0 +1,107 @@
+// models.cuh -- device model functions: continuous dynamics f(x,u) with Jacobians, replacing the
+// CasADi-generated C the reference compiles at run time (`<m>_expl_vde_forw`,
+// `<m>_constr_h_fun_jac_uxt_zt`; spec in
+// acados_template/generate_c_code_explicit_ode.py:73-80 and generate_c_code_constraint.py:98-109).
+// CasADi's differentiation conventions are kept: d|a|/da = sign(a) (0 at 0), d(if_else)/dcond = 0.
+//
+//  Usv3      3-DOF surface vessel x=[X,Y,psi,u,v,r], u=[Tport,Tstbd]; dynamics of
+//            NM/scripts/usv_position_control/usv_model.py:61-77,116-128 with the thrust-rate states
+//            removed; obstacle distance h_i = ||(X,Y)-(ox_i,oy_i)|| of
+//            NM/scripts/usv_pf_ca/usv_model.py:165-168.
+//  Pendulum  cart-pole of the reference's own golden-vector tests
+//            (AC/examples/acados_python/getting_started/common/export_pendulum_ode_model.py:37-94).
+//
+// Jacobians are returned dense, column-major: Jx[i + NX*j] = d f_i / d x_j.
+#pragma once
+#include "warp_compat.h"
+
+namespace usvmpc {
+
+DEV double dsign(double a) { return (double) ((a > 0.0) - (a < 0.0)); }
+
+struct Usv3 {
+    static constexpr int ID = 0;
+    static constexpr int NX = 6, NU = 2;
+    static constexpr int HX = 0, HY = 1;  // position states entering the obstacle distance
+
+    MDEV static void f_jac(const double* x, const double* uc, double* f, double* Jx, double* Ju)
+    {
+        const double X_u_dot = -2.25, Y_v_dot = -23.13, Y_r_dot = -1.31, N_v_dot = -16.41, N_r_dot = -2.79;
+        const double Yvv = -99.99, Yvr = -5.49, Nrv = -8.8, Nrr = -3.49;
+        const double m = 30, Iz = 4.1, B = 0.41, c = 0.78;
+        const double m11 = m - X_u_dot, m22 = m - Y_v_dot, m33 = Iz - N_r_dot;
+        const double kY = 0.5 * (-40 * 1000) * (1.1 + 0.0045 * (1.01 / 0.09) - 0.1 * (0.27 / 0.09) + 0.016 * ((0.27 / 0.09) * (0.27 / 0.09)));
+        const double psi = x[2], u = x[3], v = x[4], r = x[5];
+        const double Tp = uc[0], Ts = uc[1];
+        const double Xu = (u > 1.25) ? 64.55 : -25.0;
+        const double Xuu = (u > 1.25) ? -70.92 : 0.0;
+        const double s = dsqrt(u * u + v * v);
+        const double Yv = kY * dabs(v);
+        const double Nr = -0.52 * s;
+        const double Tu = Tp + c * Ts;
+        const double Tr = (Tp - c * Ts) * B / 2;
+        double sp, cp;
+        dsincos(psi, &sp, &cp);
+
+        f[0] = u * cp - v * sp;
+        f[1] = u * sp + v * cp;
+        f[2] = r;
+        f[3] = (Tu - (-m + 2 * Y_v_dot) * v - (Y_r_dot + N_v_dot) * r * r - (-Xu * u - Xuu * dabs(u) * u)) / m11;
+        f[4] = (-(m - X_u_dot) * u * r - (-Yv - Yvv * dabs(v) - Yvr * dabs(r)) * v) / m22;
+        f[5] = (Tr - (-2 * Y_v_dot * u * v - (Y_r_dot + N_v_dot) * r * u + X_u_dot * u * r) - (-Nr * r - Nrv * dabs(v) * r - Nrr * dabs(r) * r)) / m33;
+
+#pragma unroll
+        for (int i = 0; i < 36; i++) Jx[i] = 0.0;
+        Jx[0 + 6 * 2] = -u * sp - v * cp;  Jx[0 + 6 * 3] = cp;  Jx[0 + 6 * 4] = -sp;
+        Jx[1 + 6 * 2] = u * cp - v * sp;   Jx[1 + 6 * 3] = sp;  Jx[1 + 6 * 4] = cp;
+        Jx[2 + 6 * 5] = 1.0;
+        Jx[3 + 6 * 3] = (Xu + 2 * Xuu * dabs(u)) / m11;
+        Jx[3 + 6 * 4] = -(-m + 2 * Y_v_dot) / m11;
+        Jx[3 + 6 * 5] = -2 * (Y_r_dot + N_v_dot) * r / m11;
+        Jx[4 + 6 * 3] = -m11 * r / m22;
+        Jx[4 + 6 * 4] = (2 * (kY + Yvv) * dabs(v) + Yvr * dabs(r)) / m22;
+        Jx[4 + 6 * 5] = (-m11 * u + Yvr * dsign(r) * v) / m22;
+        Jx[5 + 6 * 3] = (2 * Y_v_dot * v + (Y_r_dot + N_v_dot) * r - X_u_dot * r - 0.52 * (u / s) * r) / m33;
+        Jx[5 + 6 * 4] = (2 * Y_v_dot * u - 0.52 * (v / s) * r + Nrv * dsign(v) * r) / m33;
+        Jx[5 + 6 * 5] = ((Y_r_dot + N_v_dot) * u - X_u_dot * u - 0.52 * s + Nrv * dabs(v) + 2 * Nrr * dabs(r)) / m33;
+#pragma unroll
+        for (int i = 0; i < 12; i++) Ju[i] = 0.0;
+        Ju[3 + 6 * 0] = 1.0 / m11;       Ju[3 + 6 * 1] = c / m11;
+        Ju[5 + 6 * 0] = (B / 2) / m33;   Ju[5 + 6 * 1] = -(c * B / 2) / m33;
+    }
+};
+
+struct Pendulum {
+    static constexpr int ID = 1;
+    static constexpr int NX = 4, NU = 1;
+    static constexpr int HX = 0, HY = 1;  // unused (the pendulum OCP has no h)
+
+    MDEV static void f_jac(const double* x, const double* uc, double* f, double* Jx, double* Ju)
+    {
+        const double M = 1.0, m = 0.1, g = 9.81, l = 0.8;
+        const double th = x[1], v1 = x[2], dth = x[3], F = uc[0];
+        double s, c;
+        dsincos(th, &s, &c);
+        const double den = M + m - m * c * c;
+        const double n3 = -m * l * s * dth * dth + m * g * c * s + F;
+        const double n4 = -m * l * c * s * dth * dth + F * c + (M + m) * g * s;
+        f[0] = v1;
+        f[1] = dth;
+        f[2] = n3 / den;
+        f[3] = n4 / (l * den);
+        const double dden = 2 * m * c * s;
+        const double dn3_th = -m * l * c * dth * dth + m * g * (c * c - s * s);
+        const double dn4_th = -m * l * (c * c - s * s) * dth * dth - F * s + (M + m) * g * c;
+#pragma unroll
+        for (int i = 0; i < 16; i++) Jx[i] = 0.0;
+        Jx[0 + 4 * 2] = 1.0;
+        Jx[1 + 4 * 3] = 1.0;
+        Jx[2 + 4 * 1] = (dn3_th * den - n3 * dden) / (den * den);
+        Jx[2 + 4 * 3] = -2 * m * l * s * dth / den;
+        Jx[3 + 4 * 1] = (dn4_th * den - n4 * dden) / (l * den * den);
+        Jx[3 + 4 * 3] = -2 * m * l * c * s * dth / (l * den);
+        Ju[0] = 0.0; Ju[1] = 0.0; Ju[2] = 1.0 / den; Ju[3] = c / (l * den);
+    }
+};
+
+}  // namespace usvmpc

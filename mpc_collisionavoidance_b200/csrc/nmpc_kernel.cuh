@@ -1,0 +1,1231 @@
+// nmpc_kernel.cuh -- the batched NMPC solve: ONE WARP PER INSTANCE runs the whole
+// SQP / SQP_RTI solve (linearise -> x0 elimination -> Mehrotra IPM on a square-root Riccati
+// recursion -> variable update) out of its own block of HBM (layout.h).
+//
+// What it replaces in the reference (AC = catkin_ws/src/nmpc_ca/acados, HP = AC/external/hpipm):
+//   ocp_nlp_sqp / ocp_nlp_sqp_rti loop            AC/acados/ocp_nlp/ocp_nlp_sqp.c:466-835, ocp_nlp_sqp_rti.c:445-829
+//   linearisation + KKT residuals                 AC/acados/ocp_nlp/ocp_nlp_common.c:1926-2084, 2549-2603
+//   ERK with forward sensitivities                AC/acados/sim/sim_erk_integrator.c:668-847
+//   LINEAR_LS cost, BGH constraints               AC/acados/ocp_nlp/ocp_nlp_cost_ls.c:713-843, ocp_nlp_constraints_bgh.c:1228-1430
+//   x0 elimination / restoration                  HP/ocp_qp/x_ocp_qp_red.c:268-454, 723-871
+//   HPIPM IPM (init, delta step, residuals)       HP/ocp_qp/x_ocp_qp_ipm.c:1387-1719, 1888-2350, 2354-2683; x_ocp_qp_res.c:336-633
+//   Riccati factorise+solve / solve               HP/ocp_qp/x_ocp_qp_kkt.c:405-766, 1096-1441
+//   core vector ops                               HP/ipm_core/x_core_qp_ipm_aux.c:38-357
+//   BLASFEO potrf/syrk/trmm/trsv/gemv             BF/blasfeo_hp_pm/d_lapack_lib4.c:1149,1503 etc. -> warp-level code below
+//
+// Work decomposition inside the warp:
+//   * the three Riccati sweeps are serial in the stage index and are done co-operatively: lane r
+//     owns row r of the (nv+1) x nv factor, inner products go through shared memory / shuffles;
+//   * everything that is independent per stage (RK4 sensitivities, cost/constraint evaluation, QP
+//     residuals, step expansion, step length, variable update) is spread over the lanes.
+// Inactive variables (x at stage 0 after x0 elimination, u at stage N) and inactive inequality rows
+// are kept in the uniform per-stage layout and masked (identity rows in the factor, zero rows in
+// B'/A'), so every stage runs the same code.
+#pragma once
+#include "layout.h"
+#include "models.cuh"
+#include "warp_compat.h"
+
+namespace usvmpc {
+
+template <class M>
+struct WarpSolver {
+    static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
+    static constexpr int HXV = NU + M::HX, HYV = NU + M::HY;
+
+    const Params& P;
+    const Layout& Y;
+    int lane, N, K, nbu, nbx, ncq, ncz, nbq, nct;
+    double* w;
+    // shared-memory scratch of this warp
+    double *Hs, *Hes, *Ws, *Wes, *sBA, *sLn, *slx, *sAL, *sG, *sg, *sL, *sz, *sq, *sx1, *sx2, *sgxy;
+    int* sxrow;
+    // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
+    // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
+    double tol_stat, tol_eq, tol_ineq, tol_comp;
+    int iter_max;
+    // IPM state (warp-uniform)
+    double res_max[4], mu, mu_aff, sigma, alpha;
+    double S1, S2;  // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
+    int solve_calls;
+
+    MDEV WarpSolver(const Params& p, int inst, double* sm) : P(p), Y(p.lay)
+    {
+        lane = lane_id();
+        N = P.N; K = P.K; nbu = P.nbu; nbx = P.nbx; ncq = P.ncq; ncz = P.ncz; nbq = nbu + nbx;
+        nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
+        w = P.ws + (long) inst * P.ws_stride;
+        double* s = sm;
+        Hs = s; s += NV * NV; Hes = s; s += NV * NV; Ws = s; s += NV * NV; Wes = s; s += NX * NX;
+        sBA = s; s += NV * NX; sLn = s; s += NX * NX; slx = s; s += NX; sAL = s; s += NR * NX;
+        sG = s; s += 2 * (NU + NX + K); sg = s; s += 2 * (NU + NX + K); sL = s; s += NR * NV;
+        sz = s; s += NV; sq = s; s += NV; sx1 = s; s += NX; sx2 = s; s += NX; sgxy = s; s += 2 * (K > 0 ? K : 1);
+        sxrow = (int*) s;
+        tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
+        if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
+        iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
+        solve_calls = 0;
+    }
+
+    MDEV double* F(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
+    MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
+    MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
+    // IPM row of the box on variable c at stage k, or -1
+    MDEV int vrow(int k, int c) const
+    {
+        if (k >= N) return -1;
+        if (c < NU) return c < nbu ? c : -1;
+        return k >= 1 ? sxrow[c - NU] : -1;
+    }
+
+    // ---------------------------------------------------------------- constants into shared memory
+    // Gauss-Newton Hessians: ocp_nlp_cost_ls_initialize, AC/acados/ocp_nlp/ocp_nlp_cost_ls.c:713-745.  With
+    // Vx=[I;0], Vu=[0;I] the output map y = Cyt'[u;x] is the permutation [x;u].  Lower triangles are read.
+    MDEV void load_constants()
+    {
+        const double* Wg = P.cst;
+        const double* Weg = P.cst + NY * NY;
+        for (int e = lane; e < NV * NV; e += 32)
+        {
+            const int i = e % NV, j = e / NV;
+            Ws[e] = i >= j ? Wg[i + NY * j] : Wg[j + NY * i];
+            const int yi = i < NU ? NX + i : i - NU, yj = j < NU ? NX + j : j - NU;
+            Hs[e] = P.dt * (yi >= yj ? Wg[yi + NY * yj] : Wg[yj + NY * yi]);
+            Hes[e] = (i >= NU && j >= NU) ? ((i >= j) ? Weg[(i - NU) + NX * (j - NU)] : Weg[(j - NU) + NX * (i - NU)]) : 0.0;
+        }
+        for (int e = lane; e < NX * NX; e += 32)
+        {
+            const int i = e % NX, j = e / NX;
+            Wes[e] = i >= j ? Weg[i + NX * j] : Weg[j + NX * i];
+        }
+        if (lane < NX)
+        {
+            int r = -1;
+            for (int j = 0; j < nbx; j++) if (P.idxbx[j] == lane) r = nbu + j;
+            sxrow[lane] = r;
+        }
+        syncwarp();
+    }
+    MDEV const double* Hk(int k) const { return k < N ? Hs : Hes; }
+
+    // ---------------------------------------------------------------- initial guess
+    // cold start of the scripts / template (acados_solver.in.c:1595-1623): x_k = x0, u = 0, pi = 0;
+    // lam, t start at zero like a freshly created nlp_out.
+    MDEV void cold_start(const double* x0)
+    {
+        for (int k = lane; k <= N; k += 32)
+        {
+            double* z = F(Y.zux, k);
+            for (int i = 0; i < NU; i++) z[i] = 0.0;
+            for (int i = 0; i < NX; i++) z[NU + i] = x0[i];
+            double* pi = F(Y.zpi, k);
+            for (int i = 0; i < NX; i++) pi[i] = 0.0;
+            double *l = F(Y.zlam, k), *t = F(Y.zt, k);
+            for (int j = 0; j < 2 * ncz; j++) { l[j] = 0.0; t[j] = 0.0; }
+        }
+        syncwarp();
+    }
+
+    // ---------------------------------------------------------------- linearisation
+    // ERK with forward sensitivities (AC/acados/sim/sim_erk_integrator.c:762-847, tableaus :253-344; seed S=[I 0],
+    // A=Sx(T), B=Su(T): ocp_nlp_dynamics_cont.c:782-804).  One lane integrates [x ; one sensitivity column] of one
+    // stage; a stage's NV columns sit on NV consecutive task slots.
+    MDEV void integrate_all()
+    {
+        const int ns = P.num_stages;
+        double a21 = 0, a32 = 0, a43 = 0, bv[4] = {0, 0, 0, 0};
+        if (ns == 1) { bv[0] = 1.0; }
+        else if (ns == 2) { a21 = 0.5; bv[1] = 1.0; }
+        else { a21 = 0.5; a32 = 0.5; a43 = 1.0; bv[0] = 1.0 / 6.0; bv[1] = 1.0 / 3.0; bv[2] = 1.0 / 3.0; bv[3] = 1.0 / 6.0; }
+        const double asub[4] = {a21, a32, a43, 0.0};
+        const double step = P.dt / P.num_steps;
+        for (int task = lane; task < N * NV; task += 32)
+        {
+            const int k = task / NV, col = task % NV;
+            const double* z = F(Y.zux, k);
+            double u[NU], x[NX], s[NX];
+#pragma unroll
+            for (int i = 0; i < NU; i++) u[i] = z[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) { x[i] = z[NU + i]; s[i] = (i == col) ? 1.0 : 0.0; }
+            for (int istep = 0; istep < P.num_steps; istep++)
+            {
+                double xr[NX], sr[NX], xa[NX], sa[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) { xr[i] = x[i]; sr[i] = s[i]; xa[i] = x[i]; sa[i] = s[i]; }
+                for (int st = 0; st < ns; st++)
+                {
+                    double f[NX], Jx[NX * NX], Ju[NX * NU], ks[NX];
+                    M::f_jac(xr, u, f, Jx, Ju);
+#pragma unroll
+                    for (int i = 0; i < NX; i++)
+                    {
+                        // VDE right-hand side of this column: Jx*Sx_col, or Jx*Su_col + Ju_col
+                        // (acados_template/generate_c_code_explicit_ode.py:73-80)
+                        double acc = 0.0;
+                        if (col >= NX)
+                        {
+#pragma unroll
+                            for (int c = 0; c < NU; c++) if (c == col - NX) acc = Ju[i + NX * c];
+                        }
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += Jx[i + NX * m] * sr[m];
+                        ks[i] = acc;
+                    }
+                    const double bb = step * bv[st];
+                    const double aa = asub[st] * step;
+#pragma unroll
+                    for (int i = 0; i < NX; i++)
+                    {
+                        xa[i] += bb * f[i]; sa[i] += bb * ks[i];
+                        xr[i] = x[i]; sr[i] = s[i];
+                        if (aa != 0.0) { xr[i] += aa * f[i]; sr[i] += aa * ks[i]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) { x[i] = xa[i]; s[i] = sa[i]; }
+            }
+            // BAt = [B'; A'] (nv x nx, column-major): ocp_nlp_dynamics_cont.c:801-804
+            double* BAt = F(Y.BAt, k);
+            const int row = col < NX ? NU + col : col - NX;
+#pragma unroll
+            for (int i = 0; i < NX; i++) BAt[row + NV * i] = s[i];
+            if (col == 0)
+            {
+                const double* zn = F(Y.zux, k + 1);
+                double* b = F(Y.b, k);
+#pragma unroll
+                for (int i = 0; i < NX; i++) b[i] = x[i] - zn[NU + i];  // dyn_fun = phi(x,u) - x_next
+            }
+        }
+        syncwarp();
+    }
+
+    // cost / constraints / adjoints / NLP residuals / QP vectors, one lane per stage.
+    // ocp_nlp_approximate_qp_matrices + _vectors_sqp (ocp_nlp_common.c:1926-2084), ocp_nlp_res_compute (:2549-2603),
+    // x0 elimination d_ocp_qp_reduce_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:268-454).  res4 = (stat, eq, ineq, comp).
+    MDEV void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
+                       double* res4)
+    {
+        integrate_all();
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        for (int k = lane; k <= N; k += 32)
+        {
+            const double* z = F(Y.zux, k);
+            const double *zl = F(Y.zlam, k), *zt = F(Y.zt, k);
+            double *zf = F(Y.zfun, k), *rq = F(Y.rq, k), *d = F(Y.d, k);
+            double cg[NV], adj[NV];
+            // ---- LINEAR_LS cost gradient (ocp_nlp_cost_ls.c:749-843)
+            if (k < N)
+            {
+                const double* yr = yrg + (P.yref_per_stage ? k * NY : 0);
+                double r[NY];
+#pragma unroll
+                for (int i = 0; i < NX; i++) r[i] = z[NU + i] - yr[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) r[NX + i] = z[i] - yr[NX + i];
+#pragma unroll
+                for (int i = 0; i < NY; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NY; j++) acc += Ws[i + NY * j] * r[j];
+                    if (i < NX) cg[NU + i] = P.dt * acc; else cg[i - NX] = P.dt * acc;
+                }
+            }
+            else
+            {
+                double r[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) r[i] = z[NU + i] - yre[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) cg[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += Wes[i + NX * j] * r[j];
+                    cg[NU + i] = acc;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) adj[i] = 0.0;
+            // ---- BGH constraints (ocp_nlp_constraints_bgh.c:1228-1430): fun = [lb - g ; g - ub], adj = J'(lam_l - lam_u)
+            for (int j = 0; j < 2 * ncz; j++) zf[j] = 0.0;
+            for (int j = 0; j < 2 * ncq; j++) d[j] = 0.0;
+            double dx0[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) dx0[i] = 0.0;
+            if (k < N)
+            {
+#pragma unroll
+                for (int j = 0; j < NU; j++)
+                    if (j < nbu)
+                    {
+                        const double g = z[j], fl = P.lbu[j] - g, fu = g - P.ubu[j];
+                        zf[j] = fl; zf[ncz + j] = fu; d[j] = fl; d[ncq + j] = fu;
+                        adj[j] += zl[j] - zl[ncz + j];
+                        const double a = dabs(fl + zt[j]), b = dabs(fu + zt[ncz + j]);
+                        r2 = a > r2 ? a : r2; r2 = b > r2 ? b : r2;
+                        const double c0 = dabs(zl[j] * zt[j]), c1 = dabs(zl[ncz + j] * zt[ncz + j]);
+                        r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                    }
+                if (k == 0)
+                {
+                    // x0 embedding: lbx = ubx = x0 on every state (acados_solver.in.c:1028-1051, bgh.c:1528)
+#pragma unroll
+                    for (int j = 0; j < NX; j++)
+                    {
+                        const double g = z[NU + j], fl = x0[j] - g, fu = g - x0[j];
+                        const int r = nbu + j;
+                        zf[r] = fl; zf[ncz + r] = fu;
+                        dx0[j] = fl;
+                        adj[NU + j] += zl[r] - zl[ncz + r];
+                        const double a = dabs(fl + zt[r]), b = dabs(fu + zt[ncz + r]);
+                        r2 = a > r2 ? a : r2; r2 = b > r2 ? b : r2;
+                        const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                        r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                    }
+                }
+                else
+                {
+                    for (int j = 0; j < nbx; j++)
+                    {
+                        const int id = P.idxbx[j], r = nbu + j;
+                        const double g = z[NU + id], fl = P.lbx[j] - g, fu = g - P.ubx[j];
+                        zf[r] = fl; zf[ncz + r] = fu; d[r] = fl; d[ncq + r] = fu;
+                        const double dl = zl[r] - zl[ncz + r];
+#pragma unroll
+                        for (int i = 0; i < NX; i++) if (i == id) adj[NU + i] += dl;
+                        const double a = dabs(fl + zt[r]), b = dabs(fu + zt[ncz + r]);
+                        r2 = a > r2 ? a : r2; r2 = b > r2 ? b : r2;
+                        const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                        r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                    }
+                }
+                // obstacle distances h_c = ||(X,Y) - (ox_c, oy_c)||, dh/d(X,Y) = ((X,Y) - o_c)/h_c
+                const double* pk = pg + (P.p_per_stage ? k * 2 * K : 0);
+                const double* lhk = lhg + (P.lh_per_stage ? k * K : 0);
+                double* gxy = F(Y.gxy, k);
+                for (int c = 0; c < K; c++)
+                {
+                    const double ddx = z[HXV] - pk[2 * c], ddy = z[HYV] - pk[2 * c + 1];
+                    const double h = dsqrt(ddx * ddx + ddy * ddy);
+                    const double gX = ddx / h, gY = ddy / h;
+                    gxy[c] = gX; gxy[K + c] = gY;
+                    const double fl = lhk[c] - h, fu = h - P.uh;
+                    const int r = nbu + NX + c, rqp = nbq + c;
+                    zf[r] = fl; zf[ncz + r] = fu;
+                    // stage 0: fold the eliminated x0 step into the bounds (x_ocp_qp_red.c:380-420)
+                    const double v = (k == 0) ? gX * dx0[M::HX] + gY * dx0[M::HY] : 0.0;
+                    d[rqp] = fl - v; d[ncq + rqp] = fu + v;
+                    const double dl = zl[r] - zl[ncz + r];
+                    adj[HXV] += gX * dl; adj[HYV] += gY * dl;
+                    const double a = dabs(fl + zt[r]), b = dabs(fu + zt[ncz + r]);
+                    r2 = a > r2 ? a : r2; r2 = b > r2 ? b : r2;
+                    const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                    r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                }
+            }
+            // ---- dynamics adjoint -[B';A'] pi_k (+ pi_{k-1} on x): ocp_nlp_common.c:2001-2019 ; stationarity residual
+            const double* BAt = F(Y.BAt, k);
+            const double* pik = F(Y.zpi, k);
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                double acc = 0.0;
+                if (k < N)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc -= BAt[i + NV * j] * pik[j];
+                }
+                if (k > 0 && i >= NU) acc += F(Y.zpi, k - 1)[i - NU];
+                if (k < N || i >= NU)
+                {
+                    const double a = dabs(cg[i] - adj[i] - acc);
+                    r0 = a > r0 ? a : r0;
+                }
+            }
+            if (k < N)
+            {
+                const double* b = F(Y.b, k);
+#pragma unroll
+                for (int i = 0; i < NX; i++) { const double a = dabs(b[i]); r1 = a > r1 ? a : r1; }
+            }
+            // ---- QP gradient; stage 0: b0 += A0' dx0, r0 += S dx0 (x_ocp_qp_red.c:300-378)
+#pragma unroll
+            for (int i = 0; i < NV; i++) rq[i] = cg[i];
+            if (k == 0 && N > 0)
+            {
+                double* b = F(Y.b, 0);
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = b[j];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) acc += BAt[NU + i + NV * j] * dx0[i];
+                    b[j] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < NU; i++)
+                {
+                    double acc = cg[i];
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += Hs[(NU + j) + NV * i] * dx0[j];
+                    rq[i] = acc;
+                }
+            }
+        }
+        res4[0] = warp_max(r0); res4[1] = warp_max(r1); res4[2] = warp_max(r2); res4[3] = warp_max(r3);
+        syncwarp();
+    }
+
+    // ---------------------------------------------------------------- IPM: per-stage (lane-parallel) passes
+    // OCP_QP_INIT_VAR, var_init_scheme 1, cold start: HP/ocp_qp/x_ocp_qp_ipm.c:1435-1470,1581-1714 (ns = 0)
+    MDEV void ipm_init()
+    {
+        const double thr0 = 1e-1, mu0 = 1.0;
+        for (int k = lane; k <= N; k += 32)
+        {
+            double *ux = F(Y.ux, k), *pi = F(Y.pi, k), *lam = F(Y.lam, k), *t = F(Y.t, k);
+            const double* d = F(Y.d, k);
+            for (int i = 0; i < NV; i++) ux[i] = 0.0;
+            for (int i = 0; i < NX; i++) pi[i] = 0.0;
+            for (int j = 0; j < 2 * ncq; j++) { lam[j] = 0.0; t[j] = 1.0; }
+            if (k >= N) continue;
+            for (int j = 0; j < nbq; j++)
+            {
+                if (!row_active(k, j)) continue;
+                const int id = j < nbu ? j : NU + P.idxbx[j - nbu];
+                double tl = ux[id] - d[j], tu = -ux[id] - d[ncq + j];
+                if (tl < thr0)
+                {
+                    if (tu < thr0) { ux[id] = 0.5 * (d[j] - d[ncq + j]); tl = thr0; tu = thr0; }
+                    else { tl = thr0; ux[id] = d[j] + thr0; }
+                }
+                else if (tu < thr0) { tu = thr0; ux[id] = -d[ncq + j] - thr0; }
+                t[j] = tl; t[ncq + j] = tu;
+            }
+            const double* gxy = F(Y.gxy, k);
+            for (int c = 0; c < K; c++)
+            {
+                const double v = (k >= 1) ? gxy[c] * ux[HXV] + gxy[K + c] * ux[HYV] : 0.0;
+                const double tl = v - d[nbq + c], tu = -v - d[ncq + nbq + c];
+                t[nbq + c] = thr0 > tl ? thr0 : tl;
+                t[ncq + nbq + c] = thr0 > tu ? thr0 : tu;
+            }
+            for (int j = 0; j < ncq; j++)
+                if (row_active(k, j)) { lam[j] = mu0 / t[j]; lam[ncq + j] = mu0 / t[ncq + j]; }
+        }
+        syncwarp();
+    }
+
+    // QP residuals.  LIN = false: OCP_QP_RES_COMPUTE (HP/ocp_qp/x_ocp_qp_res.c:336-466) at the iterate (ux,pi,lam,t)
+    // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
+    // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
+    template <bool LIN>
+    MDEV void res_pass(double* out4)
+    {
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
+        const Field &fv = LIN ? Y.dux : Y.ux, &fp = LIN ? Y.dpi : Y.pi, &fl = LIN ? Y.dlam : Y.lam, &ft = LIN ? Y.dt : Y.t;
+        const Field &og = LIN ? Y.rg2 : Y.rg, &ob = LIN ? Y.rb2 : Y.rb, &od = LIN ? Y.rd2 : Y.rd;
+        for (int k = lane; k <= N; k += 32)
+        {
+            const double *v = F(fv, k), *pk = F(fp, k), *l = F(fl, k), *tt = F(ft, k);
+            const double *H = Hk(k), *cg = LIN ? F(Y.rg, k) : F(Y.rq, k), *cd = LIN ? F(Y.rd, k) : F(Y.d, k);
+            double *rg = F(og, k), *rd = F(od, k);
+            double g[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NV; j++) acc += H[i + NV * j] * v[j];
+                g[i] = acc + cg[i];
+            }
+            if (k > 0)
+            {
+                const double* pm = F(fp, k - 1);
+#pragma unroll
+                for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
+            }
+            if (k < N)
+            {
+                for (int j = 0; j < nbq; j++)
+                {
+                    if (!row_active(k, j)) continue;
+                    const int id = j < nbu ? j : NU + P.idxbx[j - nbu];
+                    const double dl = l[ncq + j] - l[j], vv = v[id];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) if (i == id) g[i] += dl;
+                    rd[j] = cd[j] + tt[j] - vv;
+                    rd[ncq + j] = cd[ncq + j] + tt[ncq + j] + vv;
+                }
+                const double* gxy = F(Y.gxy, k);
+                for (int c = 0; c < K; c++)
+                {
+                    const int r = nbq + c;
+                    const double gX = k >= 1 ? gxy[c] : 0.0, gY = k >= 1 ? gxy[K + c] : 0.0;
+                    const double dl = l[ncq + r] - l[r];
+                    g[HXV] += gX * dl; g[HYV] += gY * dl;
+                    const double vv = gX * v[HXV] + gY * v[HYV];
+                    rd[r] = cd[r] + tt[r] - vv;
+                    rd[ncq + r] = cd[ncq + r] + tt[ncq + r] + vv;
+                }
+                const double* BAt = F(Y.BAt, k);
+                const double* vn = F(fv, k + 1);
+                const double* cb = LIN ? F(Y.rb, k) : F(Y.b, k);
+                double* rb = F(ob, k);
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = cb[j] - vn[NU + j];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) if (var_active(k, i)) acc += BAt[i + NV * j] * v[i];
+                    rb[j] = acc;
+                    const double a = dabs(acc);
+                    n1 = a > n1 ? a : n1;
+                }
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += BAt[i + NV * j] * pk[j];
+                    g[i] += acc;
+                }
+                if (LIN)
+                {
+                    const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rm = F(Y.rmc, k);
+                    double* rm2 = F(Y.rm2, k);
+                    for (int j = 0; j < 2 * ncq; j++)
+                    {
+                        if (!row_active(k, j % ncq)) { rm2[j] = 0.0; continue; }
+                        const double m = rm[j] + lam[j] * tt[j] + l[j] * t[j];
+                        rm2[j] = m;
+                        const double a = dabs(m), b = dabs(rd[j]);
+                        n3 = a > n3 ? a : n3; n2 = b > n2 ? b : n2;
+                    }
+                }
+                else
+                {
+                    for (int j = 0; j < 2 * ncq; j++)
+                    {
+                        if (!row_active(k, j % ncq)) continue;
+                        const double m = l[j] * tt[j];
+                        musum += m;
+                        const double a = dabs(m), b = dabs(rd[j]);
+                        n3 = a > n3 ? a : n3; n2 = b > n2 ? b : n2;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                const double gi = var_active(k, i) ? g[i] : 0.0;
+                rg[i] = gi;
+                const double a = dabs(gi);
+                n0 = a > n0 ? a : n0;
+            }
+        }
+        out4[0] = warp_max(n0); out4[1] = warp_max(n1); out4[2] = warp_max(n2); out4[3] = warp_max(n3);
+        if (!LIN) mu = warp_sum(musum) / nct;
+        syncwarp();
+    }
+
+    // dt, dlam from dux (tail of HP/ocp_qp/x_ocp_qp_kkt.c:748-764 + COMPUTE_LAM_T_QP, HP/ipm_core/x_core_qp_ipm_aux.c:117-142),
+    // fused with COMPUTE_ALPHA_QP (:146-216) and the sums COMPUTE_MU_AFF_QP (:329-357) needs.
+    // mode 0: affine rhs (res_m = lam*t - tau_min); 1: rhs m stored in rmc; 2: refinement (rd2, rm2 -> dlam2, dt2)
+    MDEV void expand_pass(int mode, double tau)
+    {
+        const Field &fv = mode == 2 ? Y.dux2 : Y.dux, &fl = mode == 2 ? Y.dlam2 : Y.dlam, &ft = mode == 2 ? Y.dt2 : Y.dt;
+        const Field &frd = mode == 2 ? Y.rd2 : Y.rd, &frm = mode == 2 ? Y.rm2 : Y.rmc;
+        double a_prim = -1.0, a_dual = -1.0, s1 = 0.0, s2 = 0.0;
+        for (int k = lane; k < N; k += 32)
+        {
+            const double *v = F(fv, k), *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(frd, k), *rm = F(frm, k);
+            const double* gxy = F(Y.gxy, k);
+            double *dl = F(fl, k), *dtt = F(ft, k);
+            for (int j = 0; j < ncq; j++)
+            {
+                if (!row_active(k, j)) continue;
+                double dv;
+                if (j < nbq) dv = v[j < nbu ? j : NU + P.idxbx[j - nbu]];
+                else dv = k >= 1 ? gxy[j - nbq] * v[HXV] + gxy[K + j - nbq] * v[HYV] : 0.0;
+#pragma unroll
+                for (int side = 0; side < 2; side++)
+                {
+                    const int r = j + side * ncq;
+                    double dtr = side ? -dv : dv;
+                    const double lam0 = lam[r], t0 = t[r], tinv = 1.0 / t0;
+                    const double m = mode == 0 ? lam0 * t0 - tau : rm[r];
+                    const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd[r]));
+                    dtr -= rd[r];
+                    dl[r] = dlr; dtt[r] = dtr;
+                    if (a_dual * dlr > lam0) a_dual = lam0 / dlr;
+                    if (a_prim * dtr > t0) a_prim = t0 / dtr;
+                    s1 += lam0 * dtr + t0 * dlr;
+                    s2 += dlr * dtr;
+                }
+            }
+        }
+        if (mode != 2)
+        {
+            a_prim = warp_max(a_prim); a_dual = warp_max(a_dual);
+            alpha = -(a_prim > a_dual ? a_prim : a_dual);
+            S1 = warp_sum(s1); S2 = warp_sum(s2);
+        }
+        syncwarp();
+    }
+
+    // COMPUTE_ALPHA_QP on the current step (after iterative refinement changed it)
+    MDEV void alpha_pass()
+    {
+        double a_prim = -1.0, a_dual = -1.0;
+        for (int k = lane; k < N; k += 32)
+        {
+            const double *lam = F(Y.lam, k), *t = F(Y.t, k), *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+            for (int r = 0; r < 2 * ncq; r++)
+            {
+                if (!row_active(k, r % ncq)) continue;
+                if (a_dual * dl[r] > lam[r]) a_dual = lam[r] / dl[r];
+                if (a_prim * dtt[r] > t[r]) a_prim = t[r] / dtt[r];
+            }
+        }
+        a_prim = warp_max(a_prim); a_dual = warp_max(a_dual);
+        alpha = -(a_prim > a_dual ? a_prim : a_dual);
+    }
+
+    // rmc = lam*t + corr*dt*dlam - sigma_mu : right-hand side of the corrector / centering solve
+    // (HP/ocp_qp/x_ocp_qp_ipm.c:2138-2160, 2175-2200)
+    MDEV void set_rmc(double sigma_mu, bool with_aff)
+    {
+        for (int k = lane; k < N; k += 32)
+        {
+            const double *lam = F(Y.lam, k), *t = F(Y.t, k), *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+            double* rm = F(Y.rmc, k);
+            for (int r = 0; r < 2 * ncq; r++)
+            {
+                if (!row_active(k, r % ncq)) { rm[r] = 0.0; continue; }
+                const double bkp = lam[r] * t[r];
+                rm[r] = with_aff ? bkp + dtt[r] * dl[r] - sigma_mu : bkp - sigma_mu;
+            }
+        }
+        syncwarp();
+    }
+
+    // step += refinement step
+    MDEV void add_refinement()
+    {
+        for (int k = lane; k <= N; k += 32)
+        {
+            double *a = F(Y.dux, k); const double* b = F(Y.dux2, k);
+            for (int i = 0; i < NV; i++) a[i] += b[i];
+            if (k < N)
+            {
+                double* c = F(Y.dpi, k); const double* e = F(Y.dpi2, k);
+                for (int i = 0; i < NX; i++) c[i] += e[i];
+                double *l = F(Y.dlam, k), *t = F(Y.dt, k);
+                const double *l2 = F(Y.dlam2, k), *t2 = F(Y.dt2, k);
+                for (int r = 0; r < 2 * ncq; r++)
+                    if (row_active(k, r % ncq)) { l[r] += l2[r]; t[r] += t2[r]; }
+            }
+        }
+        syncwarp();
+    }
+
+    // UPDATE_VAR_QP: HP/ipm_core/x_core_qp_ipm_aux.c:220-325 (split_step = 0)
+    MDEV void update_pass(double a)
+    {
+        const double lam_min = 1e-16, t_min = 1e-16;
+        for (int k = lane; k <= N; k += 32)
+        {
+            double* ux = F(Y.ux, k); const double* dux = F(Y.dux, k);
+            for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
+            if (k < N)
+            {
+                double* pi = F(Y.pi, k); const double* dpi = F(Y.dpi, k);
+                for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
+                double *l = F(Y.lam, k), *t = F(Y.t, k);
+                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+                for (int r = 0; r < 2 * ncq; r++)
+                {
+                    if (!row_active(k, r % ncq)) continue;
+                    double x = l[r] + a * dl[r];
+                    l[r] = x <= lam_min ? lam_min : x;
+                    x = t[r] + a * dtt[r];
+                    t[r] = x <= t_min ? t_min : x;
+                }
+            }
+        }
+        syncwarp();
+    }
+
+    // ---------------------------------------------------------------- IPM: the Riccati sweeps (serial in k)
+    MDEV void load_BA(int k)
+    {
+        if (k < N)
+        {
+            const double* g = F(Y.BAt, k);
+            for (int e = lane; e < NV * NX; e += 32) sBA[e] = var_active(k, e % NV) ? g[e] : 0.0;
+        }
+        else
+            for (int e = lane; e < NV * NX; e += 32) sBA[e] = 0.0;
+    }
+    MDEV void load_gxy(int k)
+    {
+        if (k < N)
+        {
+            const double* g = F(Y.gxy, k);
+            for (int e = lane; e < 2 * K; e += 32) sgxy[e] = k >= 1 ? g[e] : 0.0;
+        }
+    }
+    MDEV void load_Lnext(int k1)  // xx block and nothing else of the factor of stage k1
+    {
+        const double* L = F(Y.L, k1);
+        for (int e = lane; e < NX * NX; e += 32)
+        {
+            const int m = e / NX, j = e % NX;
+            sLn[e] = L[(NU + m) * NV + NU + j];
+        }
+    }
+
+    // OCP_QP_FACT_SOLVE_KKT_STEP, backward part (HP/ocp_qp/x_ocp_qp_kkt.c:405-535) with COMPUTE_GAMMA_GAMMA_QP
+    // (HP/ipm_core/x_core_qp_ipm_aux.c:38-86) for the affine right-hand side res_m = lam*t - tau.
+    // Lane r <= NV owns row r of the (NV+1) x NV matrix [H + Gamma terms + AL AL' ; gradient row].
+    MDEV void factor_sweep(double tau, double reg)
+    {
+        for (int k = N; k >= 0; k--)
+        {
+            syncwarp();
+            load_BA(k);
+            load_gxy(k);
+            {
+                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(Y.rd, k);
+                for (int r = lane; r < 2 * ncq; r += 32)
+                {
+                    double G = 0.0, g = 0.0;
+                    if (row_active(k, r % ncq))
+                    {
+                        const double tinv = 1.0 / t[r];
+                        G = tinv * lam[r];
+                        g = tinv * ((lam[r] * t[r] - tau) - lam[r] * rd[r]);
+                    }
+                    sG[r] = G; sg[r] = g;
+                }
+                if (lane < NX) sx1[lane] = k < N ? F(Y.rb, k)[lane] : 0.0;
+            }
+            syncwarp();
+            const int r = lane;
+            const double* H = Hk(k);
+            const double* rg = F(Y.rg, k);
+            double Mr[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++)
+            {
+                double v = 0.0;
+                if (r < NV)
+                {
+                    if (var_active(k, r) && var_active(k, c)) { if (c <= r) v = H[r + NV * c]; if (c == r) v += reg; }
+                    else if (c == r) v = 1.0;
+                }
+                else if (r == NV) v = var_active(k, c) ? rg[c] : 0.0;
+                const int row = vrow(k, c);
+                if (row >= 0)
+                {
+                    if (r == c) v += sG[row] + sG[ncq + row];
+                    if (r == NV) v += sg[row] - sg[ncq + row];
+                }
+                Mr[c] = v;
+            }
+            if (k < N)
+            {
+                // AL = [B'; A'; res_b'] * Lxx_{k+1} ; Pb = Lxx (Lxx' res_b) ; last row += l_{k+1,x}
+                double bar[NX], AL[NX];
+#pragma unroll
+                for (int m = 0; m < NX; m++) bar[m] = r < NV ? sBA[r + NV * m] : (r == NV ? sx1[m] : 0.0);
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = j; m < NX; m++) acc += bar[m] * sLn[m * NX + j];
+                    AL[j] = acc;
+                }
+                if (r == NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) sx2[j] = AL[j];
+                }
+                syncwarp();
+                if (r < NX)
+                {
+                    double acc = 0.0;
+                    for (int j = 0; j <= r; j++) acc += sLn[r * NX + j] * sx2[j];
+                    F(Y.Pb, k)[r] = acc;
+                }
+                if (r == NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) AL[j] += slx[j];
+                }
+                if (r <= NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) sAL[r * NX + j] = AL[j];
+                }
+                syncwarp();
+                // syrk: M += AL AL'
+                if (r <= NV)
+                {
+#pragma unroll
+                    for (int c = 0; c < NV; c++)
+                    {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += AL[m] * sAL[c * NX + m];
+                        Mr[c] += acc;
+                    }
+                }
+                // obstacle rows: D diag(Gamma_l + Gamma_u) D' touches only the (X,Y) block; gradient row gets D (gamma_l - gamma_u)
+                if (r == HXV || r == HYV || r == NV)
+                {
+                    double aX = 0.0, aY = 0.0;
+                    for (int c = 0; c < K; c++)
+                    {
+                        const double gX = sgxy[c], gY = sgxy[K + c];
+                        const double G = sG[nbq + c] + sG[ncq + nbq + c];
+                        const double left = r == NV ? sg[nbq + c] - sg[ncq + nbq + c] : (r == HXV ? gX * G : gY * G);
+                        aX += left * gX; aY += left * gY;
+                    }
+                    Mr[HXV] += aX; Mr[HYV] += aY;
+                }
+            }
+            // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
+            // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710)
+#pragma unroll
+            for (int j = 0; j < NV; j++)
+            {
+                const double a = shfl(Mr[j], j);
+                double sq = 0.0, inv = 0.0;
+                if (a > 0.0) { sq = dsqrt(a); inv = 1.0 / sq; }
+                if (r == j) Mr[j] = sq; else Mr[j] *= inv;
+#pragma unroll
+                for (int c = j + 1; c < NV; c++)
+                {
+                    const double lc = shfl(Mr[j], c);
+                    Mr[c] -= Mr[j] * lc;
+                }
+            }
+            syncwarp();
+            // store the factor; row NV is also the backward vector of the forward substitution
+            if (r <= NV)
+            {
+                double* L = F(Y.L, k);
+#pragma unroll
+                for (int c = 0; c < NV; c++) L[r * NV + c] = (c <= r) ? Mr[c] : 0.0;
+                if (r >= NU && r < NV)
+                {
+#pragma unroll
+                    for (int c = NU; c < NV; c++) sLn[(r - NU) * NX + (c - NU)] = (c <= r) ? Mr[c] : 0.0;
+                }
+                if (r == NV)
+                {
+                    double* dux = F(Y.dux, k);
+#pragma unroll
+                    for (int c = 0; c < NV; c++) dux[c] = Mr[c];
+#pragma unroll
+                    for (int c = NU; c < NV; c++) slx[c - NU] = Mr[c];
+                }
+            }
+        }
+        syncwarp();
+    }
+
+    // forward substitution shared by both solves.  On entry dux[k] holds the backward vector; scaled: its x part is
+    // l_{k,x} (row NV of the factor; HP/ocp_qp/x_ocp_qp_kkt.c:537-575), else p_k itself (:1243-1290).
+    MDEV void forward_sweep(const Field& frb, const Field& fdux, const Field& fdpi, bool scaled)
+    {
+        double xc[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xc[i] = 0.0;
+        for (int k = 0; k <= N; k++)
+        {
+            syncwarp();
+            {
+                const double* L = F(Y.L, k);
+                for (int e = lane; e < NR * NV; e += 32) sL[e] = L[e];
+                const double* q = F(fdux, k);
+                if (lane < NU) sq[lane] = q[lane];
+                if (k < N)
+                {
+                    load_BA(k);
+                    load_Lnext(k + 1);
+                    if (lane < NX) { sx1[lane] = F(frb, k)[lane]; sx2[lane] = F(fdux, k + 1)[NU + lane]; }
+                }
+            }
+            syncwarp();
+            double z[NV];
+#pragma unroll
+            for (int i = 0; i < NX; i++) z[NU + i] = xc[i];
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--)  // dtrsv_ltn on the columns solved at this stage
+            {
+                double acc = -sq[i];
+#pragma unroll
+                for (int m = i + 1; m < NV; m++) acc -= sL[m * NV + i] * z[m];
+                z[i] = acc / sL[i * NV + i];
+            }
+            if (lane == 0)
+            {
+                double* o = F(fdux, k);
+#pragma unroll
+                for (int i = 0; i < NV; i++) o[i] = var_active(k, i) ? z[i] : 0.0;
+            }
+            if (k < N)
+            {
+                double x1 = 0.0;
+                if (lane < NX)
+                {
+                    double acc = sx1[lane];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) acc += sBA[i + NV * lane] * z[i];
+                    x1 = acc;
+                }
+#pragma unroll
+                for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+                // dpi_k = Lxx (Lxx' dx_{k+1} + l_x)  |  p_{k+1} + Lxx (Lxx' dx_{k+1})
+                double tmp = 0.0;
+                if (lane < NX)
+                {
+                    double acc = 0.0;
+                    for (int m = lane; m < NX; m++) acc += sLn[m * NX + lane] * xc[m];
+                    tmp = scaled ? acc + sx2[lane] : acc;
+                }
+                double tv[NX];
+#pragma unroll
+                for (int j = 0; j < NX; j++) tv[j] = shfl(tmp, j);
+                if (lane < NX)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) if (j <= lane) acc += sLn[lane * NX + j] * tv[j];
+                    F(fdpi, k)[lane] = scaled ? acc : sx2[lane] + acc;
+                }
+            }
+        }
+        syncwarp();
+    }
+
+    // OCP_QP_SOLVE_KKT_STEP, backward part (HP/ocp_qp/x_ocp_qp_kkt.c:1096-1242) with COMPUTE_GAMMA_QP
+    // (x_core_qp_ipm_aux.c:89-113).  refine = false: rhs (rg, rb via Pb, rd, rmc) -> dux ; true: (rg2, rb2, rd2, rm2) -> dux2.
+    MDEV void solve_sweep(bool refine)
+    {
+        const Field &frg = refine ? Y.rg2 : Y.rg, &frb = refine ? Y.rb2 : Y.rb, &frd = refine ? Y.rd2 : Y.rd;
+        const Field &frm = refine ? Y.rm2 : Y.rmc, &fo = refine ? Y.dux2 : Y.dux;
+        double pn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) pn[i] = 0.0;
+        for (int k = N; k >= 0; k--)
+        {
+            syncwarp();
+            load_BA(k);
+            load_gxy(k);
+            {
+                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(frd, k), *rm = F(frm, k);
+                for (int r = lane; r < 2 * ncq; r += 32)
+                {
+                    double g = 0.0;
+                    if (row_active(k, r % ncq)) g = (1.0 / t[r]) * (rm[r] - lam[r] * rd[r]);
+                    sg[r] = g;
+                }
+                if (k < N)
+                {
+                    if (refine) { load_Lnext(k + 1); if (lane < NX) sx1[lane] = F(frb, k)[lane]; }
+                    else if (lane < NX) sx1[lane] = F(Y.Pb, k)[lane];
+                }
+            }
+            syncwarp();
+            const int i = lane;
+            double zi = 0.0;
+            if (i < NV && var_active(k, i))
+            {
+                zi = F(frg, k)[i];
+                const int row = vrow(k, i);
+                if (row >= 0) zi += sg[row] - sg[ncq + row];
+                if (k < N && (i == HXV || i == HYV))
+                {
+                    for (int c = 0; c < K; c++)
+                    {
+                        const double gd = sg[nbq + c] - sg[ncq + nbq + c];
+                        zi += (i == HXV ? sgxy[c] : sgxy[K + c]) * gd;
+                    }
+                }
+            }
+            if (k < N)
+            {
+                double tmp[NX];
+                if (!refine)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) tmp[j] = pn[j] + sx1[j];
+                }
+                else
+                {
+                    double t2[NX];
+#pragma unroll
+                    for (int j = 0; j < NX; j++)
+                    {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = j; m < NX; m++) acc += sLn[m * NX + j] * sx1[m];
+                        t2[j] = acc;
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < NX; ii++)
+                    {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j <= ii; j++) acc += sLn[ii * NX + j] * t2[j];
+                        tmp[ii] = acc + pn[ii];
+                    }
+                }
+                if (i < NV)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += sBA[i + NV * j] * tmp[j];
+                    zi += acc;
+                }
+            }
+            // dtrsv_lnn_mn(nv, nu): forward-eliminate the columns solved at this stage
+            const double* L = F(Y.L, k);
+#pragma unroll
+            for (int m = 0; m < NU; m++)
+            {
+                if (i == m) zi = zi / L[m * NV + m];
+                const double bm = shfl(zi, m);
+                if (i > m && i < NV) zi -= L[i * NV + m] * bm;
+            }
+            if (i < NV) F(fo, k)[i] = zi;
+#pragma unroll
+            for (int j = 0; j < NX; j++) pn[j] = shfl(zi, NU + j);
+        }
+        solve_calls++;
+        syncwarp();
+    }
+
+    MDEV bool itref_ok(const double* n) const
+    {
+        return (n[0] < tol_stat || n[0] < 1e-3 * res_max[0]) && (n[1] < tol_eq || n[1] < 1e-3 * res_max[1]) &&
+               (n[2] < tol_ineq || n[2] < 1e-3 * res_max[2]) && (n[3] < tol_comp || n[3] < 1e-3 * res_max[3]);
+    }
+
+    // OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:1888-2350 (pred_corr, cond_pred_corr, itref_corr_max = 2)
+    MDEV void delta_step()
+    {
+        const double tau_min = 1e-16, reg_prim = 1e-15;
+        factor_sweep(tau_min, reg_prim);
+        forward_sweep(Y.rb, Y.dux, Y.dpi, true);
+        expand_pass(0, tau_min);
+        {
+            mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+            const double tmp = mu_aff / mu;
+            sigma = tmp * tmp * tmp;
+            double sigma_mu = sigma * mu;
+            sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
+            set_rmc(sigma_mu, true);
+            solve_sweep(false);
+            forward_sweep(Y.rb, Y.dux, Y.dpi, false);
+            expand_pass(1, 0.0);
+            {
+                const double mu_aff0 = mu_aff;
+                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+                if (mu_aff > 2.0 * mu_aff0)
+                {
+                    set_rmc(sigma_mu, false);
+                    solve_sweep(false);
+                    forward_sweep(Y.rb, Y.dux, Y.dpi, false);
+                    expand_pass(1, 0.0);
+                }
+            }
+            bool refined = false;
+            for (int it = 0; it < 2; it++)
+            {
+                double n[4];
+                res_pass<true>(n);
+                if (itref_ok(n)) break;
+                solve_sweep(true);
+                forward_sweep(Y.rb2, Y.dux2, Y.dpi2, false);
+                expand_pass(2, 0.0);
+                add_refinement();
+                refined = true;
+            }
+            if (refined) alpha_pass();
+        }
+        double a = alpha;
+        if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+        update_pass(a);
+    }
+
+    // OCP_QP_IPM_SOLVE: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683 ; returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN
+    MDEV int ipm_solve(int* iters)
+    {
+        const double tau_min = 1e-16, alpha_min = 1e-8;
+        ipm_init();
+        alpha = 1.0;
+        res_pass<false>(res_max);
+        int kk;
+        for (kk = 0; kk < iter_max && alpha > alpha_min &&
+                     (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
+                      dabs(res_max[3] - tau_min) > tol_comp);
+             kk++)
+        {
+            delta_step();
+            res_pass<false>(res_max);
+        }
+        *iters = kk;
+        if (kk == iter_max) return 1;
+        if (alpha <= alpha_min) return 2;
+        if (disnan(mu)) return 3;
+        return 0;
+    }
+
+    // ---------------------------------------------------------------- after the QP
+    // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step
+    // (AC/acados/ocp_nlp/ocp_nlp_common.c:2401-2448): ux += step; pi, lam, t <- QP values.
+    MDEV void update_nlp()
+    {
+        for (int k = lane; k <= N; k += 32)
+        {
+            double *z = F(Y.zux, k), *zl = F(Y.zlam, k), *zt = F(Y.zt, k);
+            const double *ux = F(Y.ux, k), *lam = F(Y.lam, k), *t = F(Y.t, k);
+            if (k < N)
+            {
+                double* zp = F(Y.zpi, k); const double* pi = F(Y.pi, k);
+                for (int i = 0; i < NX; i++) zp[i] = pi[i];
+                for (int j = 0; j < nbu; j++) { zl[j] = lam[j]; zl[ncz + j] = lam[ncq + j]; zt[j] = t[j]; zt[ncz + j] = t[ncq + j]; }
+                for (int c = 0; c < K; c++)
+                {
+                    const int a = nbu + NX + c, b = nbq + c;
+                    zl[a] = lam[b]; zl[ncz + a] = lam[ncq + b]; zt[a] = t[b]; zt[ncz + a] = t[ncq + b];
+                }
+            }
+            if (k == 0)
+            {
+                // recover the eliminated x0 step and the multipliers of its bounds from stationarity
+                const double* zf = F(Y.zfun, 0);
+                double s[NV], tmp[NV];
+                for (int i = 0; i < NU; i++) s[i] = ux[i];
+                for (int i = 0; i < NX; i++) s[NU + i] = zf[nbu + i];  // dx0 = x0 - x_0
+                const double* rq = F(Y.rq, 0);
+                const double* BAt = F(Y.BAt, 0);
+                const double* pi = F(Y.pi, 0);
+                const double* gxy = F(Y.gxy, 0);
+                for (int i = 0; i < NX; i++)
+                {
+                    const int iv = NU + i;
+                    double acc = rq[iv];
+                    double hs = 0.0;
+                    for (int j = 0; j < NV; j++) hs += Hs[iv + NV * j] * s[j];
+                    acc += hs;
+                    if (N > 0) for (int j = 0; j < NX; j++) acc += BAt[iv + NV * j] * pi[j];
+                    if (iv == HXV || iv == HYV)
+                        for (int c = 0; c < K; c++)
+                        {
+                            const double dl = lam[ncq + nbq + c] - lam[nbq + c];
+                            acc += (iv == HXV ? gxy[c] : gxy[K + c]) * dl;
+                        }
+                    tmp[iv] = acc;
+                }
+                for (int j = 0; j < NX; j++)
+                {
+                    const int r = nbu + j;
+                    const double v = tmp[NU + j];
+                    zl[r] = 1e-16; zl[ncz + r] = 1e-16; zt[r] = 1e-16; zt[ncz + r] = 1e-16;
+                    if (v >= 0) zl[r] = v; else zl[ncz + r] = -v;
+                }
+                for (int i = 0; i < NV; i++) z[i] += s[i];
+            }
+            else
+            {
+                for (int j = 0; j < nbx; j++)
+                {
+                    const int a = nbu + j;
+                    if (k < N) { zl[a] = lam[a]; zl[ncz + a] = lam[ncq + a]; zt[a] = t[a]; zt[ncz + a] = t[ncq + a]; }
+                }
+                for (int i = 0; i < NV; i++) if (var_active(k, i)) z[i] += ux[i];
+            }
+        }
+        syncwarp();
+    }
+
+    // residuals ocp_nlp_eval_residuals reports after an SQP_RTI step: stale linearisation, new lam / t
+    // (AC/interfaces/acados_c/ocp_nlp_interface.c:909-916)
+    MDEV void rti_residuals(double* res4)
+    {
+        double r2 = 0, r3 = 0;
+        for (int k = lane; k < N; k += 32)
+        {
+            const double *zl = F(Y.zlam, k), *zt = F(Y.zt, k), *zf = F(Y.zfun, k);
+            for (int j = 0; j < 2 * ncz; j++)
+            {
+                const int jj = j % ncz;
+                const bool act = jj < nbu || jj >= nbu + NX || (k == 0 ? true : jj - nbu < nbx);
+                if (!act) continue;
+                const double a = dabs(zf[j] + zt[j]), c = dabs(zl[j] * zt[j]);
+                r2 = a > r2 ? a : r2; r3 = c > r3 ? c : r3;
+            }
+        }
+        res4[2] = warp_max(r2); res4[3] = warp_max(r3);
+    }
+
+    // ---------------------------------------------------------------- the solve
+    MDEV void run(int inst)
+    {
+        const double* x0 = P.x0 + (long) inst * NX;
+        const double* pg = P.p + (long) inst * (P.p_per_stage ? (N + 1) : 1) * 2 * K;
+        const double* lhg = P.lh + (long) inst * (P.lh_per_stage ? N : 1) * K;
+        const double* yrg = P.yref + (long) inst * (P.yref_per_stage ? N : 1) * NY;
+        const double* yre = P.yref_e + (long) inst * NX;
+        load_constants();
+        if (P.cold_start) cold_start(x0);
+        int status = 2, sqp_iter = 0, qp_total = 0, qp_status = 0, qp_iter = 0;
+        double res[4] = {0, 0, 0, 0};
+        const int max_iter = P.nlp_type == 0 ? P.max_iter : 1;
+        for (sqp_iter = 0; sqp_iter < max_iter; sqp_iter++)
+        {
+            linearize(x0, pg, lhg, yrg, yre, res);
+            if (P.nlp_type == 0 && res[0] < P.tol[0] && res[1] < P.tol[1] && res[2] < P.tol[2] && res[3] < P.tol[3])
+            {
+                status = 0;  // ACADOS_SUCCESS, ocp_nlp_sqp.c:641-672
+                break;
+            }
+            qp_status = ipm_solve(&qp_iter);
+            qp_total += qp_iter;
+            if (qp_status != 0 && qp_status != 1)
+            {
+                status = 4;  // ACADOS_QP_FAILURE, ocp_nlp_sqp.c:736-773
+                break;
+            }
+            update_nlp();
+            if (P.nlp_type == 1)
+            {
+                status = 0;  // ocp_nlp_sqp_rti.c:810-817
+                rti_residuals(res);
+                sqp_iter = 1;
+                break;
+            }
+        }
+        if (lane == 0)
+        {
+            double* st = P.stats + (long) inst * NSTAT;
+            st[0] = status; st[1] = sqp_iter; st[2] = qp_total;
+            st[3] = res[0]; st[4] = res[1]; st[5] = res[2]; st[6] = res[3];
+            st[7] = 0; st[8] = solve_calls; st[9] = qp_status; st[10] = qp_iter; st[11] = 0;
+        }
+    }
+};
+
+}  // namespace usvmpc

@@ -1,0 +1,117 @@
+// warp_compat.h -- one source for the warp-per-instance NMPC kernel, two ways to build it.
+//
+//  * nvcc (the product): the macros below map 1:1 onto CUDA warp intrinsics.
+//  * g++ -DUSVMPC_EMULATE (tests/emu only): 32 cooperative fibers stand in for the 32 lanes of ONE
+//    warp, switching at every shuffle / __syncwarp, so the very same device functions can be run,
+//    address-sanitised and compared with the oracle on a machine without a GPU.  The emulation is
+//    test infrastructure; nothing in the product path is built with USVMPC_EMULATE.
+#pragma once
+
+#ifndef USVMPC_EMULATE
+// ------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+#define DEV __device__ __forceinline__
+#define MDEV __device__ __forceinline__
+#define DEVNI __device__ __noinline__
+#define HD __host__ __device__ __forceinline__
+
+namespace usvmpc {
+DEV int lane_id() { return threadIdx.x & 31; }
+DEV double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+DEV void syncwarp() { __syncwarp(); }
+DEV double dsqrt(double a) { return sqrt(a); }
+DEV double dabs(double a) { return fabs(a); }
+DEV void dsincos(double a, double* s, double* c) { sincos(a, s, c); }
+DEV bool disnan(double a) { return isnan(a); }
+}  // namespace usvmpc
+
+#else
+// ------------------------------------------------------------------ CPU fiber emulation of one warp
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#define DEV static inline
+#define MDEV inline
+#define DEVNI static
+#define HD static inline
+
+namespace usvmpc {
+namespace emu {
+constexpr int WARP = 32;
+extern "C" void usvmpc_fiber_switch(void** save_sp, void* new_sp);
+struct Warp {
+    void* sp[WARP];
+    void* main_sp;
+    char* stacks;
+    int cur;
+    double slot_d[WARP];
+    long slot_i[WARP];
+    void (*body)(void*);
+    void* arg;
+};
+extern thread_local Warp* g_warp;
+// hand control to the next lane; returns when every other lane has reached its own next yield
+inline void yield_lane()
+{
+    Warp* w = g_warp;
+    int me = w->cur, nx = (me + 1) % WARP;
+    w->cur = nx;
+    usvmpc_fiber_switch(&w->sp[me], w->sp[nx]);
+}
+void run_warp(void (*body)(void*), void* arg);  // defined in tests/emu/emu_runtime.cpp
+}  // namespace emu
+
+DEV int lane_id() { return emu::g_warp->cur; }
+DEV double shfl(double v, int src)
+{
+    emu::Warp* w = emu::g_warp;
+    w->slot_d[w->cur] = v;
+    emu::yield_lane();
+    double r = w->slot_d[src & 31];
+    emu::yield_lane();
+    return r;
+}
+DEV int shfl(int v, int src)
+{
+    emu::Warp* w = emu::g_warp;
+    w->slot_i[w->cur] = v;
+    emu::yield_lane();
+    int r = (int) w->slot_i[src & 31];
+    emu::yield_lane();
+    return r;
+}
+DEV double shfl_xor(double v, int m) { return shfl(v, lane_id() ^ m); }
+DEV int shfl_xor(int v, int m) { return shfl(v, lane_id() ^ m); }
+DEV void syncwarp() { emu::yield_lane(); }
+DEV double dsqrt(double a) { return std::sqrt(a); }
+DEV double dabs(double a) { return std::fabs(a); }
+DEV void dsincos(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
+DEV bool disnan(double a) { return std::isnan(a); }
+}  // namespace usvmpc
+#endif
+
+namespace usvmpc {
+// butterfly reductions; every lane ends up with the result
+DEV double warp_max(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { double o = shfl_xor(v, m); v = o > v ? o : v; }
+    return v;
+}
+DEV double warp_sum(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+    return v;
+}
+DEV int warp_or(int v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v |= shfl_xor(v, m);
+    return v;
+}
+}  // namespace usvmpc
