@@ -1,0 +1,518 @@
+// usvmpc_api.cu -- C ABI (include/usvmpc.h) over the warp-per-instance NMPC kernel.
+// Host side: owns the HBM working set of B instances, moves caller data in and out with the reference's
+// field names, launches ONE persistent kernel per solve (one warp per instance, csrc/nmpc_kernel.cuh).
+// Built by mpc_collisionavoidance_b200/build.py:  nvcc -gencode arch=compute_100a,code=sm_100a -shared ...
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/usvmpc.h"
+#include "nmpc_kernel.cuh"
+
+using namespace usvmpc;
+
+namespace {
+
+constexpr int WPC = 4;  // warps (= instances) per CTA
+#ifndef USVMPC_MIN_CTAS
+#define USVMPC_MIN_CTAS 4  // resident CTAs per SM the register allocation must allow (4 x 4 = 16 warps/SM)
+#endif
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) return fail(USVMPC_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class M>
+__global__ void __launch_bounds__(WPC * 32, USVMPC_MIN_CTAS) nmpc_solve_kernel(const __grid_constant__ Params P, int smem_per_warp)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int inst = blockIdx.x * WPC + warp;
+    if (inst >= P.B) return;
+    WarpSolver<M> s(P, inst, smem + (size_t) warp * smem_per_warp);
+    s.run(inst);
+}
+
+// buf[b][k][i] <-> ws[b*stride + off + (k0+k)*fstride + c0 + i]
+__global__ void ws_copy_kernel(double* ws, long stride, int off, int fstride, int c0, int dim, int k0, int nst, int B,
+                               double* buf, int to_ws)
+{
+    const long n = (long) B * nst * dim;
+    for (long idx = blockIdx.x * (long) blockDim.x + threadIdx.x; idx < n; idx += (long) gridDim.x * blockDim.x)
+    {
+        const int i = (int) (idx % dim);
+        const int k = (int) ((idx / dim) % nst);
+        const long b = idx / ((long) dim * nst);
+        double* a = ws + b * stride + off + (long) (k0 + k) * fstride + c0 + i;
+        if (to_ws) *a = buf[idx]; else buf[idx] = *a;
+    }
+}
+
+// multipliers / slacks of one stage between the engine's NLP row layout (layout.h) and the reference's order
+// [lbu lbx lh | ubu ubx uh] with the stage's own counts (acados_template/acados_ocp_solver.py:732-735)
+__global__ void ws_rows_kernel(double* ws, long stride, int off, int ncz, int nbu, int nxslots, int nbxk, int K, int B,
+                               double* buf, int to_ws)
+{
+    const int nck = nbu + nbxk + K;
+    const long n = (long) B * 2 * nck;
+    for (long idx = blockIdx.x * (long) blockDim.x + threadIdx.x; idx < n; idx += (long) gridDim.x * blockDim.x)
+    {
+        const int j = (int) (idx % (2 * nck));
+        const long b = idx / (2 * nck);
+        const int side = j / nck, jj = j % nck;
+        const int src = jj < nbu + nbxk ? jj : nbu + nxslots + (jj - nbu - nbxk);
+        double* a = ws + b * stride + off + side * ncz + src;
+        if (to_ws) *a = buf[idx]; else buf[idx] = *a;
+    }
+}
+
+// dst[b][k][i] = src[b][i]
+__global__ void broadcast_kernel(double* dst, const double* src, int B, int nst, int dim)
+{
+    const long n = (long) B * nst * dim;
+    for (long idx = blockIdx.x * (long) blockDim.x + threadIdx.x; idx < n; idx += (long) gridDim.x * blockDim.x)
+    {
+        const int i = (int) (idx % dim);
+        const long b = idx / ((long) dim * nst);
+        dst[idx] = src[b * dim + i];
+    }
+}
+
+int grid_for(long n) { long g = (n + 255) / 256; return (int) (g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); }
+
+}  // namespace
+
+struct usvmpc_solver
+{
+    usvmpc_config cfg;
+    int B, device, nx, nu, nv;
+    Params P;
+    double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e;
+    double *d_p[2], *d_lh[2], *d_yref[2];  // [0] one row per instance, [1] one row per instance and stage
+    double* d_stage;
+    size_t stage_bytes;
+    long launches;
+    int smem_per_warp;
+};
+
+namespace {
+
+int model_dims(int model, int* nx, int* nu)
+{
+    if (model == USVMPC_MODEL_USV3) { *nx = Usv3::NX; *nu = Usv3::NU; return 0; }
+    if (model == USVMPC_MODEL_PENDULUM) { *nx = Pendulum::NX; *nu = Pendulum::NU; return 0; }
+    return -1;
+}
+
+int upload_constants(usvmpc_solver* s, cudaStream_t st)
+{
+    const int ny = s->nv, nx = s->nx;
+    double tmp[16 * 16 * 2];
+    for (int j = 0; j < ny; j++) for (int i = 0; i < ny; i++) tmp[i + ny * j] = s->cfg.W[i + ny * j];
+    for (int j = 0; j < nx; j++) for (int i = 0; i < nx; i++) tmp[ny * ny + i + nx * j] = s->cfg.W_e[i + nx * j];
+    CU(cudaMemcpyAsync(s->d_cst, tmp, sizeof(double) * (ny * ny + nx * nx), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+void refresh_params(usvmpc_solver* s)
+{
+    Params& P = s->P;
+    const usvmpc_config& c = s->cfg;
+    P.B = s->B; P.N = c.N; P.K = c.K; P.num_steps = c.num_steps; P.num_stages = c.num_stages; P.nlp_type = c.nlp_type;
+    P.max_iter = c.max_iter; P.qp_iter_max = c.qp_iter_max; P.nbx = c.nbx; P.nbu = c.nbu;
+    for (int i = 0; i < NBXMAX; i++) { P.idxbx[i] = c.idxbx[i]; P.lbx[i] = c.lbx[i]; P.ubx[i] = c.ubx[i]; }
+    for (int i = 0; i < NBUMAX; i++) { P.lbu[i] = c.lbu[i]; P.ubu[i] = c.ubu[i]; }
+    P.ncq = c.nbu + c.nbx + c.K; P.ncz = c.nbu + s->nx + c.K;
+    P.dt = c.dt; P.uh = c.uh;
+    for (int i = 0; i < 4; i++) P.tol[i] = c.tol[i];
+    P.cst = s->d_cst; P.x0 = s->d_x0; P.yref_e = s->d_yref_e;
+    P.p = s->d_p[P.p_per_stage]; P.lh = s->d_lh[P.lh_per_stage]; P.yref = s->d_yref[P.yref_per_stage];
+    P.ws = s->d_ws; P.stats = s->d_stats;
+}
+
+// make sure the per-stage copy of an input exists and is current before a single stage of it is written
+int want_per_stage(usvmpc_solver* s, double** pair, int* flag, int nst, int dim, cudaStream_t st)
+{
+    if (dim == 0) return 0;
+    if (!pair[1]) CU(cudaMalloc(&pair[1], sizeof(double) * (size_t) s->B * nst * dim));
+    if (!*flag)
+    {
+        broadcast_kernel<<<grid_for((long) s->B * nst * dim), 256, 0, st>>>(pair[1], pair[0], s->B, nst, dim);
+        CU(cudaGetLastError());
+        s->launches++;
+        *flag = 1;
+    }
+    return 0;
+}
+
+// write value [B][dim] (stage >= 0), [B][nst][dim] (ALL_STAGES) or [B][dim] for every stage (EVERY_STAGE)
+int set_input(usvmpc_solver* s, double** pair, int* flag, int nst, int dim, int stage, const double* value, cudaStream_t st)
+{
+    if (dim == 0) return 0;
+    if (stage == USVMPC_EVERY_STAGE)
+    {
+        CU(cudaMemcpyAsync(pair[0], value, sizeof(double) * (size_t) s->B * dim, cudaMemcpyDefault, st));
+        *flag = 0;
+    }
+    else if (stage == USVMPC_ALL_STAGES)
+    {
+        if (!pair[1]) CU(cudaMalloc(&pair[1], sizeof(double) * (size_t) s->B * nst * dim));
+        CU(cudaMemcpyAsync(pair[1], value, sizeof(double) * (size_t) s->B * nst * dim, cudaMemcpyDefault, st));
+        *flag = 1;
+    }
+    else
+    {
+        if (stage < 0 || stage >= nst) return fail(USVMPC_E_INVALID, "stage %d out of range [0,%d)", stage, nst);
+        int rc = want_per_stage(s, pair, flag, nst, dim, st);
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync(pair[1] + (size_t) stage * dim, sizeof(double) * nst * dim, value, sizeof(double) * dim,
+                             sizeof(double) * dim, s->B, cudaMemcpyDefault, st));
+    }
+    refresh_params(s);
+    return 0;
+}
+
+int need_stage_buf(usvmpc_solver* s, size_t bytes)
+{
+    if (bytes <= s->stage_bytes) return 0;
+    if (s->d_stage) CU(cudaFree(s->d_stage));
+    s->d_stage = nullptr; s->stage_bytes = 0;
+    CU(cudaMalloc(&s->d_stage, bytes));
+    s->stage_bytes = bytes;
+    return 0;
+}
+
+// field of the NLP iterate: resolve to (layout field, first column, dim, number of stages it exists on)
+int out_field(usvmpc_solver* s, const char* field, Field* f, int* c0, int* dim, int* nst)
+{
+    const Layout& Y = s->P.lay;
+    if (!strcmp(field, "x")) { *f = Y.zux; *c0 = s->nu; *dim = s->nx; *nst = s->cfg.N + 1; return 0; }
+    if (!strcmp(field, "u")) { *f = Y.zux; *c0 = 0; *dim = s->nu; *nst = s->cfg.N; return 0; }
+    if (!strcmp(field, "pi")) { *f = Y.zpi; *c0 = 0; *dim = s->nx; *nst = s->cfg.N; return 0; }
+    return -1;
+}
+
+int out_copy(usvmpc_solver* s, int stage, const char* field, double* value, int on_device, void* stream, int to_ws)
+{
+    if (!s || !field || !value) return fail(USVMPC_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(s->device));
+    const int N = s->cfg.N, B = s->B;
+    Field f; int c0, dim, nst;
+    if (out_field(s, field, &f, &c0, &dim, &nst) == 0)
+    {
+        int k0 = stage, ns = 1;
+        if (stage == USVMPC_ALL_STAGES) { k0 = 0; ns = nst; }
+        else if (stage < 0 || stage >= nst) return fail(USVMPC_E_INVALID, "field %s has no stage %d", field, stage);
+        const size_t bytes = sizeof(double) * (size_t) B * ns * dim;
+        double* buf = value;
+        if (!on_device)
+        {
+            int rc = need_stage_buf(s, bytes);
+            if (rc) return rc;
+            buf = s->d_stage;
+            if (to_ws) CU(cudaMemcpyAsync(buf, value, bytes, cudaMemcpyHostToDevice, st));
+        }
+        ws_copy_kernel<<<grid_for((long) B * ns * dim), 256, 0, st>>>(s->d_ws, s->P.ws_stride, f.off, f.stride, c0, dim, k0, ns, B, buf, to_ws);
+        CU(cudaGetLastError());
+        s->launches++;
+        if (!on_device)
+        {
+            if (!to_ws) CU(cudaMemcpyAsync(value, buf, bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
+    if (!strcmp(field, "lam") || !strcmp(field, "t"))
+    {
+        if (stage < 0 || stage > N) return fail(USVMPC_E_INVALID, "field %s needs a stage in [0,%d]", field, N);
+        const int nbxk = stage == 0 ? s->nx : (stage < N ? s->cfg.nbx : 0);
+        const int nbuk = stage < N ? s->cfg.nbu : 0, Kk = stage < N ? s->cfg.K : 0;
+        const int nck = nbuk + nbxk + Kk;
+        if (nck == 0) return 0;
+        const Field& fl = !strcmp(field, "lam") ? s->P.lay.zlam : s->P.lay.zt;
+        const size_t bytes = sizeof(double) * (size_t) B * 2 * nck;
+        double* buf = value;
+        if (!on_device)
+        {
+            int rc = need_stage_buf(s, bytes);
+            if (rc) return rc;
+            buf = s->d_stage;
+            if (to_ws) CU(cudaMemcpyAsync(buf, value, bytes, cudaMemcpyHostToDevice, st));
+        }
+        ws_rows_kernel<<<grid_for((long) B * 2 * nck), 256, 0, st>>>(s->d_ws, s->P.ws_stride, fl.off + stage * fl.stride, s->P.ncz,
+                                                                     s->cfg.nbu, s->nx, nbxk, s->cfg.K, B, buf, to_ws);
+        CU(cudaGetLastError());
+        s->launches++;
+        if (!on_device)
+        {
+            if (!to_ws) CU(cudaMemcpyAsync(value, buf, bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
+    if (!strcmp(field, "sl") || !strcmp(field, "su") || !strcmp(field, "z")) return 0;  // ns = nz = 0
+    return fail(USVMPC_E_FIELD, "unknown field '%s' (x, u, pi, lam, t, sl, su, z)", field);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* usvmpc_last_error(void) { return g_err; }
+const char* usvmpc_version(void) { return "usvmpc 0.1 (sm_100a, warp-per-instance fp64)"; }
+
+int usvmpc_config_default(usvmpc_config* c, int model)
+{
+    if (!c) return fail(USVMPC_E_INVALID, "null config");
+    int nx, nu;
+    if (model_dims(model, &nx, &nu)) return fail(USVMPC_E_INVALID, "unknown model %d", model);
+    memset(c, 0, sizeof(*c));
+    c->model = model; c->N = 20; c->K = 0; c->num_steps = 1; c->num_stages = 4;
+    c->nlp_type = USVMPC_SQP_RTI; c->max_iter = 100; c->qp_iter_max = 50;
+    c->dt = 0.05; c->uh = 1e6;
+    for (int i = 0; i < 4; i++) c->tol[i] = 1e-6;
+    for (int i = 0; i < nx + nu; i++) c->W[i + (nx + nu) * i] = 1.0;
+    for (int i = 0; i < nx; i++) c->W_e[i + nx * i] = 1.0;
+    return 0;
+}
+
+int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver** out)
+{
+    if (!cfg || !out) return fail(USVMPC_E_INVALID, "null argument");
+    int nx, nu;
+    if (model_dims(cfg->model, &nx, &nu)) return fail(USVMPC_E_INVALID, "unknown model %d", cfg->model);
+    if (batch < 1 || cfg->N < 1) return fail(USVMPC_E_INVALID, "batch and N must be >= 1");
+    if (cfg->K < 0 || cfg->K > KMAX) return fail(USVMPC_E_INVALID, "K=%d outside [0,%d]", cfg->K, KMAX);
+    if (cfg->nbx < 0 || cfg->nbx > nx || cfg->nbu < 0 || cfg->nbu > nu) return fail(USVMPC_E_INVALID, "nbx/nbu out of range");
+    if (cfg->num_stages != 1 && cfg->num_stages != 2 && cfg->num_stages != 4) return fail(USVMPC_E_INVALID, "ERK num_stages must be 1, 2 or 4");
+    if (cfg->num_steps < 1) return fail(USVMPC_E_INVALID, "num_steps must be >= 1");
+    for (int j = 0; j < cfg->nbx; j++)
+        if (cfg->idxbx[j] < 0 || cfg->idxbx[j] >= nx) return fail(USVMPC_E_INVALID, "idxbx[%d] out of range", j);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(USVMPC_E_CUDA, "no CUDA device %d (found %d): the engine has no CPU path", device, ndev);
+    CU(cudaSetDevice(device));
+    usvmpc_solver* s = (usvmpc_solver*) calloc(1, sizeof(usvmpc_solver));
+    s->cfg = *cfg; s->B = batch; s->device = device; s->nx = nx; s->nu = nu; s->nv = nx + nu;
+    const int N = cfg->N, K = cfg->K, B = batch, ny = nx + nu;
+    s->P.lay = make_layout(nx, nu, N, K, cfg->nbx, cfg->nbu);
+    s->P.ws_stride = s->P.lay.total;
+    s->smem_per_warp = warp_smem_doubles(nx, nu, K);
+    const int kk = K > 0 ? K : 1;
+    CU(cudaMalloc(&s->d_ws, sizeof(double) * (size_t) s->P.ws_stride * B));
+    CU(cudaMemset(s->d_ws, 0, sizeof(double) * (size_t) s->P.ws_stride * B));
+    CU(cudaMalloc(&s->d_stats, sizeof(double) * (size_t) B * NSTAT));
+    CU(cudaMemset(s->d_stats, 0, sizeof(double) * (size_t) B * NSTAT));
+    CU(cudaMalloc(&s->d_cst, sizeof(double) * (ny * ny + nx * nx)));
+    CU(cudaMalloc(&s->d_x0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMemset(s->d_x0, 0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMalloc(&s->d_yref_e, sizeof(double) * (size_t) B * nx));
+    CU(cudaMemset(s->d_yref_e, 0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMalloc(&s->d_p[0], sizeof(double) * (size_t) B * 2 * kk));
+    CU(cudaMemset(s->d_p[0], 0, sizeof(double) * (size_t) B * 2 * kk));
+    CU(cudaMalloc(&s->d_lh[0], sizeof(double) * (size_t) B * kk));
+    CU(cudaMemset(s->d_lh[0], 0, sizeof(double) * (size_t) B * kk));
+    CU(cudaMalloc(&s->d_yref[0], sizeof(double) * (size_t) B * ny));
+    CU(cudaMemset(s->d_yref[0], 0, sizeof(double) * (size_t) B * ny));
+    refresh_params(s);
+    int rc = upload_constants(s, 0);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * (size_t) s->smem_per_warp * WPC;
+    if (cfg->model == USVMPC_MODEL_PENDULUM)
+        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Pendulum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    else
+        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Usv3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    *out = s;
+    return 0;
+}
+
+int usvmpc_free(usvmpc_solver* s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_ws); cudaFree(s->d_stats); cudaFree(s->d_cst); cudaFree(s->d_x0); cudaFree(s->d_yref_e);
+    for (int i = 0; i < 2; i++) { cudaFree(s->d_p[i]); cudaFree(s->d_lh[i]); cudaFree(s->d_yref[i]); }
+    cudaFree(s->d_stage);
+    free(s);
+    return 0;
+}
+
+int usvmpc_solve(usvmpc_solver* s, void* stream)
+{
+    if (!s) return fail(USVMPC_E_INVALID, "null solver");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const int grid = (s->B + WPC - 1) / WPC;
+    const size_t smem = sizeof(double) * (size_t) s->smem_per_warp * WPC;
+    if (s->cfg.model == USVMPC_MODEL_PENDULUM)
+        nmpc_solve_kernel<Pendulum><<<grid, WPC * 32, smem, st>>>(s->P, s->smem_per_warp);
+    else
+        nmpc_solve_kernel<Usv3><<<grid, WPC * 32, smem, st>>>(s->P, s->smem_per_warp);
+    CU(cudaGetLastError());
+    s->launches++;
+    return 0;
+}
+
+int usvmpc_update_params(usvmpc_solver* s, int stage, const double* value, int np, int on_device, void* stream)
+{
+    if (!s || !value) return fail(USVMPC_E_INVALID, "null argument");
+    (void) on_device;
+    if (np != 2 * s->cfg.K) return fail(USVMPC_E_SIZE, "np=%d but the model has np=%d", np, 2 * s->cfg.K);  // tpl :1746-1751
+    CU(cudaSetDevice(s->device));
+    return set_input(s, s->d_p, &s->P.p_per_stage, s->cfg.N + 1, 2 * s->cfg.K, stage, value, (cudaStream_t) stream);
+}
+
+int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
+{
+    if (!s || !field || !value) return fail(USVMPC_E_INVALID, "null argument");
+    (void) on_device;
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const int N = s->cfg.N, ny = s->nv, nx = s->nx;
+    if (!strcmp(field, "yref") || !strcmp(field, "y_ref"))
+    {
+        if (stage == N)
+        {
+            CU(cudaMemcpyAsync(s->d_yref_e, value, sizeof(double) * (size_t) s->B * nx, cudaMemcpyDefault, st));
+            return 0;
+        }
+        return set_input(s, s->d_yref, &s->P.yref_per_stage, N, ny, stage, value, st);
+    }
+    if (!strcmp(field, "W"))
+    {
+        // shared by the batch and by all path stages; host pointer, column-major like the reference (tpl :854)
+        if (stage == N) memcpy(s->cfg.W_e, value, sizeof(double) * nx * nx);
+        else memcpy(s->cfg.W, value, sizeof(double) * ny * ny);
+        return upload_constants(s, st);
+    }
+    return fail(USVMPC_E_FIELD, "unknown cost field '%s' (yref, y_ref, W)", field);
+}
+
+int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
+{
+    if (!s || !field || !value) return fail(USVMPC_E_INVALID, "null argument");
+    (void) on_device;
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const int N = s->cfg.N;
+    if (!strcmp(field, "lbx") || !strcmp(field, "ubx"))
+    {
+        if (stage == 0)
+        {
+            CU(cudaMemcpyAsync(s->d_x0, value, sizeof(double) * (size_t) s->B * s->nx, cudaMemcpyDefault, st));
+            return 0;
+        }
+        if (stage < 0 || stage >= N) return fail(USVMPC_E_INVALID, "no state bounds at stage %d", stage);
+        memcpy(field[0] == 'l' ? s->cfg.lbx : s->cfg.ubx, value, sizeof(double) * s->cfg.nbx);
+        refresh_params(s);
+        return 0;
+    }
+    if (!strcmp(field, "lbu") || !strcmp(field, "ubu"))
+    {
+        memcpy(field[0] == 'l' ? s->cfg.lbu : s->cfg.ubu, value, sizeof(double) * s->cfg.nbu);
+        refresh_params(s);
+        return 0;
+    }
+    if (!strcmp(field, "lh")) return set_input(s, s->d_lh, &s->P.lh_per_stage, N, s->cfg.K, stage, value, st);
+    if (!strcmp(field, "uh"))
+    {
+        if (s->cfg.K > 0) s->cfg.uh = value[0];
+        refresh_params(s);
+        return 0;
+    }
+    return fail(USVMPC_E_FIELD, "unknown constraint field '%s' (lbx, ubx, lbu, ubu, lh, uh)", field);
+}
+
+int usvmpc_out_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
+{
+    return out_copy(s, stage, field, (double*) value, on_device, stream, 1);
+}
+
+int usvmpc_out_get(usvmpc_solver* s, int stage, const char* field, double* value, int on_device, void* stream)
+{
+    return out_copy(s, stage, field, value, on_device, stream, 0);
+}
+
+int usvmpc_dims_get_from_attr(usvmpc_solver* s, int stage, const char* field)
+{
+    if (!s || !field) return fail(USVMPC_E_INVALID, "null argument");
+    const int N = s->cfg.N;
+    if (stage < 0 || stage > N) return fail(USVMPC_E_INVALID, "stage %d out of range", stage);
+    const int nbxk = stage == 0 ? s->nx : (stage < N ? s->cfg.nbx : 0);
+    const int nbuk = stage < N ? s->cfg.nbu : 0, Kk = stage < N ? s->cfg.K : 0;
+    if (!strcmp(field, "x")) return s->nx;
+    if (!strcmp(field, "u")) return stage < N ? s->nu : 0;
+    if (!strcmp(field, "pi")) return stage < N ? s->nx : 0;
+    if (!strcmp(field, "lam") || !strcmp(field, "t")) return 2 * (nbuk + nbxk + Kk);
+    if (!strcmp(field, "p")) return 2 * s->cfg.K;
+    if (!strcmp(field, "yref") || !strcmp(field, "y_ref")) return stage < N ? s->nv : s->nx;
+    if (!strcmp(field, "lbx") || !strcmp(field, "ubx")) return nbxk;
+    if (!strcmp(field, "lbu") || !strcmp(field, "ubu")) return nbuk;
+    if (!strcmp(field, "lh") || !strcmp(field, "uh")) return Kk;
+    if (!strcmp(field, "sl") || !strcmp(field, "su") || !strcmp(field, "z")) return 0;
+    return fail(USVMPC_E_FIELD, "unknown field '%s'", field);
+}
+
+int usvmpc_get_stats(usvmpc_solver* s, double* value, int on_device, void* stream)
+{
+    if (!s || !value) return fail(USVMPC_E_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaMemcpyAsync(value, s->d_stats, sizeof(double) * (size_t) s->B * NSTAT, cudaMemcpyDefault, st));
+    if (!on_device) CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value)
+{
+    if (!s || !field) return fail(USVMPC_E_INVALID, "null argument");
+    usvmpc_config& c = s->cfg;
+    if (!strcmp(field, "max_iter") || !strcmp(field, "nlp_solver_max_iter")) c.max_iter = (int) value;
+    else if (!strcmp(field, "qp_iter_max") || !strcmp(field, "qp_solver_iter_max")) c.qp_iter_max = (int) value;
+    else if (!strcmp(field, "tol_stat")) c.tol[0] = value;
+    else if (!strcmp(field, "tol_eq")) c.tol[1] = value;
+    else if (!strcmp(field, "tol_ineq")) c.tol[2] = value;
+    else if (!strcmp(field, "tol_comp")) c.tol[3] = value;
+    else if (!strcmp(field, "nlp_solver_type")) c.nlp_type = (int) value ? USVMPC_SQP_RTI : USVMPC_SQP;
+    else if (!strcmp(field, "cold_start")) s->P.cold_start = value != 0.0;
+    else if (!strcmp(field, "print_level")) {}
+    else if (!strcmp(field, "rti_phase")) { if (value != 0.0) return fail(USVMPC_E_INVALID, "rti_phase %g: only 0 (prepare+feedback in one call) is implemented", value); }
+    else if (!strcmp(field, "step_length")) { if (value != 1.0) return fail(USVMPC_E_INVALID, "step_length %g: the engine takes full SQP steps like the reference scripts", value); }
+    else return fail(USVMPC_E_FIELD, "unknown option '%s'", field);
+    refresh_params(s);
+    return 0;
+}
+
+int usvmpc_info(usvmpc_solver* s, const char* what, double* value)
+{
+    if (!s || !what || !value) return fail(USVMPC_E_INVALID, "null argument");
+    if (!strcmp(what, "launches")) *value = (double) s->launches;
+    else if (!strcmp(what, "workspace_bytes")) *value = (double) sizeof(double) * s->P.ws_stride * s->B;
+    else if (!strcmp(what, "workspace_doubles_per_instance")) *value = (double) s->P.ws_stride;
+    else if (!strcmp(what, "batch")) *value = s->B;
+    else if (!strcmp(what, "warps_per_cta")) *value = WPC;
+    else if (!strcmp(what, "smem_bytes_per_cta")) *value = (double) sizeof(double) * s->smem_per_warp * WPC;
+    else if (!strcmp(what, "grid")) *value = (s->B + WPC - 1) / WPC;
+    else return fail(USVMPC_E_FIELD, "unknown info '%s'", what);
+    return 0;
+}
+
+}  // extern "C"

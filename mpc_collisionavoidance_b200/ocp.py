@@ -1,0 +1,146 @@
+"""Problem description for the batched NMPC engine.
+
+These classes carry the SAME attribute names as the reference's description objects
+(`AcadosOcp`, `AcadosOcpDims/Cost/Constraints/Options`, `AcadosModel`:
+interfaces/acados_template/acados_template/acados_ocp.py, acados_model.py) so that an
+`acados_settings.py` of the nmpc_ca scripts can be pointed at this module with its numbers unchanged.
+The reference's classes need CasADi (symbolic model) and a code generator; here the model is one of the
+engine's built-in device models, selected by `model.name`, and no code is generated.  A genuine
+`acados_template.AcadosOcp` instance is accepted as well (duck typing) as long as it stays inside the path
+the engine implements: LINEAR_LS cost with Vx=[I;0], Vu=[0;I]; BGH constraints (input boxes, state boxes,
+h = obstacle distances); ERK; GAUSS_NEWTON; PARTIAL_CONDENSING_HPIPM; SQP or SQP_RTI.
+"""
+import numpy as np
+
+from . import _lib
+
+MODELS = {"usv3": 0, "usv_model_ca": 0, "usv3_ca": 0, "pendulum": 1, "pendulum_ode": 1}
+MODEL_DIMS = {0: (6, 2), 1: (4, 1)}
+
+
+class AcadosModel:
+    def __init__(self, name="usv3"):
+        self.name = name
+
+
+class AcadosOcpDims:
+    def __init__(self):
+        self.N = None
+        self.nh = 0  # number of obstacle rows K (np = 2K)
+
+
+class AcadosOcpCost:
+    def __init__(self):
+        self.cost_type = "LINEAR_LS"
+        self.cost_type_e = "LINEAR_LS"
+        self.W = None
+        self.W_e = None
+        self.Vx = None
+        self.Vu = None
+        self.Vx_e = None
+        self.yref = None
+        self.yref_e = None
+
+
+class AcadosOcpConstraints:
+    def __init__(self):
+        self.constr_type = "BGH"
+        self.x0 = None
+        self.lbu = np.array([]); self.ubu = np.array([]); self.idxbu = np.array([], dtype=int)
+        self.lbx = np.array([]); self.ubx = np.array([]); self.idxbx = np.array([], dtype=int)
+        self.lh = np.array([]); self.uh = np.array([])
+
+
+class AcadosOcpOptions:
+    """defaults of acados_template/acados_ocp.py:1747-1780"""
+
+    def __init__(self):
+        self.qp_solver = "PARTIAL_CONDENSING_HPIPM"
+        self.hessian_approx = "GAUSS_NEWTON"
+        self.integrator_type = "ERK"
+        self.tf = None
+        self.nlp_solver_type = "SQP_RTI"
+        self.nlp_solver_step_length = 1.0
+        self.levenberg_marquardt = 0.0
+        self.sim_method_num_stages = 4
+        self.sim_method_num_steps = 1
+        self.qp_solver_iter_max = 50
+        self.qp_solver_cond_N = None
+        self.nlp_solver_tol_stat = 1e-6
+        self.nlp_solver_tol_eq = 1e-6
+        self.nlp_solver_tol_ineq = 1e-6
+        self.nlp_solver_tol_comp = 1e-6
+        self.nlp_solver_max_iter = 100
+        self.print_level = 0
+
+
+class AcadosOcp:
+    def __init__(self):
+        self.model = AcadosModel()
+        self.dims = AcadosOcpDims()
+        self.cost = AcadosOcpCost()
+        self.constraints = AcadosOcpConstraints()
+        self.solver_options = AcadosOcpOptions()
+        self.parameter_values = np.array([])
+
+
+def _arr(a):
+    return np.zeros(0) if a is None else np.atleast_1d(np.asarray(a, dtype=np.float64))
+
+
+def config_from_ocp(ocp):
+    """Validate an OCP description against the engine's path and turn it into a `usvmpc_config`."""
+    name = getattr(ocp.model, "name", "usv3")
+    if name not in MODELS:
+        raise Exception(f"model '{name}' is not one of the engine's device models {sorted(MODELS)}")
+    model = MODELS[name]
+    nx, nu = MODEL_DIMS[model]
+    ny = nx + nu
+    o, c, k = ocp.solver_options, ocp.cost, ocp.constraints
+    if c.cost_type != "LINEAR_LS" or c.cost_type_e != "LINEAR_LS":
+        raise Exception("only LINEAR_LS cost is implemented (the cost type of every nmpc_ca script)")
+    if getattr(k, "constr_type", "BGH") != "BGH":
+        raise Exception("only BGH constraints are implemented")
+    if o.qp_solver != "PARTIAL_CONDENSING_HPIPM" or o.hessian_approx != "GAUSS_NEWTON" or o.integrator_type != "ERK":
+        raise Exception("the engine implements PARTIAL_CONDENSING_HPIPM (cond_N = N) + GAUSS_NEWTON + ERK")
+    if o.nlp_solver_type not in ("SQP", "SQP_RTI"):
+        raise Exception(f"unknown nlp_solver_type {o.nlp_solver_type}")
+    if o.tf is None or ocp.dims.N is None:
+        raise Exception("solver_options.tf and dims.N must be set")
+    Vx = np.zeros((ny, nx)); Vx[:nx, :nx] = np.eye(nx)
+    Vu = np.zeros((ny, nu)); Vu[nx:, :] = np.eye(nu)
+    for given, want, nm in ((c.Vx, Vx, "Vx"), (c.Vu, Vu, "Vu"), (c.Vx_e, np.eye(nx), "Vx_e")):
+        if given is not None and not np.array_equal(np.asarray(given, dtype=float), want):
+            raise Exception(f"cost.{nm} must be the selector of y = [x; u] used by the nmpc_ca scripts")
+    cfg = _lib.Config()
+    _lib.check(_lib.load().usvmpc_config_default(cfg, model), "config_default")
+    N = int(ocp.dims.N)
+    K = int(len(_arr(k.lh)))
+    cfg.N, cfg.K = N, K
+    cfg.num_steps, cfg.num_stages = int(o.sim_method_num_steps), int(o.sim_method_num_stages)
+    cfg.nlp_type = 0 if o.nlp_solver_type == "SQP" else 1
+    cfg.max_iter, cfg.qp_iter_max = int(o.nlp_solver_max_iter), int(o.qp_solver_iter_max)
+    cfg.dt = float(o.tf) / N
+    cfg.tol[:] = [o.nlp_solver_tol_stat, o.nlp_solver_tol_eq, o.nlp_solver_tol_ineq, o.nlp_solver_tol_comp]
+    W = np.asarray(c.W, dtype=float); We = np.asarray(c.W_e, dtype=float)
+    if W.shape != (ny, ny) or We.shape != (nx, nx):
+        raise Exception(f"cost.W must be {ny}x{ny} and cost.W_e {nx}x{nx}")
+    cfg.W[:ny * ny] = W.flatten(order="F").tolist()
+    cfg.W_e[:nx * nx] = We.flatten(order="F").tolist()
+    lbu, ubu, idxbu = _arr(k.lbu), _arr(k.ubu), np.asarray(k.idxbu, dtype=int).ravel()
+    if len(lbu) != len(ubu) or len(lbu) != len(idxbu) or len(lbu) > nu or not np.array_equal(idxbu, np.arange(len(lbu))):
+        raise Exception("input bounds must be on u[0..nbu) in order (idxbu = 0..nbu-1)")
+    lbx, ubx, idxbx = _arr(k.lbx), _arr(k.ubx), np.asarray(k.idxbx, dtype=int).ravel()
+    if len(lbx) != len(ubx) or len(lbx) != len(idxbx) or len(lbx) > nx:
+        raise Exception("lbx, ubx, idxbx sizes are inconsistent")
+    cfg.nbu, cfg.nbx = len(lbu), len(lbx)
+    for i in range(len(lbu)):
+        cfg.lbu[i], cfg.ubu[i] = lbu[i], ubu[i]
+    for i in range(len(lbx)):
+        cfg.lbx[i], cfg.ubx[i], cfg.idxbx[i] = lbx[i], ubx[i], int(idxbx[i])
+    uh = _arr(k.uh)
+    if K:
+        if len(uh) != K or not np.all(uh == uh[0]):
+            raise Exception("uh must have one (common) value per obstacle row")
+        cfg.uh = float(uh[0])
+    return cfg, model, nx, nu

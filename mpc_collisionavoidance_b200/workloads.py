@@ -68,3 +68,38 @@ def _scenes(rng, B, N, K) -> Batch:
             p[ids, 2 * k], p[ids, 2 * k + 1], lh[ids, k] = ox[ok], oy[ok], r[ok]
             todo[ids] = False
     return Batch(x0, p, lh, yref, yref[:, :6].copy())
+
+
+def benchmark_ocp(config_id: int, nlp_solver_type: str = "SQP"):
+    """The benchmark OCP of SURVEY.md section 8d as an AcadosOcp-style description (same attribute names as the
+    nmpc_ca `acados_settings.py` scripts): 3-DOF USV, LINEAR_LS tracking cost, thrust and velocity boxes, K obstacle
+    distance rows with uh = 1e6, ERK4, Gauss-Newton, partial-condensing HPIPM with cond_N = N."""
+    from .ocp import AcadosOcp
+    cfg = CONFIGS[config_id]
+    N, K = cfg["N"], cfg["K"]
+    nx, nu = 6, 2
+    ocp = AcadosOcp()
+    ocp.model.name = "usv3"
+    ocp.dims.N = N
+    Q = np.diag([1, 1, 0.1, 10, 0.1, 0.1])
+    R = np.diag([1e-3, 1e-3])
+    ocp.cost.W = np.block([[Q, np.zeros((nx, nu))], [np.zeros((nu, nx)), R]])
+    ocp.cost.W_e = 5 * Q
+    Vx = np.zeros((nx + nu, nx)); Vx[:nx, :nx] = np.eye(nx)
+    Vu = np.zeros((nx + nu, nu)); Vu[nx:, :] = np.eye(nu)
+    ocp.cost.Vx, ocp.cost.Vu, ocp.cost.Vx_e = Vx, Vu, np.eye(nx)
+    ocp.cost.yref, ocp.cost.yref_e = np.zeros(nx + nu), np.zeros(nx)
+    ocp.constraints.lbu, ocp.constraints.ubu = np.array([-30.0, -30.0]), np.array([35.0, 35.0])
+    ocp.constraints.idxbu = np.array([0, 1])
+    ocp.constraints.lbx, ocp.constraints.ubx = np.array([-1.5, -1.5, -1.0]), np.array([1.5, 1.5, 1.0])
+    ocp.constraints.idxbx = np.array([3, 4, 5])
+    ocp.constraints.lh, ocp.constraints.uh = np.full(K, 0.5), np.full(K, 1e6)
+    ocp.constraints.x0 = np.array([0, 0, 0, 0.7, 0, 0.0])
+    ocp.parameter_values = np.zeros(2 * K)
+    o = ocp.solver_options
+    o.tf = DT * N
+    o.qp_solver, o.hessian_approx, o.integrator_type = "PARTIAL_CONDENSING_HPIPM", "GAUSS_NEWTON", "ERK"
+    o.nlp_solver_type = nlp_solver_type
+    o.sim_method_num_stages, o.sim_method_num_steps = 4, cfg["num_steps"]
+    o.nlp_solver_max_iter, o.qp_solver_iter_max = 100, 50
+    return ocp

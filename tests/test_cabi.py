@@ -1,0 +1,72 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/usvmpc.h declares,
+the description -> config translation mirrors the reference's field names, and the engine refuses loudly to run
+without a CUDA device (no CPU fallback).  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import refharness as rh
+from enginehelper import ocp_from_problem
+from mpc_collisionavoidance_b200 import _lib, build
+from mpc_collisionavoidance_b200.ocp import config_from_ocp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "usvmpc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(usvmpc_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_config_struct_matches_header(lib):
+    # sizeof(usvmpc_config) as laid out by ctypes must be what the C side reads: probe with config_default
+    cfg = _lib.Config()
+    assert lib.usvmpc_config_default(C.byref(cfg), 0) == 0
+    assert (cfg.N, cfg.num_stages, cfg.nlp_type, cfg.max_iter, cfg.qp_iter_max) == (20, 4, 1, 100, 50)
+    assert cfg.uh == 1e6 and list(cfg.tol) == [1e-6] * 4
+    assert cfg.W[0] == 1.0 and cfg.W[9] == 1.0 and cfg.W[1] == 0.0 and cfg.W_e[7] == 1.0
+    assert lib.usvmpc_config_default(C.byref(cfg), 7) < 0
+    assert b"unknown model" in lib.usvmpc_last_error()
+
+
+def test_description_to_config(lib):
+    P = rh.RefProblem(N=40, K=5, num_steps=4)
+    cfg, model, nx, nu = config_from_ocp(ocp_from_problem(P))
+    assert (model, nx, nu, cfg.N, cfg.K, cfg.nbx, cfg.nbu, cfg.num_steps, cfg.nlp_type) == (0, 6, 2, 40, 5, 3, 2, 4, 0)
+    assert abs(cfg.dt - 0.05) < 1e-15 and list(cfg.idxbx)[:3] == [3, 4, 5]
+    np.testing.assert_array_equal(np.array(cfg.W[:64]).reshape(8, 8, order="F"), P.W)
+    ocp = ocp_from_problem(P)
+    ocp.cost.cost_type = "NONLINEAR_LS"
+    with pytest.raises(Exception, match="LINEAR_LS"):
+        config_from_ocp(ocp)
+    ocp = ocp_from_problem(P)
+    ocp.solver_options.qp_solver = "FULL_CONDENSING_QPOASES"
+    with pytest.raises(Exception, match="PARTIAL_CONDENSING_HPIPM"):
+        config_from_ocp(ocp)
+    ocp = ocp_from_problem(P)
+    ocp.model.name = "race_car"
+    with pytest.raises(Exception, match="device models"):
+        config_from_ocp(ocp)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
+    with pytest.raises(Exception, match="CUDA|cuda"):
+        BatchedAcadosOcpSolver(ocp_from_problem(rh.RefProblem(N=20, K=3)), batch=4)
