@@ -26,13 +26,16 @@ constexpr int NSTAT = 12;    // per-instance statistics record (doubles)
 struct Field { int off, stride; };
 
 struct Layout {
-    // NLP iterate (persists between solves = warm start, like nlp_out in the reference)
+    // NLP iterate (persists between solves = warm start, like nlp_out in the reference); stage-major arrays
     Field zux, zpi, zlam, zt, zfun;
-    // QP data written by the linearisation
-    Field BAt, b, rq, gxy, d;
-    // IPM iterate, step, residuals, factor
-    Field ux, pi, lam, t, dux, dpi, dlam, dt, rg, rb, rd, rmc, L, Pb;
-    // iterative refinement scratch
+    // ---- the per-stage RECORD streamed through shared memory by the IPM sweeps (all strides = rec_size) ----
+    // order inside a record:
+    //   BAt gxy | lam t ux pi pi_prev rg rb rd L Pb rmc dux | dpi dpi_prev dlam dt | rq b d
+    // so that each sweep writes back ONE contiguous range (A: lam..dux, B/D: dux..dt, C: rmc..dux).
+    // pi_prev / dpi_prev duplicate pi / dpi of stage k-1 so that no sweep needs a neighbouring record.
+    Field BAt, gxy, lam, t, ux, pi, pi_prev, rg, rb, rd, L, Pb, rmc, dux, dpi, dpi_prev, dlam, dt, rq, b, d;
+    int rec_off, rec_size;
+    // iterative refinement scratch (rare path), stage-major arrays
     Field dux2, dpi2, dlam2, dt2, rg2, rb2, rd2, rm2;
     long total;
 };
@@ -65,27 +68,37 @@ inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
     const int N1 = N + 1, nv = nx + nu;
     const int sv = round_up(nv, 2), sx = round_up(nx, 2);
     const int ncq = nbu + nbx + K, ncz = nbu + nx + K;
-    const int scq = round_up(2 * ncq, 2), scz = round_up(2 * ncz, 2);
+    const int scq = round_up(2 * ncq, 2) > 0 ? round_up(2 * ncq, 2) : 2, scz = round_up(2 * ncz, 2);
     const int sBA = round_up(nv * nx, 2), sg = round_up(2 * K, 2) > 0 ? round_up(2 * K, 2) : 2;
     const int sL = round_up((nv + 1) * nv, 2);
     long o = 0;
     auto put = [&](Field& f, int stride) { f.off = (int) o; f.stride = stride; o += (long) stride * N1; };
     put(L.zux, sv); put(L.zpi, sx); put(L.zlam, scz); put(L.zt, scz); put(L.zfun, scz);
-    put(L.BAt, sBA); put(L.b, sx); put(L.rq, sv); put(L.gxy, sg); put(L.d, scq);
-    put(L.ux, sv); put(L.pi, sx); put(L.lam, scq); put(L.t, scq);
-    put(L.dux, sv); put(L.dpi, sx); put(L.dlam, scq); put(L.dt, scq);
-    put(L.rg, sv); put(L.rb, sx); put(L.rd, scq); put(L.rmc, scq); put(L.L, sL); put(L.Pb, sx);
+    int r = 0;
+    auto rec = [&](Field& f, int n) { f.off = r; r += n; };
+    rec(L.BAt, sBA); rec(L.gxy, sg);
+    rec(L.lam, scq); rec(L.t, scq); rec(L.ux, sv); rec(L.pi, sx); rec(L.pi_prev, sx); rec(L.rg, sv); rec(L.rb, sx);
+    rec(L.rd, scq); rec(L.L, sL); rec(L.Pb, sx); rec(L.rmc, scq); rec(L.dux, sv);
+    rec(L.dpi, sx); rec(L.dpi_prev, sx); rec(L.dlam, scq); rec(L.dt, scq);
+    rec(L.rq, sv); rec(L.b, sx); rec(L.d, scq);
+    L.rec_size = round_up(r, 2);
+    L.rec_off = (int) o;
+    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.pi_prev, &L.rg, &L.rb, &L.rd, &L.L, &L.Pb, &L.rmc,
+                   &L.dux, &L.dpi, &L.dpi_prev, &L.dlam, &L.dt, &L.rq, &L.b, &L.d};
+    for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; }
+    o += (long) L.rec_size * N1;
     put(L.dux2, sv); put(L.dpi2, sx); put(L.dlam2, scq); put(L.dt2, scq);
     put(L.rg2, sv); put(L.rb2, sx); put(L.rd2, scq); put(L.rm2, scq);
     L.total = (o + 15) / 16 * 16;  // 128-byte multiple
     return L;
 }
 
-// per-warp shared-memory scratch (doubles) used by nmpc_kernel.cuh
-inline int warp_smem_doubles(int nx, int nu, int K)
+// per-warp shared-memory (doubles) used by nmpc_kernel.cuh: two record buffers + scratch
+inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
 {
     const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
-    int n = 0;
+    const Layout L = make_layout(nx, nu, N, K, nbx, nbu);
+    int n = 2 * L.rec_size;
     n += 2 * nv * nv;          // Hs, Hes
     n += nv * nv + nx * nx;    // Ws, Wes
     n += nv * nx;              // sBA
@@ -95,7 +108,7 @@ inline int warp_smem_doubles(int nx, int nu, int K)
     n += (nv + 1) * nv;        // sL
     n += 2 * nv + 2 * nx;      // sz, sq, sx1, sx2
     n += 2 * (K > 0 ? K : 1);  // sgxy
-    n += ncq2 + 8;             // srow + misc
+    n += ncq2 + 8;             // sxrow + misc
     return (n + 1) / 2 * 2;
 }
 

@@ -14,10 +14,16 @@
 //   BLASFEO potrf/syrk/trmm/trsv/gemv             BF/blasfeo_hp_pm/d_lapack_lib4.c:1149,1503 etc. -> warp-level code below
 //
 // Work decomposition inside the warp:
-//   * the three Riccati sweeps are serial in the stage index and are done co-operatively: lane r
-//     owns row r of the (nv+1) x nv factor, inner products go through shared memory / shuffles;
-//   * everything that is independent per stage (RK4 sensitivities, cost/constraint evaluation, QP
-//     residuals, step expansion, step length, variable update) is spread over the lanes.
+//   * one IPM iteration is FOUR streaming sweeps over the per-stage records (layout.h), each pulling record k
+//     into shared memory with cp.async one stage ahead of the arithmetic and writing back only what it changed:
+//       B  forward : affine step  (forward substitution, dt/dlam, step length)
+//       C  backward: corrector right-hand side + backward substitution
+//       D  forward : corrector step + residual of the linear system (iterative-refinement test)
+//       A  backward: variable update + QP residuals + Gamma/gamma + Riccati factorisation for the next iteration
+//     The Riccati parts are serial in the stage index: lane r owns row r of the (nv+1) x nv factor, inner products
+//     go through shared memory / shuffles; everything else of a stage is spread over the lanes.
+//   * RK4 sensitivities, cost/constraint evaluation, the IPM start point and the NLP update are independent per
+//     stage and are spread over the lanes (one lane per stage or per sensitivity column).
 // Inactive variables (x at stage 0 after x0 elimination, u at stage N) and inactive inequality rows
 // are kept in the uniform per-stage layout and masked (identity rows in the factor, zero rows in
 // B'/A'), so every stage runs the same code.
@@ -40,6 +46,10 @@ struct WarpSolver {
     // shared-memory scratch of this warp
     double *Hs, *Hes, *Ws, *Wes, *sBA, *sLn, *slx, *sAL, *sG, *sg, *sL, *sz, *sq, *sx1, *sx2, *sgxy;
     int* sxrow;
+    // the two record buffers of the streaming sweeps and the offsets of the record's fields (layout.h)
+    double* buf[2];
+    int oBAt, ogxy, olam, ot, oux, opi, opip, org, orb, ord, oL, oPb, ormc, odux, odpi, odpip, odlam, odt, orq, ob, od;
+    int svv, scq;
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
     // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
     double tol_stat, tol_eq, tol_ineq, tol_comp;
@@ -56,6 +66,14 @@ struct WarpSolver {
         nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
         w = P.ws + (long) inst * P.ws_stride;
         double* s = sm;
+        buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size;
+        const int ro = Y.rec_off;
+        oBAt = Y.BAt.off - ro; ogxy = Y.gxy.off - ro; olam = Y.lam.off - ro; ot = Y.t.off - ro; oux = Y.ux.off - ro;
+        opi = Y.pi.off - ro; opip = Y.pi_prev.off - ro; org = Y.rg.off - ro; orb = Y.rb.off - ro; ord = Y.rd.off - ro;
+        oL = Y.L.off - ro; oPb = Y.Pb.off - ro; ormc = Y.rmc.off - ro; odux = Y.dux.off - ro; odpi = Y.dpi.off - ro;
+        odpip = Y.dpi_prev.off - ro; odlam = Y.dlam.off - ro; odt = Y.dt.off - ro; orq = Y.rq.off - ro; ob = Y.b.off - ro;
+        od = Y.d.off - ro;
+        svv = (NV + 1) / 2 * 2; scq = Y.rq.off - Y.dt.off;
         Hs = s; s += NV * NV; Hes = s; s += NV * NV; Ws = s; s += NV * NV; Wes = s; s += NX * NX;
         sBA = s; s += NV * NX; sLn = s; s += NX * NX; slx = s; s += NX; sAL = s; s += NR * NX;
         sG = s; s += 2 * (NU + NX + K); sg = s; s += 2 * (NU + NX + K); sL = s; s += NR * NV;
@@ -393,6 +411,14 @@ struct WarpSolver {
             for (int i = 0; i < NV; i++) ux[i] = 0.0;
             for (int i = 0; i < NX; i++) pi[i] = 0.0;
             for (int j = 0; j < 2 * ncq; j++) { lam[j] = 0.0; t[j] = 1.0; }
+            {
+                // the first sweep A applies a zero step: the step and the duplicated neighbour values start at zero
+                double *a = F(Y.dux, k), *b = F(Y.dpi, k), *c = F(Y.dlam, k), *e = F(Y.dt, k);
+                double *pp = F(Y.pi_prev, k), *dp = F(Y.dpi_prev, k);
+                for (int i = 0; i < NV; i++) a[i] = 0.0;
+                for (int i = 0; i < NX; i++) { b[i] = 0.0; pp[i] = 0.0; dp[i] = 0.0; }
+                for (int j = 0; j < 2 * ncq; j++) { c[j] = 0.0; e[j] = 0.0; }
+            }
             if (k >= N) continue;
             for (int j = 0; j < nbq; j++)
             {
@@ -421,6 +447,552 @@ struct WarpSolver {
         syncwarp();
     }
 
+    // ---------------------------------------------------------------- IPM: record streaming
+    // The IPM works on one RECORD per stage (layout.h).  Each sweep pulls record k into shared memory with
+    // asynchronous 16-byte copies (cp.async), one stage ahead of the arithmetic, computes in place and writes the
+    // range it modified back with coalesced stores.
+    MDEV double* rec_g(int k) const { return w + Y.rec_off + (long) k * Y.rec_size; }
+    MDEV void rec_fetch(int k, double* dst, int n)
+    {
+        const double* src = rec_g(k);
+        for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, src + c);
+        cp_async_commit();
+    }
+    MDEV void rec_wait() { cp_async_wait_all(); syncwarp(); }
+    MDEV void rec_store(int k, const double* src, int from, int to)
+    {
+        double* dst = rec_g(k);
+        for (int c = from + 2 * lane; c < to; c += 64) { dst[c] = src[c]; dst[c + 1] = src[c + 1]; }
+    }
+    // stage 0 after x0 elimination: no x rows in [B';A'], no Jacobian of the h rows (x_ocp_qp_red.c:268-454)
+    MDEV void rec_mask_stage0(double* R)
+    {
+        for (int e = lane; e < NV * NX; e += 32) if (e % NV >= NU) R[oBAt + e] = 0.0;
+        for (int e = lane; e < 2 * K; e += 32) R[ogxy + e] = 0.0;
+        syncwarp();
+    }
+
+    // Sweep A (backward, k = N..0), three steps of the reference fused per stage:
+    //   UPDATE_VAR_QP with step length a (x_core_qp_ipm_aux.c:220-325) -> OCP_QP_RES_COMPUTE at the new iterate
+    //   (x_ocp_qp_res.c:336-466; norms into n4, mu) -> backward part of OCP_QP_FACT_SOLVE_KKT_STEP for the affine
+    //   right-hand side res_m = lam*t - tau (x_ocp_qp_kkt.c:405-535, COMPUTE_GAMMA_GAMMA_QP x_core_qp_ipm_aux.c:38-86).
+    // The factorisation is speculative: if the residuals turn out to be converged it is simply not used.
+    MDEV void sweepA(double a, double tau, double reg, double* n4)
+    {
+        const double lam_min = 1e-16, t_min = 1e-16;
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
+        double xn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xn[i] = 0.0;
+        int cur = 0;
+        rec_fetch(N, buf[0], Y.rec_size);
+        for (int k = N; k >= 0; k--)
+        {
+            double* R = buf[cur];
+            rec_wait();
+            if (k > 0) rec_fetch(k - 1, buf[cur ^ 1], Y.rec_size);
+            if (k == 0) rec_mask_stage0(R);
+            // ---- update
+            if (lane < NV) R[oux + lane] += a * R[odux + lane];
+            else if (lane < NV + NX) { if (k < N) R[opi + lane - NV] += a * R[odpi + lane - NV]; }
+            else if (lane < NV + 2 * NX) { if (k > 0) R[opip + lane - NV - NX] += a * R[odpip + lane - NV - NX]; }
+            for (int r = lane; r < 2 * ncq; r += 32)
+                if (row_active(k, r % ncq))
+                {
+                    double x = R[olam + r] + a * R[odlam + r];
+                    R[olam + r] = x <= lam_min ? lam_min : x;
+                    x = R[ot + r] + a * R[odt + r];
+                    R[ot + r] = x <= t_min ? t_min : x;
+                }
+            syncwarp();
+            // ---- residuals, Gamma, gamma
+            const double* H = Hk(k);
+            if (lane < NV)
+            {
+                const int i = lane;
+                double g = 0.0;
+                if (var_active(k, i))
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NV; j++) acc += H[i + NV * j] * R[oux + j];
+                    g = acc + R[orq + i];
+                    if (k > 0 && i >= NU) g -= R[opip + i - NU];
+                    const int row = vrow(k, i);
+                    if (row >= 0) g += R[olam + ncq + row] - R[olam + row];
+                    if (k < N)
+                    {
+                        if (i == HXV || i == HYV)
+                            for (int c = 0; c < K; c++)
+                                g += R[ogxy + (i == HXV ? c : K + c)] * (R[olam + ncq + nbq + c] - R[olam + nbq + c]);
+                        double acc2 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[opi + j];
+                        g += acc2;
+                    }
+                }
+                R[org + i] = g;
+                const double ag = dabs(g);
+                n0 = ag > n0 ? ag : n0;
+            }
+            else if (lane < NV + NX && k < N)
+            {
+                const int j = lane - NV;
+                double acc = R[ob + j] - xn[j];
+#pragma unroll
+                for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * j] * R[oux + i];
+                R[orb + j] = acc;
+                const double ab = dabs(acc);
+                n1 = ab > n1 ? ab : n1;
+            }
+            for (int r = lane; r < 2 * ncq; r += 32)
+            {
+                double G = 0.0, gm = 0.0;
+                const int jj = r % ncq;
+                if (row_active(k, jj))
+                {
+                    double v;
+                    if (jj < nbq) v = R[oux + (jj < nbu ? jj : NU + P.idxbx[jj - nbu])];
+                    else v = R[ogxy + jj - nbq] * R[oux + HXV] + R[ogxy + K + jj - nbq] * R[oux + HYV];
+                    const double lam = R[olam + r], t = R[ot + r];
+                    const double rd = r < ncq ? R[od + r] + t - v : R[od + r] + t + v;
+                    R[ord + r] = rd;
+                    const double m = lam * t;
+                    musum += m;
+                    const double am = dabs(m), ad = dabs(rd);
+                    n3 = am > n3 ? am : n3; n2 = ad > n2 ? ad : n2;
+                    const double tinv = 1.0 / t;
+                    G = tinv * lam;
+                    gm = tinv * ((m - tau) - lam * rd);
+                }
+                sG[r] = G; sg[r] = gm;
+            }
+            syncwarp();
+            // ---- factorise: lane r <= NV owns row r of [H + Gamma terms + AL AL' ; gradient row]
+            const int r = lane;
+            double Mr[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++)
+            {
+                double v = 0.0;
+                if (r < NV)
+                {
+                    if (var_active(k, r) && var_active(k, c)) { if (c <= r) v = H[r + NV * c]; if (c == r) v += reg; }
+                    else if (c == r) v = 1.0;
+                }
+                else if (r == NV) v = R[org + c];
+                const int row = vrow(k, c);
+                if (row >= 0)
+                {
+                    if (r == c) v += sG[row] + sG[ncq + row];
+                    if (r == NV) v += sg[row] - sg[ncq + row];
+                }
+                Mr[c] = v;
+            }
+            if (k < N)
+            {
+                // AL = [B'; A'; res_b'] * Lxx_{k+1} ; Pb = Lxx (Lxx' res_b) ; last row += l_{k+1,x}
+                double bar[NX], AL[NX];
+#pragma unroll
+                for (int m = 0; m < NX; m++) bar[m] = r < NV ? R[oBAt + r + NV * m] : (r == NV ? R[orb + m] : 0.0);
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = j; m < NX; m++) acc += bar[m] * sLn[m * NX + j];
+                    AL[j] = acc;
+                }
+                if (r == NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) sx2[j] = AL[j];
+                }
+                syncwarp();
+                if (r < NX)
+                {
+                    double acc = 0.0;
+                    for (int j = 0; j <= r; j++) acc += sLn[r * NX + j] * sx2[j];
+                    R[oPb + r] = acc;
+                }
+                if (r == NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) AL[j] += slx[j];
+                }
+                if (r <= NV)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) sAL[r * NX + j] = AL[j];
+                }
+                syncwarp();
+                if (r <= NV)
+                {
+#pragma unroll
+                    for (int c = 0; c < NV; c++)
+                    {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += AL[m] * sAL[c * NX + m];
+                        Mr[c] += acc;
+                    }
+                }
+                // h rows: D diag(Gamma_l + Gamma_u) D' touches only the (X,Y) block; gradient row gets D (gamma_l - gamma_u)
+                if (r == HXV || r == HYV || r == NV)
+                {
+                    double aX = 0.0, aY = 0.0;
+                    for (int c = 0; c < K; c++)
+                    {
+                        const double gX = R[ogxy + c], gY = R[ogxy + K + c];
+                        const double G = sG[nbq + c] + sG[ncq + nbq + c];
+                        const double left = r == NV ? sg[nbq + c] - sg[ncq + nbq + c] : (r == HXV ? gX * G : gY * G);
+                        aX += left * gX; aY += left * gY;
+                    }
+                    Mr[HXV] += aX; Mr[HYV] += aY;
+                }
+            }
+            // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
+            // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710)
+#pragma unroll
+            for (int j = 0; j < NV; j++)
+            {
+                const double piv = shfl(Mr[j], j);
+                double sq = 0.0, inv = 0.0;
+                if (piv > 0.0) { sq = dsqrt(piv); inv = 1.0 / sq; }
+                if (r == j) Mr[j] = sq; else Mr[j] *= inv;
+#pragma unroll
+                for (int c = j + 1; c < NV; c++)
+                {
+                    const double lc = shfl(Mr[j], c);
+                    Mr[c] -= Mr[j] * lc;
+                }
+            }
+            syncwarp();
+            if (r <= NV)
+            {
+#pragma unroll
+                for (int c = 0; c < NV; c++) R[oL + r * NV + c] = (c <= r) ? Mr[c] : 0.0;
+                if (r >= NU && r < NV)
+                {
+#pragma unroll
+                    for (int c = NU; c < NV; c++) sLn[(r - NU) * NX + (c - NU)] = (c <= r) ? Mr[c] : 0.0;
+                }
+                if (r == NV)
+                {
+#pragma unroll
+                    for (int c = 0; c < NV; c++) R[odux + c] = Mr[c];  // backward vector of the forward substitution
+#pragma unroll
+                    for (int c = NU; c < NV; c++) slx[c - NU] = Mr[c];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NX; i++) xn[i] = R[oux + NU + i];
+            syncwarp();
+            rec_store(k, R, olam, odux + svv);
+            cur ^= 1;
+        }
+        n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
+        mu = warp_sum(musum) / nct;
+        syncwarp();
+    }
+
+    // Sweeps B / D (forward, k = 0..N): forward substitution (x_ocp_qp_kkt.c:537-575 | 1243-1290), then dt, dlam
+    // (:748-764 + COMPUTE_LAM_T_QP, x_core_qp_ipm_aux.c:117-142), step length (COMPUTE_ALPHA_QP :146-216) and the
+    // sums COMPUTE_MU_AFF_QP (:329-357) needs.  CORR = false: affine step after sweep A (dux holds row NV of the
+    // factor, res_m = lam*t - tau).  CORR = true: corrector / centering step after sweep C (dux holds the backward
+    // vector, res_m = rmc) fused with the residual norms of the linear system (OCP_QP_RES_COMPUTE_LIN,
+    // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
+    template <bool CORR>
+    MDEV void sweepF(double tau, double* nlin)
+    {
+        const int nf = odt + scq;  // everything but rq, b, d
+        double a_prim = -1.0, a_dual = -1.0, s1 = 0.0, s2 = 0.0;
+        double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+        double xc[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xc[i] = 0.0;
+        int cur = 0;
+        rec_fetch(0, buf[0], nf);
+        rec_wait();
+        if (N >= 1) rec_fetch(1, buf[1], nf);
+        for (int k = 0; k <= N; k++)
+        {
+            double* R = buf[cur];
+            double* Rn = buf[cur ^ 1];
+            if (k == 0) rec_mask_stage0(R);
+            const double* L = R + oL;
+            double z[NV];
+#pragma unroll
+            for (int i = 0; i < NX; i++) z[NU + i] = xc[i];
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--)  // dtrsv_ltn on the columns solved at this stage
+            {
+                double acc = -R[odux + i];
+#pragma unroll
+                for (int m = i + 1; m < NV; m++) acc -= L[m * NV + i] * z[m];
+                z[i] = acc / L[i * NV + i];
+            }
+            double x1 = 0.0;
+            if (k < N)
+            {
+                if (lane < NX)
+                {
+                    double acc = R[orb + lane];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * lane] * z[i];
+                    x1 = acc;
+                }
+#pragma unroll
+                for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+            }
+            syncwarp();  // every lane has read the backward vector
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int i = 0; i < NV; i++) R[odux + i] = var_active(k, i) ? z[i] : 0.0;
+            }
+            syncwarp();
+            // ---- dt, dlam, step length
+            for (int r = lane; r < 2 * ncq; r += 32)
+            {
+                const int jj = r % ncq;
+                if (!row_active(k, jj)) continue;
+                double dv;
+                if (jj < nbq) dv = R[odux + (jj < nbu ? jj : NU + P.idxbx[jj - nbu])];
+                else dv = R[ogxy + jj - nbq] * R[odux + HXV] + R[ogxy + K + jj - nbq] * R[odux + HYV];
+                double dtr = r < ncq ? dv : -dv;
+                const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = 1.0 / t0;
+                const double m = CORR ? R[ormc + r] : lam0 * t0 - tau;
+                const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd));
+                if (CORR)
+                {
+                    // residual of the linearised rows at the step: rd + dt -+ v, rm + lam*dt + dlam*t
+                    const double dtf = dtr - rd;
+                    const double e2 = dabs(r < ncq ? rd + dtf - dv : rd + dtf + dv), e3 = dabs(m + lam0 * dtf + dlr * t0);
+                    l2 = e2 > l2 ? e2 : l2; l3 = e3 > l3 ? e3 : l3;
+                }
+                dtr -= rd;
+                R[odlam + r] = dlr; R[odt + r] = dtr;
+                if (a_dual * dlr > lam0) a_dual = lam0 / dlr;
+                if (a_prim * dtr > t0) a_prim = t0 / dtr;
+                s1 += lam0 * dtr + t0 * dlr;
+                s2 += dlr * dtr;
+            }
+            // ---- dpi_k = Lxx (Lxx' dx_{k+1} + l_x)  |  p_{k+1} + Lxx (Lxx' dx_{k+1}) : needs the factor of stage k+1
+            if (k < N)
+            {
+                rec_wait();  // record k+1 has landed in the other buffer
+                const double* Ln = Rn + oL;
+                double tmp = 0.0;
+                if (lane < NX)
+                {
+                    double acc = 0.0;
+                    for (int m = lane; m < NX; m++) acc += Ln[(NU + m) * NV + NU + lane] * xc[m];
+                    tmp = CORR ? acc : acc + Rn[odux + NU + lane];
+                }
+                double tv[NX];
+#pragma unroll
+                for (int j = 0; j < NX; j++) tv[j] = shfl(tmp, j);
+                if (lane < NX)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) if (j <= lane) acc += Ln[(NU + lane) * NV + NU + j] * tv[j];
+                    const double dp = CORR ? Rn[odux + NU + lane] + acc : acc;
+                    R[odpi + lane] = dp;
+                    Rn[odpip + lane] = dp;
+                }
+            }
+            syncwarp();
+            if (CORR)
+            {
+                if (lane < NV)
+                {
+                    const int i = lane;
+                    double g = 0.0;
+                    if (var_active(k, i))
+                    {
+                        const double* H = Hk(k);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NV; j++) acc += H[i + NV * j] * R[odux + j];
+                        g = acc + R[org + i];
+                        if (k > 0 && i >= NU) g -= R[odpip + i - NU];
+                        const int row = vrow(k, i);
+                        if (row >= 0) g += R[odlam + ncq + row] - R[odlam + row];
+                        if (k < N)
+                        {
+                            if (i == HXV || i == HYV)
+                                for (int c = 0; c < K; c++)
+                                    g += R[ogxy + (i == HXV ? c : K + c)] * (R[odlam + ncq + nbq + c] - R[odlam + nbq + c]);
+                            double acc2 = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[odpi + j];
+                            g += acc2;
+                        }
+                    }
+                    const double ag = dabs(g);
+                    l0 = ag > l0 ? ag : l0;
+                }
+                else if (lane < NV + NX && k < N)
+                {
+                    const int j = lane - NV;
+                    double acc = R[orb + j] - xc[j];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * j] * R[odux + i];
+                    const double ab = dabs(acc);
+                    l1 = ab > l1 ? ab : l1;
+                }
+            }
+            rec_store(k, R, odux, nf);
+            syncwarp();
+            if (k + 2 <= N) rec_fetch(k + 2, buf[cur], nf);
+            cur ^= 1;
+        }
+        a_prim = warp_max(a_prim); a_dual = warp_max(a_dual);
+        alpha = -(a_prim > a_dual ? a_prim : a_dual);
+        S1 = warp_sum(s1); S2 = warp_sum(s2);
+        if (CORR) { nlin[0] = warp_max(l0); nlin[1] = warp_max(l1); nlin[2] = warp_max(l2); nlin[3] = warp_max(l3); }
+        syncwarp();
+    }
+
+    // Sweep C (backward, k = N..0): backward part of OCP_QP_SOLVE_KKT_STEP (x_ocp_qp_kkt.c:1096-1242) with
+    // COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113) for the right-hand side
+    //   res_m = lam*t + dt_aff*dlam_aff - sigma_mu (corrector)   |   lam*t - sigma_mu (centering only)
+    // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
+    MDEV void sweepC(bool with_aff, double sigma_mu)
+    {
+        const int nf = odt + scq;
+        double pn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) pn[i] = 0.0;
+        int cur = 0;
+        rec_fetch(N, buf[0], nf);
+        for (int k = N; k >= 0; k--)
+        {
+            double* R = buf[cur];
+            rec_wait();
+            if (k > 0) rec_fetch(k - 1, buf[cur ^ 1], nf);
+            if (k == 0) rec_mask_stage0(R);
+            for (int r = lane; r < 2 * ncq; r += 32)
+            {
+                double g = 0.0, m = 0.0;
+                if (row_active(k, r % ncq))
+                {
+                    const double lam = R[olam + r], t = R[ot + r];
+                    const double bkp = lam * t;
+                    m = with_aff ? bkp + R[odt + r] * R[odlam + r] - sigma_mu : bkp - sigma_mu;
+                    g = (1.0 / t) * (m - lam * R[ord + r]);
+                }
+                R[ormc + r] = m;
+                sg[r] = g;
+            }
+            syncwarp();
+            const int i = lane;
+            double zi = 0.0;
+            if (i < NV && var_active(k, i))
+            {
+                zi = R[org + i];
+                const int row = vrow(k, i);
+                if (row >= 0) zi += sg[row] - sg[ncq + row];
+                if (k < N)
+                {
+                    if (i == HXV || i == HYV)
+                        for (int c = 0; c < K; c++)
+                            zi += R[ogxy + (i == HXV ? c : K + c)] * (sg[nbq + c] - sg[ncq + nbq + c]);
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += R[oBAt + i + NV * j] * (pn[j] + R[oPb + j]);
+                    zi += acc;
+                }
+            }
+            // dtrsv_lnn_mn(nv, nu): forward-eliminate the columns solved at this stage
+            const double* L = R + oL;
+#pragma unroll
+            for (int m = 0; m < NU; m++)
+            {
+                if (i == m) zi = zi / L[m * NV + m];
+                const double bm = shfl(zi, m);
+                if (i > m && i < NV) zi -= L[i * NV + m] * bm;
+            }
+            if (i < NV) R[odux + i] = zi;
+#pragma unroll
+            for (int j = 0; j < NX; j++) pn[j] = shfl(zi, NU + j);
+            syncwarp();
+            rec_store(k, R, ormc, odux + svv);
+            cur ^= 1;
+        }
+        solve_calls++;
+        syncwarp();
+    }
+
+    MDEV bool itref_ok(const double* n) const
+    {
+        return (n[0] < tol_stat || n[0] < 1e-3 * res_max[0]) && (n[1] < tol_eq || n[1] < 1e-3 * res_max[1]) &&
+               (n[2] < tol_ineq || n[2] < 1e-3 * res_max[2]) && (n[3] < tol_comp || n[3] < 1e-3 * res_max[3]);
+    }
+
+    // OCP_QP_IPM_SOLVE + OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683, 1888-2350 (pred_corr,
+    // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
+    // Per iteration: B (affine) -> C, D (corrector) [-> C, D centering] [-> refinement, rare] -> A (update, residuals
+    // and the factorisation the next iteration starts from).
+    MDEV int ipm_solve(int* iters)
+    {
+        const double tau_min = 1e-16, alpha_min = 1e-8, reg_prim = 1e-15;
+        ipm_init();
+        alpha = 1.0;
+        sweepA(0.0, tau_min, reg_prim, res_max);
+        int kk;
+        for (kk = 0; kk < iter_max && alpha > alpha_min &&
+                     (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
+                      dabs(res_max[3] - tau_min) > tol_comp);
+             kk++)
+        {
+            double nlin[4];
+            sweepF<false>(tau_min, nlin);
+            mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+            const double tmp = mu_aff / mu;
+            sigma = tmp * tmp * tmp;
+            double sigma_mu = sigma * mu;
+            sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
+            sweepC(true, sigma_mu);
+            sweepF<true>(0.0, nlin);
+            {
+                const double mu_aff0 = mu_aff;
+                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+                if (mu_aff > 2.0 * mu_aff0)
+                {
+                    sweepC(false, sigma_mu);
+                    sweepF<true>(0.0, nlin);
+                }
+            }
+            bool refined = false;
+            for (int it = 0; it < 2; it++)
+            {
+                if (itref_ok(nlin)) break;
+                // rare path (a fraction of a percent of the iterations): iterative refinement on the stage-major
+                // scratch arrays, straight from HBM
+                res_pass<true>(nlin);
+                solve_sweep(true);
+                forward_sweep(Y.rb2, Y.dux2, Y.dpi2, false);
+                expand_pass(2, 0.0);
+                add_refinement();
+                refined = true;
+                res_pass<true>(nlin);
+            }
+            if (refined) alpha_pass();
+            double a = alpha;
+            if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+            sweepA(a, tau_min, reg_prim, res_max);
+        }
+        *iters = kk;
+        if (kk == iter_max) return 1;
+        if (alpha <= alpha_min) return 2;
+        if (disnan(mu)) return 3;
+        return 0;
+    }
+
+    // ---------------------------------------------------------------- IPM: rare path (iterative refinement), straight from HBM
     // QP residuals.  LIN = false: OCP_QP_RES_COMPUTE (HP/ocp_qp/x_ocp_qp_res.c:336-466) at the iterate (ux,pi,lam,t)
     // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
     // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
@@ -597,24 +1169,6 @@ struct WarpSolver {
         alpha = -(a_prim > a_dual ? a_prim : a_dual);
     }
 
-    // rmc = lam*t + corr*dt*dlam - sigma_mu : right-hand side of the corrector / centering solve
-    // (HP/ocp_qp/x_ocp_qp_ipm.c:2138-2160, 2175-2200)
-    MDEV void set_rmc(double sigma_mu, bool with_aff)
-    {
-        for (int k = lane; k < N; k += 32)
-        {
-            const double *lam = F(Y.lam, k), *t = F(Y.t, k), *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
-            double* rm = F(Y.rmc, k);
-            for (int r = 0; r < 2 * ncq; r++)
-            {
-                if (!row_active(k, r % ncq)) { rm[r] = 0.0; continue; }
-                const double bkp = lam[r] * t[r];
-                rm[r] = with_aff ? bkp + dtt[r] * dl[r] - sigma_mu : bkp - sigma_mu;
-            }
-        }
-        syncwarp();
-    }
-
     // step += refinement step
     MDEV void add_refinement()
     {
@@ -625,38 +1179,12 @@ struct WarpSolver {
             if (k < N)
             {
                 double* c = F(Y.dpi, k); const double* e = F(Y.dpi2, k);
-                for (int i = 0; i < NX; i++) c[i] += e[i];
+                double* cn = F(Y.dpi_prev, k + 1);
+                for (int i = 0; i < NX; i++) { c[i] += e[i]; cn[i] = c[i]; }
                 double *l = F(Y.dlam, k), *t = F(Y.dt, k);
                 const double *l2 = F(Y.dlam2, k), *t2 = F(Y.dt2, k);
                 for (int r = 0; r < 2 * ncq; r++)
                     if (row_active(k, r % ncq)) { l[r] += l2[r]; t[r] += t2[r]; }
-            }
-        }
-        syncwarp();
-    }
-
-    // UPDATE_VAR_QP: HP/ipm_core/x_core_qp_ipm_aux.c:220-325 (split_step = 0)
-    MDEV void update_pass(double a)
-    {
-        const double lam_min = 1e-16, t_min = 1e-16;
-        for (int k = lane; k <= N; k += 32)
-        {
-            double* ux = F(Y.ux, k); const double* dux = F(Y.dux, k);
-            for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
-            if (k < N)
-            {
-                double* pi = F(Y.pi, k); const double* dpi = F(Y.dpi, k);
-                for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
-                double *l = F(Y.lam, k), *t = F(Y.t, k);
-                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
-                for (int r = 0; r < 2 * ncq; r++)
-                {
-                    if (!row_active(k, r % ncq)) continue;
-                    double x = l[r] + a * dl[r];
-                    l[r] = x <= lam_min ? lam_min : x;
-                    x = t[r] + a * dtt[r];
-                    t[r] = x <= t_min ? t_min : x;
-                }
             }
         }
         syncwarp();
@@ -673,6 +1201,7 @@ struct WarpSolver {
         else
             for (int e = lane; e < NV * NX; e += 32) sBA[e] = 0.0;
     }
+
     MDEV void load_gxy(int k)
     {
         if (k < N)
@@ -681,6 +1210,7 @@ struct WarpSolver {
             for (int e = lane; e < 2 * K; e += 32) sgxy[e] = k >= 1 ? g[e] : 0.0;
         }
     }
+
     MDEV void load_Lnext(int k1)  // xx block and nothing else of the factor of stage k1
     {
         const double* L = F(Y.L, k1);
@@ -689,158 +1219,6 @@ struct WarpSolver {
             const int m = e / NX, j = e % NX;
             sLn[e] = L[(NU + m) * NV + NU + j];
         }
-    }
-
-    // OCP_QP_FACT_SOLVE_KKT_STEP, backward part (HP/ocp_qp/x_ocp_qp_kkt.c:405-535) with COMPUTE_GAMMA_GAMMA_QP
-    // (HP/ipm_core/x_core_qp_ipm_aux.c:38-86) for the affine right-hand side res_m = lam*t - tau.
-    // Lane r <= NV owns row r of the (NV+1) x NV matrix [H + Gamma terms + AL AL' ; gradient row].
-    MDEV void factor_sweep(double tau, double reg)
-    {
-        for (int k = N; k >= 0; k--)
-        {
-            syncwarp();
-            load_BA(k);
-            load_gxy(k);
-            {
-                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(Y.rd, k);
-                for (int r = lane; r < 2 * ncq; r += 32)
-                {
-                    double G = 0.0, g = 0.0;
-                    if (row_active(k, r % ncq))
-                    {
-                        const double tinv = 1.0 / t[r];
-                        G = tinv * lam[r];
-                        g = tinv * ((lam[r] * t[r] - tau) - lam[r] * rd[r]);
-                    }
-                    sG[r] = G; sg[r] = g;
-                }
-                if (lane < NX) sx1[lane] = k < N ? F(Y.rb, k)[lane] : 0.0;
-            }
-            syncwarp();
-            const int r = lane;
-            const double* H = Hk(k);
-            const double* rg = F(Y.rg, k);
-            double Mr[NV];
-#pragma unroll
-            for (int c = 0; c < NV; c++)
-            {
-                double v = 0.0;
-                if (r < NV)
-                {
-                    if (var_active(k, r) && var_active(k, c)) { if (c <= r) v = H[r + NV * c]; if (c == r) v += reg; }
-                    else if (c == r) v = 1.0;
-                }
-                else if (r == NV) v = var_active(k, c) ? rg[c] : 0.0;
-                const int row = vrow(k, c);
-                if (row >= 0)
-                {
-                    if (r == c) v += sG[row] + sG[ncq + row];
-                    if (r == NV) v += sg[row] - sg[ncq + row];
-                }
-                Mr[c] = v;
-            }
-            if (k < N)
-            {
-                // AL = [B'; A'; res_b'] * Lxx_{k+1} ; Pb = Lxx (Lxx' res_b) ; last row += l_{k+1,x}
-                double bar[NX], AL[NX];
-#pragma unroll
-                for (int m = 0; m < NX; m++) bar[m] = r < NV ? sBA[r + NV * m] : (r == NV ? sx1[m] : 0.0);
-#pragma unroll
-                for (int j = 0; j < NX; j++)
-                {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int m = j; m < NX; m++) acc += bar[m] * sLn[m * NX + j];
-                    AL[j] = acc;
-                }
-                if (r == NV)
-                {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) sx2[j] = AL[j];
-                }
-                syncwarp();
-                if (r < NX)
-                {
-                    double acc = 0.0;
-                    for (int j = 0; j <= r; j++) acc += sLn[r * NX + j] * sx2[j];
-                    F(Y.Pb, k)[r] = acc;
-                }
-                if (r == NV)
-                {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) AL[j] += slx[j];
-                }
-                if (r <= NV)
-                {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) sAL[r * NX + j] = AL[j];
-                }
-                syncwarp();
-                // syrk: M += AL AL'
-                if (r <= NV)
-                {
-#pragma unroll
-                    for (int c = 0; c < NV; c++)
-                    {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int m = 0; m < NX; m++) acc += AL[m] * sAL[c * NX + m];
-                        Mr[c] += acc;
-                    }
-                }
-                // obstacle rows: D diag(Gamma_l + Gamma_u) D' touches only the (X,Y) block; gradient row gets D (gamma_l - gamma_u)
-                if (r == HXV || r == HYV || r == NV)
-                {
-                    double aX = 0.0, aY = 0.0;
-                    for (int c = 0; c < K; c++)
-                    {
-                        const double gX = sgxy[c], gY = sgxy[K + c];
-                        const double G = sG[nbq + c] + sG[ncq + nbq + c];
-                        const double left = r == NV ? sg[nbq + c] - sg[ncq + nbq + c] : (r == HXV ? gX * G : gY * G);
-                        aX += left * gX; aY += left * gY;
-                    }
-                    Mr[HXV] += aX; Mr[HYV] += aY;
-                }
-            }
-            // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
-            // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710)
-#pragma unroll
-            for (int j = 0; j < NV; j++)
-            {
-                const double a = shfl(Mr[j], j);
-                double sq = 0.0, inv = 0.0;
-                if (a > 0.0) { sq = dsqrt(a); inv = 1.0 / sq; }
-                if (r == j) Mr[j] = sq; else Mr[j] *= inv;
-#pragma unroll
-                for (int c = j + 1; c < NV; c++)
-                {
-                    const double lc = shfl(Mr[j], c);
-                    Mr[c] -= Mr[j] * lc;
-                }
-            }
-            syncwarp();
-            // store the factor; row NV is also the backward vector of the forward substitution
-            if (r <= NV)
-            {
-                double* L = F(Y.L, k);
-#pragma unroll
-                for (int c = 0; c < NV; c++) L[r * NV + c] = (c <= r) ? Mr[c] : 0.0;
-                if (r >= NU && r < NV)
-                {
-#pragma unroll
-                    for (int c = NU; c < NV; c++) sLn[(r - NU) * NX + (c - NU)] = (c <= r) ? Mr[c] : 0.0;
-                }
-                if (r == NV)
-                {
-                    double* dux = F(Y.dux, k);
-#pragma unroll
-                    for (int c = 0; c < NV; c++) dux[c] = Mr[c];
-#pragma unroll
-                    for (int c = NU; c < NV; c++) slx[c - NU] = Mr[c];
-                }
-            }
-        }
-        syncwarp();
     }
 
     // forward substitution shared by both solves.  On entry dux[k] holds the backward vector; scaled: its x part is
@@ -1016,81 +1394,6 @@ struct WarpSolver {
         syncwarp();
     }
 
-    MDEV bool itref_ok(const double* n) const
-    {
-        return (n[0] < tol_stat || n[0] < 1e-3 * res_max[0]) && (n[1] < tol_eq || n[1] < 1e-3 * res_max[1]) &&
-               (n[2] < tol_ineq || n[2] < 1e-3 * res_max[2]) && (n[3] < tol_comp || n[3] < 1e-3 * res_max[3]);
-    }
-
-    // OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:1888-2350 (pred_corr, cond_pred_corr, itref_corr_max = 2)
-    MDEV void delta_step()
-    {
-        const double tau_min = 1e-16, reg_prim = 1e-15;
-        factor_sweep(tau_min, reg_prim);
-        forward_sweep(Y.rb, Y.dux, Y.dpi, true);
-        expand_pass(0, tau_min);
-        {
-            mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
-            const double tmp = mu_aff / mu;
-            sigma = tmp * tmp * tmp;
-            double sigma_mu = sigma * mu;
-            sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
-            set_rmc(sigma_mu, true);
-            solve_sweep(false);
-            forward_sweep(Y.rb, Y.dux, Y.dpi, false);
-            expand_pass(1, 0.0);
-            {
-                const double mu_aff0 = mu_aff;
-                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
-                if (mu_aff > 2.0 * mu_aff0)
-                {
-                    set_rmc(sigma_mu, false);
-                    solve_sweep(false);
-                    forward_sweep(Y.rb, Y.dux, Y.dpi, false);
-                    expand_pass(1, 0.0);
-                }
-            }
-            bool refined = false;
-            for (int it = 0; it < 2; it++)
-            {
-                double n[4];
-                res_pass<true>(n);
-                if (itref_ok(n)) break;
-                solve_sweep(true);
-                forward_sweep(Y.rb2, Y.dux2, Y.dpi2, false);
-                expand_pass(2, 0.0);
-                add_refinement();
-                refined = true;
-            }
-            if (refined) alpha_pass();
-        }
-        double a = alpha;
-        if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-        update_pass(a);
-    }
-
-    // OCP_QP_IPM_SOLVE: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683 ; returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN
-    MDEV int ipm_solve(int* iters)
-    {
-        const double tau_min = 1e-16, alpha_min = 1e-8;
-        ipm_init();
-        alpha = 1.0;
-        res_pass<false>(res_max);
-        int kk;
-        for (kk = 0; kk < iter_max && alpha > alpha_min &&
-                     (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
-                      dabs(res_max[3] - tau_min) > tol_comp);
-             kk++)
-        {
-            delta_step();
-            res_pass<false>(res_max);
-        }
-        *iters = kk;
-        if (kk == iter_max) return 1;
-        if (alpha <= alpha_min) return 2;
-        if (disnan(mu)) return 3;
-        return 0;
-    }
 
     // ---------------------------------------------------------------- after the QP
     // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step

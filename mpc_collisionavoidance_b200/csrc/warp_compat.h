@@ -26,6 +26,14 @@ DEV double dsqrt(double a) { return sqrt(a); }
 DEV double dabs(double a) { return fabs(a); }
 DEV void dsincos(double a, double* s, double* c) { sincos(a, s, c); }
 DEV bool disnan(double a) { return isnan(a); }
+// asynchronous 16-byte global -> shared copy (LDGSTS, L2-only caching: the records are streamed, not reused in L1)
+DEV void cp_async16(double* smem_dst, const double* gsrc)
+{
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 }  // namespace usvmpc
 
 #else
@@ -52,6 +60,11 @@ struct Warp {
     long slot_i[WARP];
     void (*body)(void*);
     void* arg;
+    // deferred asynchronous copies, per lane: the data lands only at cp_async_wait_all(), and the destination is
+    // poisoned in between, so that reading a prefetch buffer before waiting shows up as NaNs in the CPU tests
+    struct Pending { double* dst; const double* src; };
+    Pending pend[WARP][512];
+    int npend[WARP];
 };
 extern thread_local Warp* g_warp;
 // hand control to the next lane; returns when every other lane has reached its own next yield
@@ -91,6 +104,22 @@ DEV double dsqrt(double a) { return std::sqrt(a); }
 DEV double dabs(double a) { return std::fabs(a); }
 DEV void dsincos(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
 DEV bool disnan(double a) { return std::isnan(a); }
+DEV void cp_async16(double* smem_dst, const double* gsrc)
+{
+    emu::Warp* w = emu::g_warp;
+    const int l = w->cur;
+    if (w->npend[l] >= 512) abort();
+    w->pend[l][w->npend[l]++] = {smem_dst, gsrc};
+    smem_dst[0] = smem_dst[1] = std::nan("");
+}
+DEV void cp_async_commit() {}
+DEV void cp_async_wait_all()
+{
+    emu::Warp* w = emu::g_warp;
+    const int l = w->cur;
+    for (int i = 0; i < w->npend[l]; i++) { w->pend[l][i].dst[0] = w->pend[l][i].src[0]; w->pend[l][i].dst[1] = w->pend[l][i].src[1]; }
+    w->npend[l] = 0;
+}
 }  // namespace usvmpc
 #endif
 

@@ -52,6 +52,7 @@ class BatchedAcadosOcpSolver:
         self.sync_host_sets = True  # False: caller keeps (pinned) host buffers alive until it synchronises
         k, c = acados_ocp.constraints, acados_ocp.cost
         # initial values the generated acados_create() would bake in (acados_solver.in.c:796-1449, 1595-1623)
+        unbatched, self.unbatched = self.unbatched, False   # the initial values below are written batched
         if k.x0 is not None:
             x0 = np.tile(np.asarray(k.x0, dtype=np.float64), (self.B, 1))
             self._call_set(0, "lbx", x0)
@@ -65,6 +66,7 @@ class BatchedAcadosOcpSolver:
             pv = np.asarray(acados_ocp.parameter_values, dtype=np.float64).ravel()
             if pv.size == 2 * self.K:
                 self._call_set("every", "p", np.tile(pv, (self.B, 1)))
+        self.unbatched = unbatched
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):

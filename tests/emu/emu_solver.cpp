@@ -166,7 +166,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
     }
     Job job;
     int next = 0;
-    job.P = &P; job.model = model; job.next = &next; job.smem_doubles = warp_smem_doubles(nx, nu, P.K);
+    job.P = &P; job.model = model; job.next = &next; job.smem_doubles = warp_smem_doubles(nx, nu, P.N, P.K, P.nbx, P.nbu);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     struct timespec t0, t1;
