@@ -47,6 +47,21 @@ def workload_name(cfg_id, B):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+class quiet_stdout:
+    """the reference C stack printf()s on every non-converged solve; keep that out of the JSON line on stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
 def cpu_reference_run(cfg_id, nsample, nthreads, seed=None):
     """time the reference's CPU implementation on `nsample` instances of the workload; returns (solves/s, kind, stats)"""
     import refharness as rh
@@ -54,7 +69,8 @@ def cpu_reference_run(cfg_id, nsample, nthreads, seed=None):
     b = make_batch(cfg_id, B=nsample, seed=seed)
     if rh.available():
         try:
-            r = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=nthreads)
+            with quiet_stdout():
+                r = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=nthreads)
             return nsample / r["seconds"], "reference", r
         except OSError:
             pass

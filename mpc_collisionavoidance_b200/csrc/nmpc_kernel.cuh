@@ -129,7 +129,7 @@ struct WarpSolver {
     // ---------------------------------------------------------------- initial guess
     // cold start of the scripts / template (acados_solver.in.c:1595-1623): x_k = x0, u = 0, pi = 0;
     // lam, t start at zero like a freshly created nlp_out.
-    MDEV void cold_start(const double* x0)
+    MDEVNI void cold_start(const double* x0)
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -148,7 +148,7 @@ struct WarpSolver {
     // ERK with forward sensitivities (AC/acados/sim/sim_erk_integrator.c:762-847, tableaus :253-344; seed S=[I 0],
     // A=Sx(T), B=Su(T): ocp_nlp_dynamics_cont.c:782-804).  One lane integrates [x ; one sensitivity column] of one
     // stage; a stage's NV columns sit on NV consecutive task slots.
-    MDEV void integrate_all()
+    MDEVNI void integrate_all()
     {
         const int ns = P.num_stages;
         double a21 = 0, a32 = 0, a43 = 0, bv[4] = {0, 0, 0, 0};
@@ -222,7 +222,7 @@ struct WarpSolver {
     // cost / constraints / adjoints / NLP residuals / QP vectors, one lane per stage.
     // ocp_nlp_approximate_qp_matrices + _vectors_sqp (ocp_nlp_common.c:1926-2084), ocp_nlp_res_compute (:2549-2603),
     // x0 elimination d_ocp_qp_reduce_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:268-454).  res4 = (stat, eq, ineq, comp).
-    MDEV void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
+    MDEVNI void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
                        double* res4)
     {
         integrate_all();
@@ -401,7 +401,7 @@ struct WarpSolver {
 
     // ---------------------------------------------------------------- IPM: per-stage (lane-parallel) passes
     // OCP_QP_INIT_VAR, var_init_scheme 1, cold start: HP/ocp_qp/x_ocp_qp_ipm.c:1435-1470,1581-1714 (ns = 0)
-    MDEV void ipm_init()
+    MDEVNI void ipm_init()
     {
         const double thr0 = 1e-1, mu0 = 1.0;
         for (int k = lane; k <= N; k += 32)
@@ -477,7 +477,7 @@ struct WarpSolver {
     //   (x_ocp_qp_res.c:336-466; norms into n4, mu) -> backward part of OCP_QP_FACT_SOLVE_KKT_STEP for the affine
     //   right-hand side res_m = lam*t - tau (x_ocp_qp_kkt.c:405-535, COMPUTE_GAMMA_GAMMA_QP x_core_qp_ipm_aux.c:38-86).
     // The factorisation is speculative: if the residuals turn out to be converged it is simply not used.
-    MDEV void sweepA(double a, double tau, double reg, double* n4)
+    MDEVNI void sweepA(double a, double tau, double reg, double* n4)
     {
         const double lam_min = 1e-16, t_min = 1e-16;
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
@@ -570,7 +570,7 @@ struct WarpSolver {
             syncwarp();
             // ---- factorise: lane r <= NV owns row r of [H + Gamma terms + AL AL' ; gradient row]
             const int r = lane;
-            double Mr[NV];
+            double Mr[NV], dinv = 0.0;
 #pragma unroll
             for (int c = 0; c < NV; c++)
             {
@@ -658,8 +658,8 @@ struct WarpSolver {
             {
                 const double piv = shfl(Mr[j], j);
                 double sq = 0.0, inv = 0.0;
-                if (piv > 0.0) { sq = dsqrt(piv); inv = 1.0 / sq; }
-                if (r == j) Mr[j] = sq; else Mr[j] *= inv;
+                if (piv > 0.0) { inv = drsqrt(piv); sq = piv * inv; }
+                if (r == j) { Mr[j] = sq; if (j < NU) dinv = inv; } else Mr[j] *= inv;
 #pragma unroll
                 for (int c = j + 1; c < NV; c++)
                 {
@@ -672,6 +672,7 @@ struct WarpSolver {
             {
 #pragma unroll
                 for (int c = 0; c < NV; c++) R[oL + r * NV + c] = (c <= r) ? Mr[c] : 0.0;
+                if (r < NU) R[oL + r * NV + NV - 1] = dinv;  // 1/L[r][r] of the columns solved per stage (unused upper triangle)
                 if (r >= NU && r < NV)
                 {
 #pragma unroll
@@ -703,7 +704,7 @@ struct WarpSolver {
     // vector, res_m = rmc) fused with the residual norms of the linear system (OCP_QP_RES_COMPUTE_LIN,
     // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
     template <bool CORR>
-    MDEV void sweepF(double tau, double* nlin)
+    MDEVNI void sweepF(double tau, double* nlin)
     {
         const int nf = odt + scq;  // everything but rq, b, d
         double a_prim = -1.0, a_dual = -1.0, s1 = 0.0, s2 = 0.0;
@@ -727,20 +728,25 @@ struct WarpSolver {
 #pragma unroll
             for (int i = NU - 1; i >= 0; i--)  // dtrsv_ltn on the columns solved at this stage
             {
-                double acc = -R[odux + i];
+                // the x part of the sum does not depend on the u unknowns: two short chains instead of one long one
+                double ax = 0.0, au = -R[odux + i];
 #pragma unroll
-                for (int m = i + 1; m < NV; m++) acc -= L[m * NV + i] * z[m];
-                z[i] = acc / L[i * NV + i];
+                for (int m = NU; m < NV; m++) ax -= L[m * NV + i] * z[m];
+#pragma unroll
+                for (int m = i + 1; m < NU; m++) au -= L[m * NV + i] * z[m];
+                z[i] = (au + ax) * L[i * NV + NV - 1];
             }
             double x1 = 0.0;
             if (k < N)
             {
                 if (lane < NX)
                 {
-                    double acc = R[orb + lane];
+                    double ax = R[orb + lane], au = 0.0;
 #pragma unroll
-                    for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * lane] * z[i];
-                    x1 = acc;
+                    for (int i = NU; i < NV; i++) ax += R[oBAt + i + NV * lane] * z[i];
+#pragma unroll
+                    for (int i = 0; i < NU; i++) au += R[oBAt + i + NV * lane] * z[i];
+                    x1 = ax + au;
                 }
 #pragma unroll
                 for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
@@ -860,7 +866,7 @@ struct WarpSolver {
     // COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113) for the right-hand side
     //   res_m = lam*t + dt_aff*dlam_aff - sigma_mu (corrector)   |   lam*t - sigma_mu (centering only)
     // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
-    MDEV void sweepC(bool with_aff, double sigma_mu)
+    MDEVNI void sweepC(bool with_aff, double sigma_mu)
     {
         const int nf = odt + scq;
         double pn[NX];
@@ -911,7 +917,7 @@ struct WarpSolver {
 #pragma unroll
             for (int m = 0; m < NU; m++)
             {
-                if (i == m) zi = zi / L[m * NV + m];
+                if (i == m) zi = zi * L[m * NV + NV - 1];
                 const double bm = shfl(zi, m);
                 if (i > m && i < NV) zi -= L[i * NV + m] * bm;
             }
@@ -936,7 +942,7 @@ struct WarpSolver {
     // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
     // Per iteration: B (affine) -> C, D (corrector) [-> C, D centering] [-> refinement, rare] -> A (update, residuals
     // and the factorisation the next iteration starts from).
-    MDEV int ipm_solve(int* iters)
+    MDEVNI int ipm_solve(int* iters)
     {
         const double tau_min = 1e-16, alpha_min = 1e-8, reg_prim = 1e-15;
         ipm_init();
@@ -997,7 +1003,7 @@ struct WarpSolver {
     // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
     // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
     template <bool LIN>
-    MDEV void res_pass(double* out4)
+    MDEVNI void res_pass(double* out4)
     {
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
         const Field &fv = LIN ? Y.dux : Y.ux, &fp = LIN ? Y.dpi : Y.pi, &fl = LIN ? Y.dlam : Y.lam, &ft = LIN ? Y.dt : Y.t;
@@ -1109,7 +1115,7 @@ struct WarpSolver {
     // dt, dlam from dux (tail of HP/ocp_qp/x_ocp_qp_kkt.c:748-764 + COMPUTE_LAM_T_QP, HP/ipm_core/x_core_qp_ipm_aux.c:117-142),
     // fused with COMPUTE_ALPHA_QP (:146-216) and the sums COMPUTE_MU_AFF_QP (:329-357) needs.
     // mode 0: affine rhs (res_m = lam*t - tau_min); 1: rhs m stored in rmc; 2: refinement (rd2, rm2 -> dlam2, dt2)
-    MDEV void expand_pass(int mode, double tau)
+    MDEVNI void expand_pass(int mode, double tau)
     {
         const Field &fv = mode == 2 ? Y.dux2 : Y.dux, &fl = mode == 2 ? Y.dlam2 : Y.dlam, &ft = mode == 2 ? Y.dt2 : Y.dt;
         const Field &frd = mode == 2 ? Y.rd2 : Y.rd, &frm = mode == 2 ? Y.rm2 : Y.rmc;
@@ -1152,7 +1158,7 @@ struct WarpSolver {
     }
 
     // COMPUTE_ALPHA_QP on the current step (after iterative refinement changed it)
-    MDEV void alpha_pass()
+    MDEVNI void alpha_pass()
     {
         double a_prim = -1.0, a_dual = -1.0;
         for (int k = lane; k < N; k += 32)
@@ -1170,7 +1176,7 @@ struct WarpSolver {
     }
 
     // step += refinement step
-    MDEV void add_refinement()
+    MDEVNI void add_refinement()
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -1223,7 +1229,7 @@ struct WarpSolver {
 
     // forward substitution shared by both solves.  On entry dux[k] holds the backward vector; scaled: its x part is
     // l_{k,x} (row NV of the factor; HP/ocp_qp/x_ocp_qp_kkt.c:537-575), else p_k itself (:1243-1290).
-    MDEV void forward_sweep(const Field& frb, const Field& fdux, const Field& fdpi, bool scaled)
+    MDEVNI void forward_sweep(const Field& frb, const Field& fdux, const Field& fdpi, bool scaled)
     {
         double xc[NX];
 #pragma unroll
@@ -1298,7 +1304,7 @@ struct WarpSolver {
 
     // OCP_QP_SOLVE_KKT_STEP, backward part (HP/ocp_qp/x_ocp_qp_kkt.c:1096-1242) with COMPUTE_GAMMA_QP
     // (x_core_qp_ipm_aux.c:89-113).  refine = false: rhs (rg, rb via Pb, rd, rmc) -> dux ; true: (rg2, rb2, rd2, rm2) -> dux2.
-    MDEV void solve_sweep(bool refine)
+    MDEVNI void solve_sweep(bool refine)
     {
         const Field &frg = refine ? Y.rg2 : Y.rg, &frb = refine ? Y.rb2 : Y.rb, &frd = refine ? Y.rd2 : Y.rd;
         const Field &frm = refine ? Y.rm2 : Y.rmc, &fo = refine ? Y.dux2 : Y.dux;
@@ -1398,7 +1404,7 @@ struct WarpSolver {
     // ---------------------------------------------------------------- after the QP
     // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step
     // (AC/acados/ocp_nlp/ocp_nlp_common.c:2401-2448): ux += step; pi, lam, t <- QP values.
-    MDEV void update_nlp()
+    MDEVNI void update_nlp()
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -1466,7 +1472,7 @@ struct WarpSolver {
 
     // residuals ocp_nlp_eval_residuals reports after an SQP_RTI step: stale linearisation, new lam / t
     // (AC/interfaces/acados_c/ocp_nlp_interface.c:909-916)
-    MDEV void rti_residuals(double* res4)
+    MDEVNI void rti_residuals(double* res4)
     {
         double r2 = 0, r3 = 0;
         for (int k = lane; k < N; k += 32)

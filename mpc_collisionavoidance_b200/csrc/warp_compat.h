@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #define DEV __device__ __forceinline__
 #define MDEV __device__ __forceinline__
+#define MDEVNI __device__ __noinline__
 #define DEVNI __device__ __noinline__
 #define HD __host__ __device__ __forceinline__
 
@@ -23,6 +24,7 @@ DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m)
 DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV void syncwarp() { __syncwarp(); }
 DEV double dsqrt(double a) { return sqrt(a); }
+DEV double drsqrt(double a) { return rsqrt(a); }
 DEV double dabs(double a) { return fabs(a); }
 DEV void dsincos(double a, double* s, double* c) { sincos(a, s, c); }
 DEV bool disnan(double a) { return isnan(a); }
@@ -44,6 +46,7 @@ DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memo
 #include <cstring>
 #define DEV static inline
 #define MDEV inline
+#define MDEVNI inline
 #define DEVNI static
 #define HD static inline
 
@@ -101,6 +104,7 @@ DEV double shfl_xor(double v, int m) { return shfl(v, lane_id() ^ m); }
 DEV int shfl_xor(int v, int m) { return shfl(v, lane_id() ^ m); }
 DEV void syncwarp() { emu::yield_lane(); }
 DEV double dsqrt(double a) { return std::sqrt(a); }
+DEV double drsqrt(double a) { return 1.0 / std::sqrt(a); }
 DEV double dabs(double a) { return std::fabs(a); }
 DEV void dsincos(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
 DEV bool disnan(double a) { return std::isnan(a); }
