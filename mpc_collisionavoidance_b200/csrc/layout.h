@@ -98,17 +98,15 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
 {
     const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
     const Layout L = make_layout(nx, nu, N, K, nbx, nbu);
-    int n = 2 * L.rec_size;
+    const int ne = nv * (nv + 1) / 2 + nv, nq = nu + nx + K;
+    int n = 3 * L.rec_size;    // record buffers (the rare path's scratch is aliased onto them)
     n += 2 * nv * nv;          // Hs, Hes
     n += nv * nv + nx * nx;    // Ws, Wes
-    n += nv * nx;              // sBA
-    n += nx * nx + nx;         // sLn, slx
+    n += 3 * ne;               // Tp
     n += (nv + 1) * nx;        // sAL
-    n += 2 * ncq2;             // sG, sg
-    n += (nv + 1) * nv;        // sL
-    n += 2 * nv + 2 * nx;      // sz, sq, sx1, sx2
-    n += 2 * (K > 0 ? K : 1);  // sgxy
-    n += ncq2 + 8;             // sxrow + misc
+    n += 3 * nq + nx;          // sGs, sgd, sdl, sz
+    n += (ne + nq + nv + nx + 1) / 2 + 2;  // int tables
+    (void) ncq2;
     return (n + 1) / 2 * 2;
 }
 

@@ -38,18 +38,20 @@ template <class M>
 struct WarpSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
     static constexpr int HXV = NU + M::HX, HYV = NU + M::HY;
+    static constexpr int NE = NV * (NV + 1) / 2 + NV;  // entries of the lower trapezoid of the (NV+1) x NV factor
 
     const Params& P;
     const Layout& Y;
     int lane, N, K, nbu, nbx, ncq, ncz, nbq, nct;
     double* w;
     // shared-memory scratch of this warp
-    double *Hs, *Hes, *Ws, *Wes, *sBA, *sLn, *slx, *sAL, *sG, *sg, *sL, *sz, *sq, *sx1, *sx2, *sgxy;
-    int* sxrow;
+    double *Hs, *Hes, *Ws, *Wes, *Tp, *sAL, *sGs, *sgd, *sdl, *sz;
+    int *sent, *srvar, *svrow, *sxrow;
+    double *sBA, *sLn, *slx, *sG, *sg, *sL, *sq, *sx1, *sx2, *sgxy;  // rare path, aliased onto the record buffers
     // the two record buffers of the streaming sweeps and the offsets of the record's fields (layout.h)
-    double* buf[2];
+    double* buf[3];
     int oBAt, ogxy, olam, ot, oux, opi, opip, org, orb, ord, oL, oPb, ormc, odux, odpi, odpip, odlam, odt, orq, ob, od;
-    int svv, scq;
+    int svv, sxx, scq;
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
     // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
     double tol_stat, tol_eq, tol_ineq, tol_comp;
@@ -66,19 +68,23 @@ struct WarpSolver {
         nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
         w = P.ws + (long) inst * P.ws_stride;
         double* s = sm;
-        buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size;
+        buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size; buf[2] = s; s += Y.rec_size;
         const int ro = Y.rec_off;
         oBAt = Y.BAt.off - ro; ogxy = Y.gxy.off - ro; olam = Y.lam.off - ro; ot = Y.t.off - ro; oux = Y.ux.off - ro;
         opi = Y.pi.off - ro; opip = Y.pi_prev.off - ro; org = Y.rg.off - ro; orb = Y.rb.off - ro; ord = Y.rd.off - ro;
         oL = Y.L.off - ro; oPb = Y.Pb.off - ro; ormc = Y.rmc.off - ro; odux = Y.dux.off - ro; odpi = Y.dpi.off - ro;
         odpip = Y.dpi_prev.off - ro; odlam = Y.dlam.off - ro; odt = Y.dt.off - ro; orq = Y.rq.off - ro; ob = Y.b.off - ro;
         od = Y.d.off - ro;
-        svv = (NV + 1) / 2 * 2; scq = Y.rq.off - Y.dt.off;
+        svv = (NV + 1) / 2 * 2; sxx = (NX + 1) / 2 * 2; scq = Y.rq.off - Y.dt.off;
         Hs = s; s += NV * NV; Hes = s; s += NV * NV; Ws = s; s += NV * NV; Wes = s; s += NX * NX;
-        sBA = s; s += NV * NX; sLn = s; s += NX * NX; slx = s; s += NX; sAL = s; s += NR * NX;
-        sG = s; s += 2 * (NU + NX + K); sg = s; s += 2 * (NU + NX + K); sL = s; s += NR * NV;
-        sz = s; s += NV; sq = s; s += NV; sx1 = s; s += NX; sx2 = s; s += NX; sgxy = s; s += 2 * (K > 0 ? K : 1);
-        sxrow = (int*) s;
+        Tp = s; s += 3 * NE; sAL = s; s += NR * NX;
+        sGs = s; s += NU + NX + K; sgd = s; s += NU + NX + K; sdl = s; s += NU + NX + K; sz = s; s += NX;
+        sent = (int*) s; srvar = sent + NE; svrow = srvar + (NU + NX + K); sxrow = svrow + NV;
+        // scratch of the rare (iterative refinement) path lives in the record buffers, which are idle then
+        double* q = buf[0];
+        sBA = q; q += NV * NX; sLn = q; q += NX * NX; slx = q; q += NX; sG = q; q += 2 * (NU + NX + K);
+        sg = q; q += 2 * (NU + NX + K); sL = q; q += NR * NV; sq = q; q += NV; sx1 = q; q += NX; sx2 = q; q += NX;
+        sgxy = q;
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
@@ -123,13 +129,37 @@ struct WarpSolver {
             sxrow[lane] = r;
         }
         syncwarp();
+        // tables of the streaming sweeps: lower-trapezoid entries e -> (r, c, offset); row pair -> boxed variable
+        // (or -1: h row); variable -> row pair of its box (or -1); factor templates per stage class
+        for (int e = lane; e < NE; e += 32)
+        {
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= e && r < NV) r++;
+            const int c = e - r * (r + 1) / 2;
+            sent[e] = (r << 24) | (c << 16) | (r * NV + c);
+            for (int cls = 0; cls < 3; cls++)
+            {
+                const double* H = cls == 2 ? Hes : Hs;
+                double v = 0.0;
+                if (r < NV)
+                {
+                    const bool ar = cls == 1 || (cls == 0 ? r < NU : r >= NU), ac = cls == 1 || (cls == 0 ? c < NU : c >= NU);
+                    if (ar && ac) { v = H[r + NV * c]; if (c == r) v += 1e-15; }  // reg_prim
+                    else if (c == r) v = 1.0;
+                }
+                Tp[cls * NE + e] = v;
+            }
+        }
+        for (int jj = lane; jj < ncq; jj += 32) srvar[jj] = jj < nbu ? jj : (jj < nbq ? NU + P.idxbx[jj - nbu] : -1);
+        if (lane < NV) svrow[lane] = lane < NU ? (lane < nbu ? lane : -1) : sxrow[lane - NU];
+        syncwarp();
     }
     MDEV const double* Hk(int k) const { return k < N ? Hs : Hes; }
 
     // ---------------------------------------------------------------- initial guess
     // cold start of the scripts / template (acados_solver.in.c:1595-1623): x_k = x0, u = 0, pi = 0;
     // lam, t start at zero like a freshly created nlp_out.
-    MDEVNI void cold_start(const double* x0)
+    MDEV void cold_start(const double* x0)
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -148,7 +178,7 @@ struct WarpSolver {
     // ERK with forward sensitivities (AC/acados/sim/sim_erk_integrator.c:762-847, tableaus :253-344; seed S=[I 0],
     // A=Sx(T), B=Su(T): ocp_nlp_dynamics_cont.c:782-804).  One lane integrates [x ; one sensitivity column] of one
     // stage; a stage's NV columns sit on NV consecutive task slots.
-    MDEVNI void integrate_all()
+    MDEV void integrate_all()
     {
         const int ns = P.num_stages;
         double a21 = 0, a32 = 0, a43 = 0, bv[4] = {0, 0, 0, 0};
@@ -222,7 +252,7 @@ struct WarpSolver {
     // cost / constraints / adjoints / NLP residuals / QP vectors, one lane per stage.
     // ocp_nlp_approximate_qp_matrices + _vectors_sqp (ocp_nlp_common.c:1926-2084), ocp_nlp_res_compute (:2549-2603),
     // x0 elimination d_ocp_qp_reduce_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:268-454).  res4 = (stat, eq, ineq, comp).
-    MDEVNI void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
+    MDEV void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
                        double* res4)
     {
         integrate_all();
@@ -401,7 +431,7 @@ struct WarpSolver {
 
     // ---------------------------------------------------------------- IPM: per-stage (lane-parallel) passes
     // OCP_QP_INIT_VAR, var_init_scheme 1, cold start: HP/ocp_qp/x_ocp_qp_ipm.c:1435-1470,1581-1714 (ns = 0)
-    MDEVNI void ipm_init()
+    MDEV void ipm_init()
     {
         const double thr0 = 1e-1, mu0 = 1.0;
         for (int k = lane; k <= N; k += 32)
@@ -448,13 +478,17 @@ struct WarpSolver {
     }
 
     // ---------------------------------------------------------------- IPM: record streaming
-    // The IPM works on one RECORD per stage (layout.h).  Each sweep pulls record k into shared memory with
-    // asynchronous 16-byte copies (cp.async), one stage ahead of the arithmetic, computes in place and writes the
-    // range it modified back with coalesced stores.
+    // The IPM works on one RECORD per stage (layout.h).  Each sweep pulls record k into one of three shared-memory
+    // buffers with asynchronous 16-byte copies (cp.async), one stage ahead of the arithmetic, computes in place and
+    // writes the range it modified back with coalesced stores; the third buffer keeps the previous stage's record
+    // (its Riccati factor / solution is the input of the recursion) so nothing is copied between stages.
+    // The sweeps are written for a SMALL instruction footprint (rolled loops over shared-memory operands, work
+    // spread over all 32 lanes): a lone warp finishing a hard instance is bound by instruction fetch otherwise.
     MDEV double* rec_g(int k) const { return w + Y.rec_off + (long) k * Y.rec_size; }
     MDEV void rec_fetch(int k, double* dst, int n)
     {
         const double* src = rec_g(k);
+#pragma unroll 1
         for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, src + c);
         cp_async_commit();
     }
@@ -462,14 +496,62 @@ struct WarpSolver {
     MDEV void rec_store(int k, const double* src, int from, int to)
     {
         double* dst = rec_g(k);
-        for (int c = from + 2 * lane; c < to; c += 64) { dst[c] = src[c]; dst[c + 1] = src[c + 1]; }
+#pragma unroll 1
+        for (int c = from + 2 * lane; c < to; c += 64) st2(dst + c, src + c);
     }
     // stage 0 after x0 elimination: no x rows in [B';A'], no Jacobian of the h rows (x_ocp_qp_red.c:268-454)
     MDEV void rec_mask_stage0(double* R)
     {
+#pragma unroll 1
         for (int e = lane; e < NV * NX; e += 32) if (e % NV >= NU) R[oBAt + e] = 0.0;
+#pragma unroll 1
         for (int e = lane; e < 2 * K; e += 32) R[ogxy + e] = 0.0;
         syncwarp();
+    }
+    // inequality rows are handled as (lower, upper) pairs jj < ncq: pair active at this stage class?
+    MDEV bool pair_active(int cls, int jj) const { return cls == 1 || (cls == 0 && (jj < nbu || jj >= nbq)); }
+    // IPM row pair of the box on variable i for this stage class, or -1
+    MDEV int box_of_var(int cls, int i) const { return cls == 1 ? svrow[i] : (cls == 0 && i < NU ? svrow[i] : -1); }
+    // residual-type kernel shared by sweep A (iterate) and sweep D (step): lanes < NV produce
+    //   g_i = sum_j H[i][j] v[j] + c_i - pprev_i + (box / h-row multiplier differences) + sum_j [B';A'][i][j] p[j]
+    // and lanes NV..NV+NX-1 produce  b_j = cb_j - xnext_j + sum_i [B';A'][i][j] v[i]   (x_ocp_qp_res.c:336-466, 468-592)
+    MDEV double res_gb(const double* R, int k, int cls, int ov, int op, int opp, int oc, int ocb, const double* xnext)
+    {
+        double acc = 0.0;
+        if (lane < NV + NX)
+        {
+            const bool isg = lane < NV;
+            if (!isg && k >= N) return 0.0;
+            const double* pa = isg ? (cls == 2 ? Hes : Hs) + lane : R + oBAt + NV * (lane - NV);
+            const int sa = isg ? NV : 1;
+            if (!isg) acc = R[ocb + lane - NV] - xnext[lane - NV];
+#pragma unroll
+            for (int m = 0; m < NV; m++) acc += pa[m * sa] * R[ov + m];
+            if (isg)
+            {
+                const int i = lane;
+                double g = acc + R[oc + i];
+                if (i >= NU) g -= R[opp + i - NU];
+                const int row = box_of_var(cls, i);
+                if (row >= 0) g += sdl[row];
+                if (k < N)
+                {
+                    if (i == HXV || i == HYV)
+                    {
+                        const double* gq = R + ogxy + (i == HXV ? 0 : K);
+#pragma unroll 1
+                        for (int c = 0; c < K; c++) g += gq[c] * sdl[nbq + c];
+                    }
+                    double acc2 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[op + j];
+                    g += acc2;
+                }
+                const bool act = cls == 1 || (cls == 0 ? i < NU : i >= NU);
+                acc = act ? g : 0.0;
+            }
+        }
+        return acc;
     }
 
     // Sweep A (backward, k = N..0), three steps of the reference fused per stage:
@@ -477,220 +559,177 @@ struct WarpSolver {
     //   (x_ocp_qp_res.c:336-466; norms into n4, mu) -> backward part of OCP_QP_FACT_SOLVE_KKT_STEP for the affine
     //   right-hand side res_m = lam*t - tau (x_ocp_qp_kkt.c:405-535, COMPUTE_GAMMA_GAMMA_QP x_core_qp_ipm_aux.c:38-86).
     // The factorisation is speculative: if the residuals turn out to be converged it is simply not used.
-    MDEVNI void sweepA(double a, double tau, double reg, double* n4)
+    // The (NV+1) x NV matrix [H + Gamma terms + AL AL' ; gradient row] is built and factorised in place in the
+    // record's L field, one lower-trapezoid entry (or two) per lane.
+    MDEV void sweepA(double a, double tau, double reg, double* n4)
     {
         const double lam_min = 1e-16, t_min = 1e-16;
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
-        double xn[NX];
-#pragma unroll
-        for (int i = 0; i < NX; i++) xn[i] = 0.0;
-        int cur = 0;
-        rec_fetch(N, buf[0], Y.rec_size);
+        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
+        rec_fetch(N, R, Y.rec_size);
+#pragma unroll 1
         for (int k = N; k >= 0; k--)
         {
-            double* R = buf[cur];
             rec_wait();
-            if (k > 0) rec_fetch(k - 1, buf[cur ^ 1], Y.rec_size);
+            if (k > 0) rec_fetch(k - 1, Rn, Y.rec_size);
+            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
             if (k == 0) rec_mask_stage0(R);
-            // ---- update
-            if (lane < NV) R[oux + lane] += a * R[odux + lane];
-            else if (lane < NV + NX) { if (k < N) R[opi + lane - NV] += a * R[odpi + lane - NV]; }
-            else if (lane < NV + 2 * NX) { if (k > 0) R[opip + lane - NV - NX] += a * R[odpip + lane - NV - NX]; }
-            for (int r = lane; r < 2 * ncq; r += 32)
-                if (row_active(k, r % ncq))
-                {
-                    double x = R[olam + r] + a * R[odlam + r];
-                    R[olam + r] = x <= lam_min ? lam_min : x;
-                    x = R[ot + r] + a * R[odt + r];
-                    R[ot + r] = x <= t_min ? t_min : x;
-                }
+            // ---- update: [ux | pi | pi_prev] += a [dux | dpi | dpi_prev]
+            if (lane < svv + 2 * sxx) R[oux + lane] += a * R[odux + lane];
             syncwarp();
-            // ---- residuals, Gamma, gamma
-            const double* H = Hk(k);
+            // ---- inequality row pairs: lam, t += a (dlam, dt), clipped; rd; mu; Gamma, gamma -> the sums and
+            //      differences the factorisation and the stationarity residual need
+#pragma unroll 1
+            for (int jj = lane; jj < ncq; jj += 32)
+            {
+                double Gs = 0.0, gd = 0.0, dl = 0.0;
+                if (pair_active(cls, jj))
+                {
+                    double l0 = R[olam + jj] + a * R[odlam + jj], l1 = R[olam + ncq + jj] + a * R[odlam + ncq + jj];
+                    double t0 = R[ot + jj] + a * R[odt + jj], t1 = R[ot + ncq + jj] + a * R[odt + ncq + jj];
+                    l0 = l0 <= lam_min ? lam_min : l0; l1 = l1 <= lam_min ? lam_min : l1;
+                    t0 = t0 <= t_min ? t_min : t0; t1 = t1 <= t_min ? t_min : t1;
+                    R[olam + jj] = l0; R[olam + ncq + jj] = l1; R[ot + jj] = t0; R[ot + ncq + jj] = t1;
+                    const int var = srvar[jj];
+                    const double v = var >= 0 ? R[oux + var]
+                                              : R[ogxy + jj - nbq] * R[oux + HXV] + R[ogxy + K + jj - nbq] * R[oux + HYV];
+                    const double rd0 = R[od + jj] + t0 - v, rd1 = R[od + ncq + jj] + t1 + v;
+                    R[ord + jj] = rd0; R[ord + ncq + jj] = rd1;
+                    const double m0 = l0 * t0, m1 = l1 * t1;
+                    musum += m0; musum += m1;
+                    double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
+                    q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
+                    const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
+                    Gs = ti0 * l0 + ti1 * l1;
+                    gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+                    dl = l1 - l0;
+                }
+                sGs[jj] = Gs; sgd[jj] = gd; sdl[jj] = dl;
+            }
+            syncwarp();
+            // ---- residuals rg (lanes < NV), rb (lanes NV..NV+NX-1)
+            {
+                const double r = res_gb(R, k, cls, oux, opi, opip, orq, ob, Rp + oux + NU);
+                const double q = dabs(r);
+                if (lane < NV) { R[org + lane] = r; n0 = q > n0 ? q : n0; }
+                else if (lane < NV + NX && k < N) { R[orb + lane - NV] = r; n1 = q > n1 ? q : n1; }
+            }
+            // ---- matrix to factorise, in place in R.L: template (H + reg, identity rows of inactive variables) ...
+            double* Mx = R + oL;
+            const double* T = Tp + cls * NE;
+#pragma unroll 1
+            for (int e = lane; e < NE; e += 32) Mx[sent[e] & 0xffff] = T[e];
+            syncwarp();
+            // ... + box terms on the diagonal, gradient row = rg + box gamma differences
             if (lane < NV)
             {
-                const int i = lane;
-                double g = 0.0;
-                if (var_active(k, i))
-                {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int j = 0; j < NV; j++) acc += H[i + NV * j] * R[oux + j];
-                    g = acc + R[orq + i];
-                    if (k > 0 && i >= NU) g -= R[opip + i - NU];
-                    const int row = vrow(k, i);
-                    if (row >= 0) g += R[olam + ncq + row] - R[olam + row];
-                    if (k < N)
-                    {
-                        if (i == HXV || i == HYV)
-                            for (int c = 0; c < K; c++)
-                                g += R[ogxy + (i == HXV ? c : K + c)] * (R[olam + ncq + nbq + c] - R[olam + nbq + c]);
-                        double acc2 = 0.0;
-#pragma unroll
-                        for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[opi + j];
-                        g += acc2;
-                    }
-                }
-                R[org + i] = g;
-                const double ag = dabs(g);
-                n0 = ag > n0 ? ag : n0;
-            }
-            else if (lane < NV + NX && k < N)
-            {
-                const int j = lane - NV;
-                double acc = R[ob + j] - xn[j];
-#pragma unroll
-                for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * j] * R[oux + i];
-                R[orb + j] = acc;
-                const double ab = dabs(acc);
-                n1 = ab > n1 ? ab : n1;
-            }
-            for (int r = lane; r < 2 * ncq; r += 32)
-            {
-                double G = 0.0, gm = 0.0;
-                const int jj = r % ncq;
-                if (row_active(k, jj))
-                {
-                    double v;
-                    if (jj < nbq) v = R[oux + (jj < nbu ? jj : NU + P.idxbx[jj - nbu])];
-                    else v = R[ogxy + jj - nbq] * R[oux + HXV] + R[ogxy + K + jj - nbq] * R[oux + HYV];
-                    const double lam = R[olam + r], t = R[ot + r];
-                    const double rd = r < ncq ? R[od + r] + t - v : R[od + r] + t + v;
-                    R[ord + r] = rd;
-                    const double m = lam * t;
-                    musum += m;
-                    const double am = dabs(m), ad = dabs(rd);
-                    n3 = am > n3 ? am : n3; n2 = ad > n2 ? ad : n2;
-                    const double tinv = 1.0 / t;
-                    G = tinv * lam;
-                    gm = tinv * ((m - tau) - lam * rd);
-                }
-                sG[r] = G; sg[r] = gm;
-            }
-            syncwarp();
-            // ---- factorise: lane r <= NV owns row r of [H + Gamma terms + AL AL' ; gradient row]
-            const int r = lane;
-            double Mr[NV], dinv = 0.0;
-#pragma unroll
-            for (int c = 0; c < NV; c++)
-            {
-                double v = 0.0;
-                if (r < NV)
-                {
-                    if (var_active(k, r) && var_active(k, c)) { if (c <= r) v = H[r + NV * c]; if (c == r) v += reg; }
-                    else if (c == r) v = 1.0;
-                }
-                else if (r == NV) v = R[org + c];
-                const int row = vrow(k, c);
-                if (row >= 0)
-                {
-                    if (r == c) v += sG[row] + sG[ncq + row];
-                    if (r == NV) v += sg[row] - sg[ncq + row];
-                }
-                Mr[c] = v;
+                const int row = box_of_var(cls, lane);
+                double gr = R[org + lane];
+                if (row >= 0) { Mx[lane * NV + lane] += sGs[row]; gr += sgd[row]; }
+                Mx[NV * NV + lane] = gr;
             }
             if (k < N)
             {
-                // AL = [B'; A'; res_b'] * Lxx_{k+1} ; Pb = Lxx (Lxx' res_b) ; last row += l_{k+1,x}
-                double bar[NX], AL[NX];
-#pragma unroll
-                for (int m = 0; m < NX; m++) bar[m] = r < NV ? R[oBAt + r + NV * m] : (r == NV ? R[orb + m] : 0.0);
-#pragma unroll
-                for (int j = 0; j < NX; j++)
+                // AL = [B'; A'; res_b'] * Lxx_{k+1}  (dtrmm_rlnn), one entry (r, j) per lane and round
+                const double* Lx = Rp + oL + NU * NV + NU;  // xx block of the factor of stage k+1, row pitch NV
+#pragma unroll 1
+                for (int e = lane; e < NR * NX; e += 32)
                 {
+                    const int r = e / NX, j = e - r * NX;
+                    const double* pa = r < NV ? R + oBAt + r : R + orb;
+                    const int sa = r < NV ? NV : 1;
                     double acc = 0.0;
 #pragma unroll
-                    for (int m = j; m < NX; m++) acc += bar[m] * sLn[m * NX + j];
-                    AL[j] = acc;
-                }
-                if (r == NV)
-                {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) sx2[j] = AL[j];
+                    for (int m = 0; m < NX; m++) if (m >= j) acc += pa[m * sa] * Lx[m * NV + j];
+                    sAL[e] = acc;
                 }
                 syncwarp();
-                if (r < NX)
+                // Pb = Lxx (Lxx' res_b) ; then the last row of AL gets l_{k+1,x} added
+                double pb = 0.0;
+                if (lane < NX)
                 {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) if (j <= lane) pb += Lx[lane * NV + j] * sAL[NV * NX + j];
+                    R[oPb + lane] = pb;
+                }
+                syncwarp();
+                if (lane < NX) sAL[NV * NX + lane] += Rp[oL + NV * NV + NU + lane];
+                syncwarp();
+                // syrk: M += AL AL' on the lower trapezoid
+#pragma unroll 1
+                for (int e = lane; e < NE; e += 32)
+                {
+                    const int rc = sent[e], r = rc >> 24, c = (rc >> 16) & 0xff;
                     double acc = 0.0;
-                    for (int j = 0; j <= r; j++) acc += sLn[r * NX + j] * sx2[j];
-                    R[oPb + r] = acc;
-                }
-                if (r == NV)
-                {
 #pragma unroll
-                    for (int j = 0; j < NX; j++) AL[j] += slx[j];
-                }
-                if (r <= NV)
-                {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) sAL[r * NX + j] = AL[j];
-                }
-                syncwarp();
-                if (r <= NV)
-                {
-#pragma unroll
-                    for (int c = 0; c < NV; c++)
-                    {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int m = 0; m < NX; m++) acc += AL[m] * sAL[c * NX + m];
-                        Mr[c] += acc;
-                    }
+                    for (int m = 0; m < NX; m++) acc += sAL[r * NX + m] * sAL[c * NX + m];
+                    Mx[rc & 0xffff] += acc;
                 }
                 // h rows: D diag(Gamma_l + Gamma_u) D' touches only the (X,Y) block; gradient row gets D (gamma_l - gamma_u)
-                if (r == HXV || r == HYV || r == NV)
+                double oacc = 0.0;
+                int ooff = -1;
+                if (cls == 1 && lane < 5 && K > 0)
                 {
-                    double aX = 0.0, aY = 0.0;
-                    for (int c = 0; c < K; c++)
+                    const double* gX = R + ogxy;
+                    const double* gY = gX + K;
+                    const double* pw = (lane < 3 ? sGs : sgd) + nbq;
+                    const double* pu = lane == 0 ? gX : gY;
+                    const double* pv = (lane == 0 || lane == 1 || lane == 3) ? gX : gY;
+                    if (lane < 3)
                     {
-                        const double gX = R[ogxy + c], gY = R[ogxy + K + c];
-                        const double G = sG[nbq + c] + sG[ncq + nbq + c];
-                        const double left = r == NV ? sg[nbq + c] - sg[ncq + nbq + c] : (r == HXV ? gX * G : gY * G);
-                        aX += left * gX; aY += left * gY;
+#pragma unroll 1
+                        for (int c = 0; c < K; c++) oacc += (pu[c] * pw[c]) * pv[c];
                     }
-                    Mr[HXV] += aX; Mr[HYV] += aY;
+                    else
+                    {
+#pragma unroll 1
+                        for (int c = 0; c < K; c++) oacc += pw[c] * pv[c];
+                    }
+                    ooff = (lane < 3 ? (lane == 0 ? HXV : HYV) : NV) * NV + ((lane == 0 || lane == 1 || lane == 3) ? HXV : HYV);
                 }
+                syncwarp();
+                if (ooff >= 0) Mx[ooff] += oacc;
             }
-            // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
+            syncwarp();
+            // ---- (NV+1) x NV Cholesky in place, lower; non-positive pivot => zero column
             // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710)
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < NV; j++)
             {
-                const double piv = shfl(Mr[j], j);
-                double sq = 0.0, inv = 0.0;
-                if (piv > 0.0) { inv = drsqrt(piv); sq = piv * inv; }
-                if (r == j) { Mr[j] = sq; if (j < NU) dinv = inv; } else Mr[j] *= inv;
-#pragma unroll
-                for (int c = j + 1; c < NV; c++)
+                const double piv = Mx[j * NV + j];
+                const double inv = piv > 0.0 ? drsqrt(piv) : 0.0;
+                double nv0 = 0.0, nv1 = 0.0;
+                int o0 = -1, o1 = -1;
+                if (lane < NE)
                 {
-                    const double lc = shfl(Mr[j], c);
-                    Mr[c] -= Mr[j] * lc;
+                    const int rc = sent[lane], r = rc >> 24, c = (rc >> 16) & 0xff;
+                    if (c >= j)
+                    {
+                        o0 = rc & 0xffff;
+                        const double lr = Mx[r * NV + j] * inv;
+                        nv0 = c == j ? (r == j ? (piv > 0.0 ? piv * inv : 0.0) : lr) : Mx[o0] - lr * (Mx[c * NV + j] * inv);
+                    }
                 }
+                if (lane + 32 < NE)
+                {
+                    const int rc = sent[lane + 32], r = rc >> 24, c = (rc >> 16) & 0xff;
+                    if (c >= j)
+                    {
+                        o1 = rc & 0xffff;
+                        const double lr = Mx[r * NV + j] * inv;
+                        nv1 = c == j ? (r == j ? (piv > 0.0 ? piv * inv : 0.0) : lr) : Mx[o1] - lr * (Mx[c * NV + j] * inv);
+                    }
+                }
+                syncwarp();
+                if (o0 >= 0) Mx[o0] = nv0;
+                if (o1 >= 0) Mx[o1] = nv1;
+                if (lane == 0 && j < NU) Mx[j * NV + NV - 1] = inv;  // 1/L[j][j] of the columns solved per stage (unused upper slot)
+                syncwarp();
             }
-            syncwarp();
-            if (r <= NV)
-            {
-#pragma unroll
-                for (int c = 0; c < NV; c++) R[oL + r * NV + c] = (c <= r) ? Mr[c] : 0.0;
-                if (r < NU) R[oL + r * NV + NV - 1] = dinv;  // 1/L[r][r] of the columns solved per stage (unused upper triangle)
-                if (r >= NU && r < NV)
-                {
-#pragma unroll
-                    for (int c = NU; c < NV; c++) sLn[(r - NU) * NX + (c - NU)] = (c <= r) ? Mr[c] : 0.0;
-                }
-                if (r == NV)
-                {
-#pragma unroll
-                    for (int c = 0; c < NV; c++) R[odux + c] = Mr[c];  // backward vector of the forward substitution
-#pragma unroll
-                    for (int c = NU; c < NV; c++) slx[c - NU] = Mr[c];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NX; i++) xn[i] = R[oux + NU + i];
+            if (lane < NV) R[odux + lane] = Mx[NV * NV + lane];  // backward vector of the forward substitution
             syncwarp();
             rec_store(k, R, olam, odux + svv);
-            cur ^= 1;
+            double* t = Rp; Rp = R; R = Rn; Rn = t;
         }
         n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
         mu = warp_sum(musum) / nct;
@@ -699,166 +738,144 @@ struct WarpSolver {
 
     // Sweeps B / D (forward, k = 0..N): forward substitution (x_ocp_qp_kkt.c:537-575 | 1243-1290), then dt, dlam
     // (:748-764 + COMPUTE_LAM_T_QP, x_core_qp_ipm_aux.c:117-142), step length (COMPUTE_ALPHA_QP :146-216) and the
-    // sums COMPUTE_MU_AFF_QP (:329-357) needs.  CORR = false: affine step after sweep A (dux holds row NV of the
-    // factor, res_m = lam*t - tau).  CORR = true: corrector / centering step after sweep C (dux holds the backward
+    // sums COMPUTE_MU_AFF_QP (:329-357) needs.  corr = false: affine step after sweep A (dux holds row NV of the
+    // factor, res_m = lam*t - tau).  corr = true: corrector / centering step after sweep C (dux holds the backward
     // vector, res_m = rmc) fused with the residual norms of the linear system (OCP_QP_RES_COMPUTE_LIN,
     // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
-    template <bool CORR>
-    MDEVNI void sweepF(double tau, double* nlin)
+    MDEV void sweepF(bool corr, double tau, double* nlin)
     {
         const int nf = odt + scq;  // everything but rq, b, d
-        double a_prim = -1.0, a_dual = -1.0, s1 = 0.0, s2 = 0.0;
+        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
         double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-        double xc[NX];
-#pragma unroll
-        for (int i = 0; i < NX; i++) xc[i] = 0.0;
-        int cur = 0;
-        rec_fetch(0, buf[0], nf);
+        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
+        rec_fetch(0, R, nf);
         rec_wait();
-        if (N >= 1) rec_fetch(1, buf[1], nf);
+        if (N >= 1) rec_fetch(1, Rn, nf);
+#pragma unroll 1
         for (int k = 0; k <= N; k++)
         {
-            double* R = buf[cur];
-            double* Rn = buf[cur ^ 1];
-            if (k == 0) rec_mask_stage0(R);
-            const double* L = R + oL;
-            double z[NV];
-#pragma unroll
-            for (int i = 0; i < NX; i++) z[NU + i] = xc[i];
-#pragma unroll
-            for (int i = NU - 1; i >= 0; i--)  // dtrsv_ltn on the columns solved at this stage
+            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
+            if (k == 0)
             {
-                // the x part of the sum does not depend on the u unknowns: two short chains instead of one long one
+                rec_mask_stage0(R);
+                if (lane < NX) R[odux + NU + lane] = 0.0;  // no x step at stage 0
+                syncwarp();
+            }
+            const double* L = R + oL;
+            // ---- columns solved at this stage (dtrsv_ltn): every lane redundantly; x part of dux is already there
+            double zu[NU];
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--)
+            {
                 double ax = 0.0, au = -R[odux + i];
 #pragma unroll
-                for (int m = NU; m < NV; m++) ax -= L[m * NV + i] * z[m];
+                for (int m = NU; m < NV; m++) ax -= L[m * NV + i] * R[odux + m];
 #pragma unroll
-                for (int m = i + 1; m < NU; m++) au -= L[m * NV + i] * z[m];
-                z[i] = (au + ax) * L[i * NV + NV - 1];
+                for (int m = i + 1; m < NU; m++) au -= L[m * NV + i] * zu[m];
+                zu[i] = (au + ax) * L[i * NV + NV - 1];
+                if (cls == 2) zu[i] = 0.0;
             }
+            // ---- dx_{k+1} = res_b + [B A] dux_k
             double x1 = 0.0;
-            if (k < N)
+            if (k < N && lane < NX)
             {
-                if (lane < NX)
-                {
-                    double ax = R[orb + lane], au = 0.0;
+                double ax = R[orb + lane], au = 0.0;
 #pragma unroll
-                    for (int i = NU; i < NV; i++) ax += R[oBAt + i + NV * lane] * z[i];
+                for (int i = NU; i < NV; i++) ax += R[oBAt + i + NV * lane] * R[odux + i];
 #pragma unroll
-                    for (int i = 0; i < NU; i++) au += R[oBAt + i + NV * lane] * z[i];
-                    x1 = ax + au;
-                }
-#pragma unroll
-                for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+                for (int i = 0; i < NU; i++) au += R[oBAt + i + NV * lane] * zu[i];
+                x1 = ax + au;
             }
             syncwarp();  // every lane has read the backward vector
             if (lane == 0)
             {
 #pragma unroll
-                for (int i = 0; i < NV; i++) R[odux + i] = var_active(k, i) ? z[i] : 0.0;
+                for (int i = 0; i < NU; i++) R[odux + i] = zu[i];
             }
             syncwarp();
-            // ---- dt, dlam, step length
-            for (int r = lane; r < 2 * ncq; r += 32)
+            // ---- dt, dlam, step length on the row pairs
+#pragma unroll 1
+            for (int jj = lane; jj < ncq; jj += 32)
             {
-                const int jj = r % ncq;
-                if (!row_active(k, jj)) continue;
-                double dv;
-                if (jj < nbq) dv = R[odux + (jj < nbu ? jj : NU + P.idxbx[jj - nbu])];
-                else dv = R[ogxy + jj - nbq] * R[odux + HXV] + R[ogxy + K + jj - nbq] * R[odux + HYV];
-                double dtr = r < ncq ? dv : -dv;
-                const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = 1.0 / t0;
-                const double m = CORR ? R[ormc + r] : lam0 * t0 - tau;
-                const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd));
-                if (CORR)
+                double dld = 0.0;
+                if (pair_active(cls, jj))
                 {
-                    // residual of the linearised rows at the step: rd + dt -+ v, rm + lam*dt + dlam*t
-                    const double dtf = dtr - rd;
-                    const double e2 = dabs(r < ncq ? rd + dtf - dv : rd + dtf + dv), e3 = dabs(m + lam0 * dtf + dlr * t0);
-                    l2 = e2 > l2 ? e2 : l2; l3 = e3 > l3 ? e3 : l3;
+                    const int var = srvar[jj];
+                    const double dv = var >= 0 ? R[odux + var]
+                                               : R[ogxy + jj - nbq] * R[odux + HXV] + R[ogxy + K + jj - nbq] * R[odux + HYV];
+#pragma unroll
+                    for (int side = 0; side < 2; side++)
+                    {
+                        const int r = jj + side * ncq;
+                        double dtr = side ? -dv : dv;
+                        const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = 1.0 / t0;
+                        const double m = corr ? R[ormc + r] : lam0 * t0 - tau;
+                        const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd));
+                        dtr -= rd;
+                        if (corr)
+                        {
+                            // residual of the linearised rows at the step: rd + dt -+ v, rm + lam*dt + dlam*t
+                            const double e2 = dabs(side ? rd + dtr + dv : rd + dtr - dv), e3 = dabs(m + lam0 * dtr + dlr * t0);
+                            l2 = e2 > l2 ? e2 : l2; l3 = e3 > l3 ? e3 : l3;
+                        }
+                        R[odlam + r] = dlr; R[odt + r] = dtr;
+                        // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running
+                        // best ratio is kept as (numerator, denominator) and compared by cross-multiplication, so the
+                        // divisions happen once per sweep instead of once per row
+                        if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
+                        if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
+                        s1 += lam0 * dtr + t0 * dlr;
+                        s2 += dlr * dtr;
+                        dld = side ? dlr - dld : dlr;
+                    }
                 }
-                dtr -= rd;
-                R[odlam + r] = dlr; R[odt + r] = dtr;
-                if (a_dual * dlr > lam0) a_dual = lam0 / dlr;
-                if (a_prim * dtr > t0) a_prim = t0 / dtr;
-                s1 += lam0 * dtr + t0 * dlr;
-                s2 += dlr * dtr;
+                sdl[jj] = dld;  // dlam_upper - dlam_lower, for the residual of the linear system
             }
             // ---- dpi_k = Lxx (Lxx' dx_{k+1} + l_x)  |  p_{k+1} + Lxx (Lxx' dx_{k+1}) : needs the factor of stage k+1
             if (k < N)
             {
-                rec_wait();  // record k+1 has landed in the other buffer
-                const double* Ln = Rn + oL;
-                double tmp = 0.0;
+                rec_wait();  // record k+1 has landed
+                const double* Lx = Rn + oL + NU * NV + NU;
+                double pj = 0.0;
+                if (lane < NX) pj = Rn[odux + NU + lane];  // l_x or p of stage k+1
+                syncwarp();
+                if (lane < NX) Rn[odux + NU + lane] = x1;  // from now on the x part of dux_{k+1}
+                syncwarp();
                 if (lane < NX)
                 {
                     double acc = 0.0;
-                    for (int m = lane; m < NX; m++) acc += Ln[(NU + m) * NV + NU + lane] * xc[m];
-                    tmp = CORR ? acc : acc + Rn[odux + NU + lane];
+#pragma unroll
+                    for (int m = 0; m < NX; m++) if (m >= lane) acc += Lx[m * NV + lane] * Rn[odux + NU + m];
+                    sz[lane] = corr ? acc : acc + pj;
                 }
-                double tv[NX];
-#pragma unroll
-                for (int j = 0; j < NX; j++) tv[j] = shfl(tmp, j);
+                syncwarp();
                 if (lane < NX)
                 {
                     double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NX; j++) if (j <= lane) acc += Ln[(NU + lane) * NV + NU + j] * tv[j];
-                    const double dp = CORR ? Rn[odux + NU + lane] + acc : acc;
+                    for (int j = 0; j < NX; j++) if (j <= lane) acc += Lx[lane * NV + j] * sz[j];
+                    const double dp = corr ? pj + acc : acc;
                     R[odpi + lane] = dp;
                     Rn[odpip + lane] = dp;
                 }
             }
             syncwarp();
-            if (CORR)
+            if (corr)
             {
-                if (lane < NV)
-                {
-                    const int i = lane;
-                    double g = 0.0;
-                    if (var_active(k, i))
-                    {
-                        const double* H = Hk(k);
-                        double acc = 0.0;
-#pragma unroll
-                        for (int j = 0; j < NV; j++) acc += H[i + NV * j] * R[odux + j];
-                        g = acc + R[org + i];
-                        if (k > 0 && i >= NU) g -= R[odpip + i - NU];
-                        const int row = vrow(k, i);
-                        if (row >= 0) g += R[odlam + ncq + row] - R[odlam + row];
-                        if (k < N)
-                        {
-                            if (i == HXV || i == HYV)
-                                for (int c = 0; c < K; c++)
-                                    g += R[ogxy + (i == HXV ? c : K + c)] * (R[odlam + ncq + nbq + c] - R[odlam + nbq + c]);
-                            double acc2 = 0.0;
-#pragma unroll
-                            for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[odpi + j];
-                            g += acc2;
-                        }
-                    }
-                    const double ag = dabs(g);
-                    l0 = ag > l0 ? ag : l0;
-                }
-                else if (lane < NV + NX && k < N)
-                {
-                    const int j = lane - NV;
-                    double acc = R[orb + j] - xc[j];
-#pragma unroll
-                    for (int i = 0; i < NV; i++) acc += R[oBAt + i + NV * j] * R[odux + i];
-                    const double ab = dabs(acc);
-                    l1 = ab > l1 ? ab : l1;
-                }
+                const double r = res_gb(R, k, cls, odux, odpi, odpip, org, orb, Rn + odux + NU);
+                const double q = dabs(r);
+                if (lane < NV) l0 = q > l0 ? q : l0;
+                else if (lane < NV + NX && k < N) l1 = q > l1 ? q : l1;
             }
             rec_store(k, R, odux, nf);
             syncwarp();
-            if (k + 2 <= N) rec_fetch(k + 2, buf[cur], nf);
-            cur ^= 1;
+            double* t = Rp; Rp = R; R = Rn; Rn = t;
+            if (k + 2 <= N) rec_fetch(k + 2, Rn, nf);
         }
-        a_prim = warp_max(a_prim); a_dual = warp_max(a_dual);
+        const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
         alpha = -(a_prim > a_dual ? a_prim : a_dual);
         S1 = warp_sum(s1); S2 = warp_sum(s2);
-        if (CORR) { nlin[0] = warp_max(l0); nlin[1] = warp_max(l1); nlin[2] = warp_max(l2); nlin[3] = warp_max(l3); }
+        if (corr) { nlin[0] = warp_max(l0); nlin[1] = warp_max(l1); nlin[2] = warp_max(l2); nlin[3] = warp_max(l3); }
         syncwarp();
     }
 
@@ -866,49 +883,53 @@ struct WarpSolver {
     // COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113) for the right-hand side
     //   res_m = lam*t + dt_aff*dlam_aff - sigma_mu (corrector)   |   lam*t - sigma_mu (centering only)
     // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
-    MDEVNI void sweepC(bool with_aff, double sigma_mu)
+    MDEV void sweepC(bool with_aff, double sigma_mu)
     {
         const int nf = odt + scq;
-        double pn[NX];
-#pragma unroll
-        for (int i = 0; i < NX; i++) pn[i] = 0.0;
-        int cur = 0;
-        rec_fetch(N, buf[0], nf);
+        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
+        rec_fetch(N, R, nf);
+#pragma unroll 1
         for (int k = N; k >= 0; k--)
         {
-            double* R = buf[cur];
             rec_wait();
-            if (k > 0) rec_fetch(k - 1, buf[cur ^ 1], nf);
+            if (k > 0) rec_fetch(k - 1, Rn, nf);
+            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
             if (k == 0) rec_mask_stage0(R);
-            for (int r = lane; r < 2 * ncq; r += 32)
+#pragma unroll 1
+            for (int jj = lane; jj < ncq; jj += 32)
             {
-                double g = 0.0, m = 0.0;
-                if (row_active(k, r % ncq))
+                double gd = 0.0, m0 = 0.0, m1 = 0.0;
+                if (pair_active(cls, jj))
                 {
-                    const double lam = R[olam + r], t = R[ot + r];
-                    const double bkp = lam * t;
-                    m = with_aff ? bkp + R[odt + r] * R[odlam + r] - sigma_mu : bkp - sigma_mu;
-                    g = (1.0 / t) * (m - lam * R[ord + r]);
+                    const double la0 = R[olam + jj], la1 = R[olam + ncq + jj], t0 = R[ot + jj], t1 = R[ot + ncq + jj];
+                    m0 = la0 * t0; m1 = la1 * t1;
+                    if (with_aff) { m0 += R[odt + jj] * R[odlam + jj]; m1 += R[odt + ncq + jj] * R[odlam + ncq + jj]; }
+                    m0 -= sigma_mu; m1 -= sigma_mu;
+                    gd = (1.0 / t0) * (m0 - la0 * R[ord + jj]) - (1.0 / t1) * (m1 - la1 * R[ord + ncq + jj]);
                 }
-                R[ormc + r] = m;
-                sg[r] = g;
+                R[ormc + jj] = m0; R[ormc + ncq + jj] = m1;
+                sgd[jj] = gd;
             }
+            if (k < N && lane < NX) sz[lane] = Rp[odux + NU + lane] + R[oPb + lane];  // p_{k+1} + Pb
             syncwarp();
             const int i = lane;
             double zi = 0.0;
-            if (i < NV && var_active(k, i))
+            if (i < NV && (cls == 1 || (cls == 0 ? i < NU : i >= NU)))
             {
                 zi = R[org + i];
-                const int row = vrow(k, i);
-                if (row >= 0) zi += sg[row] - sg[ncq + row];
+                const int row = box_of_var(cls, i);
+                if (row >= 0) zi += sgd[row];
                 if (k < N)
                 {
                     if (i == HXV || i == HYV)
-                        for (int c = 0; c < K; c++)
-                            zi += R[ogxy + (i == HXV ? c : K + c)] * (sg[nbq + c] - sg[ncq + nbq + c]);
+                    {
+                        const double* gq = R + ogxy + (i == HXV ? 0 : K);
+#pragma unroll 1
+                        for (int c = 0; c < K; c++) zi += gq[c] * sgd[nbq + c];
+                    }
                     double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NX; j++) acc += R[oBAt + i + NV * j] * (pn[j] + R[oPb + j]);
+                    for (int j = 0; j < NX; j++) acc += R[oBAt + i + NV * j] * sz[j];
                     zi += acc;
                 }
             }
@@ -922,11 +943,9 @@ struct WarpSolver {
                 if (i > m && i < NV) zi -= L[i * NV + m] * bm;
             }
             if (i < NV) R[odux + i] = zi;
-#pragma unroll
-            for (int j = 0; j < NX; j++) pn[j] = shfl(zi, NU + j);
             syncwarp();
             rec_store(k, R, ormc, odux + svv);
-            cur ^= 1;
+            double* t = Rp; Rp = R; R = Rn; Rn = t;
         }
         solve_calls++;
         syncwarp();
@@ -940,36 +959,44 @@ struct WarpSolver {
 
     // OCP_QP_IPM_SOLVE + OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683, 1888-2350 (pred_corr,
     // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
-    // Per iteration: B (affine) -> C, D (corrector) [-> C, D centering] [-> refinement, rare] -> A (update, residuals
-    // and the factorisation the next iteration starts from).
-    MDEVNI int ipm_solve(int* iters)
+    // Per iteration: A (update with the previous step, residuals, factorisation) -> B (affine step) -> C, D (corrector)
+    // [-> C, D centering only] [-> refinement, rare].  Each sweep has ONE call site so that its loop exists once in
+    // the instruction stream.
+    MDEV int ipm_solve(int* iters)
     {
         const double tau_min = 1e-16, alpha_min = 1e-8, reg_prim = 1e-15;
         ipm_init();
         alpha = 1.0;
-        sweepA(0.0, tau_min, reg_prim, res_max);
-        int kk;
-        for (kk = 0; kk < iter_max && alpha > alpha_min &&
-                     (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
-                      dabs(res_max[3] - tau_min) > tol_comp);
-             kk++)
+        double a = 0.0;  // the first sweep A applies no step
+        int kk = 0;
+        for (;;)
         {
-            double nlin[4];
-            sweepF<false>(tau_min, nlin);
-            mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
-            const double tmp = mu_aff / mu;
-            sigma = tmp * tmp * tmp;
-            double sigma_mu = sigma * mu;
-            sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
-            sweepC(true, sigma_mu);
-            sweepF<true>(0.0, nlin);
+            sweepA(a, tau_min, reg_prim, res_max);
+            if (!(kk < iter_max && alpha > alpha_min &&
+                  (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
+                   dabs(res_max[3] - tau_min) > tol_comp)))
+                break;
+            double nlin[4] = {0, 0, 0, 0};
+            double sigma_mu = 0.0, mu_aff0 = 0.0;
+            for (int pass = 0; pass < 3; pass++)
             {
-                const double mu_aff0 = mu_aff;
-                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
-                if (mu_aff > 2.0 * mu_aff0)
+                // pass 0: affine step; pass 1: corrector; pass 2: centering only (conditional)
+                if (pass > 0) sweepC(pass == 1, sigma_mu);
+                sweepF(pass > 0, tau_min, nlin);
+                const double ma = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
+                if (pass == 0)
                 {
-                    sweepC(false, sigma_mu);
-                    sweepF<true>(0.0, nlin);
+                    mu_aff = ma;
+                    const double tmp = mu_aff / mu;
+                    sigma = tmp * tmp * tmp;
+                    sigma_mu = sigma * mu;
+                    sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
+                }
+                else if (pass == 1)
+                {
+                    mu_aff0 = mu_aff;
+                    mu_aff = ma;
+                    if (!(mu_aff > 2.0 * mu_aff0)) break;
                 }
             }
             bool refined = false;
@@ -987,9 +1014,9 @@ struct WarpSolver {
                 res_pass<true>(nlin);
             }
             if (refined) alpha_pass();
-            double a = alpha;
+            a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-            sweepA(a, tau_min, reg_prim, res_max);
+            kk++;
         }
         *iters = kk;
         if (kk == iter_max) return 1;
@@ -1003,7 +1030,7 @@ struct WarpSolver {
     // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
     // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
     template <bool LIN>
-    MDEVNI void res_pass(double* out4)
+    MDEV void res_pass(double* out4)
     {
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
         const Field &fv = LIN ? Y.dux : Y.ux, &fp = LIN ? Y.dpi : Y.pi, &fl = LIN ? Y.dlam : Y.lam, &ft = LIN ? Y.dt : Y.t;
@@ -1115,7 +1142,7 @@ struct WarpSolver {
     // dt, dlam from dux (tail of HP/ocp_qp/x_ocp_qp_kkt.c:748-764 + COMPUTE_LAM_T_QP, HP/ipm_core/x_core_qp_ipm_aux.c:117-142),
     // fused with COMPUTE_ALPHA_QP (:146-216) and the sums COMPUTE_MU_AFF_QP (:329-357) needs.
     // mode 0: affine rhs (res_m = lam*t - tau_min); 1: rhs m stored in rmc; 2: refinement (rd2, rm2 -> dlam2, dt2)
-    MDEVNI void expand_pass(int mode, double tau)
+    MDEV void expand_pass(int mode, double tau)
     {
         const Field &fv = mode == 2 ? Y.dux2 : Y.dux, &fl = mode == 2 ? Y.dlam2 : Y.dlam, &ft = mode == 2 ? Y.dt2 : Y.dt;
         const Field &frd = mode == 2 ? Y.rd2 : Y.rd, &frm = mode == 2 ? Y.rm2 : Y.rmc;
@@ -1158,7 +1185,7 @@ struct WarpSolver {
     }
 
     // COMPUTE_ALPHA_QP on the current step (after iterative refinement changed it)
-    MDEVNI void alpha_pass()
+    MDEV void alpha_pass()
     {
         double a_prim = -1.0, a_dual = -1.0;
         for (int k = lane; k < N; k += 32)
@@ -1176,7 +1203,7 @@ struct WarpSolver {
     }
 
     // step += refinement step
-    MDEVNI void add_refinement()
+    MDEV void add_refinement()
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -1229,7 +1256,7 @@ struct WarpSolver {
 
     // forward substitution shared by both solves.  On entry dux[k] holds the backward vector; scaled: its x part is
     // l_{k,x} (row NV of the factor; HP/ocp_qp/x_ocp_qp_kkt.c:537-575), else p_k itself (:1243-1290).
-    MDEVNI void forward_sweep(const Field& frb, const Field& fdux, const Field& fdpi, bool scaled)
+    MDEV void forward_sweep(const Field& frb, const Field& fdux, const Field& fdpi, bool scaled)
     {
         double xc[NX];
 #pragma unroll
@@ -1304,7 +1331,7 @@ struct WarpSolver {
 
     // OCP_QP_SOLVE_KKT_STEP, backward part (HP/ocp_qp/x_ocp_qp_kkt.c:1096-1242) with COMPUTE_GAMMA_QP
     // (x_core_qp_ipm_aux.c:89-113).  refine = false: rhs (rg, rb via Pb, rd, rmc) -> dux ; true: (rg2, rb2, rd2, rm2) -> dux2.
-    MDEVNI void solve_sweep(bool refine)
+    MDEV void solve_sweep(bool refine)
     {
         const Field &frg = refine ? Y.rg2 : Y.rg, &frb = refine ? Y.rb2 : Y.rb, &frd = refine ? Y.rd2 : Y.rd;
         const Field &frm = refine ? Y.rm2 : Y.rmc, &fo = refine ? Y.dux2 : Y.dux;
@@ -1404,7 +1431,7 @@ struct WarpSolver {
     // ---------------------------------------------------------------- after the QP
     // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step
     // (AC/acados/ocp_nlp/ocp_nlp_common.c:2401-2448): ux += step; pi, lam, t <- QP values.
-    MDEVNI void update_nlp()
+    MDEV void update_nlp()
     {
         for (int k = lane; k <= N; k += 32)
         {
@@ -1472,7 +1499,7 @@ struct WarpSolver {
 
     // residuals ocp_nlp_eval_residuals reports after an SQP_RTI step: stale linearisation, new lam / t
     // (AC/interfaces/acados_c/ocp_nlp_interface.c:909-916)
-    MDEVNI void rti_residuals(double* res4)
+    MDEV void rti_residuals(double* res4)
     {
         double r2 = 0, r3 = 0;
         for (int k = lane; k < N; k += 32)

@@ -34,6 +34,7 @@ DEV void cp_async16(double* smem_dst, const double* gsrc)
     const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
+DEV void st2(double* dst, const double* src) { *reinterpret_cast<double2*>(dst) = *reinterpret_cast<const double2*>(src); }
 DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 }  // namespace usvmpc
@@ -116,6 +117,7 @@ DEV void cp_async16(double* smem_dst, const double* gsrc)
     w->pend[l][w->npend[l]++] = {smem_dst, gsrc};
     smem_dst[0] = smem_dst[1] = std::nan("");
 }
+DEV void st2(double* dst, const double* src) { dst[0] = src[0]; dst[1] = src[1]; }
 DEV void cp_async_commit() {}
 DEV void cp_async_wait_all()
 {
