@@ -29,11 +29,12 @@ struct Layout {
     // NLP iterate (persists between solves = warm start, like nlp_out in the reference); stage-major arrays
     Field zux, zpi, zlam, zt, zfun;
     // ---- the per-stage RECORD streamed through shared memory by the IPM sweeps (all strides = rec_size) ----
-    // order inside a record:
-    //   BAt gxy | lam t ux pi pi_prev rg rb rd L Pb rmc dux | dpi dpi_prev dlam dt | rq b d
-    // so that each sweep writes back ONE contiguous range (A: lam..dux, B/D: dux..dt, C: rmc..dux).
+    // order inside a record (fixed-size fields first: compile-time offsets in the kernel):
+    //   BAt | ux pi pi_prev rg rb L Pb dux | dpi dpi_prev | rq b || gxy | lam t rd ti | rmc | dlam dt | d   (ti = 1/t)
+    // so that each sweep writes back two contiguous ranges (A: ux..dux + lam..rd, B/D: dux..dpi_prev + dlam..dt,
+    // C: dux + rmc).
     // pi_prev / dpi_prev duplicate pi / dpi of stage k-1 so that no sweep needs a neighbouring record.
-    Field BAt, gxy, lam, t, ux, pi, pi_prev, rg, rb, rd, L, Pb, rmc, dux, dpi, dpi_prev, dlam, dt, rq, b, d;
+    Field BAt, gxy, lam, t, ux, pi, pi_prev, rg, rb, rd, ti, L, Pb, rmc, dux, dpi, dpi_prev, dlam, dt, rq, b, d;
     int rec_off, rec_size;
     // iterative refinement scratch (rare path), stage-major arrays
     Field dux2, dpi2, dlam2, dt2, rg2, rb2, rd2, rm2;
@@ -76,14 +77,16 @@ inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
     put(L.zux, sv); put(L.zpi, sx); put(L.zlam, scz); put(L.zt, scz); put(L.zfun, scz);
     int r = 0;
     auto rec = [&](Field& f, int n) { f.off = r; r += n; };
-    rec(L.BAt, sBA); rec(L.gxy, sg);
-    rec(L.lam, scq); rec(L.t, scq); rec(L.ux, sv); rec(L.pi, sx); rec(L.pi_prev, sx); rec(L.rg, sv); rec(L.rb, sx);
-    rec(L.rd, scq); rec(L.L, sL); rec(L.Pb, sx); rec(L.rmc, scq); rec(L.dux, sv);
-    rec(L.dpi, sx); rec(L.dpi_prev, sx); rec(L.dlam, scq); rec(L.dt, scq);
-    rec(L.rq, sv); rec(L.b, sx); rec(L.d, scq);
+    // fixed-size fields first (their offsets are compile-time constants in the kernel), K-dependent ones after
+    rec(L.BAt, sBA);
+    rec(L.ux, sv); rec(L.pi, sx); rec(L.pi_prev, sx); rec(L.rg, sv); rec(L.rb, sx); rec(L.L, sL); rec(L.Pb, sx);
+    rec(L.dux, sv); rec(L.dpi, sx); rec(L.dpi_prev, sx);
+    rec(L.rq, sv); rec(L.b, sx);
+    rec(L.gxy, sg);
+    rec(L.lam, scq); rec(L.t, scq); rec(L.rd, scq); rec(L.ti, scq); rec(L.rmc, scq); rec(L.dlam, scq); rec(L.dt, scq); rec(L.d, scq);
     L.rec_size = round_up(r, 2);
     L.rec_off = (int) o;
-    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.pi_prev, &L.rg, &L.rb, &L.rd, &L.L, &L.Pb, &L.rmc,
+    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.pi_prev, &L.rg, &L.rb, &L.rd, &L.ti, &L.L, &L.Pb, &L.rmc,
                    &L.dux, &L.dpi, &L.dpi_prev, &L.dlam, &L.dt, &L.rq, &L.b, &L.d};
     for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; }
     o += (long) L.rec_size * N1;
@@ -105,7 +108,7 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
     n += 3 * ne;               // Tp
     n += (nv + 1) * nx;        // sAL
     n += 3 * nq + nx;          // sGs, sgd, sdl, sz
-    n += (ne + nq + nv + nx + 1) / 2 + 2;  // int tables
+    n += (ne + nq + nv + nx + 1) / 2 + 16;  // int tables + alignment slack
     (void) ncq2;
     return (n + 1) / 2 * 2;
 }

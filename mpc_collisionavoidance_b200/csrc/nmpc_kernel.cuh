@@ -39,6 +39,15 @@ struct WarpSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
     static constexpr int HXV = NU + M::HX, HYV = NU + M::HY;
     static constexpr int NE = NV * (NV + 1) / 2 + NV;  // entries of the lower trapezoid of the (NV+1) x NV factor
+    // record layout (layout.h): offsets of the fixed-size fields are compile-time constants
+    static constexpr int svv = (NV + 1) / 2 * 2, sxx = (NX + 1) / 2 * 2, sLL = (NR * NV + 1) / 2 * 2;
+    static constexpr int oBAt = 0, oux = (NV * NX + 1) / 2 * 2, opi = oux + svv, opip = opi + sxx, org = opip + sxx, orb = org + svv;
+    static constexpr int oL = orb + sxx, oPb = oL + sLL, odux = oPb + sxx, odpi = odux + svv, odpip = odpi + sxx;
+    static constexpr int orq = odpip + sxx, ob = orq + svv, ogxy = ob + sxx;
+    // per-warp shared-memory scratch: fixed-size part at compile-time offsets
+    static constexpr int qHs = 0, qHes = qHs + NV * NV, qWs = qHes + NV * NV, qWes = qWs + NV * NV, qTp = qWes + NX * NX;
+    static constexpr int qAL = qTp + 3 * NE, qz = qAL + NR * NX, qent = qz + sxx, qvrow = qent + (NE + 1) / 2;
+    static constexpr int qxrow = qvrow + (NV + 1) / 2, qvar = qxrow + (NX + 1) / 2;
 
     const Params& P;
     const Layout& Y;
@@ -50,8 +59,7 @@ struct WarpSolver {
     double *sBA, *sLn, *slx, *sG, *sg, *sL, *sq, *sx1, *sx2, *sgxy;  // rare path, aliased onto the record buffers
     // the two record buffers of the streaming sweeps and the offsets of the record's fields (layout.h)
     double* buf[3];
-    int oBAt, ogxy, olam, ot, oux, opi, opip, org, orb, ord, oL, oPb, ormc, odux, odpi, odpip, odlam, odt, orq, ob, od;
-    int svv, sxx, scq;
+    int olam, ot, ord, oti, ormc, odlam, odt, od, scq;  // K-dependent record offsets
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
     // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
     double tol_stat, tol_eq, tol_ineq, tol_comp;
@@ -68,18 +76,16 @@ struct WarpSolver {
         nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
         w = P.ws + (long) inst * P.ws_stride;
         double* s = sm;
+        Hs = s + qHs; Hes = s + qHes; Ws = s + qWs; Wes = s + qWes; Tp = s + qTp; sAL = s + qAL; sz = s + qz;
+        sent = (int*) (s + qent); svrow = (int*) (s + qvrow); sxrow = (int*) (s + qxrow);
+        const int nq = NU + NX + K;
+        s += qvar;
+        srvar = (int*) s; s += (nq + 1) / 2; sGs = s; s += nq; sgd = s; s += nq; sdl = s; s += nq;
+        s = sm + ((s - sm) + 1) / 2 * 2;
         buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size; buf[2] = s; s += Y.rec_size;
-        const int ro = Y.rec_off;
-        oBAt = Y.BAt.off - ro; ogxy = Y.gxy.off - ro; olam = Y.lam.off - ro; ot = Y.t.off - ro; oux = Y.ux.off - ro;
-        opi = Y.pi.off - ro; opip = Y.pi_prev.off - ro; org = Y.rg.off - ro; orb = Y.rb.off - ro; ord = Y.rd.off - ro;
-        oL = Y.L.off - ro; oPb = Y.Pb.off - ro; ormc = Y.rmc.off - ro; odux = Y.dux.off - ro; odpi = Y.dpi.off - ro;
-        odpip = Y.dpi_prev.off - ro; odlam = Y.dlam.off - ro; odt = Y.dt.off - ro; orq = Y.rq.off - ro; ob = Y.b.off - ro;
-        od = Y.d.off - ro;
-        svv = (NV + 1) / 2 * 2; sxx = (NX + 1) / 2 * 2; scq = Y.rq.off - Y.dt.off;
-        Hs = s; s += NV * NV; Hes = s; s += NV * NV; Ws = s; s += NV * NV; Wes = s; s += NX * NX;
-        Tp = s; s += 3 * NE; sAL = s; s += NR * NX;
-        sGs = s; s += NU + NX + K; sgd = s; s += NU + NX + K; sdl = s; s += NU + NX + K; sz = s; s += NX;
-        sent = (int*) s; srvar = sent + NE; svrow = srvar + (NU + NX + K); sxrow = svrow + NV;
+        scq = Y.t.off - Y.lam.off;
+        olam = Y.lam.off - Y.rec_off; ot = olam + scq; ord = ot + scq; oti = ord + scq; ormc = oti + scq; odlam = ormc + scq;
+        odt = odlam + scq; od = odt + scq;
         // scratch of the rare (iterative refinement) path lives in the record buffers, which are idle then
         double* q = buf[0];
         sBA = q; q += NV * NX; sLn = q; q += NX * NX; slx = q; q += NX; sG = q; q += 2 * (NU + NX + K);
@@ -91,6 +97,17 @@ struct WarpSolver {
         solve_calls = 0;
     }
 
+    // the host-side layout (layout.h:make_layout) must agree with the compile-time offsets above
+    static bool layout_matches(const Layout& y)
+    {
+        const int ro = y.rec_off;
+        return y.BAt.off - ro == oBAt && y.ux.off - ro == oux && y.pi.off - ro == opi && y.pi_prev.off - ro == opip &&
+               y.rg.off - ro == org && y.rb.off - ro == orb && y.L.off - ro == oL && y.Pb.off - ro == oPb &&
+               y.dux.off - ro == odux && y.dpi.off - ro == odpi && y.dpi_prev.off - ro == odpip && y.rq.off - ro == orq &&
+               y.b.off - ro == ob && y.gxy.off - ro == ogxy && y.lam.off > y.gxy.off && y.rd.off - y.t.off == y.t.off - y.lam.off && y.ti.off - y.rd.off == y.t.off - y.lam.off &&
+               y.rmc.off - y.ti.off == y.t.off - y.lam.off &&
+               y.d.off - y.dt.off == y.t.off - y.lam.off && y.rec_size == y.d.off - ro + (y.t.off - y.lam.off);
+    }
     MDEV double* F(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
     MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
     MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
@@ -600,6 +617,7 @@ struct WarpSolver {
                     double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
                     q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
                     const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
+                    R[oti + jj] = ti0; R[oti + ncq + jj] = ti1;  // kept for sweeps B, C, D
                     Gs = ti0 * l0 + ti1 * l1;
                     gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
                     dl = l1 - l0;
@@ -691,44 +709,40 @@ struct WarpSolver {
                 if (ooff >= 0) Mx[ooff] += oacc;
             }
             syncwarp();
-            // ---- (NV+1) x NV Cholesky in place, lower; non-positive pivot => zero column
-            // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710)
-#pragma unroll 1
-            for (int j = 0; j < NV; j++)
+            // ---- (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
+            // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).  Lane r <= NV takes row r
+            // into registers; pivots and multipliers travel by shuffle.
             {
-                const double piv = Mx[j * NV + j];
-                const double inv = piv > 0.0 ? drsqrt(piv) : 0.0;
-                double nv0 = 0.0, nv1 = 0.0;
-                int o0 = -1, o1 = -1;
-                if (lane < NE)
+                const int r = lane <= NV ? lane : NV;
+                double Mr[NV], dinv = 0.0;
+#pragma unroll
+                for (int c = 0; c < NV; c++) Mr[c] = Mx[r * NV + c];
+#pragma unroll
+                for (int j = 0; j < NV; j++)
                 {
-                    const int rc = sent[lane], r = rc >> 24, c = (rc >> 16) & 0xff;
-                    if (c >= j)
+                    const double piv = shfl(Mr[j], j);
+                    double sq = 0.0, inv = 0.0;
+                    if (piv > 0.0) { inv = drsqrt(piv); sq = piv * inv; }
+                    if (r == j) { Mr[j] = sq; if (j < NU) dinv = inv; } else Mr[j] *= inv;
+#pragma unroll
+                    for (int c = j + 1; c < NV; c++)
                     {
-                        o0 = rc & 0xffff;
-                        const double lr = Mx[r * NV + j] * inv;
-                        nv0 = c == j ? (r == j ? (piv > 0.0 ? piv * inv : 0.0) : lr) : Mx[o0] - lr * (Mx[c * NV + j] * inv);
+                        const double lc = shfl(Mr[j], c);
+                        Mr[c] -= Mr[j] * lc;
                     }
                 }
-                if (lane + 32 < NE)
+                if (lane <= NV)
                 {
-                    const int rc = sent[lane + 32], r = rc >> 24, c = (rc >> 16) & 0xff;
-                    if (c >= j)
-                    {
-                        o1 = rc & 0xffff;
-                        const double lr = Mx[r * NV + j] * inv;
-                        nv1 = c == j ? (r == j ? (piv > 0.0 ? piv * inv : 0.0) : lr) : Mx[o1] - lr * (Mx[c * NV + j] * inv);
-                    }
+#pragma unroll
+                    for (int c = 0; c < NV; c++) if (c <= lane) Mx[lane * NV + c] = Mr[c];
+                    if (lane < NU) Mx[lane * NV + NV - 1] = dinv;  // 1/L[j][j] of the columns solved per stage (unused upper slot)
                 }
-                syncwarp();
-                if (o0 >= 0) Mx[o0] = nv0;
-                if (o1 >= 0) Mx[o1] = nv1;
-                if (lane == 0 && j < NU) Mx[j * NV + NV - 1] = inv;  // 1/L[j][j] of the columns solved per stage (unused upper slot)
-                syncwarp();
             }
+            syncwarp();
             if (lane < NV) R[odux + lane] = Mx[NV * NV + lane];  // backward vector of the forward substitution
             syncwarp();
-            rec_store(k, R, olam, odux + svv);
+            rec_store(k, R, oux, odux + svv);
+            rec_store(k, R, olam, ormc);
             double* t = Rp; Rp = R; R = Rn; Rn = t;
         }
         n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
@@ -744,7 +758,7 @@ struct WarpSolver {
     // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
     MDEV void sweepF(bool corr, double tau, double* nlin)
     {
-        const int nf = odt + scq;  // everything but rq, b, d
+        const int nf = Y.rec_size;
         double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
         double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
         double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
@@ -808,7 +822,7 @@ struct WarpSolver {
                     {
                         const int r = jj + side * ncq;
                         double dtr = side ? -dv : dv;
-                        const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = 1.0 / t0;
+                        const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = R[oti + r];
                         const double m = corr ? R[ormc + r] : lam0 * t0 - tau;
                         const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd));
                         dtr -= rd;
@@ -867,7 +881,8 @@ struct WarpSolver {
                 if (lane < NV) l0 = q > l0 ? q : l0;
                 else if (lane < NV + NX && k < N) l1 = q > l1 ? q : l1;
             }
-            rec_store(k, R, odux, nf);
+            rec_store(k, R, odux, orq);
+            rec_store(k, R, odlam, od);
             syncwarp();
             double* t = Rp; Rp = R; R = Rn; Rn = t;
             if (k + 2 <= N) rec_fetch(k + 2, Rn, nf);
@@ -885,7 +900,7 @@ struct WarpSolver {
     // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
     MDEV void sweepC(bool with_aff, double sigma_mu)
     {
-        const int nf = odt + scq;
+        const int nf = Y.rec_size;
         double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
         rec_fetch(N, R, nf);
 #pragma unroll 1
@@ -905,7 +920,7 @@ struct WarpSolver {
                     m0 = la0 * t0; m1 = la1 * t1;
                     if (with_aff) { m0 += R[odt + jj] * R[odlam + jj]; m1 += R[odt + ncq + jj] * R[odlam + ncq + jj]; }
                     m0 -= sigma_mu; m1 -= sigma_mu;
-                    gd = (1.0 / t0) * (m0 - la0 * R[ord + jj]) - (1.0 / t1) * (m1 - la1 * R[ord + ncq + jj]);
+                    gd = R[oti + jj] * (m0 - la0 * R[ord + jj]) - R[oti + ncq + jj] * (m1 - la1 * R[ord + ncq + jj]);
                 }
                 R[ormc + jj] = m0; R[ormc + ncq + jj] = m1;
                 sgd[jj] = gd;
@@ -944,7 +959,8 @@ struct WarpSolver {
             }
             if (i < NV) R[odux + i] = zi;
             syncwarp();
-            rec_store(k, R, ormc, odux + svv);
+            rec_store(k, R, odux, odux + svv);
+            rec_store(k, R, ormc, odlam);
             double* t = Rp; Rp = R; R = Rn; Rn = t;
         }
         solve_calls++;

@@ -315,6 +315,8 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
     const int N = cfg->N, K = cfg->K, B = batch, ny = nx + nu;
     s->P.lay = make_layout(nx, nu, N, K, cfg->nbx, cfg->nbu);
     s->P.ws_stride = s->P.lay.total;
+    if (!(cfg->model == USVMPC_MODEL_PENDULUM ? WarpSolver<Pendulum>::layout_matches(s->P.lay) : WarpSolver<Usv3>::layout_matches(s->P.lay)))
+        return fail(USVMPC_E_INVALID, "internal: layout.h and the kernel's compile-time offsets disagree");
     s->smem_per_warp = warp_smem_doubles(nx, nu, N, K, cfg->nbx, cfg->nbu);
     const int kk = K > 0 ? K : 1;
     CU(cudaMalloc(&s->d_ws, sizeof(double) * (size_t) s->P.ws_stride * B));

@@ -141,6 +141,11 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
     P.x0 = x0; P.p = p; P.lh = lh; P.yref = yref; P.yref_e = yref_e;
     P.lay = make_layout(nx, nu, P.N, P.K, P.nbx, P.nbu);
     P.ws_stride = P.lay.total;
+    if (!(model == 1 ? WarpSolver<Pendulum>::layout_matches(P.lay) : WarpSolver<Usv3>::layout_matches(P.lay)))
+    {
+        fprintf(stderr, "usvmpc emu: layout.h and the kernel's compile-time offsets disagree\n");
+        abort();
+    }
     // exact-size heap block (so a sanitizer sees overruns), poisoned with NaN
     double* ws = (double*) malloc(sizeof(double) * P.ws_stride * B);
     for (long i = 0; i < (long) P.ws_stride * B; i++) ws[i] = 0.0 / 0.0;
