@@ -102,7 +102,7 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
     const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
     const Layout L = make_layout(nx, nu, N, K, nbx, nbu);
     const int ne = nv * (nv + 1) / 2 + nv, nq = nu + nx + K;
-    int n = 3 * L.rec_size;    // record buffers (the rare path's scratch is aliased onto them)
+    int n = 3 * L.rec_size + 4;  // record buffers (the rare path's scratch is aliased onto them) + 3 mbarriers
     n += 2 * nv * nv;          // Hs, Hes
     n += nv * nv + nx * nx;    // Ws, Wes
     n += 3 * ne;               // Tp

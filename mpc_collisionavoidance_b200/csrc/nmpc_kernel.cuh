@@ -59,6 +59,8 @@ struct WarpSolver {
     double *sBA, *sLn, *slx, *sG, *sg, *sL, *sq, *sx1, *sx2, *sgxy;  // rare path, aliased onto the record buffers
     // the two record buffers of the streaming sweeps and the offsets of the record's fields (layout.h)
     double* buf[3];
+    unsigned long long* bar;  // one mbarrier per record buffer (TMA completion)
+    unsigned phb;             // their phase bits
     int olam, ot, ord, oti, ormc, odlam, odt, od, scq;  // K-dependent record offsets
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
     // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
@@ -83,6 +85,8 @@ struct WarpSolver {
         srvar = (int*) s; s += (nq + 1) / 2; sGs = s; s += nq; sgd = s; s += nq; sdl = s; s += nq;
         s = sm + ((s - sm) + 1) / 2 * 2;
         buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size; buf[2] = s; s += Y.rec_size;
+        bar = (unsigned long long*) s; s += 4;
+        phb = 0;
         scq = Y.t.off - Y.lam.off;
         olam = Y.lam.off - Y.rec_off; ot = olam + scq; ord = ot + scq; oti = ord + scq; ormc = oti + scq; odlam = ormc + scq;
         odt = odlam + scq; od = odt + scq;
@@ -502,19 +506,45 @@ struct WarpSolver {
     // The sweeps are written for a SMALL instruction footprint (rolled loops over shared-memory operands, work
     // spread over all 32 lanes): a lone warp finishing a hard instance is bound by instruction fetch otherwise.
     MDEV double* rec_g(int k) const { return w + Y.rec_off + (long) k * Y.rec_size; }
-    MDEV void rec_fetch(int k, double* dst, int n)
+    // TMA: one lane issues one bulk copy for the whole record; completion is counted in bytes on the buffer's mbarrier
+    MDEV void rec_init()
     {
-        const double* src = rec_g(k);
-#pragma unroll 1
-        for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, src + c);
-        cp_async_commit();
+        if (lane == 0) { mbar_init(bar + 0); mbar_init(bar + 1); mbar_init(bar + 2); fence_mbar_init(); }
+        syncwarp();
     }
-    MDEV void rec_wait() { cp_async_wait_all(); syncwarp(); }
-    MDEV void rec_store(int k, const double* src, int from, int to)
+    MDEV void rec_fetch(int k, int b)
     {
-        double* dst = rec_g(k);
-#pragma unroll 1
-        for (int c = from + 2 * lane; c < to; c += 64) st2(dst + c, src + c);
+        if (lane == 0) bulk_g2s(buf[b], rec_g(k), Y.rec_size * 8, bar + b);
+    }
+    MDEV void rec_wait(int b)
+    {
+        mbar_wait(bar + b, (phb >> b) & 1u);
+        phb ^= 1u << b;
+    }
+    // write two ranges of the record back (bulk store, asynchronous); the generic-proxy writes to the buffer are
+    // fenced towards the async proxy first
+    MDEV void rec_store2(int k, int b, int f0, int t0, int f1, int t1)
+    {
+        fence_proxy_async_smem();
+        syncwarp();
+        if (lane == 0)
+        {
+            double* g = rec_g(k);
+            bulk_s2g(g + f0, buf[b] + f0, (t0 - f0) * 8);
+            if (t1 > f1) bulk_s2g(g + f1, buf[b] + f1, (t1 - f1) * 8);
+            bulk_commit();
+        }
+    }
+    // before a buffer that was the source of a store becomes the destination of a load again: all but the most recent
+    // store group have finished reading shared memory
+    MDEV void rec_reuse_guard() { if (lane == 0) bulk_wait_read1(); }
+    // sweep boundaries: records written through the generic proxy (start point, rare path) / the async proxy (sweeps)
+    MDEV void sweep_begin() { fence_proxy_async(); syncwarp(); }
+    MDEV void sweep_end()
+    {
+        if (lane == 0) bulk_wait_all();
+        syncwarp();
+        fence_proxy_async();
     }
     // stage 0 after x0 elimination: no x rows in [B';A'], no Jacobian of the h rows (x_ocp_qp_red.c:268-454)
     MDEV void rec_mask_stage0(double* R)
@@ -582,13 +612,15 @@ struct WarpSolver {
     {
         const double lam_min = 1e-16, t_min = 1e-16;
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
-        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
-        rec_fetch(N, R, Y.rec_size);
+        int ir = 0, in = 1, ip = 2;
+        sweep_begin();
+        rec_fetch(N, ir);
 #pragma unroll 1
         for (int k = N; k >= 0; k--)
         {
-            rec_wait();
-            if (k > 0) rec_fetch(k - 1, Rn, Y.rec_size);
+            double *R = buf[ir], *Rp = buf[ip];
+            rec_wait(ir);
+            if (k > 0) { rec_reuse_guard(); rec_fetch(k - 1, in); }
             const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
             if (k == 0) rec_mask_stage0(R);
             // ---- update: [ux | pi | pi_prev] += a [dux | dpi | dpi_prev]
@@ -741,10 +773,10 @@ struct WarpSolver {
             syncwarp();
             if (lane < NV) R[odux + lane] = Mx[NV * NV + lane];  // backward vector of the forward substitution
             syncwarp();
-            rec_store(k, R, oux, odux + svv);
-            rec_store(k, R, olam, ormc);
-            double* t = Rp; Rp = R; R = Rn; Rn = t;
+            rec_store2(k, ir, oux, odux + svv, olam, ormc);
+            { const int t = ip; ip = ir; ir = in; in = t; }
         }
+        sweep_end();
         n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
         mu = warp_sum(musum) / nct;
         syncwarp();
@@ -758,16 +790,17 @@ struct WarpSolver {
     // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
     MDEV void sweepF(bool corr, double tau, double* nlin)
     {
-        const int nf = Y.rec_size;
         double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
         double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
-        rec_fetch(0, R, nf);
-        rec_wait();
-        if (N >= 1) rec_fetch(1, Rn, nf);
+        int ir = 0, in = 1, ip = 2;
+        sweep_begin();
+        rec_fetch(0, ir);
+        rec_wait(ir);
+        if (N >= 1) rec_fetch(1, in);
 #pragma unroll 1
         for (int k = 0; k <= N; k++)
         {
+            double *R = buf[ir], *Rn = buf[in];
             const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
             if (k == 0)
             {
@@ -848,7 +881,7 @@ struct WarpSolver {
             // ---- dpi_k = Lxx (Lxx' dx_{k+1} + l_x)  |  p_{k+1} + Lxx (Lxx' dx_{k+1}) : needs the factor of stage k+1
             if (k < N)
             {
-                rec_wait();  // record k+1 has landed
+                rec_wait(in);  // record k+1 has landed
                 const double* Lx = Rn + oL + NU * NV + NU;
                 double pj = 0.0;
                 if (lane < NX) pj = Rn[odux + NU + lane];  // l_x or p of stage k+1
@@ -881,12 +914,11 @@ struct WarpSolver {
                 if (lane < NV) l0 = q > l0 ? q : l0;
                 else if (lane < NV + NX && k < N) l1 = q > l1 ? q : l1;
             }
-            rec_store(k, R, odux, orq);
-            rec_store(k, R, odlam, od);
-            syncwarp();
-            double* t = Rp; Rp = R; R = Rn; Rn = t;
-            if (k + 2 <= N) rec_fetch(k + 2, Rn, nf);
+            rec_store2(k, ir, odux, orq, odlam, od);
+            { const int t = ip; ip = ir; ir = in; in = t; }
+            if (k + 2 <= N) { rec_reuse_guard(); rec_fetch(k + 2, in); }
         }
+        sweep_end();
         const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
         alpha = -(a_prim > a_dual ? a_prim : a_dual);
         S1 = warp_sum(s1); S2 = warp_sum(s2);
@@ -900,14 +932,15 @@ struct WarpSolver {
     // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
     MDEV void sweepC(bool with_aff, double sigma_mu)
     {
-        const int nf = Y.rec_size;
-        double *R = buf[0], *Rn = buf[1], *Rp = buf[2];
-        rec_fetch(N, R, nf);
+        int ir = 0, in = 1, ip = 2;
+        sweep_begin();
+        rec_fetch(N, ir);
 #pragma unroll 1
         for (int k = N; k >= 0; k--)
         {
-            rec_wait();
-            if (k > 0) rec_fetch(k - 1, Rn, nf);
+            double *R = buf[ir], *Rp = buf[ip];
+            rec_wait(ir);
+            if (k > 0) { rec_reuse_guard(); rec_fetch(k - 1, in); }
             const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
             if (k == 0) rec_mask_stage0(R);
 #pragma unroll 1
@@ -959,10 +992,10 @@ struct WarpSolver {
             }
             if (i < NV) R[odux + i] = zi;
             syncwarp();
-            rec_store(k, R, odux, odux + svv);
-            rec_store(k, R, ormc, odlam);
-            double* t = Rp; Rp = R; R = Rn; Rn = t;
+            rec_store2(k, ir, odux, odux + svv, ormc, odlam);
+            { const int t = ip; ip = ir; ir = in; in = t; }
         }
+        sweep_end();
         solve_calls++;
         syncwarp();
     }
@@ -1542,6 +1575,7 @@ struct WarpSolver {
         const double* yrg = P.yref + (long) inst * (P.yref_per_stage ? N : 1) * NY;
         const double* yre = P.yref_e + (long) inst * NX;
         load_constants();
+        rec_init();
         if (P.cold_start) cold_start(x0);
         int status = 2, sqp_iter = 0, qp_total = 0, qp_status = 0, qp_iter = 0;
         double res[4] = {0, 0, 0, 0};

@@ -35,6 +35,43 @@ DEV void cp_async16(double* smem_dst, const double* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
 DEV void st2(double* dst, const double* src) { *reinterpret_cast<double2*>(dst) = *reinterpret_cast<const double2*>(src); }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion: one instruction moves a whole record
+DEV unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+DEV void mbar_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)) : "memory");
+}
+DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+DEV void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// global -> shared, completion counted in bytes on `bar` (issued by ONE lane)
+DEV void bulk_g2s(double* dst, const double* src, int bytes, unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// every lane waits for the phase to complete; a bounded spin turns a protocol bug into a trap instead of a hang
+DEV void mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    const unsigned a = smem_u32(bar);
+    unsigned done = 0;
+    for (int it = 0; it < (1 << 24) && !done; it++)
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.b32 %0, 1, 0, P1;\n}\n"
+                     : "=r"(done)
+                     : "r"(a), "r"(phase)
+                     : "memory");
+    if (!done) __trap();
+}
+// shared -> global (issued by ONE lane), grouped; wait_read: the shared source may be overwritten again
+DEV void bulk_s2g(double* dst, const double* src, int bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+DEV void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 }  // namespace usvmpc
@@ -69,6 +106,12 @@ struct Warp {
     struct Pending { double* dst; const double* src; };
     Pending pend[WARP][512];
     int npend[WARP];
+    // bulk (TMA-like) copies: loads land when their barrier is waited on, stores when their group is waited on
+    struct Bulk { double* dst; const double* src; int n; const void* bar; int group; };
+    Bulk bl[64];
+    int nbl;
+    Bulk bs[64];
+    int nbs, group;
 };
 extern thread_local Warp* g_warp;
 // hand control to the next lane; returns when every other lane has reached its own next yield
@@ -118,6 +161,48 @@ DEV void cp_async16(double* smem_dst, const double* gsrc)
     smem_dst[0] = smem_dst[1] = std::nan("");
 }
 DEV void st2(double* dst, const double* src) { dst[0] = src[0]; dst[1] = src[1]; }
+DEV void mbar_init(unsigned long long* bar) { *bar = 0; }
+DEV void fence_mbar_init() {}
+DEV void fence_proxy_async() {}
+DEV void fence_proxy_async_smem() {}
+DEV void bulk_g2s(double* dst, const double* src, int bytes, unsigned long long* bar)
+{
+    emu::Warp* w = emu::g_warp;
+    if (w->nbl >= 64 || (bytes & 15) || ((uintptr_t) dst & 15) || ((uintptr_t) src & 15)) abort();
+    w->bl[w->nbl++] = {dst, src, bytes / 8, bar, 0};
+    for (int i = 0; i < bytes / 8; i++) dst[i] = std::nan("");  // not there yet
+}
+DEV void mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    emu::yield_lane();  // lane 0 (which issues the copies) always runs first after a yield
+    emu::Warp* w = emu::g_warp;
+    int found = 0, j = 0;
+    for (int i = 0; i < w->nbl; i++)
+        if (w->bl[i].bar == bar) { memcpy(w->bl[i].dst, w->bl[i].src, sizeof(double) * w->bl[i].n); found = 1; }
+        else w->bl[j++] = w->bl[i];
+    w->nbl = j;
+    if (found) { if ((unsigned) (*bar & 1) != phase) abort(); *bar ^= 1; }   // phase bookkeeping must match the kernel's
+    else if ((unsigned) (*bar & 1) == phase) abort();                          // nothing in flight: the device would hang
+    emu::yield_lane();
+}
+DEV void bulk_s2g(double* dst, const double* src, int bytes)
+{
+    emu::Warp* w = emu::g_warp;
+    if (w->nbs >= 64 || (bytes & 15) || ((uintptr_t) dst & 15) || ((uintptr_t) src & 15)) abort();
+    w->bs[w->nbs++] = {dst, src, bytes / 8, nullptr, w->group};
+}
+DEV void bulk_commit() { emu::g_warp->group++; }
+DEV void bulk_wait_keep(int keep)
+{
+    emu::Warp* w = emu::g_warp;
+    int j = 0;
+    for (int i = 0; i < w->nbs; i++)
+        if (w->bs[i].group < w->group - keep) memcpy(w->bs[i].dst, w->bs[i].src, sizeof(double) * w->bs[i].n);
+        else w->bs[j++] = w->bs[i];
+    w->nbs = j;
+}
+DEV void bulk_wait_read1() { bulk_wait_keep(1); }
+DEV void bulk_wait_all() { bulk_wait_keep(0); }
 DEV void cp_async_commit() {}
 DEV void cp_async_wait_all()
 {
