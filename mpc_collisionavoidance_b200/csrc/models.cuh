@@ -69,6 +69,49 @@ struct Usv3 {
         Ju[3 + 6 * 0] = 1.0 / m11;       Ju[3 + 6 * 1] = c / m11;
         Ju[5 + 6 * 0] = (B / 2) / m33;   Ju[5 + 6 * 1] = -(c * B / 2) / m33;
     }
+
+    // one column of the variational equation: f(x,u) and ks = (df/dx) s (+ (df/du) e_ucol if ucol >= 0), using the
+    // sparsity of the Jacobian (16 of 36 entries).  Same terms in the same order as the dense product, so the result
+    // equals the CasADi-generated `<m>_expl_vde_forw` column (generate_c_code_explicit_ode.py:73-80).
+    MDEV static void vde_col(const double* x, const double* uc, const double* s, int ucol, double* f, double* ks)
+    {
+        const double X_u_dot = -2.25, Y_v_dot = -23.13, Y_r_dot = -1.31, N_v_dot = -16.41, N_r_dot = -2.79;
+        const double Yvv = -99.99, Yvr = -5.49, Nrv = -8.8, Nrr = -3.49;
+        const double m = 30, Iz = 4.1, B = 0.41, c = 0.78;
+        const double m11 = m - X_u_dot, m22 = m - Y_v_dot, m33 = Iz - N_r_dot;
+        const double kY = 0.5 * (-40 * 1000) * (1.1 + 0.0045 * (1.01 / 0.09) - 0.1 * (0.27 / 0.09) + 0.016 * ((0.27 / 0.09) * (0.27 / 0.09)));
+        const double psi = x[2], u = x[3], v = x[4], r = x[5];
+        const double Tp = uc[0], Ts = uc[1];
+        const double Xu = (u > 1.25) ? 64.55 : -25.0;
+        const double Xuu = (u > 1.25) ? -70.92 : 0.0;
+        const double sq = dsqrt(u * u + v * v);
+        const double Yv = kY * dabs(v);
+        const double Nr = -0.52 * sq;
+        const double Tu = Tp + c * Ts;
+        const double Tr = (Tp - c * Ts) * B / 2;
+        double sp, cp;
+        dsincos(psi, &sp, &cp);
+        f[0] = u * cp - v * sp;
+        f[1] = u * sp + v * cp;
+        f[2] = r;
+        f[3] = (Tu - (-m + 2 * Y_v_dot) * v - (Y_r_dot + N_v_dot) * r * r - (-Xu * u - Xuu * dabs(u) * u)) / m11;
+        f[4] = (-(m - X_u_dot) * u * r - (-Yv - Yvv * dabs(v) - Yvr * dabs(r)) * v) / m22;
+        f[5] = (Tr - (-2 * Y_v_dot * u * v - (Y_r_dot + N_v_dot) * r * u + X_u_dot * u * r) - (-Nr * r - Nrv * dabs(v) * r - Nrr * dabs(r) * r)) / m33;
+        const double J02 = -u * sp - v * cp, J12 = u * cp - v * sp;
+        const double J33 = (Xu + 2 * Xuu * dabs(u)) / m11, J34 = -(-m + 2 * Y_v_dot) / m11, J35 = -2 * (Y_r_dot + N_v_dot) * r / m11;
+        const double J43 = -m11 * r / m22, J44 = (2 * (kY + Yvv) * dabs(v) + Yvr * dabs(r)) / m22, J45 = (-m11 * u + Yvr * dsign(r) * v) / m22;
+        const double J53 = (2 * Y_v_dot * v + (Y_r_dot + N_v_dot) * r - X_u_dot * r - 0.52 * (u / sq) * r) / m33;
+        const double J54 = (2 * Y_v_dot * u - 0.52 * (v / sq) * r + Nrv * dsign(v) * r) / m33;
+        const double J55 = ((Y_r_dot + N_v_dot) * u - X_u_dot * u - 0.52 * sq + Nrv * dabs(v) + 2 * Nrr * dabs(r)) / m33;
+        const double b3 = ucol == 0 ? 1.0 / m11 : (ucol == 1 ? c / m11 : 0.0);
+        const double b5 = ucol == 0 ? (B / 2) / m33 : (ucol == 1 ? -(c * B / 2) / m33 : 0.0);
+        ks[0] = ((J02 * s[2]) + cp * s[3]) + (-sp) * s[4];
+        ks[1] = ((J12 * s[2]) + sp * s[3]) + cp * s[4];
+        ks[2] = s[5];
+        ks[3] = ((b3 + J33 * s[3]) + J34 * s[4]) + J35 * s[5];
+        ks[4] = ((J43 * s[3]) + J44 * s[4]) + J45 * s[5];
+        ks[5] = ((b5 + J53 * s[3]) + J54 * s[4]) + J55 * s[5];
+    }
 };
 
 struct Pendulum {
@@ -101,6 +144,21 @@ struct Pendulum {
         Jx[3 + 4 * 1] = (dn4_th * den - n4 * dden) / (l * den * den);
         Jx[3 + 4 * 3] = -2 * m * l * c * s * dth / (l * den);
         Ju[0] = 0.0; Ju[1] = 0.0; Ju[2] = 1.0 / den; Ju[3] = c / (l * den);
+    }
+
+    // one column of the variational equation (see Usv3::vde_col): dense product on the 4x4 Jacobian
+    MDEV static void vde_col(const double* x, const double* uc, const double* s, int ucol, double* f, double* ks)
+    {
+        double Jx[NX * NX], Ju[NX * NU];
+        f_jac(x, uc, f, Jx, Ju);
+#pragma unroll
+        for (int i = 0; i < NX; i++)
+        {
+            double acc = ucol == 0 ? Ju[i] : 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) acc += Jx[i + NX * m] * s[m];
+            ks[i] = acc;
+        }
     }
 };
 

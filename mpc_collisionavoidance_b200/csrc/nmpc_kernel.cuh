@@ -202,11 +202,10 @@ struct WarpSolver {
     MDEV void integrate_all()
     {
         const int ns = P.num_stages;
-        double a21 = 0, a32 = 0, a43 = 0, bv[4] = {0, 0, 0, 0};
-        if (ns == 1) { bv[0] = 1.0; }
-        else if (ns == 2) { a21 = 0.5; bv[1] = 1.0; }
-        else { a21 = 0.5; a32 = 0.5; a43 = 1.0; bv[0] = 1.0 / 6.0; bv[1] = 1.0 / 3.0; bv[2] = 1.0 / 3.0; bv[3] = 1.0 / 6.0; }
-        const double asub[4] = {a21, a32, a43, 0.0};
+        double a21 = 0, a32 = 0, a43 = 0, bv0 = 0, bv1 = 0, bv2 = 0, bv3 = 0;
+        if (ns == 1) { bv0 = 1.0; }
+        else if (ns == 2) { a21 = 0.5; bv1 = 1.0; }
+        else { a21 = 0.5; a32 = 0.5; a43 = 1.0; bv0 = 1.0 / 6.0; bv1 = 1.0 / 3.0; bv2 = 1.0 / 3.0; bv3 = 1.0 / 6.0; }
         const double step = P.dt / P.num_steps;
         for (int task = lane; task < N * NV; task += 32)
         {
@@ -222,27 +221,16 @@ struct WarpSolver {
                 double xr[NX], sr[NX], xa[NX], sa[NX];
 #pragma unroll
                 for (int i = 0; i < NX; i++) { xr[i] = x[i]; sr[i] = s[i]; xa[i] = x[i]; sa[i] = s[i]; }
-                for (int st = 0; st < ns; st++)
+#pragma unroll
+                for (int st = 0; st < 4; st++)
                 {
-                    double f[NX], Jx[NX * NX], Ju[NX * NU], ks[NX];
-                    M::f_jac(xr, u, f, Jx, Ju);
-#pragma unroll
-                    for (int i = 0; i < NX; i++)
-                    {
-                        // VDE right-hand side of this column: Jx*Sx_col, or Jx*Su_col + Ju_col
-                        // (acados_template/generate_c_code_explicit_ode.py:73-80)
-                        double acc = 0.0;
-                        if (col >= NX)
-                        {
-#pragma unroll
-                            for (int c = 0; c < NU; c++) if (c == col - NX) acc = Ju[i + NX * c];
-                        }
-#pragma unroll
-                        for (int m = 0; m < NX; m++) acc += Jx[i + NX * m] * sr[m];
-                        ks[i] = acc;
-                    }
-                    const double bb = step * bv[st];
-                    const double aa = asub[st] * step;
+                    if (st >= ns) break;
+                    double f[NX], ks[NX];
+                    // VDE right-hand side of this column: Jx*Sx_col, or Jx*Su_col + Ju_col
+                    // (acados_template/generate_c_code_explicit_ode.py:73-80)
+                    M::vde_col(xr, u, sr, col >= NX ? col - NX : -1, f, ks);
+                    const double bb = step * (st == 0 ? bv0 : st == 1 ? bv1 : st == 2 ? bv2 : bv3);
+                    const double aa = (st == 0 ? a21 : st == 1 ? a32 : st == 2 ? a43 : 0.0) * step;
 #pragma unroll
                     for (int i = 0; i < NX; i++)
                     {
