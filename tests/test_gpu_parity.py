@@ -201,3 +201,29 @@ def test_full_size_properties():
     assert (r["status"][idx][oka] == 0).all()
     good, worst = _close(r["x"][idx], a["x"], oka)
     assert good, worst
+
+
+def test_closed_loop_rti_against_oracle():
+    # the loop the node really runs -- SQP_RTI, warm start from the previous iterate,
+    # x0 <- predicted x_1.  Oracle: the same loop, one instance at a time.
+    from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
+    from mpc_collisionavoidance_b200.closed_loop import simulate_closed_loop
+    B, N, K, steps = 6, 20, 3, 8
+    b = make_batch(1, B=B, seed=11)
+    P = rh.RefProblem(N=N, K=K, num_steps=1, nlp_type=1)
+    s = BatchedAcadosOcpSolver(ocp_from_problem(P), batch=B)
+    s.set("every", "yref", b.yref); s.set(N, "yref", b.yref_e)
+    s.set("every", "p", b.p); s.constraints_set("every", "lh", b.lh)
+    s.set("all", "x", np.repeat(b.x0[:, None, :], N + 1, axis=1))
+    X, U, S = simulate_closed_loop(s, b.x0, steps)
+    assert (S == 0).all()
+    for i in range(B):
+        o = op.OracleSolver(P)
+        x = b.x0[i].copy()
+        xi, ui, pii = np.repeat(x[None], N + 1, axis=0), np.zeros((N, 2)), np.zeros((N, 6))
+        for k in range(steps):
+            r = o.solve(x, b.p[i], b.lh[i], b.yref[i], b.yref_e[i], xinit=xi, uinit=ui, piinit=pii)
+            assert r["status"] == 0
+            np.testing.assert_allclose(U[i, k], r["u"][0], rtol=1e-6, atol=1e-6 * 35)
+            np.testing.assert_allclose(X[i, k + 1], r["x"][1], rtol=1e-6, atol=1e-6)
+            x, xi, ui, pii = r["x"][1].copy(), r["x"], r["u"], r["pi"]
