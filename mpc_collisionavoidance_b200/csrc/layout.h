@@ -28,13 +28,11 @@ struct Field { int off, stride; };
 struct Layout {
     // NLP iterate (persists between solves = warm start, like nlp_out in the reference); stage-major arrays
     Field zux, zpi, zlam, zt, zfun;
-    // ---- the per-stage RECORD streamed through shared memory by the IPM sweeps (all strides = rec_size) ----
-    // order inside a record (fixed-size fields first: compile-time offsets in the kernel):
-    //   BAt | ux pi pi_prev rg rb L Pb dux | dpi dpi_prev | rq b || gxy | lam t rd ti | rmc | dlam dt | d   (ti = 1/t)
-    // so that each sweep writes back two contiguous ranges (A: ux..dux + lam..rd, B/D: dux..dpi_prev + dlam..dt,
-    // C: dux + rmc).
-    // pi_prev / dpi_prev duplicate pi / dpi of stage k-1 so that no sweep needs a neighbouring record.
-    Field BAt, gxy, lam, t, ux, pi, pi_prev, rg, rb, rd, ti, L, Pb, rmc, dux, dpi, dpi_prev, dlam, dt, rq, b, d;
+    // ---- the per-stage RECORD (all strides = rec_size).  Order (fixed-size fields first: compile-time offsets):
+    //   BAt | ux pi rg rb L Pb bv | dux dpi | rq b || gxy | lam t rd ti | rmc | dlam dt | d        (ti = 1/t)
+    // The HEAD [BAt .. bv] is what the serial Riccati (chain) sweeps stream through shared memory with TMA; the
+    // rest is only touched by the stage-parallel passes (one lane per stage).
+    Field BAt, gxy, lam, t, ux, pi, rg, rb, rd, ti, L, Pb, bv, rmc, dux, dpi, dlam, dt, rq, b, d;
     int rec_off, rec_size;
     // iterative refinement scratch (rare path), stage-major arrays
     Field dux2, dpi2, dlam2, dt2, rg2, rb2, rd2, rm2;
@@ -79,15 +77,15 @@ inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
     auto rec = [&](Field& f, int n) { f.off = r; r += n; };
     // fixed-size fields first (their offsets are compile-time constants in the kernel), K-dependent ones after
     rec(L.BAt, sBA);
-    rec(L.ux, sv); rec(L.pi, sx); rec(L.pi_prev, sx); rec(L.rg, sv); rec(L.rb, sx); rec(L.L, sL); rec(L.Pb, sx);
-    rec(L.dux, sv); rec(L.dpi, sx); rec(L.dpi_prev, sx);
+    rec(L.ux, sv); rec(L.pi, sx); rec(L.rg, sv); rec(L.rb, sx); rec(L.L, sL); rec(L.Pb, sx); rec(L.bv, sv);
+    rec(L.dux, sv); rec(L.dpi, sx);
     rec(L.rq, sv); rec(L.b, sx);
     rec(L.gxy, sg);
     rec(L.lam, scq); rec(L.t, scq); rec(L.rd, scq); rec(L.ti, scq); rec(L.rmc, scq); rec(L.dlam, scq); rec(L.dt, scq); rec(L.d, scq);
     L.rec_size = round_up(r, 2);
     L.rec_off = (int) o;
-    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.pi_prev, &L.rg, &L.rb, &L.rd, &L.ti, &L.L, &L.Pb, &L.rmc,
-                   &L.dux, &L.dpi, &L.dpi_prev, &L.dlam, &L.dt, &L.rq, &L.b, &L.d};
+    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.rg, &L.rb, &L.rd, &L.ti, &L.L, &L.Pb, &L.bv, &L.rmc,
+                   &L.dux, &L.dpi, &L.dlam, &L.dt, &L.rq, &L.b, &L.d};
     for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; }
     o += (long) L.rec_size * N1;
     put(L.dux2, sv); put(L.dpi2, sx); put(L.dlam2, scq); put(L.dt2, scq);
@@ -102,7 +100,11 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
     const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
     const Layout L = make_layout(nx, nu, N, K, nbx, nbu);
     const int ne = nv * (nv + 1) / 2 + nv, nq = nu + nx + K;
-    int n = 3 * L.rec_size + 4;  // record buffers (the rare path's scratch is aliased onto them) + 3 mbarriers
+    int n = 3 * (L.bv.off - L.rec_off + round_up(nv, 2)) + 4;  // record-head buffers (the rare path's scratch is aliased onto them) + mbarriers
+    {
+        const int rare = nv * nx + nx * nx + nx + 4 * nq + (nv + 1) * nv + nv + 2 * nx + 2 * (K > 0 ? K : 1);
+        if (n < rare + 4) n = rare + 4;
+    }
     n += 2 * nv * nv;          // Hs, Hes
     n += nv * nv + nx * nx;    // Ws, Wes
     n += 3 * ne;               // Tp

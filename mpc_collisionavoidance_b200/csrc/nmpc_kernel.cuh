@@ -41,9 +41,10 @@ struct WarpSolver {
     static constexpr int NE = NV * (NV + 1) / 2 + NV;  // entries of the lower trapezoid of the (NV+1) x NV factor
     // record layout (layout.h): offsets of the fixed-size fields are compile-time constants
     static constexpr int svv = (NV + 1) / 2 * 2, sxx = (NX + 1) / 2 * 2, sLL = (NR * NV + 1) / 2 * 2;
-    static constexpr int oBAt = 0, oux = (NV * NX + 1) / 2 * 2, opi = oux + svv, opip = opi + sxx, org = opip + sxx, orb = org + svv;
-    static constexpr int oL = orb + sxx, oPb = oL + sLL, odux = oPb + sxx, odpi = odux + svv, odpip = odpi + sxx;
-    static constexpr int orq = odpip + sxx, ob = orq + svv, ogxy = ob + sxx;
+    static constexpr int oBAt = 0, oux = (NV * NX + 1) / 2 * 2, opi = oux + svv, org = opi + sxx, orb = org + svv;
+    static constexpr int oL = orb + sxx, oPb = oL + sLL, obv = oPb + sxx, odux = obv + svv, odpi = odux + svv;
+    static constexpr int orq = odpi + sxx, ob = orq + svv, ogxy = ob + sxx;
+    static constexpr int HEAD = obv + svv;  // what the chain sweeps stream: [B';A'] ux pi rg rb L Pb bv
     // per-warp shared-memory scratch: fixed-size part at compile-time offsets
     static constexpr int qHs = 0, qHes = qHs + NV * NV, qWs = qHes + NV * NV, qWes = qWs + NV * NV, qTp = qWes + NX * NX;
     static constexpr int qAL = qTp + 3 * NE, qz = qAL + NR * NX, qent = qz + sxx, qvrow = qent + (NE + 1) / 2;
@@ -84,7 +85,7 @@ struct WarpSolver {
         s += qvar;
         srvar = (int*) s; s += (nq + 1) / 2; sGs = s; s += nq; sgd = s; s += nq; sdl = s; s += nq;
         s = sm + ((s - sm) + 1) / 2 * 2;
-        buf[0] = s; s += Y.rec_size; buf[1] = s; s += Y.rec_size; buf[2] = s; s += Y.rec_size;
+        buf[0] = s; s += HEAD; buf[1] = s; s += HEAD; buf[2] = s; s += HEAD;
         bar = (unsigned long long*) s; s += 4;
         phb = 0;
         scq = Y.t.off - Y.lam.off;
@@ -104,13 +105,12 @@ struct WarpSolver {
     // the host-side layout (layout.h:make_layout) must agree with the compile-time offsets above
     static bool layout_matches(const Layout& y)
     {
-        const int ro = y.rec_off;
-        return y.BAt.off - ro == oBAt && y.ux.off - ro == oux && y.pi.off - ro == opi && y.pi_prev.off - ro == opip &&
-               y.rg.off - ro == org && y.rb.off - ro == orb && y.L.off - ro == oL && y.Pb.off - ro == oPb &&
-               y.dux.off - ro == odux && y.dpi.off - ro == odpi && y.dpi_prev.off - ro == odpip && y.rq.off - ro == orq &&
-               y.b.off - ro == ob && y.gxy.off - ro == ogxy && y.lam.off > y.gxy.off && y.rd.off - y.t.off == y.t.off - y.lam.off && y.ti.off - y.rd.off == y.t.off - y.lam.off &&
-               y.rmc.off - y.ti.off == y.t.off - y.lam.off &&
-               y.d.off - y.dt.off == y.t.off - y.lam.off && y.rec_size == y.d.off - ro + (y.t.off - y.lam.off);
+        const int ro = y.rec_off, sc = y.t.off - y.lam.off;
+        return y.BAt.off - ro == oBAt && y.ux.off - ro == oux && y.pi.off - ro == opi && y.rg.off - ro == org &&
+               y.rb.off - ro == orb && y.L.off - ro == oL && y.Pb.off - ro == oPb && y.bv.off - ro == obv &&
+               y.dux.off - ro == odux && y.dpi.off - ro == odpi && y.rq.off - ro == orq && y.b.off - ro == ob &&
+               y.gxy.off - ro == ogxy && y.lam.off > y.gxy.off && y.rd.off - y.t.off == sc && y.ti.off - y.rd.off == sc &&
+               y.rmc.off - y.ti.off == sc && y.d.off - y.dt.off == sc && y.rec_size == y.d.off - ro + sc;
     }
     MDEV double* F(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
     MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
@@ -451,11 +451,10 @@ struct WarpSolver {
             for (int i = 0; i < NX; i++) pi[i] = 0.0;
             for (int j = 0; j < 2 * ncq; j++) { lam[j] = 0.0; t[j] = 1.0; }
             {
-                // the first sweep A applies a zero step: the step and the duplicated neighbour values start at zero
+                // the first passA applies a zero step: the step starts at zero
                 double *a = F(Y.dux, k), *b = F(Y.dpi, k), *c = F(Y.dlam, k), *e = F(Y.dt, k);
-                double *pp = F(Y.pi_prev, k), *dp = F(Y.dpi_prev, k);
                 for (int i = 0; i < NV; i++) a[i] = 0.0;
-                for (int i = 0; i < NX; i++) { b[i] = 0.0; pp[i] = 0.0; dp[i] = 0.0; }
+                for (int i = 0; i < NX; i++) b[i] = 0.0;
                 for (int j = 0; j < 2 * ncq; j++) { c[j] = 0.0; e[j] = 0.0; }
             }
             if (k >= N) continue;
@@ -486,15 +485,170 @@ struct WarpSolver {
         syncwarp();
     }
 
-    // ---------------------------------------------------------------- IPM: record streaming
-    // The IPM works on one RECORD per stage (layout.h).  Each sweep pulls record k into one of three shared-memory
-    // buffers with asynchronous 16-byte copies (cp.async), one stage ahead of the arithmetic, computes in place and
-    // writes the range it modified back with coalesced stores; the third buffer keeps the previous stage's record
-    // (its Riccati factor / solution is the input of the recursion) so nothing is copied between stages.
-    // The sweeps are written for a SMALL instruction footprint (rolled loops over shared-memory operands, work
-    // spread over all 32 lanes): a lone warp finishing a hard instance is bound by instruction fetch otherwise.
+    // ---------------------------------------------------------------- IPM: one iteration = lean chain sweeps + stage-parallel passes
+    // Only the Riccati recursions are serial in the stage index.  They run as CHAIN sweeps: the warp streams the head of
+    // each stage record ([B';A'], res_b, the matrix to factorise / its factor, Pb, the backward vector) through shared
+    // memory with TMA and does nothing but the recursion.  Everything else of an IPM iteration (variable update,
+    // residuals, Gamma/gamma, assembly of the matrix to factorise, dt/dlam, step length, dpi, right-hand sides) is
+    // independent per stage and runs as PASSES with one lane per stage, straight on the records in HBM/L2.
+    //
+    //   passA  : UPDATE_VAR_QP + OCP_QP_RES_COMPUTE + COMPUTE_GAMMA_GAMMA_QP + assembly of H + Gamma terms (+ gradient row)
+    //   chainA : backward: AL = [B';A';b'] Lxx, Pb, syrk, Cholesky                       (x_ocp_qp_kkt.c:455-535)
+    //   chainF : forward : columns solved per stage, dx_{k+1} = b + [B A] dux             (x_ocp_qp_kkt.c:537-575 | 1243-1290)
+    //   passF  : dt, dlam, step length, mu_aff sums, dpi [, residual of the linear system] (x_ocp_qp_kkt.c:748-764, x_core_qp_ipm_aux.c:117-216)
+    //   passC  : corrector / centering right-hand side, COMPUTE_GAMMA_QP, constraint part of the backward vector
+    //   chainC : backward: z = z0 + [B';A'] (p_{k+1} + Pb), eliminate the columns solved per stage (x_ocp_qp_kkt.c:1096-1242)
+    MDEV int stage_class(int k) const { return k == 0 ? 0 : (k < N ? 1 : 2); }
+
+    MDEV void passA(double a, double tau, double* n4)
+    {
+        const double lam_min = 1e-16, t_min = 1e-16;
+        // ---- UPDATE_VAR_QP: HP/ipm_core/x_core_qp_ipm_aux.c:220-325 (split_step = 0)
+#pragma unroll 1
+        for (int k = lane; k <= N; k += 32)
+        {
+            double* ux = F(Y.ux, k); const double* dux = F(Y.dux, k);
+#pragma unroll
+            for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
+            if (k < N)
+            {
+                double* pi = F(Y.pi, k); const double* dpi = F(Y.dpi, k);
+#pragma unroll
+                for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
+                double *l = F(Y.lam, k), *t = F(Y.t, k);
+                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+#pragma unroll 1
+                for (int r = 0; r < 2 * ncq; r++)
+                {
+                    if (!row_active(k, r < ncq ? r : r - ncq)) continue;
+                    double x = l[r] + a * dl[r];
+                    l[r] = x <= lam_min ? lam_min : x;
+                    x = t[r] + a * dtt[r];
+                    t[r] = x <= t_min ? t_min : x;
+                }
+            }
+        }
+        syncwarp();
+        // ---- OCP_QP_RES_COMPUTE (x_ocp_qp_res.c:336-466) + Gamma, gamma for res_m = lam*t - tau + matrix to factorise
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
+#pragma unroll 1
+        for (int k = lane; k <= N; k += 32)
+        {
+            const int cls = stage_class(k);
+            const double *v = F(Y.ux, k), *H = Hk(k), *rq = F(Y.rq, k);
+            double* Lk = F(Y.L, k);
+            const double* T = Tp + cls * NE;
+#pragma unroll 1
+            for (int e = 0; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
+            double g[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NV; j++) acc += H[i + NV * j] * v[j];
+                g[i] = acc + rq[i];
+            }
+            if (k > 0)
+            {
+                const double* pm = F(Y.pi, k - 1);
+#pragma unroll
+                for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
+            }
+            if (k < N)
+            {
+                const double *l = F(Y.lam, k), *tt = F(Y.t, k), *cd = F(Y.d, k), *pk = F(Y.pi, k);
+                double *rd = F(Y.rd, k), *ti = F(Y.ti, k);
+#pragma unroll 1
+                for (int j = 0; j < nbq; j++)
+                {
+                    if (!row_active(k, j)) continue;
+                    const int id = srvar[j];
+                    const double l0 = l[j], l1 = l[ncq + j], t0 = tt[j], t1 = tt[ncq + j], vv = v[id];
+                    const double dl = l1 - l0;
+#pragma unroll
+                    for (int i = 0; i < NV; i++) if (i == id) g[i] += dl;
+                    const double rd0 = cd[j] + t0 - vv, rd1 = cd[ncq + j] + t1 + vv;
+                    rd[j] = rd0; rd[ncq + j] = rd1;
+                    const double m0 = l0 * t0, m1 = l1 * t1;
+                    musum += m0; musum += m1;
+                    double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
+                    q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
+                    const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
+                    ti[j] = ti0; ti[ncq + j] = ti1;
+                    Lk[id * NV + id] += ti0 * l0 + ti1 * l1;
+                    Lk[NV * NV + id] += ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+                }
+                const double* gxy = F(Y.gxy, k);
+                double aXX = 0, aYX = 0, aYY = 0, bX = 0, bY = 0;
+#pragma unroll 1
+                for (int c = 0; c < K; c++)
+                {
+                    const int r = nbq + c;
+                    const double gX = k >= 1 ? gxy[c] : 0.0, gY = k >= 1 ? gxy[K + c] : 0.0;
+                    const double l0 = l[r], l1 = l[ncq + r], t0 = tt[r], t1 = tt[ncq + r];
+                    const double dl = l1 - l0;
+                    g[HXV] += gX * dl; g[HYV] += gY * dl;
+                    const double vv = gX * v[HXV] + gY * v[HYV];
+                    const double rd0 = cd[r] + t0 - vv, rd1 = cd[ncq + r] + t1 + vv;
+                    rd[r] = rd0; rd[ncq + r] = rd1;
+                    const double m0 = l0 * t0, m1 = l1 * t1;
+                    musum += m0; musum += m1;
+                    double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
+                    q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
+                    const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
+                    ti[r] = ti0; ti[ncq + r] = ti1;
+                    const double Gs = ti0 * l0 + ti1 * l1;
+                    const double gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+                    aXX += (gX * Gs) * gX; aYX += (gY * Gs) * gX; aYY += (gY * Gs) * gY;
+                    bX += gd * gX; bY += gd * gY;
+                }
+                if (K > 0)
+                {
+                    Lk[HXV * NV + HXV] += aXX; Lk[HYV * NV + HXV] += aYX; Lk[HYV * NV + HYV] += aYY;
+                    Lk[NV * NV + HXV] += bX; Lk[NV * NV + HYV] += bY;
+                }
+                const double* BAt = F(Y.BAt, k);
+                const double* vn = F(Y.ux, k + 1);
+                const double* cb = F(Y.b, k);
+                double* rb = F(Y.rb, k);
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = cb[j] - vn[NU + j];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) if (k > 0 || i < NU) acc += BAt[i + NV * j] * v[i];
+                    rb[j] = acc;
+                    const double q = dabs(acc);
+                    n1 = q > n1 ? q : n1;
+                }
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += BAt[i + NV * j] * pk[j];
+                    g[i] += acc;
+                }
+            }
+            double* rg = F(Y.rg, k);
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                const double gi = var_active(k, i) ? g[i] : 0.0;
+                rg[i] = gi;
+                Lk[NV * NV + i] += gi;
+                const double q = dabs(gi);
+                n0 = q > n0 ? q : n0;
+            }
+        }
+        n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
+        mu = warp_sum(musum) / nct;
+        syncwarp();
+    }
+
+    // TMA streaming of the record heads for the chain sweeps: two buffers + the previous stage's
     MDEV double* rec_g(int k) const { return w + Y.rec_off + (long) k * Y.rec_size; }
-    // TMA: one lane issues one bulk copy for the whole record; completion is counted in bytes on the buffer's mbarrier
     MDEV void rec_init()
     {
         if (lane == 0) { mbar_init(bar + 0); mbar_init(bar + 1); mbar_init(bar + 2); fence_mbar_init(); }
@@ -502,31 +656,20 @@ struct WarpSolver {
     }
     MDEV void rec_fetch(int k, int b)
     {
-        if (lane == 0) bulk_g2s(buf[b], rec_g(k), Y.rec_size * 8, bar + b);
+        if (lane == 0) bulk_g2s(buf[b], rec_g(k), HEAD * 8, bar + b);
     }
     MDEV void rec_wait(int b)
     {
         mbar_wait(bar + b, (phb >> b) & 1u);
         phb ^= 1u << b;
     }
-    // write two ranges of the record back (bulk store, asynchronous); the generic-proxy writes to the buffer are
-    // fenced towards the async proxy first
-    MDEV void rec_store2(int k, int b, int f0, int t0, int f1, int t1)
+    MDEV void rec_store(int k, int b, int f0, int t0)
     {
         fence_proxy_async_smem();
         syncwarp();
-        if (lane == 0)
-        {
-            double* g = rec_g(k);
-            bulk_s2g(g + f0, buf[b] + f0, (t0 - f0) * 8);
-            if (t1 > f1) bulk_s2g(g + f1, buf[b] + f1, (t1 - f1) * 8);
-            bulk_commit();
-        }
+        if (lane == 0) { bulk_s2g(rec_g(k) + f0, buf[b] + f0, (t0 - f0) * 8); bulk_commit(); }
     }
-    // before a buffer that was the source of a store becomes the destination of a load again: all but the most recent
-    // store group have finished reading shared memory
     MDEV void rec_reuse_guard() { if (lane == 0) bulk_wait_read1(); }
-    // sweep boundaries: records written through the generic proxy (start point, rare path) / the async proxy (sweeps)
     MDEV void sweep_begin() { fence_proxy_async(); syncwarp(); }
     MDEV void sweep_end()
     {
@@ -534,72 +677,18 @@ struct WarpSolver {
         syncwarp();
         fence_proxy_async();
     }
-    // stage 0 after x0 elimination: no x rows in [B';A'], no Jacobian of the h rows (x_ocp_qp_red.c:268-454)
-    MDEV void rec_mask_stage0(double* R)
+    // stage 0 after x0 elimination: no x rows in [B';A'] (x_ocp_qp_red.c:268-454)
+    MDEV void mask_stage0(double* R)
     {
 #pragma unroll 1
         for (int e = lane; e < NV * NX; e += 32) if (e % NV >= NU) R[oBAt + e] = 0.0;
-#pragma unroll 1
-        for (int e = lane; e < 2 * K; e += 32) R[ogxy + e] = 0.0;
         syncwarp();
     }
-    // inequality rows are handled as (lower, upper) pairs jj < ncq: pair active at this stage class?
-    MDEV bool pair_active(int cls, int jj) const { return cls == 1 || (cls == 0 && (jj < nbu || jj >= nbq)); }
-    // IPM row pair of the box on variable i for this stage class, or -1
-    MDEV int box_of_var(int cls, int i) const { return cls == 1 ? svrow[i] : (cls == 0 && i < NU ? svrow[i] : -1); }
-    // residual-type kernel shared by sweep A (iterate) and sweep D (step): lanes < NV produce
-    //   g_i = sum_j H[i][j] v[j] + c_i - pprev_i + (box / h-row multiplier differences) + sum_j [B';A'][i][j] p[j]
-    // and lanes NV..NV+NX-1 produce  b_j = cb_j - xnext_j + sum_i [B';A'][i][j] v[i]   (x_ocp_qp_res.c:336-466, 468-592)
-    MDEV double res_gb(const double* R, int k, int cls, int ov, int op, int opp, int oc, int ocb, const double* xnext)
-    {
-        double acc = 0.0;
-        if (lane < NV + NX)
-        {
-            const bool isg = lane < NV;
-            if (!isg && k >= N) return 0.0;
-            const double* pa = isg ? (cls == 2 ? Hes : Hs) + lane : R + oBAt + NV * (lane - NV);
-            const int sa = isg ? NV : 1;
-            if (!isg) acc = R[ocb + lane - NV] - xnext[lane - NV];
-#pragma unroll
-            for (int m = 0; m < NV; m++) acc += pa[m * sa] * R[ov + m];
-            if (isg)
-            {
-                const int i = lane;
-                double g = acc + R[oc + i];
-                if (i >= NU) g -= R[opp + i - NU];
-                const int row = box_of_var(cls, i);
-                if (row >= 0) g += sdl[row];
-                if (k < N)
-                {
-                    if (i == HXV || i == HYV)
-                    {
-                        const double* gq = R + ogxy + (i == HXV ? 0 : K);
-#pragma unroll 1
-                        for (int c = 0; c < K; c++) g += gq[c] * sdl[nbq + c];
-                    }
-                    double acc2 = 0.0;
-#pragma unroll
-                    for (int j = 0; j < NX; j++) acc2 += R[oBAt + i + NV * j] * R[op + j];
-                    g += acc2;
-                }
-                const bool act = cls == 1 || (cls == 0 ? i < NU : i >= NU);
-                acc = act ? g : 0.0;
-            }
-        }
-        return acc;
-    }
 
-    // Sweep A (backward, k = N..0), three steps of the reference fused per stage:
-    //   UPDATE_VAR_QP with step length a (x_core_qp_ipm_aux.c:220-325) -> OCP_QP_RES_COMPUTE at the new iterate
-    //   (x_ocp_qp_res.c:336-466; norms into n4, mu) -> backward part of OCP_QP_FACT_SOLVE_KKT_STEP for the affine
-    //   right-hand side res_m = lam*t - tau (x_ocp_qp_kkt.c:405-535, COMPUTE_GAMMA_GAMMA_QP x_core_qp_ipm_aux.c:38-86).
-    // The factorisation is speculative: if the residuals turn out to be converged it is simply not used.
-    // The (NV+1) x NV matrix [H + Gamma terms + AL AL' ; gradient row] is built and factorised in place in the
-    // record's L field, one lower-trapezoid entry (or two) per lane.
-    MDEV void sweepA(double a, double tau, double reg, double* n4)
+    // chainA: Riccati factorisation, backward.  On entry the L field of every record holds H + Gamma terms with the
+    // gradient row (passA); on exit the factor (NV+1) x NV, Pb and the backward vector (row NV).
+    MDEV void chainA()
     {
-        const double lam_min = 1e-16, t_min = 1e-16;
-        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
         int ir = 0, in = 1, ip = 2;
         sweep_begin();
         rec_fetch(N, ir);
@@ -609,63 +698,8 @@ struct WarpSolver {
             double *R = buf[ir], *Rp = buf[ip];
             rec_wait(ir);
             if (k > 0) { rec_reuse_guard(); rec_fetch(k - 1, in); }
-            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
-            if (k == 0) rec_mask_stage0(R);
-            // ---- update: [ux | pi | pi_prev] += a [dux | dpi | dpi_prev]
-            if (lane < svv + 2 * sxx) R[oux + lane] += a * R[odux + lane];
-            syncwarp();
-            // ---- inequality row pairs: lam, t += a (dlam, dt), clipped; rd; mu; Gamma, gamma -> the sums and
-            //      differences the factorisation and the stationarity residual need
-#pragma unroll 1
-            for (int jj = lane; jj < ncq; jj += 32)
-            {
-                double Gs = 0.0, gd = 0.0, dl = 0.0;
-                if (pair_active(cls, jj))
-                {
-                    double l0 = R[olam + jj] + a * R[odlam + jj], l1 = R[olam + ncq + jj] + a * R[odlam + ncq + jj];
-                    double t0 = R[ot + jj] + a * R[odt + jj], t1 = R[ot + ncq + jj] + a * R[odt + ncq + jj];
-                    l0 = l0 <= lam_min ? lam_min : l0; l1 = l1 <= lam_min ? lam_min : l1;
-                    t0 = t0 <= t_min ? t_min : t0; t1 = t1 <= t_min ? t_min : t1;
-                    R[olam + jj] = l0; R[olam + ncq + jj] = l1; R[ot + jj] = t0; R[ot + ncq + jj] = t1;
-                    const int var = srvar[jj];
-                    const double v = var >= 0 ? R[oux + var]
-                                              : R[ogxy + jj - nbq] * R[oux + HXV] + R[ogxy + K + jj - nbq] * R[oux + HYV];
-                    const double rd0 = R[od + jj] + t0 - v, rd1 = R[od + ncq + jj] + t1 + v;
-                    R[ord + jj] = rd0; R[ord + ncq + jj] = rd1;
-                    const double m0 = l0 * t0, m1 = l1 * t1;
-                    musum += m0; musum += m1;
-                    double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
-                    q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
-                    const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
-                    R[oti + jj] = ti0; R[oti + ncq + jj] = ti1;  // kept for sweeps B, C, D
-                    Gs = ti0 * l0 + ti1 * l1;
-                    gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
-                    dl = l1 - l0;
-                }
-                sGs[jj] = Gs; sgd[jj] = gd; sdl[jj] = dl;
-            }
-            syncwarp();
-            // ---- residuals rg (lanes < NV), rb (lanes NV..NV+NX-1)
-            {
-                const double r = res_gb(R, k, cls, oux, opi, opip, orq, ob, Rp + oux + NU);
-                const double q = dabs(r);
-                if (lane < NV) { R[org + lane] = r; n0 = q > n0 ? q : n0; }
-                else if (lane < NV + NX && k < N) { R[orb + lane - NV] = r; n1 = q > n1 ? q : n1; }
-            }
-            // ---- matrix to factorise, in place in R.L: template (H + reg, identity rows of inactive variables) ...
+            if (k == 0) mask_stage0(R);
             double* Mx = R + oL;
-            const double* T = Tp + cls * NE;
-#pragma unroll 1
-            for (int e = lane; e < NE; e += 32) Mx[sent[e] & 0xffff] = T[e];
-            syncwarp();
-            // ... + box terms on the diagonal, gradient row = rg + box gamma differences
-            if (lane < NV)
-            {
-                const int row = box_of_var(cls, lane);
-                double gr = R[org + lane];
-                if (row >= 0) { Mx[lane * NV + lane] += sGs[row]; gr += sgd[row]; }
-                Mx[NV * NV + lane] = gr;
-            }
             if (k < N)
             {
                 // AL = [B'; A'; res_b'] * Lxx_{k+1}  (dtrmm_rlnn), one entry (r, j) per lane and round
@@ -703,33 +737,9 @@ struct WarpSolver {
                     for (int m = 0; m < NX; m++) acc += sAL[r * NX + m] * sAL[c * NX + m];
                     Mx[rc & 0xffff] += acc;
                 }
-                // h rows: D diag(Gamma_l + Gamma_u) D' touches only the (X,Y) block; gradient row gets D (gamma_l - gamma_u)
-                double oacc = 0.0;
-                int ooff = -1;
-                if (cls == 1 && lane < 5 && K > 0)
-                {
-                    const double* gX = R + ogxy;
-                    const double* gY = gX + K;
-                    const double* pw = (lane < 3 ? sGs : sgd) + nbq;
-                    const double* pu = lane == 0 ? gX : gY;
-                    const double* pv = (lane == 0 || lane == 1 || lane == 3) ? gX : gY;
-                    if (lane < 3)
-                    {
-#pragma unroll 1
-                        for (int c = 0; c < K; c++) oacc += (pu[c] * pw[c]) * pv[c];
-                    }
-                    else
-                    {
-#pragma unroll 1
-                        for (int c = 0; c < K; c++) oacc += pw[c] * pv[c];
-                    }
-                    ooff = (lane < 3 ? (lane == 0 ? HXV : HYV) : NV) * NV + ((lane == 0 || lane == 1 || lane == 3) ? HXV : HYV);
-                }
                 syncwarp();
-                if (ooff >= 0) Mx[ooff] += oacc;
             }
-            syncwarp();
-            // ---- (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
+            // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
             // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).  Lane r <= NV takes row r
             // into registers; pivots and multipliers travel by shuffle.
             {
@@ -756,216 +766,105 @@ struct WarpSolver {
 #pragma unroll
                     for (int c = 0; c < NV; c++) if (c <= lane) Mx[lane * NV + c] = Mr[c];
                     if (lane < NU) Mx[lane * NV + NV - 1] = dinv;  // 1/L[j][j] of the columns solved per stage (unused upper slot)
+                    if (lane == NV)
+                    {
+#pragma unroll
+                        for (int c = 0; c < NV; c++) R[obv + c] = Mr[c];  // backward vector of the forward substitution
+                    }
                 }
             }
-            syncwarp();
-            if (lane < NV) R[odux + lane] = Mx[NV * NV + lane];  // backward vector of the forward substitution
-            syncwarp();
-            rec_store2(k, ir, oux, odux + svv, olam, ormc);
+            rec_store(k, ir, oL, obv + svv);
             { const int t = ip; ip = ir; ir = in; in = t; }
         }
         sweep_end();
-        n4[0] = warp_max(n0); n4[1] = warp_max(n1); n4[2] = warp_max(n2); n4[3] = warp_max(n3);
-        mu = warp_sum(musum) / nct;
-        syncwarp();
     }
 
-    // Sweeps B / D (forward, k = 0..N): forward substitution (x_ocp_qp_kkt.c:537-575 | 1243-1290), then dt, dlam
-    // (:748-764 + COMPUTE_LAM_T_QP, x_core_qp_ipm_aux.c:117-142), step length (COMPUTE_ALPHA_QP :146-216) and the
-    // sums COMPUTE_MU_AFF_QP (:329-357) needs.  corr = false: affine step after sweep A (dux holds row NV of the
-    // factor, res_m = lam*t - tau).  corr = true: corrector / centering step after sweep C (dux holds the backward
-    // vector, res_m = rmc) fused with the residual norms of the linear system (OCP_QP_RES_COMPUTE_LIN,
-    // x_ocp_qp_res.c:468-633) that decide on iterative refinement.
-    MDEV void sweepF(bool corr, double tau, double* nlin)
+    // chainF: forward substitution.  bv holds the backward vector (row NV of the factor after chainA, the eliminated
+    // right-hand side after chainC); dux receives the primal step.
+    MDEV void chainF()
     {
-        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
-        double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-        int ir = 0, in = 1, ip = 2;
+        int ir = 0, in = 1;
+        double xc[NX], xme = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; i++) xc[i] = 0.0;
         sweep_begin();
         rec_fetch(0, ir);
-        rec_wait(ir);
-        if (N >= 1) rec_fetch(1, in);
 #pragma unroll 1
         for (int k = 0; k <= N; k++)
         {
-            double *R = buf[ir], *Rn = buf[in];
-            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
-            if (k == 0)
-            {
-                rec_mask_stage0(R);
-                if (lane < NX) R[odux + NU + lane] = 0.0;  // no x step at stage 0
-                syncwarp();
-            }
+            double* R = buf[ir];
+            rec_wait(ir);
+            if (k < N) rec_fetch(k + 1, in);
+            if (k == 0) mask_stage0(R);
             const double* L = R + oL;
-            // ---- columns solved at this stage (dtrsv_ltn): every lane redundantly; x part of dux is already there
             double zu[NU];
 #pragma unroll
-            for (int i = NU - 1; i >= 0; i--)
+            for (int i = NU - 1; i >= 0; i--)  // dtrsv_ltn on the columns solved at this stage, every lane redundantly
             {
-                double ax = 0.0, au = -R[odux + i];
+                double ax = 0.0, au = -R[obv + i];
 #pragma unroll
-                for (int m = NU; m < NV; m++) ax -= L[m * NV + i] * R[odux + m];
+                for (int m = NU; m < NV; m++) ax -= L[m * NV + i] * xc[m - NU];
 #pragma unroll
                 for (int m = i + 1; m < NU; m++) au -= L[m * NV + i] * zu[m];
                 zu[i] = (au + ax) * L[i * NV + NV - 1];
-                if (cls == 2) zu[i] = 0.0;
+                if (k == N) zu[i] = 0.0;
             }
-            // ---- dx_{k+1} = res_b + [B A] dux_k
-            double x1 = 0.0;
-            if (k < N && lane < NX)
-            {
-                double ax = R[orb + lane], au = 0.0;
-#pragma unroll
-                for (int i = NU; i < NV; i++) ax += R[oBAt + i + NV * lane] * R[odux + i];
-#pragma unroll
-                for (int i = 0; i < NU; i++) au += R[oBAt + i + NV * lane] * zu[i];
-                x1 = ax + au;
-            }
-            syncwarp();  // every lane has read the backward vector
+            double* g = rec_g(k);
+            if (lane < NX) g[odux + NU + lane] = xme;
             if (lane == 0)
             {
 #pragma unroll
-                for (int i = 0; i < NU; i++) R[odux + i] = zu[i];
+                for (int i = 0; i < NU; i++) g[odux + i] = zu[i];
             }
-            syncwarp();
-            // ---- dt, dlam, step length on the row pairs
-#pragma unroll 1
-            for (int jj = lane; jj < ncq; jj += 32)
-            {
-                double dld = 0.0;
-                if (pair_active(cls, jj))
-                {
-                    const int var = srvar[jj];
-                    const double dv = var >= 0 ? R[odux + var]
-                                               : R[ogxy + jj - nbq] * R[odux + HXV] + R[ogxy + K + jj - nbq] * R[odux + HYV];
-#pragma unroll
-                    for (int side = 0; side < 2; side++)
-                    {
-                        const int r = jj + side * ncq;
-                        double dtr = side ? -dv : dv;
-                        const double lam0 = R[olam + r], t0 = R[ot + r], rd = R[ord + r], tinv = R[oti + r];
-                        const double m = corr ? R[ormc + r] : lam0 * t0 - tau;
-                        const double dlr = -tinv * (m + (lam0 * dtr) - (lam0 * rd));
-                        dtr -= rd;
-                        if (corr)
-                        {
-                            // residual of the linearised rows at the step: rd + dt -+ v, rm + lam*dt + dlam*t
-                            const double e2 = dabs(side ? rd + dtr + dv : rd + dtr - dv), e3 = dabs(m + lam0 * dtr + dlr * t0);
-                            l2 = e2 > l2 ? e2 : l2; l3 = e3 > l3 ? e3 : l3;
-                        }
-                        R[odlam + r] = dlr; R[odt + r] = dtr;
-                        // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running
-                        // best ratio is kept as (numerator, denominator) and compared by cross-multiplication, so the
-                        // divisions happen once per sweep instead of once per row
-                        if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
-                        if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
-                        s1 += lam0 * dtr + t0 * dlr;
-                        s2 += dlr * dtr;
-                        dld = side ? dlr - dld : dlr;
-                    }
-                }
-                sdl[jj] = dld;  // dlam_upper - dlam_lower, for the residual of the linear system
-            }
-            // ---- dpi_k = Lxx (Lxx' dx_{k+1} + l_x)  |  p_{k+1} + Lxx (Lxx' dx_{k+1}) : needs the factor of stage k+1
             if (k < N)
             {
-                rec_wait(in);  // record k+1 has landed
-                const double* Lx = Rn + oL + NU * NV + NU;
-                double pj = 0.0;
-                if (lane < NX) pj = Rn[odux + NU + lane];  // l_x or p of stage k+1
-                syncwarp();
-                if (lane < NX) Rn[odux + NU + lane] = x1;  // from now on the x part of dux_{k+1}
-                syncwarp();
+                double x1 = 0.0;
                 if (lane < NX)
                 {
-                    double acc = 0.0;
+                    double ax = R[orb + lane], au = 0.0;
 #pragma unroll
-                    for (int m = 0; m < NX; m++) if (m >= lane) acc += Lx[m * NV + lane] * Rn[odux + NU + m];
-                    sz[lane] = corr ? acc : acc + pj;
-                }
-                syncwarp();
-                if (lane < NX)
-                {
-                    double acc = 0.0;
+                    for (int i = NU; i < NV; i++) ax += R[oBAt + i + NV * lane] * xc[i - NU];
 #pragma unroll
-                    for (int j = 0; j < NX; j++) if (j <= lane) acc += Lx[lane * NV + j] * sz[j];
-                    const double dp = corr ? pj + acc : acc;
-                    R[odpi + lane] = dp;
-                    Rn[odpip + lane] = dp;
+                    for (int i = 0; i < NU; i++) au += R[oBAt + i + NV * lane] * zu[i];
+                    x1 = ax + au;
                 }
+                xme = x1;
+#pragma unroll
+                for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
             }
-            syncwarp();
-            if (corr)
-            {
-                const double r = res_gb(R, k, cls, odux, odpi, odpip, org, orb, Rn + odux + NU);
-                const double q = dabs(r);
-                if (lane < NV) l0 = q > l0 ? q : l0;
-                else if (lane < NV + NX && k < N) l1 = q > l1 ? q : l1;
-            }
-            rec_store2(k, ir, odux, orq, odlam, od);
-            { const int t = ip; ip = ir; ir = in; in = t; }
-            if (k + 2 <= N) { rec_reuse_guard(); rec_fetch(k + 2, in); }
+            { const int t = ir; ir = in; in = t; }
         }
-        sweep_end();
-        const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
-        alpha = -(a_prim > a_dual ? a_prim : a_dual);
-        S1 = warp_sum(s1); S2 = warp_sum(s2);
-        if (corr) { nlin[0] = warp_max(l0); nlin[1] = warp_max(l1); nlin[2] = warp_max(l2); nlin[3] = warp_max(l3); }
         syncwarp();
+        fence_proxy_async();
     }
 
-    // Sweep C (backward, k = N..0): backward part of OCP_QP_SOLVE_KKT_STEP (x_ocp_qp_kkt.c:1096-1242) with
-    // COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113) for the right-hand side
-    //   res_m = lam*t + dt_aff*dlam_aff - sigma_mu (corrector)   |   lam*t - sigma_mu (centering only)
-    // (x_ocp_qp_ipm.c:2138-2160, 2175-2200), which is stored in rmc for sweep D.
-    MDEV void sweepC(bool with_aff, double sigma_mu)
+    // chainC: backward substitution of OCP_QP_SOLVE_KKT_STEP.  bv holds rhs_g + constraint terms (passC) on entry, the
+    // eliminated vector on exit.
+    MDEV void chainC()
     {
-        int ir = 0, in = 1, ip = 2;
+        int ir = 0, in = 1;
+        double pn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) pn[i] = 0.0;
         sweep_begin();
         rec_fetch(N, ir);
 #pragma unroll 1
         for (int k = N; k >= 0; k--)
         {
-            double *R = buf[ir], *Rp = buf[ip];
+            double* R = buf[ir];
             rec_wait(ir);
-            if (k > 0) { rec_reuse_guard(); rec_fetch(k - 1, in); }
-            const int cls = k == 0 ? 0 : (k < N ? 1 : 2);
-            if (k == 0) rec_mask_stage0(R);
-#pragma unroll 1
-            for (int jj = lane; jj < ncq; jj += 32)
-            {
-                double gd = 0.0, m0 = 0.0, m1 = 0.0;
-                if (pair_active(cls, jj))
-                {
-                    const double la0 = R[olam + jj], la1 = R[olam + ncq + jj], t0 = R[ot + jj], t1 = R[ot + ncq + jj];
-                    m0 = la0 * t0; m1 = la1 * t1;
-                    if (with_aff) { m0 += R[odt + jj] * R[odlam + jj]; m1 += R[odt + ncq + jj] * R[odlam + ncq + jj]; }
-                    m0 -= sigma_mu; m1 -= sigma_mu;
-                    gd = R[oti + jj] * (m0 - la0 * R[ord + jj]) - R[oti + ncq + jj] * (m1 - la1 * R[ord + ncq + jj]);
-                }
-                R[ormc + jj] = m0; R[ormc + ncq + jj] = m1;
-                sgd[jj] = gd;
-            }
-            if (k < N && lane < NX) sz[lane] = Rp[odux + NU + lane] + R[oPb + lane];  // p_{k+1} + Pb
-            syncwarp();
+            if (k > 0) rec_fetch(k - 1, in);
+            if (k == 0) mask_stage0(R);
             const int i = lane;
             double zi = 0.0;
-            if (i < NV && (cls == 1 || (cls == 0 ? i < NU : i >= NU)))
+            if (i < NV && var_active(k, i))
             {
-                zi = R[org + i];
-                const int row = box_of_var(cls, i);
-                if (row >= 0) zi += sgd[row];
+                zi = R[obv + i];
                 if (k < N)
                 {
-                    if (i == HXV || i == HYV)
-                    {
-                        const double* gq = R + ogxy + (i == HXV ? 0 : K);
-#pragma unroll 1
-                        for (int c = 0; c < K; c++) zi += gq[c] * sgd[nbq + c];
-                    }
                     double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NX; j++) acc += R[oBAt + i + NV * j] * sz[j];
+                    for (int j = 0; j < NX; j++) acc += R[oBAt + i + NV * j] * (pn[j] + R[oPb + j]);
                     zi += acc;
                 }
             }
@@ -978,13 +877,120 @@ struct WarpSolver {
                 const double bm = shfl(zi, m);
                 if (i > m && i < NV) zi -= L[i * NV + m] * bm;
             }
-            if (i < NV) R[odux + i] = zi;
-            syncwarp();
-            rec_store2(k, ir, odux, odux + svv, ormc, odlam);
-            { const int t = ip; ip = ir; ir = in; in = t; }
+            if (i < NV) rec_g(k)[obv + i] = zi;
+#pragma unroll
+            for (int j = 0; j < NX; j++) pn[j] = shfl(zi, NU + j);
+            { const int t = ir; ir = in; in = t; }
         }
-        sweep_end();
         solve_calls++;
+        syncwarp();
+        fence_proxy_async();
+    }
+
+    // passC: right-hand side of the corrector / centering solve res_m = lam*t [+ dt_aff*dlam_aff] - sigma_mu
+    // (x_ocp_qp_ipm.c:2138-2160, 2175-2200) -> rmc; COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113); bv = rhs_g + J'(gamma_l - gamma_u)
+    MDEV void passC(bool with_aff, double sigma_mu)
+    {
+#pragma unroll 1
+        for (int k = lane; k <= N; k += 32)
+        {
+            const double* rg = F(Y.rg, k);
+            double* bv = F(Y.bv, k);
+            double z[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) z[i] = rg[i];
+            if (k < N)
+            {
+                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *ti = F(Y.ti, k), *rd = F(Y.rd, k);
+                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k), *gxy = F(Y.gxy, k);
+                double* rm = F(Y.rmc, k);
+#pragma unroll 1
+                for (int j = 0; j < ncq; j++)
+                {
+                    if (!row_active(k, j)) { rm[j] = 0.0; rm[ncq + j] = 0.0; continue; }
+                    double m0 = lam[j] * t[j], m1 = lam[ncq + j] * t[ncq + j];
+                    if (with_aff) { m0 += dtt[j] * dl[j]; m1 += dtt[ncq + j] * dl[ncq + j]; }
+                    m0 -= sigma_mu; m1 -= sigma_mu;
+                    rm[j] = m0; rm[ncq + j] = m1;
+                    const double gd = ti[j] * (m0 - lam[j] * rd[j]) - ti[ncq + j] * (m1 - lam[ncq + j] * rd[ncq + j]);
+                    if (j < nbq)
+                    {
+                        const int id = srvar[j];
+#pragma unroll
+                        for (int i = 0; i < NV; i++) if (i == id) z[i] += gd;
+                    }
+                    else if (k >= 1) { z[HXV] += gxy[j - nbq] * gd; z[HYV] += gxy[K + j - nbq] * gd; }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) bv[i] = var_active(k, i) ? z[i] : 0.0;
+        }
+        syncwarp();
+    }
+
+    // passF: dt, dlam from dux (x_ocp_qp_kkt.c:748-764 + COMPUTE_LAM_T_QP), COMPUTE_ALPHA_QP, the sums COMPUTE_MU_AFF_QP
+    // needs, and dpi_k = Lxx (Lxx' dx_{k+1} + l_x) | p_{k+1} + Lxx (Lxx' dx_{k+1}) (x_ocp_qp_kkt.c:560-575 | 1270-1290).
+    // corr = false: affine step (res_m = lam*t - tau, bv = row NV of the factor); true: res_m = rmc, bv = eliminated rhs.
+    MDEV void passF(bool corr, double tau)
+    {
+        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
+#pragma unroll 1
+        for (int k = lane; k < N; k += 32)
+        {
+            const double *v = F(Y.dux, k), *lam = F(Y.lam, k), *t = F(Y.t, k), *ti = F(Y.ti, k), *rd = F(Y.rd, k);
+            const double *rm = F(Y.rmc, k), *gxy = F(Y.gxy, k);
+            double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+#pragma unroll 1
+            for (int j = 0; j < ncq; j++)
+            {
+                if (!row_active(k, j)) continue;
+                double dv;
+                if (j < nbq) dv = v[srvar[j]];
+                else dv = k >= 1 ? gxy[j - nbq] * v[HXV] + gxy[K + j - nbq] * v[HYV] : 0.0;
+#pragma unroll
+                for (int side = 0; side < 2; side++)
+                {
+                    const int r = j + side * ncq;
+                    double dtr = side ? -dv : dv;
+                    const double lam0 = lam[r], t0 = t[r];
+                    const double m = corr ? rm[r] : lam0 * t0 - tau;
+                    const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * rd[r]));
+                    dtr -= rd[r];
+                    dl[r] = dlr; dtt[r] = dtr;
+                    // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best
+                    // is kept as (numerator, denominator) and compared by cross-multiplication: one division per sweep
+                    if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
+                    if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
+                    s1 += lam0 * dtr + t0 * dlr;
+                    s2 += dlr * dtr;
+                }
+            }
+            // dpi_k from the factor of stage k+1
+            const double* Ln = F(Y.L, k + 1);
+            const double* bn = F(Y.bv, k + 1);
+            const double* xn = F(Y.dux, k + 1);
+            double* dpi = F(Y.dpi, k);
+            double tmp[NX];
+#pragma unroll
+            for (int j = 0; j < NX; j++)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = j; m < NX; m++) acc += Ln[(NU + m) * NV + NU + j] * xn[NU + m];
+                tmp[j] = corr ? acc : acc + bn[NU + j];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j <= i; j++) acc += Ln[(NU + i) * NV + NU + j] * tmp[j];
+                dpi[i] = corr ? bn[NU + i] + acc : acc;
+            }
+        }
+        const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
+        alpha = -(a_prim > a_dual ? a_prim : a_dual);
+        S1 = warp_sum(s1); S2 = warp_sum(s2);
         syncwarp();
     }
 
@@ -996,30 +1002,28 @@ struct WarpSolver {
 
     // OCP_QP_IPM_SOLVE + OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683, 1888-2350 (pred_corr,
     // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
-    // Per iteration: A (update with the previous step, residuals, factorisation) -> B (affine step) -> C, D (corrector)
-    // [-> C, D centering only] [-> refinement, rare].  Each sweep has ONE call site so that its loop exists once in
-    // the instruction stream.
     MDEV int ipm_solve(int* iters)
     {
-        const double tau_min = 1e-16, alpha_min = 1e-8, reg_prim = 1e-15;
+        const double tau_min = 1e-16, alpha_min = 1e-8;
         ipm_init();
         alpha = 1.0;
-        double a = 0.0;  // the first sweep A applies no step
+        double a = 0.0;  // the first passA applies no step
         int kk = 0;
         for (;;)
         {
-            sweepA(a, tau_min, reg_prim, res_max);
+            passA(a, tau_min, res_max);
             if (!(kk < iter_max && alpha > alpha_min &&
                   (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
                    dabs(res_max[3] - tau_min) > tol_comp)))
                 break;
-            double nlin[4] = {0, 0, 0, 0};
+            chainA();
             double sigma_mu = 0.0, mu_aff0 = 0.0;
             for (int pass = 0; pass < 3; pass++)
             {
                 // pass 0: affine step; pass 1: corrector; pass 2: centering only (conditional)
-                if (pass > 0) sweepC(pass == 1, sigma_mu);
-                sweepF(pass > 0, tau_min, nlin);
+                if (pass > 0) { passC(pass == 1, sigma_mu); chainC(); }
+                chainF();
+                passF(pass > 0, tau_min);
                 const double ma = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
                 if (pass == 0)
                 {
@@ -1036,19 +1040,20 @@ struct WarpSolver {
                     if (!(mu_aff > 2.0 * mu_aff0)) break;
                 }
             }
+            // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN); iterative refinement is rare
+            double nlin[4];
+            res_pass<true, false>(nlin);
             bool refined = false;
             for (int it = 0; it < 2; it++)
             {
                 if (itref_ok(nlin)) break;
-                // rare path (a fraction of a percent of the iterations): iterative refinement on the stage-major
-                // scratch arrays, straight from HBM
-                res_pass<true>(nlin);
+                res_pass<true, true>(nlin);
                 solve_sweep(true);
                 forward_sweep(Y.rb2, Y.dux2, Y.dpi2, false);
                 expand_pass(2, 0.0);
                 add_refinement();
                 refined = true;
-                res_pass<true>(nlin);
+                res_pass<true, false>(nlin);
             }
             if (refined) alpha_pass();
             a = alpha;
@@ -1066,7 +1071,7 @@ struct WarpSolver {
     // QP residuals.  LIN = false: OCP_QP_RES_COMPUTE (HP/ocp_qp/x_ocp_qp_res.c:336-466) at the iterate (ux,pi,lam,t)
     // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
     // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
-    template <bool LIN>
+    template <bool LIN, bool WRITE>
     MDEV void res_pass(double* out4)
     {
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
@@ -1101,8 +1106,9 @@ struct WarpSolver {
                     const double dl = l[ncq + j] - l[j], vv = v[id];
 #pragma unroll
                     for (int i = 0; i < NV; i++) if (i == id) g[i] += dl;
-                    rd[j] = cd[j] + tt[j] - vv;
-                    rd[ncq + j] = cd[ncq + j] + tt[ncq + j] + vv;
+                    const double e0 = cd[j] + tt[j] - vv, e1 = cd[ncq + j] + tt[ncq + j] + vv;
+                    if (WRITE) { rd[j] = e0; rd[ncq + j] = e1; }
+                    { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
                 const double* gxy = F(Y.gxy, k);
                 for (int c = 0; c < K; c++)
@@ -1112,8 +1118,9 @@ struct WarpSolver {
                     const double dl = l[ncq + r] - l[r];
                     g[HXV] += gX * dl; g[HYV] += gY * dl;
                     const double vv = gX * v[HXV] + gY * v[HYV];
-                    rd[r] = cd[r] + tt[r] - vv;
-                    rd[ncq + r] = cd[ncq + r] + tt[ncq + r] + vv;
+                    const double e0 = cd[r] + tt[r] - vv, e1 = cd[ncq + r] + tt[ncq + r] + vv;
+                    if (WRITE) { rd[r] = e0; rd[ncq + r] = e1; }
+                    { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
                 const double* BAt = F(Y.BAt, k);
                 const double* vn = F(fv, k + 1);
@@ -1125,7 +1132,7 @@ struct WarpSolver {
                     double acc = cb[j] - vn[NU + j];
 #pragma unroll
                     for (int i = 0; i < NV; i++) if (var_active(k, i)) acc += BAt[i + NV * j] * v[i];
-                    rb[j] = acc;
+                    if (WRITE) rb[j] = acc;
                     const double a = dabs(acc);
                     n1 = a > n1 ? a : n1;
                 }
@@ -1143,11 +1150,11 @@ struct WarpSolver {
                     double* rm2 = F(Y.rm2, k);
                     for (int j = 0; j < 2 * ncq; j++)
                     {
-                        if (!row_active(k, j % ncq)) { rm2[j] = 0.0; continue; }
+                        if (!row_active(k, j % ncq)) { if (WRITE) rm2[j] = 0.0; continue; }
                         const double m = rm[j] + lam[j] * tt[j] + l[j] * t[j];
-                        rm2[j] = m;
-                        const double a = dabs(m), b = dabs(rd[j]);
-                        n3 = a > n3 ? a : n3; n2 = b > n2 ? b : n2;
+                        if (WRITE) rm2[j] = m;
+                        const double a = dabs(m);
+                        n3 = a > n3 ? a : n3;
                     }
                 }
                 else
@@ -1157,8 +1164,8 @@ struct WarpSolver {
                         if (!row_active(k, j % ncq)) continue;
                         const double m = l[j] * tt[j];
                         musum += m;
-                        const double a = dabs(m), b = dabs(rd[j]);
-                        n3 = a > n3 ? a : n3; n2 = b > n2 ? b : n2;
+                        const double a = dabs(m);
+                        n3 = a > n3 ? a : n3;
                     }
                 }
             }
@@ -1166,7 +1173,7 @@ struct WarpSolver {
             for (int i = 0; i < NV; i++)
             {
                 const double gi = var_active(k, i) ? g[i] : 0.0;
-                rg[i] = gi;
+                if (WRITE) rg[i] = gi;
                 const double a = dabs(gi);
                 n0 = a > n0 ? a : n0;
             }
@@ -1249,8 +1256,7 @@ struct WarpSolver {
             if (k < N)
             {
                 double* c = F(Y.dpi, k); const double* e = F(Y.dpi2, k);
-                double* cn = F(Y.dpi_prev, k + 1);
-                for (int i = 0; i < NX; i++) { c[i] += e[i]; cn[i] = c[i]; }
+                for (int i = 0; i < NX; i++) c[i] += e[i];
                 double *l = F(Y.dlam, k), *t = F(Y.dt, k);
                 const double *l2 = F(Y.dlam2, k), *t2 = F(Y.dt2, k);
                 for (int r = 0; r < 2 * ncq; r++)

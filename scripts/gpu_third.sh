@@ -3,6 +3,6 @@ set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.err; tail -3 gpurun_out/bench_v5.err; cat gpurun_out/bench_v5.json
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:nmpc_solve -s 3 -c 1 -f -o gpurun_out/prof_v5 python bench.py --steps 1 --warmup 3 --no-cpu --batch 512 > gpurun_out/ncu_full_v5.log 2>&1
-tail -2 gpurun_out/ncu_full_v5.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err; tail -3 gpurun_out/bench_v7.err; cat gpurun_out/bench_v7.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:nmpc_solve -s 3 -c 1 -f -o gpurun_out/prof_v7 python bench.py --steps 1 --warmup 3 --no-cpu --batch 512 > gpurun_out/ncu_full_v7.log 2>&1
+tail -2 gpurun_out/ncu_full_v7.log
