@@ -23,6 +23,7 @@ struct Usv3 {
     static constexpr int ID = 0;
     static constexpr int NX = 6, NU = 2;
     static constexpr int HX = 0, HY = 1;  // position states entering the obstacle distance
+    static constexpr int NKIN = 2;        // leading states (X, Y) the dynamics do not depend on: their sensitivity columns stay unit vectors
 
     MDEV static void f_jac(const double* x, const double* uc, double* f, double* Jx, double* Ju)
     {
@@ -118,6 +119,7 @@ struct Pendulum {
     static constexpr int ID = 1;
     static constexpr int NX = 4, NU = 1;
     static constexpr int HX = 0, HY = 1;  // unused (the pendulum OCP has no h)
+    static constexpr int NKIN = 1;        // the cart position does not enter the dynamics
 
     MDEV static void f_jac(const double* x, const double* uc, double* f, double* Jx, double* Ju)
     {

@@ -207,9 +207,12 @@ struct WarpSolver {
         else if (ns == 2) { a21 = 0.5; bv1 = 1.0; }
         else { a21 = 0.5; a32 = 0.5; a43 = 1.0; bv0 = 1.0 / 6.0; bv1 = 1.0 / 3.0; bv2 = 1.0 / 3.0; bv3 = 1.0 / 6.0; }
         const double step = P.dt / P.num_steps;
-        for (int task = lane; task < N * NV; task += 32)
+        // columns of states that do not enter the dynamics stay unit vectors exactly (their VDE right-hand side is
+        // Jx e_c = 0): no lane integrates them, the first task of the stage writes them
+        constexpr int NCOL = NV - M::NKIN;
+        for (int task = lane; task < N * NCOL; task += 32)
         {
-            const int k = task / NV, col = task % NV;
+            const int k = task / NCOL, col = M::NKIN + task % NCOL;
             const double* z = F(Y.zux, k);
             double u[NU], x[NX], s[NX];
 #pragma unroll
@@ -247,8 +250,14 @@ struct WarpSolver {
             const int row = col < NX ? NU + col : col - NX;
 #pragma unroll
             for (int i = 0; i < NX; i++) BAt[row + NV * i] = s[i];
-            if (col == 0)
+            if (col == M::NKIN)
             {
+#pragma unroll
+                for (int c = 0; c < M::NKIN; c++)
+                {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) BAt[NU + c + NV * i] = (i == c) ? 1.0 : 0.0;
+                }
                 const double* zn = F(Y.zux, k + 1);
                 double* b = F(Y.b, k);
 #pragma unroll
@@ -507,17 +516,17 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            double* ux = F(Y.ux, k); const double* dux = F(Y.dux, k);
+            double* __restrict__ ux = F(Y.ux, k); const double* __restrict__ dux = F(Y.dux, k);
 #pragma unroll
             for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
             if (k < N)
             {
-                double* pi = F(Y.pi, k); const double* dpi = F(Y.dpi, k);
+                double* __restrict__ pi = F(Y.pi, k); const double* __restrict__ dpi = F(Y.dpi, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
-                double *l = F(Y.lam, k), *t = F(Y.t, k);
-                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
-#pragma unroll 1
+                double* __restrict__ l = F(Y.lam, k), * __restrict__ t = F(Y.t, k);
+                const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
+#pragma unroll 4
                 for (int r = 0; r < 2 * ncq; r++)
                 {
                     if (!row_active(k, r < ncq ? r : r - ncq)) continue;
@@ -535,9 +544,9 @@ struct WarpSolver {
         for (int k = lane; k <= N; k += 32)
         {
             const int cls = stage_class(k);
-            const double *v = F(Y.ux, k), *H = Hk(k), *rq = F(Y.rq, k);
-            double* Lk = F(Y.L, k);
-            const double* T = Tp + cls * NE;
+            const double* __restrict__ v = F(Y.ux, k), * __restrict__ H = Hk(k), * __restrict__ rq = F(Y.rq, k);
+            double* __restrict__ Lk = F(Y.L, k);
+            const double* __restrict__ T = Tp + cls * NE;
 #pragma unroll 1
             for (int e = 0; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
             double g[NV];
@@ -551,15 +560,15 @@ struct WarpSolver {
             }
             if (k > 0)
             {
-                const double* pm = F(Y.pi, k - 1);
+                const double* __restrict__ pm = F(Y.pi, k - 1);
 #pragma unroll
                 for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
             }
             if (k < N)
             {
-                const double *l = F(Y.lam, k), *tt = F(Y.t, k), *cd = F(Y.d, k), *pk = F(Y.pi, k);
-                double *rd = F(Y.rd, k), *ti = F(Y.ti, k);
-#pragma unroll 1
+                const double* __restrict__ l = F(Y.lam, k), * __restrict__ tt = F(Y.t, k), * __restrict__ cd = F(Y.d, k), * __restrict__ pk = F(Y.pi, k);
+                double* __restrict__ rd = F(Y.rd, k), * __restrict__ ti = F(Y.ti, k);
+#pragma unroll 5
                 for (int j = 0; j < nbq; j++)
                 {
                     if (!row_active(k, j)) continue;
@@ -579,9 +588,9 @@ struct WarpSolver {
                     Lk[id * NV + id] += ti0 * l0 + ti1 * l1;
                     Lk[NV * NV + id] += ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
                 }
-                const double* gxy = F(Y.gxy, k);
+                const double* __restrict__ gxy = F(Y.gxy, k);
                 double aXX = 0, aYX = 0, aYY = 0, bX = 0, bY = 0;
-#pragma unroll 1
+#pragma unroll 5
                 for (int c = 0; c < K; c++)
                 {
                     const int r = nbq + c;
@@ -608,10 +617,10 @@ struct WarpSolver {
                     Lk[HXV * NV + HXV] += aXX; Lk[HYV * NV + HXV] += aYX; Lk[HYV * NV + HYV] += aYY;
                     Lk[NV * NV + HXV] += bX; Lk[NV * NV + HYV] += bY;
                 }
-                const double* BAt = F(Y.BAt, k);
-                const double* vn = F(Y.ux, k + 1);
-                const double* cb = F(Y.b, k);
-                double* rb = F(Y.rb, k);
+                const double* __restrict__ BAt = F(Y.BAt, k);
+                const double* __restrict__ vn = F(Y.ux, k + 1);
+                const double* __restrict__ cb = F(Y.b, k);
+                double* __restrict__ rb = F(Y.rb, k);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -631,7 +640,7 @@ struct WarpSolver {
                     g[i] += acc;
                 }
             }
-            double* rg = F(Y.rg, k);
+            double* __restrict__ rg = F(Y.rg, k);
 #pragma unroll
             for (int i = 0; i < NV; i++)
             {
@@ -894,17 +903,17 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            const double* rg = F(Y.rg, k);
-            double* bv = F(Y.bv, k);
+            const double* __restrict__ rg = F(Y.rg, k);
+            double* __restrict__ bv = F(Y.bv, k);
             double z[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++) z[i] = rg[i];
             if (k < N)
             {
-                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *ti = F(Y.ti, k), *rd = F(Y.rd, k);
-                const double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k), *gxy = F(Y.gxy, k);
-                double* rm = F(Y.rmc, k);
-#pragma unroll 1
+                const double* __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
+                const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k), * __restrict__ gxy = F(Y.gxy, k);
+                double* __restrict__ rm = F(Y.rmc, k);
+#pragma unroll 5
                 for (int j = 0; j < ncq; j++)
                 {
                     if (!row_active(k, j)) { rm[j] = 0.0; rm[ncq + j] = 0.0; continue; }
@@ -937,10 +946,10 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k < N; k += 32)
         {
-            const double *v = F(Y.dux, k), *lam = F(Y.lam, k), *t = F(Y.t, k), *ti = F(Y.ti, k), *rd = F(Y.rd, k);
-            const double *rm = F(Y.rmc, k), *gxy = F(Y.gxy, k);
-            double *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
-#pragma unroll 1
+            const double* __restrict__ v = F(Y.dux, k), * __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
+            const double* __restrict__ rm = F(Y.rmc, k), * __restrict__ gxy = F(Y.gxy, k);
+            double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
+#pragma unroll 5
             for (int j = 0; j < ncq; j++)
             {
                 if (!row_active(k, j)) continue;
@@ -966,10 +975,10 @@ struct WarpSolver {
                 }
             }
             // dpi_k from the factor of stage k+1
-            const double* Ln = F(Y.L, k + 1);
-            const double* bn = F(Y.bv, k + 1);
-            const double* xn = F(Y.dux, k + 1);
-            double* dpi = F(Y.dpi, k);
+            const double* __restrict__ Ln = F(Y.L, k + 1);
+            const double* __restrict__ bn = F(Y.bv, k + 1);
+            const double* __restrict__ xn = F(Y.dux, k + 1);
+            double* __restrict__ dpi = F(Y.dpi, k);
             double tmp[NX];
 #pragma unroll
             for (int j = 0; j < NX; j++)
