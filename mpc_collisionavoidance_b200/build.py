@@ -28,14 +28,16 @@ def up_to_date(lib=LIB):
     return os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in SOURCES)
 
 
-def build(force=False, min_ctas=None, out=LIB, verbose=False):
+def build(force=False, min_ctas=None, out=LIB, verbose=False, defines=()):
     """Compile for sm_100a.  `min_ctas` = resident CTAs (4 warps each) per SM the register allocator must allow."""
-    if not force and min_ctas is None and up_to_date(out):
+    if not force and min_ctas is None and not defines and up_to_date(out):
         return out
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xptxas", "-v", "-shared", "-Xcompiler", "-fPIC", "-o", out, SOURCES[0]]
     if min_ctas is not None:
         cmd.insert(1, f"-DUSVMPC_MIN_CTAS={int(min_ctas)}")
+    for d in defines:
+        cmd.insert(1, "-D" + d)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

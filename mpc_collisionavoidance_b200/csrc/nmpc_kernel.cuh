@@ -526,7 +526,7 @@ struct WarpSolver {
                 for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
                 double* __restrict__ l = F(Y.lam, k), * __restrict__ t = F(Y.t, k);
                 const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
-#pragma unroll 4
+#pragma unroll 1
                 for (int r = 0; r < 2 * ncq; r++)
                 {
                     if (!row_active(k, r < ncq ? r : r - ncq)) continue;
@@ -568,7 +568,7 @@ struct WarpSolver {
             {
                 const double* __restrict__ l = F(Y.lam, k), * __restrict__ tt = F(Y.t, k), * __restrict__ cd = F(Y.d, k), * __restrict__ pk = F(Y.pi, k);
                 double* __restrict__ rd = F(Y.rd, k), * __restrict__ ti = F(Y.ti, k);
-#pragma unroll 5
+#pragma unroll 1
                 for (int j = 0; j < nbq; j++)
                 {
                     if (!row_active(k, j)) continue;
@@ -590,7 +590,7 @@ struct WarpSolver {
                 }
                 const double* __restrict__ gxy = F(Y.gxy, k);
                 double aXX = 0, aYX = 0, aYY = 0, bX = 0, bY = 0;
-#pragma unroll 5
+#pragma unroll 1
                 for (int c = 0; c < K; c++)
                 {
                     const int r = nbq + c;
@@ -658,6 +658,11 @@ struct WarpSolver {
 
     // TMA streaming of the record heads for the chain sweeps: two buffers + the previous stage's
     MDEV double* rec_g(int k) const { return w + Y.rec_off + (long) k * Y.rec_size; }
+#ifndef USVMPC_STREAM_TMA
+#define USVMPC_STREAM_TMA 1
+#endif
+#if USVMPC_STREAM_TMA
+    // TMA: one lane issues one bulk copy for the record head; completion is counted in bytes on the buffer's mbarrier
     MDEV void rec_init()
     {
         if (lane == 0) { mbar_init(bar + 0); mbar_init(bar + 1); mbar_init(bar + 2); fence_mbar_init(); }
@@ -686,6 +691,33 @@ struct WarpSolver {
         syncwarp();
         fence_proxy_async();
     }
+    MDEV void sweep_end_nostore() { syncwarp(); fence_proxy_async(); }
+#else
+    // alternative streaming path: per-lane 16-byte cp.async (LDGSTS) loads and plain coalesced stores, all in the
+    // generic proxy (no proxy fences, the L1 keeps what the passes read)
+    MDEV void rec_init() {}
+    MDEV void rec_fetch(int k, int b)
+    {
+        const double* src = rec_g(k);
+        double* dst = buf[b];
+#pragma unroll 1
+        for (int c = 2 * lane; c < HEAD; c += 64) cp_async16(dst + c, src + c);
+        cp_async_commit();
+    }
+    MDEV void rec_wait(int b) { (void) b; cp_async_wait_all(); syncwarp(); }
+    MDEV void rec_store(int k, int b, int f0, int t0)
+    {
+        syncwarp();
+        double* dst = rec_g(k);
+        const double* src = buf[b];
+#pragma unroll 1
+        for (int c = f0 + 2 * lane; c < t0; c += 64) st2(dst + c, src + c);
+    }
+    MDEV void rec_reuse_guard() {}
+    MDEV void sweep_begin() { syncwarp(); }
+    MDEV void sweep_end() { syncwarp(); }
+    MDEV void sweep_end_nostore() { syncwarp(); }
+#endif
     // stage 0 after x0 elimination: no x rows in [B';A'] (x_ocp_qp_red.c:268-454)
     MDEV void mask_stage0(double* R)
     {
@@ -843,8 +875,7 @@ struct WarpSolver {
             }
             { const int t = ir; ir = in; in = t; }
         }
-        syncwarp();
-        fence_proxy_async();
+        sweep_end_nostore();
     }
 
     // chainC: backward substitution of OCP_QP_SOLVE_KKT_STEP.  bv holds rhs_g + constraint terms (passC) on entry, the
@@ -892,8 +923,7 @@ struct WarpSolver {
             { const int t = ir; ir = in; in = t; }
         }
         solve_calls++;
-        syncwarp();
-        fence_proxy_async();
+        sweep_end_nostore();
     }
 
     // passC: right-hand side of the corrector / centering solve res_m = lam*t [+ dt_aff*dlam_aff] - sigma_mu
@@ -913,7 +943,7 @@ struct WarpSolver {
                 const double* __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
                 const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k), * __restrict__ gxy = F(Y.gxy, k);
                 double* __restrict__ rm = F(Y.rmc, k);
-#pragma unroll 5
+#pragma unroll 1
                 for (int j = 0; j < ncq; j++)
                 {
                     if (!row_active(k, j)) { rm[j] = 0.0; rm[ncq + j] = 0.0; continue; }
@@ -949,7 +979,7 @@ struct WarpSolver {
             const double* __restrict__ v = F(Y.dux, k), * __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
             const double* __restrict__ rm = F(Y.rmc, k), * __restrict__ gxy = F(Y.gxy, k);
             double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
-#pragma unroll 5
+#pragma unroll 1
             for (int j = 0; j < ncq; j++)
             {
                 if (!row_active(k, j)) continue;
