@@ -23,17 +23,20 @@ constexpr int NSTAT = 12;    // per-instance statistics record (doubles)
 // stats: 0 status, 1 sqp_iter, 2 qp_iter (total), 3..6 res_stat/eq/ineq/comp, 7 reserved,
 //        8 solve-only Riccati sweeps, 9 last QP status, 10 last QP iterations, 11 reserved
 
-struct Field { int off, stride; };
+struct Field { int off, stride, es; };  // offset of (stage 0, element 0), stage stride, element stride (doubles)
 
 struct Layout {
     // NLP iterate (persists between solves = warm start, like nlp_out in the reference); stage-major arrays
     Field zux, zpi, zlam, zt, zfun;
-    // ---- the per-stage RECORD (all strides = rec_size).  Order (fixed-size fields first: compile-time offsets):
-    //   BAt | ux pi rg rb L Pb bv | dux dpi | rq b || gxy | lam t rd ti | rmc | dlam dt | d        (ti = 1/t)
-    // The HEAD [BAt .. bv] is what the serial Riccati (chain) sweeps stream through shared memory with TMA; the
-    // rest is only touched by the stage-parallel passes (one lane per stage).
-    Field BAt, gxy, lam, t, ux, pi, rg, rb, rd, ti, L, Pb, bv, rmc, dux, dpi, dlam, dt, rq, b, d;
+    // ---- the per-stage RECORD HEAD: what the serial Riccati (chain) sweeps stream through shared memory with TMA,
+    //      one contiguous block per stage (stride rec_size, compile-time offsets in the kernel):
+    //        BAt | rb | L | Pb | bv
+    Field BAt, rb, L, Pb, bv;
     int rec_off, rec_size;
+    // ---- everything only the stage-parallel passes touch (one lane per stage) is stored TRANSPOSED,
+    //      [element][stage] with the stage index fastest, so that the 32 lanes of a pass read consecutive addresses
+    Field BAtT, ux, pi, rg, dux, dpi, rq, b, gxy, lam, t, rd, ti, rmc, dlam, dt, d;
+    int nsp;  // padded number of stages of the transposed arrays
     // iterative refinement scratch (rare path), stage-major arrays
     Field dux2, dpi2, dlam2, dt2, rg2, rb2, rd2, rm2;
     long total;
@@ -71,23 +74,21 @@ inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
     const int sBA = round_up(nv * nx, 2), sg = round_up(2 * K, 2) > 0 ? round_up(2 * K, 2) : 2;
     const int sL = round_up((nv + 1) * nv, 2);
     long o = 0;
-    auto put = [&](Field& f, int stride) { f.off = (int) o; f.stride = stride; o += (long) stride * N1; };
+    auto put = [&](Field& f, int stride) { f.off = (int) o; f.stride = stride; f.es = 1; o += (long) stride * N1; };
     put(L.zux, sv); put(L.zpi, sx); put(L.zlam, scz); put(L.zt, scz); put(L.zfun, scz);
     int r = 0;
     auto rec = [&](Field& f, int n) { f.off = r; r += n; };
-    // fixed-size fields first (their offsets are compile-time constants in the kernel), K-dependent ones after
-    rec(L.BAt, sBA);
-    rec(L.ux, sv); rec(L.pi, sx); rec(L.rg, sv); rec(L.rb, sx); rec(L.L, sL); rec(L.Pb, sx); rec(L.bv, sv);
-    rec(L.dux, sv); rec(L.dpi, sx);
-    rec(L.rq, sv); rec(L.b, sx);
-    rec(L.gxy, sg);
-    rec(L.lam, scq); rec(L.t, scq); rec(L.rd, scq); rec(L.ti, scq); rec(L.rmc, scq); rec(L.dlam, scq); rec(L.dt, scq); rec(L.d, scq);
+    rec(L.BAt, sBA); rec(L.rb, sx); rec(L.L, sL); rec(L.Pb, sx); rec(L.bv, sv);
     L.rec_size = round_up(r, 2);
     L.rec_off = (int) o;
-    Field* fs[] = {&L.BAt, &L.gxy, &L.lam, &L.t, &L.ux, &L.pi, &L.rg, &L.rb, &L.rd, &L.ti, &L.L, &L.Pb, &L.bv, &L.rmc,
-                   &L.dux, &L.dpi, &L.dlam, &L.dt, &L.rq, &L.b, &L.d};
-    for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; }
+    Field* fs[] = {&L.BAt, &L.rb, &L.L, &L.Pb, &L.bv};
+    for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; f->es = 1; }
     o += (long) L.rec_size * N1;
+    L.nsp = round_up(N1, 4);
+    auto tr = [&](Field& f, int dim) { f.off = (int) o; f.stride = 1; f.es = L.nsp; o += (long) dim * L.nsp; };
+    tr(L.BAtT, sBA); tr(L.ux, sv); tr(L.pi, sx); tr(L.rg, sv); tr(L.dux, sv); tr(L.dpi, sx); tr(L.rq, sv); tr(L.b, sx);
+    tr(L.gxy, sg); tr(L.lam, scq); tr(L.t, scq); tr(L.rd, scq); tr(L.ti, scq); tr(L.rmc, scq); tr(L.dlam, scq);
+    tr(L.dt, scq); tr(L.d, scq);
     put(L.dux2, sv); put(L.dpi2, sx); put(L.dlam2, scq); put(L.dt2, scq);
     put(L.rg2, sv); put(L.rb2, sx); put(L.rd2, scq); put(L.rm2, scq);
     L.total = (o + 15) / 16 * 16;  // 128-byte multiple
@@ -100,7 +101,7 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
     const int nv = nx + nu, ncq2 = 2 * (nu + nx + K);
     const Layout L = make_layout(nx, nu, N, K, nbx, nbu);
     const int ne = nv * (nv + 1) / 2 + nv, nq = nu + nx + K;
-    int n = 3 * (L.bv.off - L.rec_off + round_up(nv, 2)) + 4;  // record-head buffers (the rare path's scratch is aliased onto them) + mbarriers
+    int n = 3 * L.rec_size + 4;  // record-head buffers (the rare path's scratch is aliased onto them) + mbarriers
     {
         const int rare = nv * nx + nx * nx + nx + 4 * nq + (nv + 1) * nv + nv + 2 * nx + 2 * (K > 0 ? K : 1);
         if (n < rare + 4) n = rare + 4;

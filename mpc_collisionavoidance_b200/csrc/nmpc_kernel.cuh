@@ -34,6 +34,13 @@
 
 namespace usvmpc {
 
+// pointer to the elements of one stage of a field: element stride 1 (stage-major / record) or nsp (transposed)
+struct SP {
+    double* p;
+    int es;
+    MDEV double& operator[](int i) const { return p[(long) i * es]; }
+};
+
 template <class M>
 struct WarpSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
@@ -41,10 +48,8 @@ struct WarpSolver {
     static constexpr int NE = NV * (NV + 1) / 2 + NV;  // entries of the lower trapezoid of the (NV+1) x NV factor
     // record layout (layout.h): offsets of the fixed-size fields are compile-time constants
     static constexpr int svv = (NV + 1) / 2 * 2, sxx = (NX + 1) / 2 * 2, sLL = (NR * NV + 1) / 2 * 2;
-    static constexpr int oBAt = 0, oux = (NV * NX + 1) / 2 * 2, opi = oux + svv, org = opi + sxx, orb = org + svv;
-    static constexpr int oL = orb + sxx, oPb = oL + sLL, obv = oPb + sxx, odux = obv + svv, odpi = odux + svv;
-    static constexpr int orq = odpi + sxx, ob = orq + svv, ogxy = ob + sxx;
-    static constexpr int HEAD = obv + svv;  // what the chain sweeps stream: [B';A'] ux pi rg rb L Pb bv
+    static constexpr int oBAt = 0, orb = (NV * NX + 1) / 2 * 2, oL = orb + sxx, oPb = oL + sLL, obv = oPb + sxx;
+    static constexpr int HEAD = obv + svv;  // what the chain sweeps stream: [B';A'] rb L Pb bv
     // per-warp shared-memory scratch: fixed-size part at compile-time offsets
     static constexpr int qHs = 0, qHes = qHs + NV * NV, qWs = qHes + NV * NV, qWes = qWs + NV * NV, qTp = qWes + NX * NX;
     static constexpr int qAL = qTp + 3 * NE, qz = qAL + NR * NX, qent = qz + sxx, qvrow = qent + (NE + 1) / 2;
@@ -62,7 +67,6 @@ struct WarpSolver {
     double* buf[3];
     unsigned long long* bar;  // one mbarrier per record buffer (TMA completion)
     unsigned phb;             // their phase bits
-    int olam, ot, ord, oti, ormc, odlam, odt, od, scq;  // K-dependent record offsets
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116
     // and, in SQP mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
     double tol_stat, tol_eq, tol_ineq, tol_comp;
@@ -88,9 +92,6 @@ struct WarpSolver {
         buf[0] = s; s += HEAD; buf[1] = s; s += HEAD; buf[2] = s; s += HEAD;
         bar = (unsigned long long*) s; s += 4;
         phb = 0;
-        scq = Y.t.off - Y.lam.off;
-        olam = Y.lam.off - Y.rec_off; ot = olam + scq; ord = ot + scq; oti = ord + scq; ormc = oti + scq; odlam = ormc + scq;
-        odt = odlam + scq; od = odt + scq;
         // scratch of the rare (iterative refinement) path lives in the record buffers, which are idle then
         double* q = buf[0];
         sBA = q; q += NV * NX; sLn = q; q += NX * NX; slx = q; q += NX; sG = q; q += 2 * (NU + NX + K);
@@ -105,14 +106,11 @@ struct WarpSolver {
     // the host-side layout (layout.h:make_layout) must agree with the compile-time offsets above
     static bool layout_matches(const Layout& y)
     {
-        const int ro = y.rec_off, sc = y.t.off - y.lam.off;
-        return y.BAt.off - ro == oBAt && y.ux.off - ro == oux && y.pi.off - ro == opi && y.rg.off - ro == org &&
-               y.rb.off - ro == orb && y.L.off - ro == oL && y.Pb.off - ro == oPb && y.bv.off - ro == obv &&
-               y.dux.off - ro == odux && y.dpi.off - ro == odpi && y.rq.off - ro == orq && y.b.off - ro == ob &&
-               y.gxy.off - ro == ogxy && y.lam.off > y.gxy.off && y.rd.off - y.t.off == sc && y.ti.off - y.rd.off == sc &&
-               y.rmc.off - y.ti.off == sc && y.d.off - y.dt.off == sc && y.rec_size == y.d.off - ro + sc;
+        const int ro = y.rec_off;
+        return y.BAt.off - ro == oBAt && y.rb.off - ro == orb && y.L.off - ro == oL && y.Pb.off - ro == oPb &&
+               y.bv.off - ro == obv && y.rec_size == HEAD;
     }
-    MDEV double* F(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
+    MDEV SP F(const Field& f, int k) const { return SP{w + f.off + (long) k * f.stride, f.es}; }
     MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
     MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
     // IPM row of the box on variable c at stage k, or -1
@@ -184,12 +182,12 @@ struct WarpSolver {
     {
         for (int k = lane; k <= N; k += 32)
         {
-            double* z = F(Y.zux, k);
+            const SP z = F(Y.zux, k);
             for (int i = 0; i < NU; i++) z[i] = 0.0;
             for (int i = 0; i < NX; i++) z[NU + i] = x0[i];
-            double* pi = F(Y.zpi, k);
+            const SP pi = F(Y.zpi, k);
             for (int i = 0; i < NX; i++) pi[i] = 0.0;
-            double *l = F(Y.zlam, k), *t = F(Y.zt, k);
+            const SP l = F(Y.zlam, k), t = F(Y.zt, k);
             for (int j = 0; j < 2 * ncz; j++) { l[j] = 0.0; t[j] = 0.0; }
         }
         syncwarp();
@@ -213,7 +211,7 @@ struct WarpSolver {
         for (int task = lane; task < N * NCOL; task += 32)
         {
             const int k = task / NCOL, col = M::NKIN + task % NCOL;
-            const double* z = F(Y.zux, k);
+            const SP z = F(Y.zux, k);
             double u[NU], x[NX], s[NX];
 #pragma unroll
             for (int i = 0; i < NU; i++) u[i] = z[i];
@@ -246,20 +244,20 @@ struct WarpSolver {
                 for (int i = 0; i < NX; i++) { x[i] = xa[i]; s[i] = sa[i]; }
             }
             // BAt = [B'; A'] (nv x nx, column-major): ocp_nlp_dynamics_cont.c:801-804
-            double* BAt = F(Y.BAt, k);
+            const SP BAt = F(Y.BAt, k), BAtT = F(Y.BAtT, k);  // record head (chain sweeps) and transposed copy (passes)
             const int row = col < NX ? NU + col : col - NX;
 #pragma unroll
-            for (int i = 0; i < NX; i++) BAt[row + NV * i] = s[i];
+            for (int i = 0; i < NX; i++) { BAt[row + NV * i] = s[i]; BAtT[row + NV * i] = s[i]; }
             if (col == M::NKIN)
             {
 #pragma unroll
                 for (int c = 0; c < M::NKIN; c++)
                 {
 #pragma unroll
-                    for (int i = 0; i < NX; i++) BAt[NU + c + NV * i] = (i == c) ? 1.0 : 0.0;
+                    for (int i = 0; i < NX; i++) { BAt[NU + c + NV * i] = (i == c) ? 1.0 : 0.0; BAtT[NU + c + NV * i] = (i == c) ? 1.0 : 0.0; }
                 }
-                const double* zn = F(Y.zux, k + 1);
-                double* b = F(Y.b, k);
+                const SP zn = F(Y.zux, k + 1);
+                const SP b = F(Y.b, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) b[i] = x[i] - zn[NU + i];  // dyn_fun = phi(x,u) - x_next
             }
@@ -277,9 +275,9 @@ struct WarpSolver {
         double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
         for (int k = lane; k <= N; k += 32)
         {
-            const double* z = F(Y.zux, k);
-            const double *zl = F(Y.zlam, k), *zt = F(Y.zt, k);
-            double *zf = F(Y.zfun, k), *rq = F(Y.rq, k), *d = F(Y.d, k);
+            const SP z = F(Y.zux, k);
+            const SP zl = F(Y.zlam, k), zt = F(Y.zt, k);
+            const SP zf = F(Y.zfun, k), rq = F(Y.rq, k), d = F(Y.d, k);
             double cg[NV], adj[NV];
             // ---- LINEAR_LS cost gradient (ocp_nlp_cost_ls.c:749-843)
             if (k < N)
@@ -373,7 +371,7 @@ struct WarpSolver {
                 // obstacle distances h_c = ||(X,Y) - (ox_c, oy_c)||, dh/d(X,Y) = ((X,Y) - o_c)/h_c
                 const double* pk = pg + (P.p_per_stage ? k * 2 * K : 0);
                 const double* lhk = lhg + (P.lh_per_stage ? k * K : 0);
-                double* gxy = F(Y.gxy, k);
+                const SP gxy = F(Y.gxy, k);
                 for (int c = 0; c < K; c++)
                 {
                     const double ddx = z[HXV] - pk[2 * c], ddy = z[HYV] - pk[2 * c + 1];
@@ -395,8 +393,8 @@ struct WarpSolver {
                 }
             }
             // ---- dynamics adjoint -[B';A'] pi_k (+ pi_{k-1} on x): ocp_nlp_common.c:2001-2019 ; stationarity residual
-            const double* BAt = F(Y.BAt, k);
-            const double* pik = F(Y.zpi, k);
+            const SP BAt = F(Y.BAtT, k);
+            const SP pik = F(Y.zpi, k);
 #pragma unroll
             for (int i = 0; i < NV; i++)
             {
@@ -415,7 +413,7 @@ struct WarpSolver {
             }
             if (k < N)
             {
-                const double* b = F(Y.b, k);
+                const SP b = F(Y.b, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) { const double a = dabs(b[i]); r1 = a > r1 ? a : r1; }
             }
@@ -424,7 +422,7 @@ struct WarpSolver {
             for (int i = 0; i < NV; i++) rq[i] = cg[i];
             if (k == 0 && N > 0)
             {
-                double* b = F(Y.b, 0);
+                const SP b = F(Y.b, 0);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -454,14 +452,14 @@ struct WarpSolver {
         const double thr0 = 1e-1, mu0 = 1.0;
         for (int k = lane; k <= N; k += 32)
         {
-            double *ux = F(Y.ux, k), *pi = F(Y.pi, k), *lam = F(Y.lam, k), *t = F(Y.t, k);
-            const double* d = F(Y.d, k);
+            const SP ux = F(Y.ux, k), pi = F(Y.pi, k), lam = F(Y.lam, k), t = F(Y.t, k);
+            const SP d = F(Y.d, k);
             for (int i = 0; i < NV; i++) ux[i] = 0.0;
             for (int i = 0; i < NX; i++) pi[i] = 0.0;
             for (int j = 0; j < 2 * ncq; j++) { lam[j] = 0.0; t[j] = 1.0; }
             {
                 // the first passA applies a zero step: the step starts at zero
-                double *a = F(Y.dux, k), *b = F(Y.dpi, k), *c = F(Y.dlam, k), *e = F(Y.dt, k);
+                const SP a = F(Y.dux, k), b = F(Y.dpi, k), c = F(Y.dlam, k), e = F(Y.dt, k);
                 for (int i = 0; i < NV; i++) a[i] = 0.0;
                 for (int i = 0; i < NX; i++) b[i] = 0.0;
                 for (int j = 0; j < 2 * ncq; j++) { c[j] = 0.0; e[j] = 0.0; }
@@ -480,7 +478,7 @@ struct WarpSolver {
                 else if (tu < thr0) { tu = thr0; ux[id] = -d[ncq + j] - thr0; }
                 t[j] = tl; t[ncq + j] = tu;
             }
-            const double* gxy = F(Y.gxy, k);
+            const SP gxy = F(Y.gxy, k);
             for (int c = 0; c < K; c++)
             {
                 const double v = (k >= 1) ? gxy[c] * ux[HXV] + gxy[K + c] * ux[HYV] : 0.0;
@@ -516,16 +514,16 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            double* __restrict__ ux = F(Y.ux, k); const double* __restrict__ dux = F(Y.dux, k);
+            const SP ux = F(Y.ux, k); const SP dux = F(Y.dux, k);
 #pragma unroll
             for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
             if (k < N)
             {
-                double* __restrict__ pi = F(Y.pi, k); const double* __restrict__ dpi = F(Y.dpi, k);
+                const SP pi = F(Y.pi, k); const SP dpi = F(Y.dpi, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
-                double* __restrict__ l = F(Y.lam, k), * __restrict__ t = F(Y.t, k);
-                const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
+                const SP l = F(Y.lam, k), t = F(Y.t, k);
+                const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k);
 #pragma unroll 1
                 for (int r = 0; r < 2 * ncq; r++)
                 {
@@ -544,8 +542,9 @@ struct WarpSolver {
         for (int k = lane; k <= N; k += 32)
         {
             const int cls = stage_class(k);
-            const double* __restrict__ v = F(Y.ux, k), * __restrict__ H = Hk(k), * __restrict__ rq = F(Y.rq, k);
-            double* __restrict__ Lk = F(Y.L, k);
+            const SP v = F(Y.ux, k), rq = F(Y.rq, k);
+            const double* __restrict__ H = Hk(k);
+            const SP Lk = F(Y.L, k);
             const double* __restrict__ T = Tp + cls * NE;
 #pragma unroll 1
             for (int e = 0; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
@@ -560,14 +559,14 @@ struct WarpSolver {
             }
             if (k > 0)
             {
-                const double* __restrict__ pm = F(Y.pi, k - 1);
+                const SP pm = F(Y.pi, k - 1);
 #pragma unroll
                 for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
             }
             if (k < N)
             {
-                const double* __restrict__ l = F(Y.lam, k), * __restrict__ tt = F(Y.t, k), * __restrict__ cd = F(Y.d, k), * __restrict__ pk = F(Y.pi, k);
-                double* __restrict__ rd = F(Y.rd, k), * __restrict__ ti = F(Y.ti, k);
+                const SP l = F(Y.lam, k), tt = F(Y.t, k), cd = F(Y.d, k), pk = F(Y.pi, k);
+                const SP rd = F(Y.rd, k), ti = F(Y.ti, k);
 #pragma unroll 1
                 for (int j = 0; j < nbq; j++)
                 {
@@ -588,7 +587,7 @@ struct WarpSolver {
                     Lk[id * NV + id] += ti0 * l0 + ti1 * l1;
                     Lk[NV * NV + id] += ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
                 }
-                const double* __restrict__ gxy = F(Y.gxy, k);
+                const SP gxy = F(Y.gxy, k);
                 double aXX = 0, aYX = 0, aYY = 0, bX = 0, bY = 0;
 #pragma unroll 1
                 for (int c = 0; c < K; c++)
@@ -617,10 +616,10 @@ struct WarpSolver {
                     Lk[HXV * NV + HXV] += aXX; Lk[HYV * NV + HXV] += aYX; Lk[HYV * NV + HYV] += aYY;
                     Lk[NV * NV + HXV] += bX; Lk[NV * NV + HYV] += bY;
                 }
-                const double* __restrict__ BAt = F(Y.BAt, k);
-                const double* __restrict__ vn = F(Y.ux, k + 1);
-                const double* __restrict__ cb = F(Y.b, k);
-                double* __restrict__ rb = F(Y.rb, k);
+                const SP BAt = F(Y.BAtT, k);
+                const SP vn = F(Y.ux, k + 1);
+                const SP cb = F(Y.b, k);
+                const SP rb = F(Y.rb, k);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -640,7 +639,7 @@ struct WarpSolver {
                     g[i] += acc;
                 }
             }
-            double* __restrict__ rg = F(Y.rg, k);
+            const SP rg = F(Y.rg, k);
 #pragma unroll
             for (int i = 0; i < NV; i++)
             {
@@ -850,12 +849,12 @@ struct WarpSolver {
                 zu[i] = (au + ax) * L[i * NV + NV - 1];
                 if (k == N) zu[i] = 0.0;
             }
-            double* g = rec_g(k);
-            if (lane < NX) g[odux + NU + lane] = xme;
+            const SP g = F(Y.dux, k);
+            if (lane < NX) g[NU + lane] = xme;
             if (lane == 0)
             {
 #pragma unroll
-                for (int i = 0; i < NU; i++) g[odux + i] = zu[i];
+                for (int i = 0; i < NU; i++) g[i] = zu[i];
             }
             if (k < N)
             {
@@ -933,16 +932,16 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            const double* __restrict__ rg = F(Y.rg, k);
-            double* __restrict__ bv = F(Y.bv, k);
+            const SP rg = F(Y.rg, k);
+            const SP bv = F(Y.bv, k);
             double z[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++) z[i] = rg[i];
             if (k < N)
             {
-                const double* __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
-                const double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k), * __restrict__ gxy = F(Y.gxy, k);
-                double* __restrict__ rm = F(Y.rmc, k);
+                const SP lam = F(Y.lam, k), t = F(Y.t, k), ti = F(Y.ti, k), rd = F(Y.rd, k);
+                const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k), gxy = F(Y.gxy, k);
+                const SP rm = F(Y.rmc, k);
 #pragma unroll 1
                 for (int j = 0; j < ncq; j++)
                 {
@@ -976,9 +975,9 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k < N; k += 32)
         {
-            const double* __restrict__ v = F(Y.dux, k), * __restrict__ lam = F(Y.lam, k), * __restrict__ t = F(Y.t, k), * __restrict__ ti = F(Y.ti, k), * __restrict__ rd = F(Y.rd, k);
-            const double* __restrict__ rm = F(Y.rmc, k), * __restrict__ gxy = F(Y.gxy, k);
-            double* __restrict__ dl = F(Y.dlam, k), * __restrict__ dtt = F(Y.dt, k);
+            const SP v = F(Y.dux, k), lam = F(Y.lam, k), t = F(Y.t, k), ti = F(Y.ti, k), rd = F(Y.rd, k);
+            const SP rm = F(Y.rmc, k), gxy = F(Y.gxy, k);
+            const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k);
 #pragma unroll 1
             for (int j = 0; j < ncq; j++)
             {
@@ -1005,10 +1004,10 @@ struct WarpSolver {
                 }
             }
             // dpi_k from the factor of stage k+1
-            const double* __restrict__ Ln = F(Y.L, k + 1);
-            const double* __restrict__ bn = F(Y.bv, k + 1);
-            const double* __restrict__ xn = F(Y.dux, k + 1);
-            double* __restrict__ dpi = F(Y.dpi, k);
+            const SP Ln = F(Y.L, k + 1);
+            const SP bn = F(Y.bv, k + 1);
+            const SP xn = F(Y.dux, k + 1);
+            const SP dpi = F(Y.dpi, k);
             double tmp[NX];
 #pragma unroll
             for (int j = 0; j < NX; j++)
@@ -1118,9 +1117,10 @@ struct WarpSolver {
         const Field &og = LIN ? Y.rg2 : Y.rg, &ob = LIN ? Y.rb2 : Y.rb, &od = LIN ? Y.rd2 : Y.rd;
         for (int k = lane; k <= N; k += 32)
         {
-            const double *v = F(fv, k), *pk = F(fp, k), *l = F(fl, k), *tt = F(ft, k);
-            const double *H = Hk(k), *cg = LIN ? F(Y.rg, k) : F(Y.rq, k), *cd = LIN ? F(Y.rd, k) : F(Y.d, k);
-            double *rg = F(og, k), *rd = F(od, k);
+            const SP v = F(fv, k), pk = F(fp, k), l = F(fl, k), tt = F(ft, k);
+            const double* H = Hk(k);
+            const SP cg = LIN ? F(Y.rg, k) : F(Y.rq, k), cd = LIN ? F(Y.rd, k) : F(Y.d, k);
+            const SP rg = F(og, k), rd = F(od, k);
             double g[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++)
@@ -1132,7 +1132,7 @@ struct WarpSolver {
             }
             if (k > 0)
             {
-                const double* pm = F(fp, k - 1);
+                const SP pm = F(fp, k - 1);
 #pragma unroll
                 for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
             }
@@ -1149,7 +1149,7 @@ struct WarpSolver {
                     if (WRITE) { rd[j] = e0; rd[ncq + j] = e1; }
                     { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
-                const double* gxy = F(Y.gxy, k);
+                const SP gxy = F(Y.gxy, k);
                 for (int c = 0; c < K; c++)
                 {
                     const int r = nbq + c;
@@ -1161,10 +1161,10 @@ struct WarpSolver {
                     if (WRITE) { rd[r] = e0; rd[ncq + r] = e1; }
                     { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
-                const double* BAt = F(Y.BAt, k);
-                const double* vn = F(fv, k + 1);
-                const double* cb = LIN ? F(Y.rb, k) : F(Y.b, k);
-                double* rb = F(ob, k);
+                const SP BAt = F(Y.BAtT, k);
+                const SP vn = F(fv, k + 1);
+                const SP cb = LIN ? F(Y.rb, k) : F(Y.b, k);
+                const SP rb = F(ob, k);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -1185,8 +1185,8 @@ struct WarpSolver {
                 }
                 if (LIN)
                 {
-                    const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rm = F(Y.rmc, k);
-                    double* rm2 = F(Y.rm2, k);
+                    const SP lam = F(Y.lam, k), t = F(Y.t, k), rm = F(Y.rmc, k);
+                    const SP rm2 = F(Y.rm2, k);
                     for (int j = 0; j < 2 * ncq; j++)
                     {
                         if (!row_active(k, j % ncq)) { if (WRITE) rm2[j] = 0.0; continue; }
@@ -1232,9 +1232,9 @@ struct WarpSolver {
         double a_prim = -1.0, a_dual = -1.0, s1 = 0.0, s2 = 0.0;
         for (int k = lane; k < N; k += 32)
         {
-            const double *v = F(fv, k), *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(frd, k), *rm = F(frm, k);
-            const double* gxy = F(Y.gxy, k);
-            double *dl = F(fl, k), *dtt = F(ft, k);
+            const SP v = F(fv, k), lam = F(Y.lam, k), t = F(Y.t, k), rd = F(frd, k), rm = F(frm, k);
+            const SP gxy = F(Y.gxy, k);
+            const SP dl = F(fl, k), dtt = F(ft, k);
             for (int j = 0; j < ncq; j++)
             {
                 if (!row_active(k, j)) continue;
@@ -1273,7 +1273,7 @@ struct WarpSolver {
         double a_prim = -1.0, a_dual = -1.0;
         for (int k = lane; k < N; k += 32)
         {
-            const double *lam = F(Y.lam, k), *t = F(Y.t, k), *dl = F(Y.dlam, k), *dtt = F(Y.dt, k);
+            const SP lam = F(Y.lam, k), t = F(Y.t, k), dl = F(Y.dlam, k), dtt = F(Y.dt, k);
             for (int r = 0; r < 2 * ncq; r++)
             {
                 if (!row_active(k, r % ncq)) continue;
@@ -1290,14 +1290,14 @@ struct WarpSolver {
     {
         for (int k = lane; k <= N; k += 32)
         {
-            double *a = F(Y.dux, k); const double* b = F(Y.dux2, k);
+            const SP a = F(Y.dux, k); const SP b = F(Y.dux2, k);
             for (int i = 0; i < NV; i++) a[i] += b[i];
             if (k < N)
             {
-                double* c = F(Y.dpi, k); const double* e = F(Y.dpi2, k);
+                const SP c = F(Y.dpi, k); const SP e = F(Y.dpi2, k);
                 for (int i = 0; i < NX; i++) c[i] += e[i];
-                double *l = F(Y.dlam, k), *t = F(Y.dt, k);
-                const double *l2 = F(Y.dlam2, k), *t2 = F(Y.dt2, k);
+                const SP l = F(Y.dlam, k), t = F(Y.dt, k);
+                const SP l2 = F(Y.dlam2, k), t2 = F(Y.dt2, k);
                 for (int r = 0; r < 2 * ncq; r++)
                     if (row_active(k, r % ncq)) { l[r] += l2[r]; t[r] += t2[r]; }
             }
@@ -1310,7 +1310,7 @@ struct WarpSolver {
     {
         if (k < N)
         {
-            const double* g = F(Y.BAt, k);
+            const SP g = F(Y.BAt, k);
             for (int e = lane; e < NV * NX; e += 32) sBA[e] = var_active(k, e % NV) ? g[e] : 0.0;
         }
         else
@@ -1321,14 +1321,14 @@ struct WarpSolver {
     {
         if (k < N)
         {
-            const double* g = F(Y.gxy, k);
+            const SP g = F(Y.gxy, k);
             for (int e = lane; e < 2 * K; e += 32) sgxy[e] = k >= 1 ? g[e] : 0.0;
         }
     }
 
     MDEV void load_Lnext(int k1)  // xx block and nothing else of the factor of stage k1
     {
-        const double* L = F(Y.L, k1);
+        const SP L = F(Y.L, k1);
         for (int e = lane; e < NX * NX; e += 32)
         {
             const int m = e / NX, j = e % NX;
@@ -1347,9 +1347,9 @@ struct WarpSolver {
         {
             syncwarp();
             {
-                const double* L = F(Y.L, k);
+                const SP L = F(Y.L, k);
                 for (int e = lane; e < NR * NV; e += 32) sL[e] = L[e];
-                const double* q = F(fdux, k);
+                const SP q = F(fdux, k);
                 if (lane < NU) sq[lane] = q[lane];
                 if (k < N)
                 {
@@ -1372,7 +1372,7 @@ struct WarpSolver {
             }
             if (lane == 0)
             {
-                double* o = F(fdux, k);
+                const SP o = F(fdux, k);
 #pragma unroll
                 for (int i = 0; i < NV; i++) o[i] = var_active(k, i) ? z[i] : 0.0;
             }
@@ -1426,7 +1426,7 @@ struct WarpSolver {
             load_BA(k);
             load_gxy(k);
             {
-                const double *lam = F(Y.lam, k), *t = F(Y.t, k), *rd = F(frd, k), *rm = F(frm, k);
+                const SP lam = F(Y.lam, k), t = F(Y.t, k), rd = F(frd, k), rm = F(frm, k);
                 for (int r = lane; r < 2 * ncq; r += 32)
                 {
                     double g = 0.0;
@@ -1493,7 +1493,7 @@ struct WarpSolver {
                 }
             }
             // dtrsv_lnn_mn(nv, nu): forward-eliminate the columns solved at this stage
-            const double* L = F(Y.L, k);
+            const SP L = F(Y.L, k);
 #pragma unroll
             for (int m = 0; m < NU; m++)
             {
@@ -1517,11 +1517,11 @@ struct WarpSolver {
     {
         for (int k = lane; k <= N; k += 32)
         {
-            double *z = F(Y.zux, k), *zl = F(Y.zlam, k), *zt = F(Y.zt, k);
-            const double *ux = F(Y.ux, k), *lam = F(Y.lam, k), *t = F(Y.t, k);
+            const SP z = F(Y.zux, k), zl = F(Y.zlam, k), zt = F(Y.zt, k);
+            const SP ux = F(Y.ux, k), lam = F(Y.lam, k), t = F(Y.t, k);
             if (k < N)
             {
-                double* zp = F(Y.zpi, k); const double* pi = F(Y.pi, k);
+                const SP zp = F(Y.zpi, k); const SP pi = F(Y.pi, k);
                 for (int i = 0; i < NX; i++) zp[i] = pi[i];
                 for (int j = 0; j < nbu; j++) { zl[j] = lam[j]; zl[ncz + j] = lam[ncq + j]; zt[j] = t[j]; zt[ncz + j] = t[ncq + j]; }
                 for (int c = 0; c < K; c++)
@@ -1533,14 +1533,14 @@ struct WarpSolver {
             if (k == 0)
             {
                 // recover the eliminated x0 step and the multipliers of its bounds from stationarity
-                const double* zf = F(Y.zfun, 0);
+                const SP zf = F(Y.zfun, 0);
                 double s[NV], tmp[NV];
                 for (int i = 0; i < NU; i++) s[i] = ux[i];
                 for (int i = 0; i < NX; i++) s[NU + i] = zf[nbu + i];  // dx0 = x0 - x_0
-                const double* rq = F(Y.rq, 0);
-                const double* BAt = F(Y.BAt, 0);
-                const double* pi = F(Y.pi, 0);
-                const double* gxy = F(Y.gxy, 0);
+                const SP rq = F(Y.rq, 0);
+                const SP BAt = F(Y.BAt, 0);
+                const SP pi = F(Y.pi, 0);
+                const SP gxy = F(Y.gxy, 0);
                 for (int i = 0; i < NX; i++)
                 {
                     const int iv = NU + i;
@@ -1586,7 +1586,7 @@ struct WarpSolver {
         double r2 = 0, r3 = 0;
         for (int k = lane; k < N; k += 32)
         {
-            const double *zl = F(Y.zlam, k), *zt = F(Y.zt, k), *zf = F(Y.zfun, k);
+            const SP zl = F(Y.zlam, k), zt = F(Y.zt, k), zf = F(Y.zfun, k);
             for (int j = 0; j < 2 * ncz; j++)
             {
                 const int jj = j % ncz;
