@@ -667,20 +667,20 @@ struct WarpSolver {
         if (lane == 0) { mbar_init(bar + 0); mbar_init(bar + 1); mbar_init(bar + 2); fence_mbar_init(); }
         syncwarp();
     }
-    MDEV void rec_fetch(int k, int b)
+    MDEV void rec_fetch(const double* g, int b)
     {
-        if (lane == 0) bulk_g2s(buf[b], rec_g(k), HEAD * 8, bar + b);
+        if (lane == 0) bulk_g2s(buf[b], g, HEAD * 8, bar + b);
     }
     MDEV void rec_wait(int b)
     {
         mbar_wait(bar + b, (phb >> b) & 1u);
         phb ^= 1u << b;
     }
-    MDEV void rec_store(int k, int b, int f0, int t0)
+    MDEV void rec_store(double* g, int b, int f0, int t0)
     {
         fence_proxy_async_smem();
         syncwarp();
-        if (lane == 0) { bulk_s2g(rec_g(k) + f0, buf[b] + f0, (t0 - f0) * 8); bulk_commit(); }
+        if (lane == 0) { bulk_s2g(g + f0, buf[b] + f0, (t0 - f0) * 8); bulk_commit(); }
     }
     MDEV void rec_reuse_guard() { if (lane == 0) bulk_wait_read1(); }
     MDEV void sweep_begin() { fence_proxy_async(); syncwarp(); }
@@ -695,19 +695,17 @@ struct WarpSolver {
     // alternative streaming path: per-lane 16-byte cp.async (LDGSTS) loads and plain coalesced stores, all in the
     // generic proxy (no proxy fences, the L1 keeps what the passes read)
     MDEV void rec_init() {}
-    MDEV void rec_fetch(int k, int b)
+    MDEV void rec_fetch(const double* src, int b)
     {
-        const double* src = rec_g(k);
         double* dst = buf[b];
 #pragma unroll 1
         for (int c = 2 * lane; c < HEAD; c += 64) cp_async16(dst + c, src + c);
         cp_async_commit();
     }
     MDEV void rec_wait(int b) { (void) b; cp_async_wait_all(); syncwarp(); }
-    MDEV void rec_store(int k, int b, int f0, int t0)
+    MDEV void rec_store(double* dst, int b, int f0, int t0)
     {
         syncwarp();
-        double* dst = rec_g(k);
         const double* src = buf[b];
 #pragma unroll 1
         for (int c = f0 + 2 * lane; c < t0; c += 64) st2(dst + c, src + c);
@@ -731,13 +729,14 @@ struct WarpSolver {
     {
         int ir = 0, in = 1, ip = 2;
         sweep_begin();
-        rec_fetch(N, ir);
+        double* gk = rec_g(N);  // record head of stage k in HBM
+        rec_fetch(gk, ir);
 #pragma unroll 1
-        for (int k = N; k >= 0; k--)
+        for (int k = N; k >= 0; k--, gk -= HEAD)
         {
             double *R = buf[ir], *Rp = buf[ip];
             rec_wait(ir);
-            if (k > 0) { rec_reuse_guard(); rec_fetch(k - 1, in); }
+            if (k > 0) { rec_reuse_guard(); rec_fetch(gk - HEAD, in); }
             if (k == 0) mask_stage0(R);
             double* Mx = R + oL;
             if (k < N)
@@ -813,7 +812,7 @@ struct WarpSolver {
                     }
                 }
             }
-            rec_store(k, ir, oL, obv + svv);
+            rec_store(gk, ir, oL, obv + svv);
             { const int t = ip; ip = ir; ir = in; in = t; }
         }
         sweep_end();
@@ -828,13 +827,14 @@ struct WarpSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) xc[i] = 0.0;
         sweep_begin();
-        rec_fetch(0, ir);
+        const double* gk = rec_g(0);
+        rec_fetch(gk, ir);
 #pragma unroll 1
-        for (int k = 0; k <= N; k++)
+        for (int k = 0; k <= N; k++, gk += HEAD)
         {
             double* R = buf[ir];
             rec_wait(ir);
-            if (k < N) rec_fetch(k + 1, in);
+            if (k < N) rec_fetch(gk + HEAD, in);
             if (k == 0) mask_stage0(R);
             const double* L = R + oL;
             double zu[NU];
@@ -886,13 +886,14 @@ struct WarpSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) pn[i] = 0.0;
         sweep_begin();
-        rec_fetch(N, ir);
+        double* gk = rec_g(N);
+        rec_fetch(gk, ir);
 #pragma unroll 1
-        for (int k = N; k >= 0; k--)
+        for (int k = N; k >= 0; k--, gk -= HEAD)
         {
             double* R = buf[ir];
             rec_wait(ir);
-            if (k > 0) rec_fetch(k - 1, in);
+            if (k > 0) rec_fetch(gk - HEAD, in);
             if (k == 0) mask_stage0(R);
             const int i = lane;
             double zi = 0.0;
@@ -916,7 +917,7 @@ struct WarpSolver {
                 const double bm = shfl(zi, m);
                 if (i > m && i < NV) zi -= L[i * NV + m] * bm;
             }
-            if (i < NV) rec_g(k)[obv + i] = zi;
+            if (i < NV) gk[obv + i] = zi;
 #pragma unroll
             for (int j = 0; j < NX; j++) pn[j] = shfl(zi, NU + j);
             { const int t = ir; ir = in; in = t; }
