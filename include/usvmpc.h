@@ -112,6 +112,10 @@ int usvmpc_dims_get_from_attr(usvmpc_solver* s, int stage, const char* field);
 /* replaces ocp_nlp_get(..."sqp_iter"|"res_*"|"statistics"...) (ocp_nlp_interface.c:935): value [B][USVMPC_NSTAT] */
 int usvmpc_get_stats(usvmpc_solver* s, double* value, int on_device, void* stream);
 
+/* replaces ocp_nlp_eval_cost + ocp_nlp_get(..."cost_value"...) (ocp_nlp_interface.c:919,935): LINEAR_LS cost of the
+ * current iterate, value [B] */
+int usvmpc_eval_cost(usvmpc_solver* s, double* value, int on_device, void* stream);
+
 /* replaces ocp_nlp_solver_opts_set (ocp_nlp_interface.c:943).  Fields: "max_iter", "qp_iter_max", "tol_stat",
  * "tol_eq", "tol_ineq", "tol_comp", "nlp_solver_type" (0/1), "cold_start" (extension: 1 = every solve starts from
  * x_k = x0, u = 0, pi = 0 instead of the previous iterate), "print_level", "rti_phase" (0 only), "step_length" (1 only) */

@@ -94,6 +94,40 @@ __global__ void broadcast_kernel(double* dst, const double* src, int B, int nst,
     }
 }
 
+// LINEAR_LS cost of the current iterate, one thread per instance: sum_k dt/2 ||[x_k;u_k] - yref_k||^2_W + 1/2 ||x_N - yref_e||^2_We
+// (ocp_nlp_cost_ls_compute_fun, acados/ocp_nlp/ocp_nlp_cost_ls.c:847; stage scaling dt, acados_solver.in.c:806-810)
+__global__ void eval_cost_kernel(Params P, int nx, int nu, double* out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int ny = nx + nu, N = P.N;
+    const double* W = P.cst;
+    const double* We = P.cst + ny * ny;
+    const double* w = P.ws + (long) b * P.ws_stride;
+    double cost = 0.0;
+    for (int k = 0; k <= N; k++)
+    {
+        const double* z = w + P.lay.zux.off + (long) k * P.lay.zux.stride;
+        const double* yr = k < N ? P.yref + ((long) b * (P.yref_per_stage ? N : 1) + (P.yref_per_stage ? k : 0)) * ny : P.yref_e + (long) b * nx;
+        const int n = k < N ? ny : nx;
+        double acc = 0.0;
+        for (int i = 0; i < n; i++)
+        {
+            const double ri = (i < nx ? z[nu + i] : z[i - nx]) - yr[i];
+            double wr = 0.0;
+            for (int j = 0; j < n; j++)
+            {
+                const double rj = (j < nx ? z[nu + j] : z[j - nx]) - yr[j];
+                const double wij = k < N ? (i >= j ? W[i + ny * j] : W[j + ny * i]) : (i >= j ? We[i + nx * j] : We[j + nx * i]);
+                wr += wij * rj;
+            }
+            acc += ri * wr;
+        }
+        cost += (k < N ? P.dt : 1.0) * 0.5 * acc;
+    }
+    out[b] = cost;
+}
+
 int grid_for(long n) { long g = (n + 255) / 256; return (int) (g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); }
 
 }  // namespace
@@ -480,6 +514,29 @@ int usvmpc_get_stats(usvmpc_solver* s, double* value, int on_device, void* strea
     cudaStream_t st = (cudaStream_t) stream;
     CU(cudaMemcpyAsync(value, s->d_stats, sizeof(double) * (size_t) s->B * NSTAT, cudaMemcpyDefault, st));
     if (!on_device) CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int usvmpc_eval_cost(usvmpc_solver* s, double* value, int on_device, void* stream)
+{
+    if (!s || !value) return fail(USVMPC_E_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    double* buf = value;
+    if (!on_device)
+    {
+        int rc = need_stage_buf(s, sizeof(double) * (size_t) s->B);
+        if (rc) return rc;
+        buf = s->d_stage;
+    }
+    eval_cost_kernel<<<(s->B + 127) / 128, 128, 0, st>>>(s->P, s->nx, s->nu, buf);
+    CU(cudaGetLastError());
+    s->launches++;
+    if (!on_device)
+    {
+        CU(cudaMemcpyAsync(value, buf, sizeof(double) * (size_t) s->B, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

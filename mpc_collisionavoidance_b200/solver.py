@@ -247,6 +247,12 @@ class BatchedAcadosOcpSolver:
         r = self.stats_table()[:, 3:7]
         return r[0] if self.unbatched else r
 
+    def get_cost(self):
+        """cost value of the current solution per instance ([B]; float unbatched), like AcadosOcpSolver.get_cost (:878)"""
+        out = np.zeros(self.B)
+        _lib.check(self.lib.usvmpc_eval_cost(self.h, C.c_void_p(out.ctypes.data), 0, self._stream()), "get_cost")
+        return float(out[0]) if self.unbatched else out
+
     def options_set(self, field_, value_):
         if field_ == "globalization":
             if value_ != "fixed_step":

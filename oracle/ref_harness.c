@@ -515,6 +515,10 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
         }
     }
     ocp_nlp_cost_model_set(c->config, c->dims, c->in, N, "yref", (void *) yref_e);
+    /* every solve starts from the state of a freshly created solver: x, u, pi as given, multipliers and slacks of
+     * the inequalities zero.  (The SQP update blends lam, t as (1-alpha)*old + alpha*qp: a NaN left behind by a
+     * diverged instance would otherwise survive 0*NaN and poison every later instance solved with this context.) */
+    static const double zeros_ineq[2 * (MAXNX + 8 + MAXK)] = {0};
     for (int i = 0; i <= N; i++)
     {
         ocp_nlp_out_set(c->config, c->dims, c->out, i, "x", (void *) (xinit ? xinit + i * nx : x0));
@@ -523,6 +527,8 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
             ocp_nlp_out_set(c->config, c->dims, c->out, i, "u", (void *) (uinit ? uinit + i * nu : zeros));
             ocp_nlp_out_set(c->config, c->dims, c->out, i, "pi", (void *) (piinit ? piinit + i * nx : zeros));
         }
+        ocp_nlp_out_set(c->config, c->dims, c->out, i, "lam", (void *) zeros_ineq);
+        ocp_nlp_out_set(c->config, c->dims, c->out, i, "t", (void *) zeros_ineq);
     }
     g_tap.ipm_iters = 0; g_tap.lq_calls = 0; g_tap.solve_calls = 0; g_tap.calls = 0; g_tap.got = 0;
     int status = ocp_nlp_solve(c->solver, c->in, c->out);
@@ -602,6 +608,9 @@ static double now_s(void)
 typedef struct
 {
     void *ctx;
+    /* creation arguments, kept to re-create the context after a failed solve (see batch_worker) */
+    const int *c_icfg, *c_idxbx;
+    const double *c_dcfg, *c_W, *c_We, *c_lbu, *c_ubu, *c_lbx, *c_ubx;
     int B, N, K, nx, nu, p_per_stage, lh_per_stage, yref_per_stage;
     long sp, slh, sy;
     const double *x0, *p, *lh, *yref, *yref_e;
@@ -616,10 +625,18 @@ static void *batch_worker(void *arg)
     {
         int i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
         if (i >= j->B) break;
-        usvref_solve(j->ctx, j->x0 + (long) i * j->nx, j->p + i * j->sp, j->p_per_stage, j->lh + i * j->slh,
-                     j->lh_per_stage, j->yref + i * j->sy, j->yref_per_stage, j->yref_e + (long) i * j->nx, NULL, NULL,
-                     NULL, j->x_out + (long) i * (j->N + 1) * j->nx, j->u_out + (long) i * j->N * j->nu, NULL, NULL,
-                     NULL, j->stats + (long) i * 9);
+        int st = usvref_solve(j->ctx, j->x0 + (long) i * j->nx, j->p + i * j->sp, j->p_per_stage, j->lh + i * j->slh,
+                              j->lh_per_stage, j->yref + i * j->sy, j->yref_per_stage, j->yref_e + (long) i * j->nx, NULL,
+                              NULL, NULL, j->x_out + (long) i * (j->N + 1) * j->nx, j->u_out + (long) i * j->N * j->nu,
+                              NULL, NULL, NULL, j->stats + (long) i * 9);
+        if (st != 0 && st != 2)
+        {
+            /* a QP failure (NaN / minimum step) leaves non-finite values in the reference's QP-solver memory and every
+             * later solve with this context fails in its first QP: what a user of the reference has to do then is
+             * to create the solver again, so that is what the harness does (observed: instance 414 of config 2). */
+            usvref_free(j->ctx);
+            j->ctx = usvref_create(j->c_icfg, j->c_dcfg, j->c_W, j->c_We, j->c_lbu, j->c_ubu, j->c_idxbx, j->c_lbx, j->c_ubx);
+        }
     }
     return NULL;
 }
@@ -643,6 +660,8 @@ double usvref_solve_batch(const int *icfg, const double *dcfg, const double *W, 
     {
         batch_job *j = &jobs[t];
         j->ctx = usvref_create(icfg, dcfg, W, We, lbu, ubu, idxbx, lbx, ubx);
+        j->c_icfg = icfg; j->c_dcfg = dcfg; j->c_W = W; j->c_We = We; j->c_lbu = lbu; j->c_ubu = ubu;
+        j->c_idxbx = idxbx; j->c_lbx = lbx; j->c_ubx = ubx;
         j->B = B; j->N = N; j->K = K; j->nx = nx; j->nu = nu;
         j->p_per_stage = p_per_stage; j->lh_per_stage = lh_per_stage; j->yref_per_stage = yref_per_stage;
         j->sp = (long) (p_per_stage ? (N + 1) : 1) * np; j->slh = (long) (lh_per_stage ? N : 1) * K;

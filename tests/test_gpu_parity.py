@@ -227,3 +227,33 @@ def test_closed_loop_rti_against_oracle():
             np.testing.assert_allclose(U[i, k], r["u"][0], rtol=1e-6, atol=1e-6 * 35)
             np.testing.assert_allclose(X[i, k + 1], r["x"][1], rtol=1e-6, atol=1e-6)
             x, xi, ui, pii = r["x"][1].copy(), r["x"], r["u"], r["pi"]
+
+
+def test_get_cost_matches_numpy():
+    # the reference's own check (test_ocp_setting.py:336-362): get_cost() vs a numpy recomputation, 1e-10 relative
+    b = make_batch(1, B=5, seed=3)
+    P = rh.RefProblem(N=20, K=3, num_steps=1)
+    r = engine_solve(P, b.x0, b.p, b.lh, b.yref, b.yref_e)
+    cost = r["solver"].get_cost()
+    W, We, dt = np.array(P.W), np.array(P.We), P.dt
+    for i in range(5):
+        c = 0.0
+        for k in range(20):
+            y = np.concatenate([r["x"][i, k], r["u"][i, k]]) - b.yref[i]
+            c += 0.5 * dt * y @ W @ y
+        ye = r["x"][i, 20] - b.yref_e[i]
+        c += 0.5 * ye @ We @ ye
+        assert abs(cost[i] - c) <= 1e-10 * max(1.0, abs(c))
+
+
+def test_long_horizon_config4_shape():
+    # BASELINE.json config 4 shape (N=100, 5 obstacles) in fp64 against the oracle on a small batch
+    b = make_batch(4, B=6, seed=44)
+    P = rh.RefProblem(N=100, K=5, num_steps=4, max_iter=40)
+    a = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=6)
+    r = engine_solve(P, b.x0, b.p, b.lh, b.yref, b.yref_e)
+    ok = a["status"] == 0
+    assert ok.any() and (r["status"][ok] == 0).all()
+    for k in ("x", "u"):
+        good, worst = _close(r[k], a[k], ok)
+        assert good, (k, worst)
