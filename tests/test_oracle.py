@@ -135,16 +135,18 @@ def test_live_reference_stack_agrees():
 
 @pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built (needs /root/reference: make -C oracle ref)")
 def test_live_reference_stack_agrees_through_a_qp_failure():
-    # the first 512 scenes of config 2 contain instance 414, on which the reference's first QP step diverges
-    # (ACADOS_QP_FAILURE); the harness re-creates the reference solver after such a failure (its QP memory keeps
-    # non-finite values otherwise) and every later instance must still agree with the restatement
-    b = make_batch(2, B=512)
+    # instance 414 of the headline batch (config 2, default seed) is one on which the reference's first QP step
+    # diverges (ACADOS_QP_FAILURE); the harness re-creates the reference solver after such a failure (its QP memory
+    # keeps non-finite values otherwise) and every later instance must still agree with the restatement
+    full = make_batch(2)
+    sl = slice(400, 448)
     P = rh.RefProblem(N=40, K=5, num_steps=4)
-    a = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=8)
-    c = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=8)
-    assert a["status"][414] == 4
+    args = (full.x0[sl], full.p[sl], full.lh[sl], full.yref[sl], full.yref_e[sl])
+    a = rh.solve_batch(P, *args, nthreads=2)
+    c = op.solve_batch(P, *args, nthreads=8)
+    assert a["status"][14] == 4
     np.testing.assert_array_equal(a["status"], c["status"])
     np.testing.assert_array_equal(a["sqp_iter"], c["sqp_iter"])
     ok = a["status"] == 0
-    assert ok.mean() > 0.9
+    assert ok.mean() > 0.8
     assert np.abs(a["x"][ok] - c["x"][ok]).max() < 1e-6
