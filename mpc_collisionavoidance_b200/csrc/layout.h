@@ -17,6 +17,7 @@
 namespace usvmpc {
 
 constexpr int KMAX = 32;     // max obstacles per stage
+constexpr int NSPC = 128;    // stage pitch of the transposed arrays (compile-time so that element offsets fold); N <= 127
 constexpr int NBXMAX = 8;
 constexpr int NBUMAX = 4;
 constexpr int NSTAT = 12;    // per-instance statistics record (doubles)
@@ -84,7 +85,7 @@ inline Layout make_layout(int nx, int nu, int N, int K, int nbx, int nbu)
     Field* fs[] = {&L.BAt, &L.rb, &L.L, &L.Pb, &L.bv};
     for (Field* f : fs) { f->off += L.rec_off; f->stride = L.rec_size; f->es = 1; }
     o += (long) L.rec_size * N1;
-    L.nsp = round_up(N1, 4);
+    L.nsp = NSPC;
     auto tr = [&](Field& f, int dim) { f.off = (int) o; f.stride = 1; f.es = L.nsp; o += (long) dim * L.nsp; };
     tr(L.BAtT, sBA); tr(L.ux, sv); tr(L.pi, sx); tr(L.rg, sv); tr(L.dux, sv); tr(L.dpi, sx); tr(L.rq, sv); tr(L.b, sx);
     tr(L.gxy, sg); tr(L.lam, scq); tr(L.t, scq); tr(L.rd, scq); tr(L.ti, scq); tr(L.rmc, scq); tr(L.dlam, scq);

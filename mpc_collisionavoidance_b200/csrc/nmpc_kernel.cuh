@@ -41,6 +41,12 @@ struct SP {
     MDEV double& operator[](int i) const { return p[(long) i * es]; }
 };
 
+// the same for the transposed arrays, whose element stride is the compile-time constant NSPC
+struct TP {
+    double* p;
+    MDEV double& operator[](int i) const { return p[i * NSPC]; }
+};
+
 template <class M>
 struct WarpSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
@@ -111,6 +117,7 @@ struct WarpSolver {
                y.bv.off - ro == obv && y.rec_size == HEAD;
     }
     MDEV SP F(const Field& f, int k) const { return SP{w + f.off + (long) k * f.stride, f.es}; }
+    MDEV TP FT(const Field& f, int k) const { return TP{w + f.off + k}; }  // transposed fields only
     MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
     MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
     // IPM row of the box on variable c at stage k, or -1
@@ -244,7 +251,8 @@ struct WarpSolver {
                 for (int i = 0; i < NX; i++) { x[i] = xa[i]; s[i] = sa[i]; }
             }
             // BAt = [B'; A'] (nv x nx, column-major): ocp_nlp_dynamics_cont.c:801-804
-            const SP BAt = F(Y.BAt, k), BAtT = F(Y.BAtT, k);  // record head (chain sweeps) and transposed copy (passes)
+            const SP BAt = F(Y.BAt, k);    // record head (chain sweeps)
+            const TP BAtT = FT(Y.BAtT, k);  // transposed copy (passes)
             const int row = col < NX ? NU + col : col - NX;
 #pragma unroll
             for (int i = 0; i < NX; i++) { BAt[row + NV * i] = s[i]; BAtT[row + NV * i] = s[i]; }
@@ -257,7 +265,7 @@ struct WarpSolver {
                     for (int i = 0; i < NX; i++) { BAt[NU + c + NV * i] = (i == c) ? 1.0 : 0.0; BAtT[NU + c + NV * i] = (i == c) ? 1.0 : 0.0; }
                 }
                 const SP zn = F(Y.zux, k + 1);
-                const SP b = F(Y.b, k);
+                const TP b = FT(Y.b, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) b[i] = x[i] - zn[NU + i];  // dyn_fun = phi(x,u) - x_next
             }
@@ -452,14 +460,14 @@ struct WarpSolver {
         const double thr0 = 1e-1, mu0 = 1.0;
         for (int k = lane; k <= N; k += 32)
         {
-            const SP ux = F(Y.ux, k), pi = F(Y.pi, k), lam = F(Y.lam, k), t = F(Y.t, k);
-            const SP d = F(Y.d, k);
+            const TP ux = FT(Y.ux, k), pi = FT(Y.pi, k), lam = FT(Y.lam, k), t = FT(Y.t, k);
+            const TP d = FT(Y.d, k);
             for (int i = 0; i < NV; i++) ux[i] = 0.0;
             for (int i = 0; i < NX; i++) pi[i] = 0.0;
             for (int j = 0; j < 2 * ncq; j++) { lam[j] = 0.0; t[j] = 1.0; }
             {
                 // the first passA applies a zero step: the step starts at zero
-                const SP a = F(Y.dux, k), b = F(Y.dpi, k), c = F(Y.dlam, k), e = F(Y.dt, k);
+                const TP a = FT(Y.dux, k), b = FT(Y.dpi, k), c = FT(Y.dlam, k), e = FT(Y.dt, k);
                 for (int i = 0; i < NV; i++) a[i] = 0.0;
                 for (int i = 0; i < NX; i++) b[i] = 0.0;
                 for (int j = 0; j < 2 * ncq; j++) { c[j] = 0.0; e[j] = 0.0; }
@@ -478,7 +486,7 @@ struct WarpSolver {
                 else if (tu < thr0) { tu = thr0; ux[id] = -d[ncq + j] - thr0; }
                 t[j] = tl; t[ncq + j] = tu;
             }
-            const SP gxy = F(Y.gxy, k);
+            const TP gxy = FT(Y.gxy, k);
             for (int c = 0; c < K; c++)
             {
                 const double v = (k >= 1) ? gxy[c] * ux[HXV] + gxy[K + c] * ux[HYV] : 0.0;
@@ -514,16 +522,16 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            const SP ux = F(Y.ux, k); const SP dux = F(Y.dux, k);
+            const TP ux = FT(Y.ux, k); const TP dux = FT(Y.dux, k);
 #pragma unroll
             for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
             if (k < N)
             {
-                const SP pi = F(Y.pi, k); const SP dpi = F(Y.dpi, k);
+                const TP pi = FT(Y.pi, k); const TP dpi = FT(Y.dpi, k);
 #pragma unroll
                 for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
-                const SP l = F(Y.lam, k), t = F(Y.t, k);
-                const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k);
+                const TP l = FT(Y.lam, k), t = FT(Y.t, k);
+                const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
 #pragma unroll 1
                 for (int r = 0; r < 2 * ncq; r++)
                 {
@@ -542,13 +550,13 @@ struct WarpSolver {
         for (int k = lane; k <= N; k += 32)
         {
             const int cls = stage_class(k);
-            const SP v = F(Y.ux, k), rq = F(Y.rq, k);
+            const TP v = FT(Y.ux, k), rq = FT(Y.rq, k);
             const double* __restrict__ H = Hk(k);
             const SP Lk = F(Y.L, k);
             const double* __restrict__ T = Tp + cls * NE;
 #pragma unroll 1
             for (int e = 0; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
-            double g[NV];
+            double g[NV], dg[NV], gg[NV];  // stationarity residual; additions to the diagonal / to the gradient row
 #pragma unroll
             for (int i = 0; i < NV; i++)
             {
@@ -556,17 +564,19 @@ struct WarpSolver {
 #pragma unroll
                 for (int j = 0; j < NV; j++) acc += H[i + NV * j] * v[j];
                 g[i] = acc + rq[i];
+                dg[i] = 0.0; gg[i] = 0.0;
             }
+            double aYX = 0.0;
             if (k > 0)
             {
-                const SP pm = F(Y.pi, k - 1);
+                const TP pm = FT(Y.pi, k - 1);
 #pragma unroll
                 for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
             }
             if (k < N)
             {
-                const SP l = F(Y.lam, k), tt = F(Y.t, k), cd = F(Y.d, k), pk = F(Y.pi, k);
-                const SP rd = F(Y.rd, k), ti = F(Y.ti, k);
+                const TP l = FT(Y.lam, k), tt = FT(Y.t, k), cd = FT(Y.d, k), pk = FT(Y.pi, k);
+                const TP rd = FT(Y.rd, k), ti = FT(Y.ti, k);
 #pragma unroll 1
                 for (int j = 0; j < nbq; j++)
                 {
@@ -574,8 +584,6 @@ struct WarpSolver {
                     const int id = srvar[j];
                     const double l0 = l[j], l1 = l[ncq + j], t0 = tt[j], t1 = tt[ncq + j], vv = v[id];
                     const double dl = l1 - l0;
-#pragma unroll
-                    for (int i = 0; i < NV; i++) if (i == id) g[i] += dl;
                     const double rd0 = cd[j] + t0 - vv, rd1 = cd[ncq + j] + t1 + vv;
                     rd[j] = rd0; rd[ncq + j] = rd1;
                     const double m0 = l0 * t0, m1 = l1 * t1;
@@ -584,11 +592,12 @@ struct WarpSolver {
                     q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
                     const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
                     ti[j] = ti0; ti[ncq + j] = ti1;
-                    Lk[id * NV + id] += ti0 * l0 + ti1 * l1;
-                    Lk[NV * NV + id] += ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+                    const double Gs = ti0 * l0 + ti1 * l1;
+                    const double gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+#pragma unroll
+                    for (int i = 0; i < NV; i++) if (i == id) { g[i] += dl; dg[i] += Gs; gg[i] += gd; }
                 }
-                const SP gxy = F(Y.gxy, k);
-                double aXX = 0, aYX = 0, aYY = 0, bX = 0, bY = 0;
+                const TP gxy = FT(Y.gxy, k);
 #pragma unroll 1
                 for (int c = 0; c < K; c++)
                 {
@@ -608,17 +617,12 @@ struct WarpSolver {
                     ti[r] = ti0; ti[ncq + r] = ti1;
                     const double Gs = ti0 * l0 + ti1 * l1;
                     const double gd = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
-                    aXX += (gX * Gs) * gX; aYX += (gY * Gs) * gX; aYY += (gY * Gs) * gY;
-                    bX += gd * gX; bY += gd * gY;
+                    dg[HXV] += (gX * Gs) * gX; aYX += (gY * Gs) * gX; dg[HYV] += (gY * Gs) * gY;
+                    gg[HXV] += gd * gX; gg[HYV] += gd * gY;
                 }
-                if (K > 0)
-                {
-                    Lk[HXV * NV + HXV] += aXX; Lk[HYV * NV + HXV] += aYX; Lk[HYV * NV + HYV] += aYY;
-                    Lk[NV * NV + HXV] += bX; Lk[NV * NV + HYV] += bY;
-                }
-                const SP BAt = F(Y.BAtT, k);
-                const SP vn = F(Y.ux, k + 1);
-                const SP cb = F(Y.b, k);
+                const TP BAt = FT(Y.BAtT, k);
+                const TP vn = FT(Y.ux, k + 1);
+                const TP cb = FT(Y.b, k);
                 const SP rb = F(Y.rb, k);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
@@ -639,13 +643,16 @@ struct WarpSolver {
                     g[i] += acc;
                 }
             }
-            const SP rg = F(Y.rg, k);
+            const TP rg = FT(Y.rg, k);
+            if (K > 0 && k < N) Lk[HYV * NV + HXV] = T[HYV * (HYV + 1) / 2 + HXV] + aYX;
 #pragma unroll
             for (int i = 0; i < NV; i++)
             {
                 const double gi = var_active(k, i) ? g[i] : 0.0;
                 rg[i] = gi;
-                Lk[NV * NV + i] += gi;
+                // finish the matrix to factorise: diagonal = template + Gamma terms, gradient row = rg + gamma terms
+                Lk[i * NV + i] = T[i * (i + 1) / 2 + i] + dg[i];
+                Lk[NV * NV + i] = gi + gg[i];
                 const double q = dabs(gi);
                 n0 = q > n0 ? q : n0;
             }
@@ -849,7 +856,7 @@ struct WarpSolver {
                 zu[i] = (au + ax) * L[i * NV + NV - 1];
                 if (k == N) zu[i] = 0.0;
             }
-            const SP g = F(Y.dux, k);
+            const TP g = FT(Y.dux, k);
             if (lane < NX) g[NU + lane] = xme;
             if (lane == 0)
             {
@@ -933,16 +940,16 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            const SP rg = F(Y.rg, k);
+            const TP rg = FT(Y.rg, k);
             const SP bv = F(Y.bv, k);
             double z[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++) z[i] = rg[i];
             if (k < N)
             {
-                const SP lam = F(Y.lam, k), t = F(Y.t, k), ti = F(Y.ti, k), rd = F(Y.rd, k);
-                const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k), gxy = F(Y.gxy, k);
-                const SP rm = F(Y.rmc, k);
+                const TP lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
+                const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k), gxy = FT(Y.gxy, k);
+                const TP rm = FT(Y.rmc, k);
 #pragma unroll 1
                 for (int j = 0; j < ncq; j++)
                 {
@@ -976,9 +983,9 @@ struct WarpSolver {
 #pragma unroll 1
         for (int k = lane; k < N; k += 32)
         {
-            const SP v = F(Y.dux, k), lam = F(Y.lam, k), t = F(Y.t, k), ti = F(Y.ti, k), rd = F(Y.rd, k);
-            const SP rm = F(Y.rmc, k), gxy = F(Y.gxy, k);
-            const SP dl = F(Y.dlam, k), dtt = F(Y.dt, k);
+            const TP v = FT(Y.dux, k), lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
+            const TP rm = FT(Y.rmc, k), gxy = FT(Y.gxy, k);
+            const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
 #pragma unroll 1
             for (int j = 0; j < ncq; j++)
             {
@@ -1007,8 +1014,8 @@ struct WarpSolver {
             // dpi_k from the factor of stage k+1
             const SP Ln = F(Y.L, k + 1);
             const SP bn = F(Y.bv, k + 1);
-            const SP xn = F(Y.dux, k + 1);
-            const SP dpi = F(Y.dpi, k);
+            const TP xn = FT(Y.dux, k + 1);
+            const TP dpi = FT(Y.dpi, k);
             double tmp[NX];
 #pragma unroll
             for (int j = 0; j < NX; j++)
@@ -1081,18 +1088,18 @@ struct WarpSolver {
             }
             // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN); iterative refinement is rare
             double nlin[4];
-            res_pass<true, false>(nlin);
+            res_pass<false>(nlin);
             bool refined = false;
             for (int it = 0; it < 2; it++)
             {
                 if (itref_ok(nlin)) break;
-                res_pass<true, true>(nlin);
+                res_pass<true>(nlin);
                 solve_sweep(true);
                 forward_sweep(Y.rb2, Y.dux2, Y.dpi2, false);
                 expand_pass(2, 0.0);
                 add_refinement();
                 refined = true;
-                res_pass<true, false>(nlin);
+                res_pass<false>(nlin);
             }
             if (refined) alpha_pass();
             a = alpha;
@@ -1107,21 +1114,19 @@ struct WarpSolver {
     }
 
     // ---------------------------------------------------------------- IPM: rare path (iterative refinement), straight from HBM
-    // QP residuals.  LIN = false: OCP_QP_RES_COMPUTE (HP/ocp_qp/x_ocp_qp_res.c:336-466) at the iterate (ux,pi,lam,t)
-    // -> (rg,rb,rd), norms into out4, mu.  LIN = true: OCP_QP_RES_COMPUTE_LIN (:468-592): residual of the Newton
-    // system with right-hand side (rg,rb,rd,rmc) at the step (dux,dpi,dlam,dt) -> (rg2,rb2,rd2,rm2).
-    template <bool LIN, bool WRITE>
+    // OCP_QP_RES_COMPUTE_LIN (HP/ocp_qp/x_ocp_qp_res.c:468-633): residual of the Newton system with right-hand side
+    // (rg, rb, rd, rmc) at the step (dux, dpi, dlam, dt); norms into out4.  WRITE: also store it (rg2, rb2, rd2, rm2) as
+    // the right-hand side of an iterative-refinement solve.
+    template <bool WRITE>
     MDEV void res_pass(double* out4)
     {
-        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
-        const Field &fv = LIN ? Y.dux : Y.ux, &fp = LIN ? Y.dpi : Y.pi, &fl = LIN ? Y.dlam : Y.lam, &ft = LIN ? Y.dt : Y.t;
-        const Field &og = LIN ? Y.rg2 : Y.rg, &ob = LIN ? Y.rb2 : Y.rb, &od = LIN ? Y.rd2 : Y.rd;
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         for (int k = lane; k <= N; k += 32)
         {
-            const SP v = F(fv, k), pk = F(fp, k), l = F(fl, k), tt = F(ft, k);
+            const TP v = FT(Y.dux, k), pk = FT(Y.dpi, k), l = FT(Y.dlam, k), tt = FT(Y.dt, k);
             const double* H = Hk(k);
-            const SP cg = LIN ? F(Y.rg, k) : F(Y.rq, k), cd = LIN ? F(Y.rd, k) : F(Y.d, k);
-            const SP rg = F(og, k), rd = F(od, k);
+            const TP cg = FT(Y.rg, k), cd = FT(Y.rd, k);
+            const SP rg = F(Y.rg2, k), rd = F(Y.rd2, k);
             double g[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++)
@@ -1133,7 +1138,7 @@ struct WarpSolver {
             }
             if (k > 0)
             {
-                const SP pm = F(fp, k - 1);
+                const TP pm = FT(Y.dpi, k - 1);
 #pragma unroll
                 for (int i = 0; i < NX; i++) g[NU + i] -= pm[i];
             }
@@ -1150,7 +1155,7 @@ struct WarpSolver {
                     if (WRITE) { rd[j] = e0; rd[ncq + j] = e1; }
                     { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
-                const SP gxy = F(Y.gxy, k);
+                const TP gxy = FT(Y.gxy, k);
                 for (int c = 0; c < K; c++)
                 {
                     const int r = nbq + c;
@@ -1162,10 +1167,10 @@ struct WarpSolver {
                     if (WRITE) { rd[r] = e0; rd[ncq + r] = e1; }
                     { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
                 }
-                const SP BAt = F(Y.BAtT, k);
-                const SP vn = F(fv, k + 1);
-                const SP cb = LIN ? F(Y.rb, k) : F(Y.b, k);
-                const SP rb = F(ob, k);
+                const TP BAt = FT(Y.BAtT, k);
+                const TP vn = FT(Y.dux, k + 1);
+                const SP cb = F(Y.rb, k);
+                const SP rb = F(Y.rb2, k);
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -1184,26 +1189,14 @@ struct WarpSolver {
                     for (int j = 0; j < NX; j++) acc += BAt[i + NV * j] * pk[j];
                     g[i] += acc;
                 }
-                if (LIN)
                 {
-                    const SP lam = F(Y.lam, k), t = F(Y.t, k), rm = F(Y.rmc, k);
+                    const TP lam = FT(Y.lam, k), t = FT(Y.t, k), rm = FT(Y.rmc, k);
                     const SP rm2 = F(Y.rm2, k);
                     for (int j = 0; j < 2 * ncq; j++)
                     {
                         if (!row_active(k, j % ncq)) { if (WRITE) rm2[j] = 0.0; continue; }
                         const double m = rm[j] + lam[j] * tt[j] + l[j] * t[j];
                         if (WRITE) rm2[j] = m;
-                        const double a = dabs(m);
-                        n3 = a > n3 ? a : n3;
-                    }
-                }
-                else
-                {
-                    for (int j = 0; j < 2 * ncq; j++)
-                    {
-                        if (!row_active(k, j % ncq)) continue;
-                        const double m = l[j] * tt[j];
-                        musum += m;
                         const double a = dabs(m);
                         n3 = a > n3 ? a : n3;
                     }
@@ -1219,7 +1212,6 @@ struct WarpSolver {
             }
         }
         out4[0] = warp_max(n0); out4[1] = warp_max(n1); out4[2] = warp_max(n2); out4[3] = warp_max(n3);
-        if (!LIN) mu = warp_sum(musum) / nct;
         syncwarp();
     }
 

@@ -334,6 +334,7 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
     int nx, nu;
     if (model_dims(cfg->model, &nx, &nu)) return fail(USVMPC_E_INVALID, "unknown model %d", cfg->model);
     if (batch < 1 || cfg->N < 1) return fail(USVMPC_E_INVALID, "batch and N must be >= 1");
+    if (cfg->N + 1 > NSPC) return fail(USVMPC_E_INVALID, "N=%d: the engine is built for horizons up to %d", cfg->N, NSPC - 1);
     if (cfg->K < 0 || cfg->K > KMAX) return fail(USVMPC_E_INVALID, "K=%d outside [0,%d]", cfg->K, KMAX);
     if (cfg->nbx < 0 || cfg->nbx > nx || cfg->nbu < 0 || cfg->nbu > nu) return fail(USVMPC_E_INVALID, "nbx/nbu out of range");
     if (cfg->num_stages != 1 && cfg->num_stages != 2 && cfg->num_stages != 4) return fail(USVMPC_E_INVALID, "ERK num_stages must be 1, 2 or 4");
