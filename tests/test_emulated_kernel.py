@@ -96,3 +96,14 @@ def test_per_stage_inputs():
     np.testing.assert_array_equal(a["status"], c["status"])
     np.testing.assert_array_equal(a["qp_iter"], c["qp_iter"])
     assert np.abs(a["x"] - c["x"]).max() < 1e-8
+
+
+def test_long_horizon_four_pass_rounds():
+    # N = 100: 101 stages = four rounds of the one-lane-per-stage passes
+    b = make_batch(4, B=2, seed=44)
+    P = rh.RefProblem(N=100, K=5, num_steps=4, nlp_type=1)
+    a = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=2)
+    c = ep.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=2)
+    np.testing.assert_array_equal(a["status"], c["status"])
+    np.testing.assert_array_equal(a["qp_iter"], c["qp_iter"])
+    assert np.abs(a["x"] - c["x"]).max() < 1e-7 and np.abs(a["u"] - c["u"]).max() < 1e-6

@@ -247,13 +247,18 @@ def test_get_cost_matches_numpy():
 
 
 def test_long_horizon_config4_shape():
-    # BASELINE.json config 4 shape (N=100, 5 obstacles) in fp64 against the oracle on a small batch
+    # BASELINE.json config 4 shape (N=100, 5 obstacles) in fp64: 101 stages = four rounds of the lane-per-stage
+    # passes.  From a cold start the full-step SQP of the reference does not converge on these scenes (the oracle
+    # returns MAXITER), so parity is checked where the iterates are still deterministic: one SQP_RTI step and the
+    # iterate after 3 SQP iterations, status class included.
     b = make_batch(4, B=6, seed=44)
-    P = rh.RefProblem(N=100, K=5, num_steps=4, max_iter=40)
-    a = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=6)
-    r = engine_solve(P, b.x0, b.p, b.lh, b.yref, b.yref_e)
-    ok = a["status"] == 0
-    assert ok.any() and (r["status"][ok] == 0).all()
-    for k in ("x", "u"):
-        good, worst = _close(r[k], a[k], ok)
-        assert good, (k, worst)
+    for nlp_type, max_iter in ((1, 1), (0, 3)):
+        P = rh.RefProblem(N=100, K=5, num_steps=4, nlp_type=nlp_type, max_iter=max_iter)
+        a = op.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=6)
+        r = engine_solve(P, b.x0, b.p, b.lh, b.yref, b.yref_e)
+        np.testing.assert_array_equal(r["status"], a["status"])
+        np.testing.assert_array_equal(r["qp_iter"], a["qp_iter"])
+        every = np.ones(6, dtype=bool)
+        for k in ("x", "u"):
+            good, worst = _close(r[k], a[k], every)
+            assert good, (nlp_type, k, worst)
