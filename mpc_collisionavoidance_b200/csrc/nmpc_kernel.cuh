@@ -789,10 +789,10 @@ struct WarpSolver {
             // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).  Lane r <= NV takes row r
             // into registers; pivots and multipliers travel by shuffle.
             {
-                const int r = lane <= NV ? lane : NV;
+                const int r = lane;
                 double Mr[NV], dinv = 0.0;
 #pragma unroll
-                for (int c = 0; c < NV; c++) Mr[c] = Mx[r * NV + c];
+                for (int c = 0; c < NV; c++) Mr[c] = r <= NV ? Mx[r * NV + c] : 0.0;
 #pragma unroll
                 for (int j = 0; j < NV; j++)
                 {
@@ -841,6 +841,7 @@ struct WarpSolver {
         {
             double* R = buf[ir];
             rec_wait(ir);
+            syncwarp();  // every lane is done with the other buffer before it becomes a copy destination again
             if (k < N) rec_fetch(gk + HEAD, in);
             if (k == 0) mask_stage0(R);
             const double* L = R + oL;
@@ -900,6 +901,7 @@ struct WarpSolver {
         {
             double* R = buf[ir];
             rec_wait(ir);
+            syncwarp();  // every lane is done with the other buffer before it becomes a copy destination again
             if (k > 0) rec_fetch(gk - HEAD, in);
             if (k == 0) mask_stage0(R);
             const int i = lane;
