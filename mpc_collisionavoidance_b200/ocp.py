@@ -144,3 +144,62 @@ def config_from_ocp(ocp):
             raise Exception("uh must have one (common) value per obstacle row")
         cfg.uh = float(uh[0])
     return cfg, model, nx, nu
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# acados JSON problem description: the on-disk format the reference writes with
+# ocp_formulation_json_dump (acados_template/acados_ocp_solver.py:416-444): one dict per description class, attribute
+# names without the class prefix, numpy arrays as nested lists; x0 appears as constraints.lbx_0 / ubx_0.
+_JSON_FIELDS = {
+    "cost": ["cost_type", "cost_type_e", "W", "W_e", "Vx", "Vu", "Vx_e", "yref", "yref_e"],
+    "constraints": ["constr_type", "lbu", "ubu", "idxbu", "lbx", "ubx", "idxbx", "lh", "uh"],
+    "solver_options": ["qp_solver", "hessian_approx", "integrator_type", "tf", "nlp_solver_type", "nlp_solver_step_length",
+                       "sim_method_num_stages", "sim_method_num_steps", "qp_solver_iter_max", "nlp_solver_tol_stat",
+                       "nlp_solver_tol_eq", "nlp_solver_tol_ineq", "nlp_solver_tol_comp", "nlp_solver_max_iter", "print_level"],
+}
+
+
+def ocp_to_dict(ocp):
+    """AcadosOcp description -> dict in the layout of the reference's acados_ocp_nlp.json"""
+    tolist = lambda v: v.tolist() if isinstance(v, np.ndarray) else v
+    d = {"model": {"name": ocp.model.name}, "dims": {"N": ocp.dims.N, "nh": int(len(_arr(ocp.constraints.lh)))},
+         "parameter_values": tolist(np.asarray(ocp.parameter_values))}
+    for sec, names in _JSON_FIELDS.items():
+        obj = getattr(ocp, sec)
+        d[sec] = {n: tolist(getattr(obj, n, None)) for n in names}
+    if ocp.constraints.x0 is not None:
+        x0 = np.asarray(ocp.constraints.x0, dtype=float)
+        d["constraints"].update(lbx_0=x0.tolist(), ubx_0=x0.tolist(), idxbx_0=list(range(len(x0))))
+    return d
+
+
+def ocp_from_dict(d):
+    """dict in the layout of acados_ocp_nlp.json (as written by the reference or by ocp_to_dict) -> AcadosOcp"""
+    ocp = AcadosOcp()
+    ocp.model.name = d.get("model", {}).get("name", "usv3")
+    ocp.dims.N = d["dims"]["N"]
+    for sec, names in _JSON_FIELDS.items():
+        obj, src = getattr(ocp, sec), d.get(sec, {})
+        for n in names:
+            if n in src and src[n] is not None:
+                v = src[n]
+                setattr(obj, n, np.asarray(v) if isinstance(v, list) else v)
+    c = d.get("constraints", {})
+    if c.get("lbx_0") is not None and len(c["lbx_0"]):
+        if c.get("ubx_0") is not None and not np.array_equal(np.asarray(c["lbx_0"]), np.asarray(c["ubx_0"])):
+            raise Exception("lbx_0 != ubx_0: only a fixed initial state is implemented")
+        ocp.constraints.x0 = np.asarray(c["lbx_0"], dtype=float)
+    ocp.parameter_values = np.asarray(d.get("parameter_values", []), dtype=float)
+    return ocp
+
+
+def ocp_formulation_json_dump(acados_ocp, json_file="acados_ocp_nlp.json"):
+    import json
+    with open(json_file, "w") as f:
+        json.dump(ocp_to_dict(acados_ocp), f, indent=4, sort_keys=True)
+
+
+def ocp_formulation_json_load(json_file="acados_ocp_nlp.json"):
+    import json
+    with open(json_file) as f:
+        return ocp_from_dict(json.load(f))

@@ -70,3 +70,19 @@ def test_no_cpu_fallback(lib):
     from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
     with pytest.raises(Exception, match="CUDA|cuda"):
         BatchedAcadosOcpSolver(ocp_from_problem(rh.RefProblem(N=20, K=3)), batch=4)
+
+
+def test_json_description_round_trip(lib, tmp_path):
+    # acados_ocp_nlp.json layout (acados_ocp_solver.py:416-444): description -> json -> description -> same config
+    from mpc_collisionavoidance_b200.ocp import ocp_formulation_json_dump, ocp_formulation_json_load
+    from mpc_collisionavoidance_b200.workloads import benchmark_ocp
+    ocp = benchmark_ocp(2)
+    f = str(tmp_path / "acados_ocp_nlp.json")
+    ocp_formulation_json_dump(ocp, f)
+    back = ocp_formulation_json_load(f)
+    a, b = config_from_ocp(ocp)[0], config_from_ocp(back)[0]
+    assert bytes(a) == bytes(b)
+    np.testing.assert_array_equal(back.constraints.x0, ocp.constraints.x0)
+    import json
+    d = json.load(open(f))
+    assert d["constraints"]["lbx_0"] == d["constraints"]["ubx_0"] and d["solver_options"]["nlp_solver_type"] == "SQP"
