@@ -111,7 +111,6 @@ inline int warp_smem_doubles(int nx, int nu, int N, int K, int nbx, int nbu)
     n += nv * nv + nx * nx;    // Ws, Wes
     n += 3 * ne;               // Tp
     n += (nv + 1) * nx;        // sAL
-    n += 3 * nq + nx;          // sGs, sgd, sdl, sz
     n += (ne + nq + nv + nx + 1) / 2 + 16;  // int tables + alignment slack
     (void) ncq2;
     return (n + 1) / 2 * 2;

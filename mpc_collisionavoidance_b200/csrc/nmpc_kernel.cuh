@@ -58,16 +58,16 @@ struct WarpSolver {
     static constexpr int HEAD = obv + svv;  // what the chain sweeps stream: [B';A'] rb L Pb bv
     // per-warp shared-memory scratch: fixed-size part at compile-time offsets
     static constexpr int qHs = 0, qHes = qHs + NV * NV, qWs = qHes + NV * NV, qWes = qWs + NV * NV, qTp = qWes + NX * NX;
-    static constexpr int qAL = qTp + 3 * NE, qz = qAL + NR * NX, qent = qz + sxx, qvrow = qent + (NE + 1) / 2;
-    static constexpr int qxrow = qvrow + (NV + 1) / 2, qvar = qxrow + (NX + 1) / 2;
+    static constexpr int qAL = qTp + 3 * NE, qent = qAL + (NR * NX + 1) / 2 * 2, qxrow = qent + (NE + 1) / 2;
+    static constexpr int qvar = qxrow + (NX + 1) / 2;
 
     const Params& P;
     const Layout& Y;
     int lane, N, K, nbu, nbx, ncq, ncz, nbq, nct;
     double* w;
     // shared-memory scratch of this warp
-    double *Hs, *Hes, *Ws, *Wes, *Tp, *sAL, *sGs, *sgd, *sdl, *sz;
-    int *sent, *srvar, *svrow, *sxrow;
+    double *Hs, *Hes, *Ws, *Wes, *Tp, *sAL;
+    int *sent, *srvar, *sxrow;
     double *sBA, *sLn, *slx, *sG, *sg, *sL, *sq, *sx1, *sx2, *sgxy;  // rare path, aliased onto the record buffers
     // the two record buffers of the streaming sweeps and the offsets of the record's fields (layout.h)
     double* buf[3];
@@ -89,11 +89,11 @@ struct WarpSolver {
         nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
         w = P.ws + (long) inst * P.ws_stride;
         double* s = sm;
-        Hs = s + qHs; Hes = s + qHes; Ws = s + qWs; Wes = s + qWes; Tp = s + qTp; sAL = s + qAL; sz = s + qz;
-        sent = (int*) (s + qent); svrow = (int*) (s + qvrow); sxrow = (int*) (s + qxrow);
+        Hs = s + qHs; Hes = s + qHes; Ws = s + qWs; Wes = s + qWes; Tp = s + qTp; sAL = s + qAL;
+        sent = (int*) (s + qent); sxrow = (int*) (s + qxrow);
         const int nq = NU + NX + K;
         s += qvar;
-        srvar = (int*) s; s += (nq + 1) / 2; sGs = s; s += nq; sgd = s; s += nq; sdl = s; s += nq;
+        srvar = (int*) s; s += (nq + 1) / 2;
         s = sm + ((s - sm) + 1) / 2 * 2;
         buf[0] = s; s += HEAD; buf[1] = s; s += HEAD; buf[2] = s; s += HEAD;
         bar = (unsigned long long*) s; s += 4;
@@ -155,8 +155,8 @@ struct WarpSolver {
             sxrow[lane] = r;
         }
         syncwarp();
-        // tables of the streaming sweeps: lower-trapezoid entries e -> (r, c, offset); row pair -> boxed variable
-        // (or -1: h row); variable -> row pair of its box (or -1); factor templates per stage class
+        // tables: lower-trapezoid entries e -> (r, c, offset); row pair -> boxed variable (or -1: h row); templates of
+        // the matrix to factorise per stage class
         for (int e = lane; e < NE; e += 32)
         {
             int r = 0;
@@ -177,7 +177,6 @@ struct WarpSolver {
             }
         }
         for (int jj = lane; jj < ncq; jj += 32) srvar[jj] = jj < nbu ? jj : (jj < nbq ? NU + P.idxbx[jj - nbu] : -1);
-        if (lane < NV) svrow[lane] = lane < NU ? (lane < nbu ? lane : -1) : sxrow[lane - NU];
         syncwarp();
     }
     MDEV const double* Hk(int k) const { return k < N ? Hs : Hes; }
