@@ -936,62 +936,41 @@ struct WarpSolver {
 
     // passC: right-hand side of the corrector / centering solve res_m = lam*t [+ dt_aff*dlam_aff] - sigma_mu
     // (x_ocp_qp_ipm.c:2138-2160, 2175-2200) -> rmc; COMPUTE_GAMMA_QP (x_core_qp_ipm_aux.c:89-113); bv = rhs_g + J'(gamma_l - gamma_u)
-    // The passes below work on TWO stages per lane in lock-step (stage k and stage k+32): the two instruction streams
-    // are independent, so their loads overlap -- a pass is bound by L2 latency, not by issue slots.  When a lane has
-    // no second stage the second stream runs on the first stage's data with its stores and reductions switched off.
     MDEV void passC(bool with_aff, double sigma_mu)
     {
 #pragma unroll 1
-        for (int k0 = lane; k0 <= N; k0 += 64)
+        for (int k = lane; k <= N; k += 32)
         {
-            const bool vb = k0 + 32 <= N;
-            const int kk[2] = {k0, vb ? k0 + 32 : k0};
-            double z[2][NV];
+            const TP rg = FT(Y.rg, k);
+            const SP bv = F(Y.bv, k);
+            double z[NV];
 #pragma unroll
-            for (int s = 0; s < 2; s++)
+            for (int i = 0; i < NV; i++) z[i] = rg[i];
+            if (k < N)
             {
-                const TP rg = FT(Y.rg, kk[s]);
-#pragma unroll
-                for (int i = 0; i < NV; i++) z[s][i] = rg[i];
-            }
+                const TP lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
+                const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k), gxy = FT(Y.gxy, k);
+                const TP rm = FT(Y.rmc, k);
 #pragma unroll 1
-            for (int j = 0; j < ncq; j++)
-            {
-#pragma unroll
-                for (int s = 0; s < 2; s++)
+                for (int j = 0; j < ncq; j++)
                 {
-                    const int k = kk[s];
-                    const bool on = (s == 0 || vb) && k < N;
-                    const bool act = on && row_active(k, j);
-                    const int kl = k < N ? k : N - 1;  // a stage whose row arrays exist (loads only)
-                    const TP lam = FT(Y.lam, kl), t = FT(Y.t, kl), ti = FT(Y.ti, kl), rd = FT(Y.rd, kl);
-                    const TP dl = FT(Y.dlam, kl), dtt = FT(Y.dt, kl), gxy = FT(Y.gxy, kl), rm = FT(Y.rmc, kl);
+                    if (!row_active(k, j)) { rm[j] = 0.0; rm[ncq + j] = 0.0; continue; }
                     double m0 = lam[j] * t[j], m1 = lam[ncq + j] * t[ncq + j];
                     if (with_aff) { m0 += dtt[j] * dl[j]; m1 += dtt[ncq + j] * dl[ncq + j]; }
                     m0 -= sigma_mu; m1 -= sigma_mu;
-                    if (!act) { m0 = 0.0; m1 = 0.0; }
-                    if (on) { rm[j] = m0; rm[ncq + j] = m1; }
+                    rm[j] = m0; rm[ncq + j] = m1;
                     const double gd = ti[j] * (m0 - lam[j] * rd[j]) - ti[ncq + j] * (m1 - lam[ncq + j] * rd[ncq + j]);
-                    if (act)
+                    if (j < nbq)
                     {
-                        if (j < nbq)
-                        {
-                            const int id = srvar[j];
+                        const int id = srvar[j];
 #pragma unroll
-                            for (int i = 0; i < NV; i++) if (i == id) z[s][i] += gd;
-                        }
-                        else if (k >= 1) { z[s][HXV] += gxy[j - nbq] * gd; z[s][HYV] += gxy[K + j - nbq] * gd; }
+                        for (int i = 0; i < NV; i++) if (i == id) z[i] += gd;
                     }
+                    else if (k >= 1) { z[HXV] += gxy[j - nbq] * gd; z[HYV] += gxy[K + j - nbq] * gd; }
                 }
             }
 #pragma unroll
-            for (int s = 0; s < 2; s++)
-                if (s == 0 || vb)
-                {
-                    const SP bv = F(Y.bv, kk[s]);
-#pragma unroll
-                    for (int i = 0; i < NV; i++) bv[i] = var_active(kk[s], i) ? z[s][i] : 0.0;
-                }
+            for (int i = 0; i < NV; i++) bv[i] = var_active(k, i) ? z[i] : 0.0;
         }
         syncwarp();
     }
@@ -1003,75 +982,57 @@ struct WarpSolver {
     {
         double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
 #pragma unroll 1
-        for (int k0 = lane; k0 < N; k0 += 64)
+        for (int k = lane; k < N; k += 32)
         {
-            const bool vb = k0 + 32 < N;
-            const int kk[2] = {k0, vb ? k0 + 32 : k0};
+            const TP v = FT(Y.dux, k), lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
+            const TP rm = FT(Y.rmc, k), gxy = FT(Y.gxy, k);
+            const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
 #pragma unroll 1
             for (int j = 0; j < ncq; j++)
             {
+                if (!row_active(k, j)) continue;
+                double dv;
+                if (j < nbq) dv = v[srvar[j]];
+                else dv = k >= 1 ? gxy[j - nbq] * v[HXV] + gxy[K + j - nbq] * v[HYV] : 0.0;
 #pragma unroll
-                for (int s = 0; s < 2; s++)
+                for (int side = 0; side < 2; side++)
                 {
-                    const int k = kk[s];
-                    const bool act = (s == 0 || vb) && row_active(k, j);
-                    const TP v = FT(Y.dux, k), lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
-                    const TP rm = FT(Y.rmc, k), gxy = FT(Y.gxy, k), dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
-                    double dv;
-                    if (j < nbq) dv = v[srvar[j]];
-                    else dv = k >= 1 ? gxy[j - nbq] * v[HXV] + gxy[K + j - nbq] * v[HYV] : 0.0;
-#pragma unroll
-                    for (int side = 0; side < 2; side++)
-                    {
-                        const int r = j + side * ncq;
-                        double dtr = side ? -dv : dv;
-                        const double lam0 = lam[r], t0 = t[r];
-                        const double m = corr ? rm[r] : lam0 * t0 - tau;
-                        const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * rd[r]));
-                        dtr -= rd[r];
-                        if (act)
-                        {
-                            dl[r] = dlr; dtt[r] = dtr;
-                            // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running
-                            // best is kept as (numerator, denominator) and compared by cross-multiplication: one division
-                            // per pass
-                            if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
-                            if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
-                            s1 += lam0 * dtr + t0 * dlr;
-                            s2 += dlr * dtr;
-                        }
-                    }
+                    const int r = j + side * ncq;
+                    double dtr = side ? -dv : dv;
+                    const double lam0 = lam[r], t0 = t[r];
+                    const double m = corr ? rm[r] : lam0 * t0 - tau;
+                    const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * rd[r]));
+                    dtr -= rd[r];
+                    dl[r] = dlr; dtt[r] = dtr;
+                    // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best
+                    // is kept as (numerator, denominator) and compared by cross-multiplication: one division per sweep
+                    if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
+                    if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
+                    s1 += lam0 * dtr + t0 * dlr;
+                    s2 += dlr * dtr;
                 }
             }
             // dpi_k from the factor of stage k+1
-            double tmp[2][NX];
+            const SP Ln = F(Y.L, k + 1);
+            const SP bn = F(Y.bv, k + 1);
+            const TP xn = FT(Y.dux, k + 1);
+            const TP dpi = FT(Y.dpi, k);
+            double tmp[NX];
 #pragma unroll
-            for (int s = 0; s < 2; s++)
+            for (int j = 0; j < NX; j++)
             {
-                const SP Ln = F(Y.L, kk[s] + 1), bn = F(Y.bv, kk[s] + 1);
-                const TP xn = FT(Y.dux, kk[s] + 1);
+                double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < NX; j++)
-                {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int m = j; m < NX; m++) acc += Ln[(NU + m) * NV + NU + j] * xn[NU + m];
-                    tmp[s][j] = corr ? acc : acc + bn[NU + j];
-                }
+                for (int m = j; m < NX; m++) acc += Ln[(NU + m) * NV + NU + j] * xn[NU + m];
+                tmp[j] = corr ? acc : acc + bn[NU + j];
             }
 #pragma unroll
-            for (int s = 0; s < 2; s++)
+            for (int i = 0; i < NX; i++)
             {
-                const SP Ln = F(Y.L, kk[s] + 1), bn = F(Y.bv, kk[s] + 1);
-                const TP dpi = FT(Y.dpi, kk[s]);
+                double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < NX; i++)
-                {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int j = 0; j <= i; j++) acc += Ln[(NU + i) * NV + NU + j] * tmp[s][j];
-                    if (s == 0 || vb) dpi[i] = corr ? bn[NU + i] + acc : acc;
-                }
+                for (int j = 0; j <= i; j++) acc += Ln[(NU + i) * NV + NU + j] * tmp[j];
+                dpi[i] = corr ? bn[NU + i] + acc : acc;
             }
         }
         const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
