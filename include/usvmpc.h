@@ -121,6 +121,14 @@ int usvmpc_eval_cost(usvmpc_solver* s, double* value, int on_device, void* strea
  * x_k = x0, u = 0, pi = 0 instead of the previous iterate), "print_level", "rti_phase" (0 only), "step_length" (1 only) */
 int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value);
 
+/* Obstacle front end of the guidance node (nmpc_ca/src/nmpc_guidance_ca1.cpp:251-363, obstaclesCallback + body2NED):
+ * device pointers only.  pose [B][3] = (nedx, nedy, psi); obs_body [B][max_obs][3] = (x, y, radius) in the body frame;
+ * len [B] = number of valid obstacles per instance.  Writes p_out [B][2K] = (ox_1, oy_1, ...) in NED -- the argument of
+ * usvmpc_update_params -- and r_out [B][K] = radius + boat_radius -- the argument of constraints "lh".  The K obstacles
+ * with the smallest clearance are kept; unused slots hold (init_obs_pos, init_obs_pos, 0). */
+int usvmpc_obstacle_frontend(const double* pose, const double* obs_body, const int* len, int batch, int max_obs, int K,
+                             double boat_radius, double init_obs_pos, double* p_out, double* r_out, void* stream);
+
 /* engine introspection for benchmarks: kernels launched so far, bytes of HBM held, batch, launch geometry */
 int usvmpc_info(usvmpc_solver* s, const char* what, double* value);
 

@@ -23,7 +23,7 @@ class Config(C.Structure):
 SYMBOLS = ["usvmpc_last_error", "usvmpc_version", "usvmpc_config_default", "usvmpc_create", "usvmpc_free",
            "usvmpc_solve", "usvmpc_update_params", "usvmpc_cost_model_set", "usvmpc_constraints_model_set",
            "usvmpc_out_set", "usvmpc_out_get", "usvmpc_dims_get_from_attr", "usvmpc_get_stats",
-           "usvmpc_solver_opts_set", "usvmpc_info", "usvmpc_eval_cost"]
+           "usvmpc_solver_opts_set", "usvmpc_info", "usvmpc_eval_cost", "usvmpc_obstacle_frontend"]
 
 _lib = None
 
@@ -52,6 +52,7 @@ def load():
     lib.usvmpc_get_stats.argtypes = [vp, dp, ci, vp]
     lib.usvmpc_solver_opts_set.argtypes = [vp, cp, C.c_double]
     lib.usvmpc_eval_cost.argtypes = [vp, dp, ci, vp]
+    lib.usvmpc_obstacle_frontend.argtypes = [dp, dp, vp, ci, ci, ci, C.c_double, C.c_double, dp, dp, vp]
     lib.usvmpc_info.argtypes = [vp, cp, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(lib, name)

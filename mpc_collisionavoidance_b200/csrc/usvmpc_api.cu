@@ -128,6 +128,54 @@ __global__ void eval_cost_kernel(Params P, int nx, int nu, double* out)
     out[b] = cost;
 }
 
+// Obstacle front end of the guidance node (nmpc_ca/src/nmpc_guidance_ca1.cpp:251-363): per instance, from up to M
+// obstacles given in the BODY frame as (x, y, radius): inflate by the boat radius, keep the K with the smallest
+// clearance sqrt(x^2+y^2) - radius when there are more than K, rotate/translate to NED with the vessel pose
+// (nedx, nedy, psi), pad with far-away zero-radius obstacles otherwise.  The node does the transform in float
+// (Eigen::Vector3f / Matrix3f); so does this kernel.  One thread per instance.
+__global__ void obstacle_frontend_kernel(const double* pose, const double* obs, const int* len, int B, int M, int K,
+                                         double boat_radius, double init_pos, double* p_out, double* r_out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* o = obs + (long) b * M * 3;
+    const double nedx = pose[b * 3 + 0], nedy = pose[b * 3 + 1], psi = pose[b * 3 + 2];
+    const float c = (float) cos(psi), s = (float) sin(psi);
+    int n = len[b];
+    n = n < 0 ? 0 : (n > M ? M : n);
+    unsigned long long taken = 0ull;  // M <= 64
+    for (int i = 0; i < K; i++)
+    {
+        int pick = -1;
+        if (n > K)
+        {
+            // i-th smallest clearance (ties: lower index first)
+            double best = 0.0;
+            for (int j = 0; j < n; j++)
+            {
+                if (taken >> j & 1ull) continue;
+                const double bx = o[j * 3], by = o[j * 3 + 1], rad = o[j * 3 + 2] + boat_radius;
+                const double d = sqrt(bx * bx + by * by) - rad;
+                if (pick < 0 || d < best) { pick = j; best = d; }
+            }
+            taken |= 1ull << pick;
+        }
+        else if (i < n) pick = i;
+        float x, y, r;
+        if (pick >= 0)
+        {
+            const float bx = (float) o[pick * 3], by = (float) o[pick * 3 + 1];
+            x = (float) ((double) (c * bx + (-s) * by + 0.0f * 0.0f) + nedx);
+            y = (float) ((double) (s * bx + c * by + 0.0f * 0.0f) + nedy);
+            r = (float) (o[pick * 3 + 2] + boat_radius);
+        }
+        else { x = (float) init_pos; y = (float) init_pos; r = 0.0f; }
+        p_out[(long) b * 2 * K + 2 * i] = x;
+        p_out[(long) b * 2 * K + 2 * i + 1] = y;
+        r_out[(long) b * K + i] = r;
+    }
+}
+
 int grid_for(long n) { long g = (n + 255) / 256; return (int) (g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); }
 
 }  // namespace
@@ -558,6 +606,17 @@ int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value)
     else if (!strcmp(field, "step_length")) { if (value != 1.0) return fail(USVMPC_E_INVALID, "step_length %g: the engine takes full SQP steps like the reference scripts", value); }
     else return fail(USVMPC_E_FIELD, "unknown option '%s'", field);
     refresh_params(s);
+    return 0;
+}
+
+int usvmpc_obstacle_frontend(const double* pose, const double* obs_body, const int* len, int batch, int max_obs, int K,
+                             double boat_radius, double init_obs_pos, double* p_out, double* r_out, void* stream)
+{
+    if (!pose || !obs_body || !len || !p_out || !r_out) return fail(USVMPC_E_INVALID, "null argument");
+    if (batch < 1 || K < 1 || max_obs < 1 || max_obs > 64) return fail(USVMPC_E_INVALID, "need batch >= 1, K >= 1, 1 <= max_obs <= 64");
+    obstacle_frontend_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t) stream>>>(pose, obs_body, len, batch, max_obs, K, boat_radius,
+                                                                                     init_obs_pos, p_out, r_out);
+    CU(cudaGetLastError());
     return 0;
 }
 

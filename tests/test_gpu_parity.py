@@ -262,3 +262,23 @@ def test_long_horizon_config4_shape():
         for k in ("x", "u"):
             good, worst = _close(r[k], a[k], every)
             assert good, (nlp_type, k, worst)
+
+
+def test_obstacle_frontend_against_oracle():
+    # nearest-K selection + body->NED + radius inflation (nmpc_guidance_ca1.cpp:251-363)
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from obstacle_frontend import obstacle_frontend
+    from mpc_collisionavoidance_b200.frontend import select_obstacles
+    rng = np.random.default_rng(8)
+    B, M, K = 64, 21, 8           # the simulator's buoy field has 21 obstacles, the node keeps 8
+    pose = np.stack([rng.uniform(-5, 5, B), rng.uniform(-5, 5, B), rng.uniform(-3.2, 3.2, B)], 1)
+    obs = np.concatenate([rng.uniform(-15, 15, (B, M, 2)), rng.uniform(0.1, 1.0, (B, M, 1))], 2)
+    lens = rng.integers(0, M + 1, B).astype(np.int32)
+    lens[:4] = [0, 3, 8, 21]
+    p_ref, r_ref, _ = obstacle_frontend(pose, obs, lens, K)
+    p, r = select_obstacles(torch.tensor(pose).cuda(), torch.tensor(obs).cuda(), torch.tensor(lens).cuda(), K)
+    # float32 arithmetic in both; the device cos/sin may differ from libm in the last bit before the float rounding
+    np.testing.assert_allclose(p.cpu().numpy(), p_ref, rtol=2e-6, atol=2e-6)
+    np.testing.assert_array_equal(r.cpu().numpy(), r_ref)

@@ -150,3 +150,22 @@ def test_live_reference_stack_agrees_through_a_qp_failure():
     ok = a["status"] == 0
     assert ok.mean() > 0.8
     assert np.abs(a["x"][ok] - c["x"][ok]).max() < 1e-6
+
+
+def test_obstacle_frontend_restatement_properties():
+    # oracle/obstacle_frontend.py (nmpc_guidance_ca1.cpp:251-363): nearest-K by clearance, rigid transform, padding
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from obstacle_frontend import obstacle_frontend
+    rng = np.random.default_rng(1)
+    pose = np.array([[2.0, -1.0, 0.7]])
+    obs = np.concatenate([rng.uniform(-10, 10, (1, 12, 2)), rng.uniform(0.1, 1, (1, 12, 1))], 2)
+    p, r, ch = obstacle_frontend(pose, obs, [12], 8)
+    clear = np.hypot(obs[0, :, 0], obs[0, :, 1]) - (obs[0, :, 2] + 0.5)
+    assert set(ch[0]) == set(np.argsort(clear)[:8]) and (np.diff(clear[ch[0]]) >= 0).all()
+    # rigid transform: distance from the vessel is preserved
+    d_ned = np.hypot(p[0, 0::2] - 2.0, p[0, 1::2] + 1.0)
+    np.testing.assert_allclose(d_ned, np.hypot(obs[0, ch[0], 0], obs[0, ch[0], 1]), rtol=1e-5)
+    np.testing.assert_allclose(r[0], obs[0, ch[0], 2] + 0.5, rtol=1e-6)
+    p2, r2, _ = obstacle_frontend(pose, obs, [3], 8)
+    assert (p2[0, 6:] == 1000.0).all() and (r2[0, 3:] == 0).all()
