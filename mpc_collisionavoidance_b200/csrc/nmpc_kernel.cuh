@@ -81,6 +81,14 @@ struct WarpSolver {
     double res_max[4], mu, mu_aff, sigma, alpha;
     double S1, S2;  // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
     int solve_calls;
+#ifdef USVMPC_PROFILE
+    // phase clocks of one warp (diagnostic builds only): 0 passA 1 chainA 2 chainF 3 passF 4 passC 5 chainC 6 res_pass
+    // 7 refinement 8 linearize 9 update_nlp 10 ipm_init
+    long long prof[20], tprev;
+#define PROF(i) { const long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; }
+#else
+#define PROF(i)
+#endif
 
     MDEV WarpSolver(const Params& p, int inst, double* sm) : P(p), Y(p.lay)
     {
@@ -741,9 +749,12 @@ struct WarpSolver {
         for (int k = N; k >= 0; k--, gk -= HEAD)
         {
             double *R = buf[ir], *Rp = buf[ip];
+            PROF(1)
             rec_wait(ir);
+            PROF(12)
             if (k > 0) { rec_reuse_guard(); rec_fetch(gk - HEAD, in); }
             if (k == 0) mask_stage0(R);
+            PROF(13)
             double* Mx = R + oL;
             if (k < N)
             {
@@ -761,6 +772,7 @@ struct WarpSolver {
                     sAL[e] = acc;
                 }
                 syncwarp();
+                PROF(14)
                 // Pb = Lxx (Lxx' res_b) ; then the last row of AL gets l_{k+1,x} added
                 double pb = 0.0;
                 if (lane < NX)
@@ -772,6 +784,7 @@ struct WarpSolver {
                 syncwarp();
                 if (lane < NX) sAL[NV * NX + lane] += Rp[oL + NV * NV + NU + lane];
                 syncwarp();
+                PROF(15)
                 // syrk: M += AL AL' on the lower trapezoid
 #pragma unroll 1
                 for (int e = lane; e < NE; e += 32)
@@ -783,6 +796,7 @@ struct WarpSolver {
                     Mx[rc & 0xffff] += acc;
                 }
                 syncwarp();
+                PROF(16)
             }
             // (NV+1) x NV Cholesky, lower; non-positive pivot => zero column
             // (dpotrf_l_mn pivot rule, BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).  Lane r <= NV takes row r
@@ -818,7 +832,9 @@ struct WarpSolver {
                     }
                 }
             }
+            PROF(17)
             rec_store(gk, ir, oL, obv + svv);
+            PROF(18)
             { const int t = ip; ip = ir; ir = in; in = t; }
         }
         sweep_end();
@@ -1053,24 +1069,35 @@ struct WarpSolver {
     {
         const double tau_min = 1e-16, alpha_min = 1e-8;
         ipm_init();
+        PROF(10)
         alpha = 1.0;
         double a = 0.0;  // the first passA applies no step
         int kk = 0;
         for (;;)
         {
             passA(a, tau_min, res_max);
+            PROF(0)
             if (!(kk < iter_max && alpha > alpha_min &&
                   (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
                    dabs(res_max[3] - tau_min) > tol_comp)))
                 break;
             chainA();
+            PROF(1)
             double sigma_mu = 0.0, mu_aff0 = 0.0;
             for (int pass = 0; pass < 3; pass++)
             {
                 // pass 0: affine step; pass 1: corrector; pass 2: centering only (conditional)
-                if (pass > 0) { passC(pass == 1, sigma_mu); chainC(); }
+                if (pass > 0)
+                {
+                    passC(pass == 1, sigma_mu);
+                    PROF(4)
+                    chainC();
+                    PROF(5)
+                }
                 chainF();
+                PROF(2)
                 passF(pass > 0, tau_min);
+                PROF(3)
                 const double ma = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
                 if (pass == 0)
                 {
@@ -1090,6 +1117,7 @@ struct WarpSolver {
             // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN); iterative refinement is rare
             double nlin[4];
             res_pass<false>(nlin);
+            PROF(6)
             bool refined = false;
             for (int it = 0; it < 2; it++)
             {
@@ -1103,6 +1131,7 @@ struct WarpSolver {
                 res_pass<false>(nlin);
             }
             if (refined) alpha_pass();
+            PROF(7)
             a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
             kk++;
@@ -1604,12 +1633,17 @@ struct WarpSolver {
         load_constants();
         rec_init();
         if (P.cold_start) cold_start(x0);
+#ifdef USVMPC_PROFILE
+        for (int i = 0; i < 20; i++) prof[i] = 0;
+        tprev = clock64();
+#endif
         int status = 2, sqp_iter = 0, qp_total = 0, qp_status = 0, qp_iter = 0;
         double res[4] = {0, 0, 0, 0};
         const int max_iter = P.nlp_type == 0 ? P.max_iter : 1;
         for (sqp_iter = 0; sqp_iter < max_iter; sqp_iter++)
         {
             linearize(x0, pg, lhg, yrg, yre, res);
+            PROF(8)
             if (P.nlp_type == 0 && res[0] < P.tol[0] && res[1] < P.tol[1] && res[2] < P.tol[2] && res[3] < P.tol[3])
             {
                 status = 0;  // ACADOS_SUCCESS, ocp_nlp_sqp.c:641-672
@@ -1623,6 +1657,7 @@ struct WarpSolver {
                 break;
             }
             update_nlp();
+            PROF(9)
             if (P.nlp_type == 1)
             {
                 status = 0;  // ocp_nlp_sqp_rti.c:810-817
@@ -1637,6 +1672,15 @@ struct WarpSolver {
             st[0] = status; st[1] = sqp_iter; st[2] = qp_total;
             st[3] = res[0]; st[4] = res[1]; st[5] = res[2]; st[6] = res[3];
             st[7] = 0; st[8] = solve_calls; st[9] = qp_status; st[10] = qp_iter; st[11] = 0;
+#ifdef USVMPC_PROFILE
+            if (qp_total >= USVMPC_PROFILE)  // the define is the threshold: only long-running instances report
+                printf("PROF inst %d sqp %d qp %d | passA %lld chainA %lld chainF %lld passF %lld passC %lld chainC %lld "
+                       "res %lld refine %lld lin %lld upd %lld init %lld\n", inst, sqp_iter, qp_total, prof[0], prof[1],
+                       prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10]);
+            if (qp_total >= USVMPC_PROFILE)
+                printf("PROFA wait %lld fetch %lld trmm %lld pb %lld syrk %lld chol %lld store %lld\n", prof[12], prof[13],
+                       prof[14], prof[15], prof[16], prof[17], prof[18]);
+#endif
         }
     }
 };

@@ -16,7 +16,10 @@ using namespace usvmpc;
 
 namespace {
 
-constexpr int WPC = 4;  // warps (= instances) per CTA
+#ifndef USVMPC_WPC
+#define USVMPC_WPC 4
+#endif
+constexpr int WPC = USVMPC_WPC;  // warps (= instances) per CTA
 #ifndef USVMPC_MIN_CTAS
 #define USVMPC_MIN_CTAS 4  // resident CTAs per SM the register allocation must allow (4 x 4 = 16 warps/SM)
 #endif
