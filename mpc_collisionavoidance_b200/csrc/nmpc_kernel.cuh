@@ -525,28 +525,55 @@ struct WarpSolver {
     MDEV void passA(double a, double tau, double* n4)
     {
         const double lam_min = 1e-16, t_min = 1e-16;
-        // ---- UPDATE_VAR_QP: HP/ipm_core/x_core_qp_ipm_aux.c:220-325 (split_step = 0)
+        // ---- UPDATE_VAR_QP: HP/ipm_core/x_core_qp_ipm_aux.c:220-325 (split_step = 0).  A load that follows a store to a
+        // possibly aliasing address cannot be hoisted, so an element-at-a-time loop pays one L2 latency per element: the
+        // loads of a chunk are issued together (CBAR), then the arithmetic, then the stores.
 #pragma unroll 1
         for (int k = lane; k <= N; k += 32)
         {
-            const TP ux = FT(Y.ux, k); const TP dux = FT(Y.dux, k);
+            const TP ux = FT(Y.ux, k), dux = FT(Y.dux, k), pi = FT(Y.pi, k), dpi = FT(Y.dpi, k);
+            {
+                double z[NV], dz[NV], y[NX], dy[NX];
 #pragma unroll
-            for (int i = 0; i < NV; i++) ux[i] += a * dux[i];
+                for (int i = 0; i < NV; i++) { z[i] = ux[i]; dz[i] = dux[i]; }
+#pragma unroll
+                for (int i = 0; i < NX; i++) { y[i] = pi[i]; dy[i] = dpi[i]; }  // stage N: pads of the arrays, not stored
+                CBAR();
+#pragma unroll
+                for (int i = 0; i < NV; i++) ux[i] = z[i] + a * dz[i];
+                if (k < N)
+                {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) pi[i] = y[i] + a * dy[i];
+                }
+            }
             if (k < N)
             {
-                const TP pi = FT(Y.pi, k); const TP dpi = FT(Y.dpi, k);
-#pragma unroll
-                for (int i = 0; i < NX; i++) pi[i] += a * dpi[i];
                 const TP l = FT(Y.lam, k), t = FT(Y.t, k);
                 const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
+                constexpr int UC = 10;
+                const int ne = 2 * ncq;
 #pragma unroll 1
-                for (int r = 0; r < 2 * ncq; r++)
+                for (int r0 = 0; r0 < ne; r0 += UC)
                 {
-                    if (!row_active(k, r < ncq ? r : r - ncq)) continue;
-                    double x = l[r] + a * dl[r];
-                    l[r] = x <= lam_min ? lam_min : x;
-                    x = t[r] + a * dtt[r];
-                    t[r] = x <= t_min ? t_min : x;
+                    double lv[UC], dv[UC], tv[UC], ev[UC];
+#pragma unroll
+                    for (int i = 0; i < UC; i++)
+                    {
+                        const int r = r0 + i < ne ? r0 + i : ne - 1;
+                        lv[i] = l[r]; dv[i] = dl[r]; tv[i] = t[r]; ev[i] = dtt[r];
+                    }
+                    CBAR();
+#pragma unroll
+                    for (int i = 0; i < UC; i++)
+                    {
+                        const int r = r0 + i;
+                        if (r >= ne || !row_active(k, r < ncq ? r : r - ncq)) continue;
+                        double x = lv[i] + a * dv[i];
+                        l[r] = x <= lam_min ? lam_min : x;
+                        x = tv[i] + a * ev[i];
+                        t[r] = x <= t_min ? t_min : x;
+                    }
                 }
             }
         }

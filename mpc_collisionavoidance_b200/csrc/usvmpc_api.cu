@@ -428,6 +428,11 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
         CU(cudaFuncSetAttribute(nmpc_solve_kernel<Pendulum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     else
         CU(cudaFuncSetAttribute(nmpc_solve_kernel<Usv3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (const char* e = getenv("USVMPC_CARVEOUT"))  // diagnostic: shared-memory carve-out in percent (the rest is L1)
+    {
+        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Pendulum>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Usv3>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    }
     *out = s;
     return 0;
 }

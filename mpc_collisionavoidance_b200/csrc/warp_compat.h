@@ -10,6 +10,8 @@
 #ifndef USVMPC_EMULATE
 // ------------------------------------------------------------------ CUDA
 #include <cuda_runtime.h>
+// compiler-level memory barrier: the loads written before it are issued before anything written after it
+#define CBAR() asm volatile("" ::: "memory")
 #define DEV __device__ __forceinline__
 #define MDEV __device__ __forceinline__
 #define MDEVNI __device__ __noinline__
@@ -82,6 +84,7 @@ DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memo
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#define CBAR() asm volatile("" ::: "memory")
 #define DEV static inline
 #define MDEV inline
 #define MDEVNI inline
