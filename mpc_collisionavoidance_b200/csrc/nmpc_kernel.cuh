@@ -588,8 +588,19 @@ struct WarpSolver {
             const double* __restrict__ H = Hk(k);
             const SP Lk = F(Y.L, k);
             const double* __restrict__ T = Tp + cls * NE;
+            {
+                // four entries at a time, loads before stores (a load cannot be hoisted above a store that may alias)
+                int e = 0;
 #pragma unroll 1
-            for (int e = 0; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
+                for (; e + 4 <= NE; e += 4)
+                {
+                    const int o0 = sent[e] & 0xffff, o1 = sent[e + 1] & 0xffff, o2 = sent[e + 2] & 0xffff, o3 = sent[e + 3] & 0xffff;
+                    const double t0 = T[e], t1 = T[e + 1], t2 = T[e + 2], t3 = T[e + 3];
+                    Lk[o0] = t0; Lk[o1] = t1; Lk[o2] = t2; Lk[o3] = t3;
+                }
+#pragma unroll 1
+                for (; e < NE; e++) Lk[sent[e] & 0xffff] = T[e];
+            }
             double g[NV], dg[NV], gg[NV];  // stationarity residual; additions to the diagonal / to the gradient row
 #pragma unroll
             for (int i = 0; i < NV; i++)
@@ -899,13 +910,7 @@ struct WarpSolver {
                 zu[i] = (au + ax) * L[i * NV + NV - 1];
                 if (k == N) zu[i] = 0.0;
             }
-            const TP g = FT(Y.dux, k);
-            if (lane < NX) g[NU + lane] = xme;
-            if (lane == 0)
-            {
-#pragma unroll
-                for (int i = 0; i < NU; i++) g[i] = zu[i];
-            }
+            const double xk = xme;
             if (k < N)
             {
                 double x1 = 0.0;
@@ -921,6 +926,15 @@ struct WarpSolver {
                 xme = x1;
 #pragma unroll
                 for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+            }
+            // the stage's step goes to HBM after the last shared-memory load of the stage: a load cannot be hoisted above a
+            // store that may alias, and the loads above can start before the substitution has finished
+            const TP g = FT(Y.dux, k);
+            if (lane < NX) g[NU + lane] = xk;
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int i = 0; i < NU; i++) g[i] = zu[i];
             }
             { const int t = ir; ir = in; in = t; }
         }
@@ -998,18 +1012,22 @@ struct WarpSolver {
                 for (int j = 0; j < ncq; j++)
                 {
                     if (!row_active(k, j)) { rm[j] = 0.0; rm[ncq + j] = 0.0; continue; }
-                    double m0 = lam[j] * t[j], m1 = lam[ncq + j] * t[ncq + j];
+                    // every load of the row before its first store (a load cannot be hoisted above a store that may alias)
+                    const double l0 = lam[j], l1 = lam[ncq + j], i0 = ti[j], i1 = ti[ncq + j], e0 = rd[j], e1 = rd[ncq + j];
+                    double gX = 0.0, gY = 0.0;
+                    if (j >= nbq && k >= 1) { gX = gxy[j - nbq]; gY = gxy[K + j - nbq]; }
+                    double m0 = l0 * t[j], m1 = l1 * t[ncq + j];
                     if (with_aff) { m0 += dtt[j] * dl[j]; m1 += dtt[ncq + j] * dl[ncq + j]; }
                     m0 -= sigma_mu; m1 -= sigma_mu;
                     rm[j] = m0; rm[ncq + j] = m1;
-                    const double gd = ti[j] * (m0 - lam[j] * rd[j]) - ti[ncq + j] * (m1 - lam[ncq + j] * rd[ncq + j]);
+                    const double gd = i0 * (m0 - l0 * e0) - i1 * (m1 - l1 * e1);
                     if (j < nbq)
                     {
                         const int id = srvar[j];
 #pragma unroll
                         for (int i = 0; i < NV; i++) if (i == id) z[i] += gd;
                     }
-                    else if (k >= 1) { z[HXV] += gxy[j - nbq] * gd; z[HYV] += gxy[K + j - nbq] * gd; }
+                    else if (k >= 1) { z[HXV] += gX * gd; z[HYV] += gY * gd; }
                 }
             }
 #pragma unroll
@@ -1030,22 +1048,32 @@ struct WarpSolver {
             const TP v = FT(Y.dux, k), lam = FT(Y.lam, k), t = FT(Y.t, k), ti = FT(Y.ti, k), rd = FT(Y.rd, k);
             const TP rm = FT(Y.rmc, k), gxy = FT(Y.gxy, k);
             const TP dl = FT(Y.dlam, k), dtt = FT(Y.dt, k);
+            const double vx = v[HXV], vy = v[HYV];
 #pragma unroll 1
             for (int j = 0; j < ncq; j++)
             {
                 if (!row_active(k, j)) continue;
+                // both sides' loads before the first store of the row (a load cannot be hoisted above a store that may alias)
+                double bl[2], bt[2], bi[2], be[2], bm[2];
+#pragma unroll
+                for (int side = 0; side < 2; side++)
+                {
+                    const int r = j + side * ncq;
+                    bl[side] = lam[r]; bt[side] = t[r]; bi[side] = ti[r]; be[side] = rd[r];
+                    bm[side] = corr ? rm[r] : 0.0;
+                }
                 double dv;
                 if (j < nbq) dv = v[srvar[j]];
-                else dv = k >= 1 ? gxy[j - nbq] * v[HXV] + gxy[K + j - nbq] * v[HYV] : 0.0;
+                else dv = k >= 1 ? gxy[j - nbq] * vx + gxy[K + j - nbq] * vy : 0.0;
 #pragma unroll
                 for (int side = 0; side < 2; side++)
                 {
                     const int r = j + side * ncq;
                     double dtr = side ? -dv : dv;
-                    const double lam0 = lam[r], t0 = t[r];
-                    const double m = corr ? rm[r] : lam0 * t0 - tau;
-                    const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * rd[r]));
-                    dtr -= rd[r];
+                    const double lam0 = bl[side], t0 = bt[side];
+                    const double m = corr ? bm[side] : lam0 * t0 - tau;
+                    const double dlr = -bi[side] * (m + (lam0 * dtr) - (lam0 * be[side]));
+                    dtr -= be[side];
                     dl[r] = dlr; dtt[r] = dtr;
                     // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best
                     // is kept as (numerator, denominator) and compared by cross-multiplication: one division per sweep
@@ -1069,14 +1097,17 @@ struct WarpSolver {
                 for (int m = j; m < NX; m++) acc += Ln[(NU + m) * NV + NU + j] * xn[NU + m];
                 tmp[j] = corr ? acc : acc + bn[NU + j];
             }
+            double dpv[NX];
 #pragma unroll
             for (int i = 0; i < NX; i++)
             {
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j <= i; j++) acc += Ln[(NU + i) * NV + NU + j] * tmp[j];
-                dpi[i] = corr ? bn[NU + i] + acc : acc;
+                dpv[i] = corr ? bn[NU + i] + acc : acc;
             }
+#pragma unroll
+            for (int i = 0; i < NX; i++) dpi[i] = dpv[i];  // stores after the last load
         }
         const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
         alpha = -(a_prim > a_dual ? a_prim : a_dual);
