@@ -669,13 +669,15 @@ struct WarpSolver {
                 const TP vn = FT(Y.ux, k + 1);
                 const TP cb = FT(Y.b, k);
                 const SP rb = F(Y.rb, k);
+                // no store between the loads: the residual goes to the record after both products
+                double rbv[NX];
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
                     double acc = cb[j] - vn[NU + j];
 #pragma unroll
                     for (int i = 0; i < NV; i++) if (k > 0 || i < NU) acc += BAt[i + NV * j] * v[i];
-                    rb[j] = acc;
+                    rbv[j] = acc;
                     const double q = dabs(acc);
                     n1 = q > n1 ? q : n1;
                 }
@@ -687,6 +689,8 @@ struct WarpSolver {
                     for (int j = 0; j < NX; j++) acc += BAt[i + NV * j] * pk[j];
                     g[i] += acc;
                 }
+#pragma unroll
+                for (int j = 0; j < NX; j++) rb[j] = rbv[j];
             }
             const TP rg = FT(Y.rg, k);
             if (K > 0 && k < N) Lk[HYV * NV + HXV] = T[HYV * (HYV + 1) / 2 + HXV] + aYX;
@@ -743,6 +747,29 @@ struct WarpSolver {
         fence_proxy_async();
     }
     MDEV void sweep_end_nostore() { syncwarp(); fence_proxy_async(); }
+    // The sweeps that only READ the records (chainF, chainC) stream them with per-lane 16-byte cp.async instead: no
+    // mbarrier round trip per stage (try_wait costs ~90 cycles even when the data is there) and no proxy fences, because
+    // cp.async is a generic-proxy access like the passes' stores.  chainA, which also writes the records back, keeps TMA.
+#ifndef USVMPC_READ_LDGSTS
+#define USVMPC_READ_LDGSTS 1
+#endif
+#if USVMPC_READ_LDGSTS
+    MDEV void rd_fetch(const double* src, int b)
+    {
+        double* dst = buf[b];
+#pragma unroll 1
+        for (int c = 2 * lane; c < HEAD; c += 64) cp_async16(dst + c, src + c);
+        cp_async_commit();
+    }
+    MDEV void rd_wait(int b) { (void) b; cp_async_wait_all(); }
+    MDEV void rd_begin() { syncwarp(); }
+    MDEV void rd_end() { syncwarp(); }
+#else
+    MDEV void rd_fetch(const double* src, int b) { rec_fetch(src, b); }
+    MDEV void rd_wait(int b) { rec_wait(b); }
+    MDEV void rd_begin() { sweep_begin(); }
+    MDEV void rd_end() { sweep_end_nostore(); }
+#endif
 #else
     // alternative streaming path: per-lane 16-byte cp.async (LDGSTS) loads and plain coalesced stores, all in the
     // generic proxy (no proxy fences, the L1 keeps what the passes read)
@@ -766,6 +793,10 @@ struct WarpSolver {
     MDEV void sweep_begin() { syncwarp(); }
     MDEV void sweep_end() { syncwarp(); }
     MDEV void sweep_end_nostore() { syncwarp(); }
+    MDEV void rd_fetch(const double* src, int b) { rec_fetch(src, b); }
+    MDEV void rd_wait(int b) { rec_wait(b); }
+    MDEV void rd_begin() { sweep_begin(); }
+    MDEV void rd_end() { sweep_end_nostore(); }
 #endif
     // stage 0 after x0 elimination: no x rows in [B';A'] (x_ocp_qp_red.c:268-454)
     MDEV void mask_stage0(double* R)
@@ -847,16 +878,17 @@ struct WarpSolver {
 #pragma unroll
                 for (int j = 0; j < NV; j++)
                 {
+                    // the pivot and the unscaled column travel together; scaling the received entries locally gives the
+                    // same bits as shuffling the scaled ones and takes the second shuffle off the dependent chain
                     const double piv = shfl(Mr[j], j);
+                    double raw[NV];
+#pragma unroll
+                    for (int c = j + 1; c < NV; c++) raw[c] = shfl(Mr[j], c);
                     double sq = 0.0, inv = 0.0;
                     if (piv > 0.0) { inv = drsqrt(piv); sq = piv * inv; }
                     if (r == j) { Mr[j] = sq; if (j < NU) dinv = inv; } else Mr[j] *= inv;
 #pragma unroll
-                    for (int c = j + 1; c < NV; c++)
-                    {
-                        const double lc = shfl(Mr[j], c);
-                        Mr[c] -= Mr[j] * lc;
-                    }
+                    for (int c = j + 1; c < NV; c++) Mr[c] -= Mr[j] * (raw[c] * inv);
                 }
                 if (lane <= NV)
                 {
@@ -886,16 +918,16 @@ struct WarpSolver {
         double xc[NX], xme = 0.0;
 #pragma unroll
         for (int i = 0; i < NX; i++) xc[i] = 0.0;
-        sweep_begin();
+        rd_begin();
         const double* gk = rec_g(0);
-        rec_fetch(gk, ir);
+        rd_fetch(gk, ir);
 #pragma unroll 1
         for (int k = 0; k <= N; k++, gk += HEAD)
         {
             double* R = buf[ir];
-            rec_wait(ir);
+            rd_wait(ir);
             syncwarp();  // every lane is done with the other buffer before it becomes a copy destination again
-            if (k < N) rec_fetch(gk + HEAD, in);
+            if (k < N) rd_fetch(gk + HEAD, in);
             if (k == 0) mask_stage0(R);
             const double* L = R + oL;
             double zu[NU];
@@ -910,7 +942,13 @@ struct WarpSolver {
                 zu[i] = (au + ax) * L[i * NV + NV - 1];
                 if (k == N) zu[i] = 0.0;
             }
-            const double xk = xme;
+            const TP g = FT(Y.dux, k);
+            if (lane < NX) g[NU + lane] = xme;
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int i = 0; i < NU; i++) g[i] = zu[i];
+            }
             if (k < N)
             {
                 double x1 = 0.0;
@@ -927,18 +965,9 @@ struct WarpSolver {
 #pragma unroll
                 for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
             }
-            // the stage's step goes to HBM after the last shared-memory load of the stage: a load cannot be hoisted above a
-            // store that may alias, and the loads above can start before the substitution has finished
-            const TP g = FT(Y.dux, k);
-            if (lane < NX) g[NU + lane] = xk;
-            if (lane == 0)
-            {
-#pragma unroll
-                for (int i = 0; i < NU; i++) g[i] = zu[i];
-            }
             { const int t = ir; ir = in; in = t; }
         }
-        sweep_end_nostore();
+        rd_end();
     }
 
     // chainC: backward substitution of OCP_QP_SOLVE_KKT_STEP.  bv holds rhs_g + constraint terms (passC) on entry, the
@@ -949,16 +978,16 @@ struct WarpSolver {
         double pn[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) pn[i] = 0.0;
-        sweep_begin();
+        rd_begin();
         double* gk = rec_g(N);
-        rec_fetch(gk, ir);
+        rd_fetch(gk, ir);
 #pragma unroll 1
         for (int k = N; k >= 0; k--, gk -= HEAD)
         {
             double* R = buf[ir];
-            rec_wait(ir);
+            rd_wait(ir);
             syncwarp();  // every lane is done with the other buffer before it becomes a copy destination again
-            if (k > 0) rec_fetch(gk - HEAD, in);
+            if (k > 0) rd_fetch(gk - HEAD, in);
             if (k == 0) mask_stage0(R);
             const int i = lane;
             double zi = 0.0;
@@ -988,7 +1017,7 @@ struct WarpSolver {
             { const int t = ir; ir = in; in = t; }
         }
         solve_calls++;
-        sweep_end_nostore();
+        rd_end();
     }
 
     // passC: right-hand side of the corrector / centering solve res_m = lam*t [+ dt_aff*dlam_aff] - sigma_mu
