@@ -80,6 +80,7 @@ struct WarpSolver {
     // IPM state (warp-uniform)
     double res_max[4], mu, mu_aff, sigma, alpha;
     double S1, S2;  // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
+    double lin_d, lin_m;  // residual norms of the linearised inequality / complementarity rows at the last passF step
     int solve_calls;
 #ifdef USVMPC_PROFILE
     // phase clocks of one warp (diagnostic builds only): 0 passA 1 chainA 2 chainF 3 passF 4 passC 5 chainC 6 res_pass
@@ -1071,6 +1072,7 @@ struct WarpSolver {
     MDEV void passF(bool corr, double tau)
     {
         double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2 = 0.0;  // best dual / primal ratio = -1
+        double nd = 0.0, nm = 0.0;  // OCP_QP_RES_COMPUTE_LIN rows res_d, res_m of this very step: their inputs are in registers here
 #pragma unroll 1
         for (int k = lane; k < N; k += 32)
         {
@@ -1110,6 +1112,13 @@ struct WarpSolver {
                     if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
                     s1 += lam0 * dtr + t0 * dlr;
                     s2 += dlr * dtr;
+                    {
+                        // rd + dt -/+ J dux  and  rhs_m + lam*dt + dlam*t  (HP/ocp_qp/x_ocp_qp_res.c:560-633), as res_pass has them
+                        const double e = side ? be[side] + dtr + dv : be[side] + dtr - dv;
+                        const double mm = m + lam0 * dtr + dlr * t0;
+                        double q = dabs(e); nd = q > nd ? q : nd;
+                        q = dabs(mm); nm = q > nm ? q : nm;
+                    }
                 }
             }
             // dpi_k from the factor of stage k+1
@@ -1141,6 +1150,7 @@ struct WarpSolver {
         const double a_prim = warp_max(bpn / bpd), a_dual = warp_max(bdn / bdd);
         alpha = -(a_prim > a_dual ? a_prim : a_dual);
         S1 = warp_sum(s1); S2 = warp_sum(s2);
+        lin_d = warp_max(nd); lin_m = warp_max(nm);
         syncwarp();
     }
 
@@ -1215,7 +1225,7 @@ struct WarpSolver {
                 expand_pass(2, 0.0);
                 add_refinement();
                 refined = true;
-                res_pass<false>(nlin);
+                res_pass<true>(nlin);  // the step is no longer passF's: all four norms from scratch (the stores are harmless)
             }
             if (refined) alpha_pass();
             PROF(7)
@@ -1265,12 +1275,16 @@ struct WarpSolver {
                 {
                     if (!row_active(k, j)) continue;
                     const int id = j < nbu ? j : NU + P.idxbx[j - nbu];
-                    const double dl = l[ncq + j] - l[j], vv = v[id];
+                    const double dl = l[ncq + j] - l[j];
 #pragma unroll
                     for (int i = 0; i < NV; i++) if (i == id) g[i] += dl;
-                    const double e0 = cd[j] + tt[j] - vv, e1 = cd[ncq + j] + tt[ncq + j] + vv;
-                    if (WRITE) { rd[j] = e0; rd[ncq + j] = e1; }
-                    { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
+                    if (WRITE)  // without WRITE the step is passF's and so are these rows' norms (lin_d)
+                    {
+                        const double vv = v[id];
+                        const double e0 = cd[j] + tt[j] - vv, e1 = cd[ncq + j] + tt[ncq + j] + vv;
+                        rd[j] = e0; rd[ncq + j] = e1;
+                        const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2;
+                    }
                 }
                 const TP gxy = FT(Y.gxy, k);
                 for (int c = 0; c < K; c++)
@@ -1279,10 +1293,13 @@ struct WarpSolver {
                     const double gX = k >= 1 ? gxy[c] : 0.0, gY = k >= 1 ? gxy[K + c] : 0.0;
                     const double dl = l[ncq + r] - l[r];
                     g[HXV] += gX * dl; g[HYV] += gY * dl;
-                    const double vv = gX * v[HXV] + gY * v[HYV];
-                    const double e0 = cd[r] + tt[r] - vv, e1 = cd[ncq + r] + tt[ncq + r] + vv;
-                    if (WRITE) { rd[r] = e0; rd[ncq + r] = e1; }
-                    { const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2; }
+                    if (WRITE)
+                    {
+                        const double vv = gX * v[HXV] + gY * v[HYV];
+                        const double e0 = cd[r] + tt[r] - vv, e1 = cd[ncq + r] + tt[ncq + r] + vv;
+                        rd[r] = e0; rd[ncq + r] = e1;
+                        const double q0 = dabs(e0), q1 = dabs(e1); n2 = q0 > n2 ? q0 : n2; n2 = q1 > n2 ? q1 : n2;
+                    }
                 }
                 const TP BAt = FT(Y.BAtT, k);
                 const TP vn = FT(Y.dux, k + 1);
@@ -1306,6 +1323,7 @@ struct WarpSolver {
                     for (int j = 0; j < NX; j++) acc += BAt[i + NV * j] * pk[j];
                     g[i] += acc;
                 }
+                if (WRITE)
                 {
                     const TP lam = FT(Y.lam, k), t = FT(Y.t, k), rm = FT(Y.rmc, k);
                     const SP rm2 = F(Y.rm2, k);
@@ -1329,6 +1347,7 @@ struct WarpSolver {
             }
         }
         out4[0] = warp_max(n0); out4[1] = warp_max(n1); out4[2] = warp_max(n2); out4[3] = warp_max(n3);
+        if (!WRITE) { out4[2] = lin_d; out4[3] = lin_m; }
         syncwarp();
     }
 
