@@ -511,9 +511,10 @@ struct WarpSolver {
     // ---------------------------------------------------------------- IPM: one iteration = lean chain sweeps + stage-parallel passes
     // Only the Riccati recursions are serial in the stage index.  They run as CHAIN sweeps: the warp streams the head of
     // each stage record ([B';A'], res_b, the matrix to factorise / its factor, Pb, the backward vector) through shared
-    // memory with TMA and does nothing but the recursion.  Everything else of an IPM iteration (variable update,
-    // residuals, Gamma/gamma, assembly of the matrix to factorise, dt/dlam, step length, dpi, right-hand sides) is
-    // independent per stage and runs as PASSES with one lane per stage, straight on the records in HBM/L2.
+    // memory (TMA for chainA, cp.async for the read-only chainF / chainC) and does nothing but the recursion.
+    // Everything else of an IPM iteration (variable update, residuals, Gamma/gamma, assembly of the matrix to factorise,
+    // dt/dlam, step length, dpi, right-hand sides) is independent per stage and runs as PASSES with one lane per
+    // stage, straight on the records in HBM/L2.
     //
     //   passA  : UPDATE_VAR_QP + OCP_QP_RES_COMPUTE + COMPUTE_GAMMA_GAMMA_QP + assembly of H + Gamma terms (+ gradient row)
     //   chainA : backward: AL = [B';A';b'] Lxx, Pb, syrk, Cholesky                       (x_ocp_qp_kkt.c:455-535)
