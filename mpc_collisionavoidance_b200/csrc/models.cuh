@@ -80,12 +80,15 @@ struct Usv3 {
         const double Yvv = -99.99, Yvr = -5.49, Nrv = -8.8, Nrr = -3.49;
         const double m = 30, Iz = 4.1, B = 0.41, c = 0.78;
         const double m11 = m - X_u_dot, m22 = m - Y_v_dot, m33 = Iz - N_r_dot;
+        // the inertia terms are compile-time constants: multiply by their reciprocals (folded by the compiler) instead of
+        // twelve fp64 divisions per evaluation; differs from the division by at most one ulp per term
+        const double i11 = 1.0 / m11, i22 = 1.0 / m22, i33 = 1.0 / m33;
         const double kY = 0.5 * (-40 * 1000) * (1.1 + 0.0045 * (1.01 / 0.09) - 0.1 * (0.27 / 0.09) + 0.016 * ((0.27 / 0.09) * (0.27 / 0.09)));
         const double psi = x[2], u = x[3], v = x[4], r = x[5];
         const double Tp = uc[0], Ts = uc[1];
         const double Xu = (u > 1.25) ? 64.55 : -25.0;
         const double Xuu = (u > 1.25) ? -70.92 : 0.0;
-        const double sq = dsqrt(u * u + v * v);
+        const double sq = dsqrt(u * u + v * v), isq = 1.0 / sq;
         const double Yv = kY * dabs(v);
         const double Nr = -0.52 * sq;
         const double Tu = Tp + c * Ts;
@@ -95,15 +98,15 @@ struct Usv3 {
         f[0] = u * cp - v * sp;
         f[1] = u * sp + v * cp;
         f[2] = r;
-        f[3] = (Tu - (-m + 2 * Y_v_dot) * v - (Y_r_dot + N_v_dot) * r * r - (-Xu * u - Xuu * dabs(u) * u)) / m11;
-        f[4] = (-(m - X_u_dot) * u * r - (-Yv - Yvv * dabs(v) - Yvr * dabs(r)) * v) / m22;
-        f[5] = (Tr - (-2 * Y_v_dot * u * v - (Y_r_dot + N_v_dot) * r * u + X_u_dot * u * r) - (-Nr * r - Nrv * dabs(v) * r - Nrr * dabs(r) * r)) / m33;
+        f[3] = (Tu - (-m + 2 * Y_v_dot) * v - (Y_r_dot + N_v_dot) * r * r - (-Xu * u - Xuu * dabs(u) * u)) * i11;
+        f[4] = (-(m - X_u_dot) * u * r - (-Yv - Yvv * dabs(v) - Yvr * dabs(r)) * v) * i22;
+        f[5] = (Tr - (-2 * Y_v_dot * u * v - (Y_r_dot + N_v_dot) * r * u + X_u_dot * u * r) - (-Nr * r - Nrv * dabs(v) * r - Nrr * dabs(r) * r)) * i33;
         const double J02 = -u * sp - v * cp, J12 = u * cp - v * sp;
-        const double J33 = (Xu + 2 * Xuu * dabs(u)) / m11, J34 = -(-m + 2 * Y_v_dot) / m11, J35 = -2 * (Y_r_dot + N_v_dot) * r / m11;
-        const double J43 = -m11 * r / m22, J44 = (2 * (kY + Yvv) * dabs(v) + Yvr * dabs(r)) / m22, J45 = (-m11 * u + Yvr * dsign(r) * v) / m22;
-        const double J53 = (2 * Y_v_dot * v + (Y_r_dot + N_v_dot) * r - X_u_dot * r - 0.52 * (u / sq) * r) / m33;
-        const double J54 = (2 * Y_v_dot * u - 0.52 * (v / sq) * r + Nrv * dsign(v) * r) / m33;
-        const double J55 = ((Y_r_dot + N_v_dot) * u - X_u_dot * u - 0.52 * sq + Nrv * dabs(v) + 2 * Nrr * dabs(r)) / m33;
+        const double J33 = (Xu + 2 * Xuu * dabs(u)) * i11, J34 = -(-m + 2 * Y_v_dot) / m11, J35 = -2 * (Y_r_dot + N_v_dot) * r * i11;
+        const double J43 = -m11 * r * i22, J44 = (2 * (kY + Yvv) * dabs(v) + Yvr * dabs(r)) * i22, J45 = (-m11 * u + Yvr * dsign(r) * v) * i22;
+        const double J53 = (2 * Y_v_dot * v + (Y_r_dot + N_v_dot) * r - X_u_dot * r - 0.52 * (u * isq) * r) * i33;
+        const double J54 = (2 * Y_v_dot * u - 0.52 * (v * isq) * r + Nrv * dsign(v) * r) * i33;
+        const double J55 = ((Y_r_dot + N_v_dot) * u - X_u_dot * u - 0.52 * sq + Nrv * dabs(v) + 2 * Nrr * dabs(r)) * i33;
         const double b3 = ucol == 0 ? 1.0 / m11 : (ucol == 1 ? c / m11 : 0.0);
         const double b5 = ucol == 0 ? (B / 2) / m33 : (ucol == 1 ? -(c * B / 2) / m33 : 0.0);
         ks[0] = ((J02 * s[2]) + cp * s[3]) + (-sp) * s[4];
