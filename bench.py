@@ -224,7 +224,7 @@ def run_engine(args):
 
     out_host = {"x": torch.empty((B, N + 1, nx), dtype=torch.float64).pin_memory(),
                 "u": torch.empty((B, N, nu), dtype=torch.float64).pin_memory(),
-                "stats": torch.empty((B, 12), dtype=torch.float64).pin_memory()}
+                "stats": torch.empty((B, 16), dtype=torch.float64).pin_memory()}
 
     def step_e2e():
         set_inputs(host)                                   # H2D from pinned host memory

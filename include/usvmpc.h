@@ -45,7 +45,7 @@ extern "C" {
 #define USVMPC_E_FIELD (-3)
 #define USVMPC_E_SIZE (-4)
 
-#define USVMPC_NSTAT 12
+#define USVMPC_NSTAT 16
 /* statistics record per instance (doubles):
  *  0 status  1 sqp_iter  2 qp_iter(total)  3 res_stat  4 res_eq  5 res_ineq  6 res_comp  7 -
  *  8 solve-only Riccati sweeps  9 last QP status (HPIPM)  10 last QP iterations  11 -          */

@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("USVMPC_LIB", os.path.join(HERE, "libusvmpc.so"))
 
 ALL_STAGES = -1
 EVERY_STAGE = -2
-NSTAT = 12
+NSTAT = 16
 
 
 class Config(C.Structure):

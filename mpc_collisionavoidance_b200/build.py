@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libusvmpc.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("usvmpc_api.cu", "nmpc_kernel.cuh", "models.cuh", "layout.h", "warp_compat.h")]
+SOURCES = [os.path.join(CSRC, f) for f in ("usvmpc_api.cu", "cta_kernel.cuh", "models.cuh", "cta_layout.h", "cta_compat.h")]
 SOURCES.append(os.path.join(HERE, "..", "include", "usvmpc.h"))
 
 

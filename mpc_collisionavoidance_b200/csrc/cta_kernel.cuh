@@ -1,0 +1,1461 @@
+// cta_kernel.cuh -- the batched NMPC solve: ONE THREAD BLOCK PER INSTANCE, working set resident in shared memory.
+//
+// A persistent block pulls instances from a device-side queue and runs the whole SQP / SQP_RTI solve of one
+// instance at a time: linearise -> x0 elimination -> Mehrotra IPM on a Riccati recursion -> variable update.
+//
+// What it replaces in the reference (AC = catkin_ws/src/nmpc_ca/acados, HP = AC/external/hpipm):
+//   ocp_nlp_sqp / ocp_nlp_sqp_rti loop            AC/acados/ocp_nlp/ocp_nlp_sqp.c:466-835, ocp_nlp_sqp_rti.c:445-829
+//   linearisation + KKT residuals                 AC/acados/ocp_nlp/ocp_nlp_common.c:1926-2084, 2549-2603
+//   ERK with forward sensitivities                AC/acados/sim/sim_erk_integrator.c:668-847
+//   LINEAR_LS cost, BGH constraints               AC/acados/ocp_nlp/ocp_nlp_cost_ls.c:713-843, ocp_nlp_constraints_bgh.c:1228-1430
+//   x0 elimination / restoration                  HP/ocp_qp/x_ocp_qp_red.c:268-454, 723-871
+//   HPIPM IPM (init, delta step, residuals)       HP/ocp_qp/x_ocp_qp_ipm.c:1387-1719, 1888-2350, 2354-2683; x_ocp_qp_res.c:336-633
+//   Riccati factorise+solve / solve               HP/ocp_qp/x_ocp_qp_kkt.c:405-766, 1096-1441
+//   core vector ops                               HP/ipm_core/x_core_qp_ipm_aux.c:38-357
+//   BLASFEO potrf/syrk/trmm/trsv/gemv             BF/blasfeo_hp_pm/d_lapack_lib4.c:1149,1503 etc. -> block/warp-level code below
+//
+// Work decomposition inside the block (T threads, W = T/32 warps):
+//   * everything of an IPM iteration that is independent per stage -- variable update, residuals, Gamma/gamma, assembly
+//     of the matrices to factorise, gains, dt/dlam, step lengths, right-hand sides -- is a PASS: the (stage, row) or
+//     (stage, variable) items are spread over all T threads, block-wide reductions give norms / step lengths;
+//   * only the Riccati recursions are serial in the stage index.  They run as CHAINS on warp 0, straight out of shared
+//     memory, and are cut down to what really is serial:
+//       chainA  backward: P_k, p_k from P_{k+1}, p_{k+1}: M = (H + Gamma terms) + G' P_{k+1} G, eliminate the NU input
+//               columns (Cholesky with HPIPM's pivot rule); the Schur complement IS P_k, so the x block is never
+//               factorised (the reference factorises it only to form G' P G as a product of triangular factors);
+//       chainC  backward: p_k = Acl_k' p_{k+1} + e_k          (one NX x NX mat-vec per stage)
+//       chainF  forward : dx_{k+1} = Acl_k dx_k + c_k          (one NX x NX mat-vec per stage)
+//     with the closed-loop matrices Acl_k = A_k + B_k K_k, the gains K_k and the affine terms c_k, e_k computed by
+//     passes between the chains.  Mathematically this is the reference's recursion (x_ocp_qp_kkt.c:455-575,
+//     1096-1290); iteration counts, status and converged trajectories are the reference's (tests/).
+// Inactive variables (x at stage 0 after x0 elimination, u at stage N) and inactive inequality rows are kept in
+// the uniform per-stage layout and masked (identity rows in the matrix, zero rows in [B';A']), so every stage runs
+// the same code.
+#pragma once
+#include "cta_compat.h"
+#include "cta_layout.h"
+#include "models.cuh"
+
+namespace usvmpc {
+
+// exact x / d for 0 <= x, x * (d - 1) < 2^32
+struct FastDiv {
+    int d;
+    unsigned magic;
+    MDEV void set(int dd) { d = dd > 0 ? dd : 1; magic = (unsigned) ((0x100000000ull + (unsigned) d - 1) / (unsigned) d); }
+    MDEV int div(int x) const { return d == 1 ? x : (int) (((unsigned long long) (unsigned) x * magic) >> 32); }
+};
+
+template <class M>
+struct CtaSolver {
+    static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
+    static constexpr int HXV = NU + M::HX, HYV = NU + M::HY;
+    static constexpr int NE = NV * (NV + 1) / 2 + NV;  // entries of the lower trapezoid of the (NV+1) x NV matrix
+    static constexpr int NEP = NX * (NX + 1) / 2;
+    MDEV static constexpr int MI(int r, int c) { return r * (r + 1) / 2 + c; }  // packed index, c <= r (row NV = gradient row)
+
+    const Params& P;
+    int tid, lane, wid, T, W;
+    int N, K, nbu, nbx, ncq, ncz, nbq, nct, s2;
+    FastDiv dq, dnv, dnx;
+    double *sm, *gs, *w;
+    // constants in shared memory
+    double *Hs, *Hes, *Ws, *Wes, *Tp, *red, *sA0, *sW, *sP;
+    int *sxrow, *srvar;
+    int redbuf;
+    // working-set fields
+    double *G, *Mx, *Acl, *Kg, *cc, *ee, *Pb, *rb, *zv, *dux, *kk, *dinv;
+    double *ux, *pi, *lam, *t, *dlam, *dt, *rd, *rmc, *rg, *dpi, *gxy, *ti, *d, *rq, *b;
+    double *rg2, *rb2, *rd2, *rm2, *dux2, *dpi2, *dlam2, *dt2;
+    // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116 and, in SQP
+    // mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
+    double tol_stat, tol_eq, tol_ineq, tol_comp;
+    int iter_max;
+    // IPM state (block-uniform)
+    double res_max[4], mu, mu_aff, sigma, alpha;
+    double S1, S2;        // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
+    double lin_d, lin_m;  // residual norms of the linearised inequality / complementarity rows at the last expanded step
+    int solve_calls, lq_count, itref_count;
+#ifdef USVMPC_PROFILE
+    // phase clocks of thread 0 (diagnostic builds only)
+    long long prof[24], tprev;
+#define PROF(i) { if (tid == 0) { const long long t_ = clock_now(); prof[i] += t_ - tprev; tprev = t_; } }
+#else
+#define PROF(i)
+#endif
+
+    MDEV double* fld(int id) const { const SField& f = P.plan.f[id]; return (f.space ? gs : sm) + f.off; }
+
+    MDEV CtaSolver(const Params& p, double* smem, double* gscratch) : P(p), sm(smem), gs(gscratch)
+    {
+        tid = thread_id(); lane = tid & 31; wid = tid >> 5; T = block_threads(); W = T >> 5;
+        N = P.N; K = P.K; nbu = P.nbu; nbx = P.nbx; ncq = P.ncq; ncz = P.ncz; nbq = nbu + nbx; s2 = 2 * ncq;
+        nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
+        dq.set(ncq); dnv.set(NV); dnx.set(NX);
+        double* c = sm + P.plan.const_off;
+        Hs = c; c += NV * NV; Hes = c; c += NV * NV; Ws = c; c += NV * NV; Wes = c; c += NX * NX; Tp = c;
+        red = sm + P.plan.red_off;
+        redbuf = 0;
+        double* m = sm + P.plan.misc_off;
+        sA0 = m; m += NV * NX; sW = m; m += NX * NR; sP = m; m += NX * NX + 2;
+        sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
+        G = fld(F_G); Mx = fld(F_M); Acl = fld(F_ACL); Kg = fld(F_KG); cc = fld(F_CC); ee = fld(F_EE); Pb = fld(F_PB);
+        rb = fld(F_RB); zv = fld(F_ZV); dux = fld(F_DUX); kk = fld(F_KK); dinv = fld(F_DINV);
+        ux = fld(F_UX); pi = fld(F_PI); lam = fld(F_LAM); t = fld(F_T); dlam = fld(F_DLAM); dt = fld(F_DT); rd = fld(F_RD);
+        rmc = fld(F_RMC); rg = fld(F_RG); dpi = fld(F_DPI); gxy = fld(F_GXY); ti = fld(F_TI); d = fld(F_D); rq = fld(F_RQ);
+        b = fld(F_B);
+        rg2 = fld(F_RG2); rb2 = fld(F_RB2); rd2 = fld(F_RD2); rm2 = fld(F_RM2); dux2 = fld(F_DUX2); dpi2 = fld(F_DPI2);
+        dlam2 = fld(F_DLAM2); dt2 = fld(F_DT2);
+        tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
+        if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
+        iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
+        solve_calls = 0; lq_count = 0; itref_count = 0;
+    }
+
+    MDEV double* Z(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
+    MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
+    MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
+    // IPM row of the box on variable c at stage k, or -1
+    MDEV int vrow(int k, int c) const
+    {
+        if (k >= N) return -1;
+        if (c < NU) return c < nbu ? c : -1;
+        return k >= 1 ? sxrow[c - NU] : -1;
+    }
+    MDEV int stage_class(int k) const { return k == 0 ? 0 : (k < N ? 1 : 2); }
+    MDEV const double* Hk(int k) const { return k < N ? Hs : Hes; }
+
+    // ---------------------------------------------------------------- block-wide reductions (every thread gets the result)
+    template <int NM, int NS>
+    MDEV void block_reduce(double* vmax, double* vsum)
+    {
+#pragma unroll
+        for (int i = 0; i < NM; i++) vmax[i] = warp_max(vmax[i]);
+#pragma unroll
+        for (int i = 0; i < NS; i++) vsum[i] = warp_sum(vsum[i]);
+        double* r = red + redbuf * W * 8;
+        redbuf ^= 1;
+        if (lane == 0)
+        {
+#pragma unroll
+            for (int i = 0; i < NM; i++) r[wid * 8 + i] = vmax[i];
+#pragma unroll
+            for (int i = 0; i < NS; i++) r[wid * 8 + NM + i] = vsum[i];
+        }
+        syncthreads();
+        for (int q = 0; q < W; q++)
+        {
+            if (q == wid) continue;
+#pragma unroll
+            for (int i = 0; i < NM; i++) { const double o = r[q * 8 + i]; vmax[i] = o > vmax[i] ? o : vmax[i]; }
+        }
+        // sums in warp order so that every thread adds the same numbers in the same order
+        if (NS > 0)
+        {
+            double s[NS > 0 ? NS : 1];
+#pragma unroll
+            for (int i = 0; i < NS; i++) s[i] = 0.0;
+            for (int q = 0; q < W; q++)
+            {
+#pragma unroll
+                for (int i = 0; i < NS; i++) s[i] += r[q * 8 + NM + i];
+            }
+#pragma unroll
+            for (int i = 0; i < NS; i++) vsum[i] = s[i];
+        }
+    }
+
+    // ---------------------------------------------------------------- constants into shared memory
+    // Gauss-Newton Hessians: ocp_nlp_cost_ls_initialize, AC/acados/ocp_nlp/ocp_nlp_cost_ls.c:713-745.  With
+    // Vx=[I;0], Vu=[0;I] the output map y = Cyt'[u;x] is the permutation [x;u].  Lower triangles are read.
+    MDEV void load_constants()
+    {
+        const double* Wg = P.cst;
+        const double* Weg = P.cst + NY * NY;
+        for (int e = tid; e < NV * NV; e += T)
+        {
+            const int i = e % NV, j = e / NV;
+            Ws[e] = i >= j ? Wg[i + NY * j] : Wg[j + NY * i];
+            const int yi = i < NU ? NX + i : i - NU, yj = j < NU ? NX + j : j - NU;
+            Hs[e] = P.dt * (yi >= yj ? Wg[yi + NY * yj] : Wg[yj + NY * yi]);
+            Hes[e] = (i >= NU && j >= NU) ? ((i >= j) ? Weg[(i - NU) + NX * (j - NU)] : Weg[(j - NU) + NX * (i - NU)]) : 0.0;
+        }
+        for (int e = tid; e < NX * NX; e += T)
+        {
+            const int i = e % NX, j = e / NX;
+            Wes[e] = i >= j ? Weg[i + NX * j] : Weg[j + NX * i];
+        }
+        if (tid < NX)
+        {
+            int r = -1;
+            for (int j = 0; j < nbx; j++) if (P.idxbx[j] == tid) r = nbu + j;
+            sxrow[tid] = r;
+        }
+        for (int jj = tid; jj < ncq; jj += T) srvar[jj] = jj < nbu ? jj : (jj < nbq ? NU + P.idxbx[jj - nbu] : -1);
+        syncthreads();
+        // templates of the matrix to factorise per stage class (0: stage 0, 1: path, 2: terminal): Hessian + reg_prim on
+        // the active variables, identity on the inactive ones
+        for (int e = tid; e < 3 * NE; e += T)
+        {
+            const int cls = e / NE, q = e - cls * NE;
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= q && r < NV) r++;
+            const int c = q - r * (r + 1) / 2;
+            const double* H = cls == 2 ? Hes : Hs;
+            double v = 0.0;
+            if (r < NV)
+            {
+                const bool ar = cls == 1 || (cls == 0 ? r < NU : r >= NU), ac = cls == 1 || (cls == 0 ? c < NU : c >= NU);
+                if (ar && ac) { v = H[r + NV * c]; if (c == r) v += 1e-15; }  // reg_prim
+                else if (c == r) v = 1.0;
+            }
+            Tp[e] = v;
+        }
+        syncthreads();
+    }
+
+    // ---------------------------------------------------------------- initial guess
+    // cold start of the scripts / template (acados_solver.in.c:1595-1623): x_k = x0, u = 0, pi = 0;
+    // lam, t start at zero like a freshly created nlp_out.
+    MDEV void cold_start(const double* x0)
+    {
+        for (int k = tid; k <= N; k += T)
+        {
+            double* z = Z(P.lay.zux, k);
+            for (int i = 0; i < NU; i++) z[i] = 0.0;
+            for (int i = 0; i < NX; i++) z[NU + i] = x0[i];
+            double* p = Z(P.lay.zpi, k);
+            for (int i = 0; i < NX; i++) p[i] = 0.0;
+            double* l = Z(P.lay.zlam, k); double* tt = Z(P.lay.zt, k);
+            for (int j = 0; j < 2 * ncz; j++) { l[j] = 0.0; tt[j] = 0.0; }
+        }
+        syncthreads();
+    }
+
+    // ---------------------------------------------------------------- linearisation
+    // ERK with forward sensitivities (AC/acados/sim/sim_erk_integrator.c:762-847, tableaus :253-344; seed S=[I 0],
+    // A=Sx(T), B=Su(T): ocp_nlp_dynamics_cont.c:782-804).  One thread integrates [x ; one sensitivity column] of one
+    // stage.
+    MDEV void integrate_all()
+    {
+        const int ns = P.num_stages;
+        double a21 = 0, a32 = 0, a43 = 0, bv0 = 0, bv1 = 0, bv2 = 0, bv3 = 0;
+        if (ns == 1) { bv0 = 1.0; }
+        else if (ns == 2) { a21 = 0.5; bv1 = 1.0; }
+        else { a21 = 0.5; a32 = 0.5; a43 = 1.0; bv0 = 1.0 / 6.0; bv1 = 1.0 / 3.0; bv2 = 1.0 / 3.0; bv3 = 1.0 / 6.0; }
+        const double step = P.dt / P.num_steps;
+        // columns of states that do not enter the dynamics stay unit vectors exactly (their VDE right-hand side is
+        // Jx e_c = 0): no thread integrates them, the first task of the stage writes them
+        constexpr int NCOL = NV - M::NKIN;
+        for (int task = tid; task < N * NCOL; task += T)
+        {
+            const int k = task / NCOL, col = M::NKIN + task % NCOL;
+            const double* z = Z(P.lay.zux, k);
+            double u[NU], x[NX], s[NX];
+#pragma unroll
+            for (int i = 0; i < NU; i++) u[i] = z[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) { x[i] = z[NU + i]; s[i] = (i == col) ? 1.0 : 0.0; }
+            for (int istep = 0; istep < P.num_steps; istep++)
+            {
+                double xr[NX], sr[NX], xa[NX], sa[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) { xr[i] = x[i]; sr[i] = s[i]; xa[i] = x[i]; sa[i] = s[i]; }
+#pragma unroll
+                for (int st = 0; st < 4; st++)
+                {
+                    if (st >= ns) break;
+                    double f[NX], ks[NX];
+                    // VDE right-hand side of this column: Jx*Sx_col, or Jx*Su_col + Ju_col
+                    // (acados_template/generate_c_code_explicit_ode.py:73-80)
+                    M::vde_col(xr, u, sr, col >= NX ? col - NX : -1, f, ks);
+                    const double bb = step * (st == 0 ? bv0 : st == 1 ? bv1 : st == 2 ? bv2 : bv3);
+                    const double aa = (st == 0 ? a21 : st == 1 ? a32 : st == 2 ? a43 : 0.0) * step;
+#pragma unroll
+                    for (int i = 0; i < NX; i++)
+                    {
+                        xa[i] += bb * f[i]; sa[i] += bb * ks[i];
+                        xr[i] = x[i]; sr[i] = s[i];
+                        if (aa != 0.0) { xr[i] += aa * f[i]; sr[i] += aa * ks[i]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) { x[i] = xa[i]; s[i] = sa[i]; }
+            }
+            // G = [B'; A'] (nv x nx, column-major): ocp_nlp_dynamics_cont.c:801-804
+            double* Gk = G + k * (NV * NX);
+            const int row = col < NX ? NU + col : col - NX;
+#pragma unroll
+            for (int i = 0; i < NX; i++) Gk[row + NV * i] = s[i];
+            if (col == M::NKIN)
+            {
+#pragma unroll
+                for (int c = 0; c < M::NKIN; c++)
+                {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) Gk[NU + c + NV * i] = (i == c) ? 1.0 : 0.0;
+                }
+                const double* zn = Z(P.lay.zux, k + 1);
+                double* bk = b + k * NX;
+#pragma unroll
+                for (int i = 0; i < NX; i++) bk[i] = x[i] - zn[NU + i];  // dyn_fun = phi(x,u) - x_next
+            }
+        }
+        syncthreads();
+    }
+
+    // cost / constraints / adjoints / NLP residuals / QP vectors, one thread per stage.
+    // ocp_nlp_approximate_qp_matrices + _vectors_sqp (ocp_nlp_common.c:1926-2084), ocp_nlp_res_compute (:2549-2603),
+    // x0 elimination d_ocp_qp_reduce_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:268-454).  res4 = (stat, eq, ineq, comp).
+    MDEV void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
+                       double* res4)
+    {
+        integrate_all();
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        for (int k = tid; k <= N; k += T)
+        {
+            const double* z = Z(P.lay.zux, k);
+            const double* zl = Z(P.lay.zlam, k);
+            const double* zt = Z(P.lay.zt, k);
+            double* zf = Z(P.lay.zfun, k);
+            double* rqk = rq + k * NV;
+            double* dk = d + k * s2;
+            double cg[NV], adj[NV];
+            // ---- LINEAR_LS cost gradient (ocp_nlp_cost_ls.c:749-843)
+            if (k < N)
+            {
+                const double* yr = yrg + (P.yref_per_stage ? k * NY : 0);
+                double r[NY];
+#pragma unroll
+                for (int i = 0; i < NX; i++) r[i] = z[NU + i] - yr[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) r[NX + i] = z[i] - yr[NX + i];
+#pragma unroll
+                for (int i = 0; i < NY; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NY; j++) acc += Ws[i + NY * j] * r[j];
+                    if (i < NX) cg[NU + i] = P.dt * acc; else cg[i - NX] = P.dt * acc;
+                }
+            }
+            else
+            {
+                double r[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) r[i] = z[NU + i] - yre[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) cg[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; i++)
+                {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += Wes[i + NX * j] * r[j];
+                    cg[NU + i] = acc;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) adj[i] = 0.0;
+            // ---- BGH constraints (ocp_nlp_constraints_bgh.c:1228-1430): fun = [lb - g ; g - ub], adj = J'(lam_l - lam_u)
+            for (int j = 0; j < 2 * ncz; j++) zf[j] = 0.0;
+            for (int j = 0; j < s2; j++) dk[j] = 0.0;
+            double dx0[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) dx0[i] = 0.0;
+            if (k < N)
+            {
+                for (int j = 0; j < nbu; j++)
+                {
+                    const double g = z[j], fl = P.lbu[k * nbu + j] - g, fu = g - P.ubu[k * nbu + j];
+                    zf[j] = fl; zf[ncz + j] = fu; dk[j] = fl; dk[ncq + j] = fu;
+                    const double dl = zl[j] - zl[ncz + j];
+#pragma unroll
+                    for (int i = 0; i < NU; i++) if (i == j) adj[i] += dl;
+                    const double a = dabs(fl + zt[j]), bb = dabs(fu + zt[ncz + j]);
+                    r2 = a > r2 ? a : r2; r2 = bb > r2 ? bb : r2;
+                    const double c0 = dabs(zl[j] * zt[j]), c1 = dabs(zl[ncz + j] * zt[ncz + j]);
+                    r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                }
+                if (k == 0)
+                {
+                    // x0 embedding: lbx = ubx = x0 on every state (acados_solver.in.c:1028-1051, bgh.c:1528)
+#pragma unroll
+                    for (int j = 0; j < NX; j++)
+                    {
+                        const double g = z[NU + j], fl = x0[j] - g, fu = g - x0[j];
+                        const int r = nbu + j;
+                        zf[r] = fl; zf[ncz + r] = fu;
+                        dx0[j] = fl;
+                        adj[NU + j] += zl[r] - zl[ncz + r];
+                        const double a = dabs(fl + zt[r]), bb = dabs(fu + zt[ncz + r]);
+                        r2 = a > r2 ? a : r2; r2 = bb > r2 ? bb : r2;
+                        const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                        r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                    }
+                }
+                else
+                {
+                    for (int j = 0; j < nbx; j++)
+                    {
+                        const int id = P.idxbx[j], r = nbu + j;
+                        const double g = z[NU + id], fl = P.lbx[k * nbx + j] - g, fu = g - P.ubx[k * nbx + j];
+                        zf[r] = fl; zf[ncz + r] = fu; dk[r] = fl; dk[ncq + r] = fu;
+                        const double dl = zl[r] - zl[ncz + r];
+#pragma unroll
+                        for (int i = 0; i < NX; i++) if (i == id) adj[NU + i] += dl;
+                        const double a = dabs(fl + zt[r]), bb = dabs(fu + zt[ncz + r]);
+                        r2 = a > r2 ? a : r2; r2 = bb > r2 ? bb : r2;
+                        const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                        r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                    }
+                }
+                // obstacle distances h_c = ||(X,Y) - (ox_c, oy_c)||, dh/d(X,Y) = ((X,Y) - o_c)/h_c
+                const double* pk = pg + (P.p_per_stage ? k * 2 * K : 0);
+                const double* lhk = lhg + (P.lh_per_stage ? k * K : 0);
+                double* gk = gxy + k * 2 * K;
+                for (int c = 0; c < K; c++)
+                {
+                    const double ddx = z[HXV] - pk[2 * c], ddy = z[HYV] - pk[2 * c + 1];
+                    const double h = dsqrt(ddx * ddx + ddy * ddy);
+                    const double gX = ddx / h, gY = ddy / h;
+                    gk[c] = gX; gk[K + c] = gY;
+                    const double fl = lhk[c] - h, fu = h - P.uh[k * K + c];
+                    const int r = nbu + NX + c, rqp = nbq + c;
+                    zf[r] = fl; zf[ncz + r] = fu;
+                    // stage 0: fold the eliminated x0 step into the bounds (x_ocp_qp_red.c:380-420)
+                    const double v = (k == 0) ? gX * dx0[M::HX] + gY * dx0[M::HY] : 0.0;
+                    dk[rqp] = fl - v; dk[ncq + rqp] = fu + v;
+                    const double dl = zl[r] - zl[ncz + r];
+                    adj[HXV] += gX * dl; adj[HYV] += gY * dl;
+                    const double a = dabs(fl + zt[r]), bb = dabs(fu + zt[ncz + r]);
+                    r2 = a > r2 ? a : r2; r2 = bb > r2 ? bb : r2;
+                    const double c0 = dabs(zl[r] * zt[r]), c1 = dabs(zl[ncz + r] * zt[ncz + r]);
+                    r3 = c0 > r3 ? c0 : r3; r3 = c1 > r3 ? c1 : r3;
+                }
+            }
+            // ---- dynamics adjoint -[B';A'] pi_k (+ pi_{k-1} on x): ocp_nlp_common.c:2001-2019 ; stationarity residual
+            const double* Gk = G + k * (NV * NX);
+            const double* pik = Z(P.lay.zpi, k);
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+            {
+                double acc = 0.0;
+                if (k < N)
+                {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc -= Gk[i + NV * j] * pik[j];
+                }
+                if (k > 0 && i >= NU) acc += Z(P.lay.zpi, k - 1)[i - NU];
+                if (k < N || i >= NU)
+                {
+                    const double a = dabs(cg[i] - adj[i] - acc);
+                    r0 = a > r0 ? a : r0;
+                }
+            }
+            if (k < N)
+            {
+                const double* bk = b + k * NX;
+#pragma unroll
+                for (int i = 0; i < NX; i++) { const double a = dabs(bk[i]); r1 = a > r1 ? a : r1; }
+            }
+            // ---- QP gradient; stage 0: b0 += A0' dx0, r0 += S dx0 (x_ocp_qp_red.c:300-378)
+#pragma unroll
+            for (int i = 0; i < NV; i++) rqk[i] = cg[i];
+            if (k == 0 && N > 0)
+            {
+                double* bk = b;
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+                {
+                    double acc = bk[j];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) acc += Gk[NU + i + NV * j] * dx0[i];
+                    bk[j] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < NU; i++)
+                {
+                    double acc = cg[i];
+#pragma unroll
+                    for (int j = 0; j < NX; j++) acc += Hs[(NU + j) + NV * i] * dx0[j];
+                    rqk[i] = acc;
+                }
+                // stage 0 after x0 elimination has no x rows in [B';A'] (x_ocp_qp_red.c:268-454): keep the unmasked block
+                // for the restoration of the stage-0 multipliers, mask the working copy
+                for (int e = 0; e < NV * NX; e++)
+                {
+                    sA0[e] = Gk[e];
+                    if (e % NV >= NU) G[e] = 0.0;
+                }
+            }
+        }
+        double vm[4] = {r0, r1, r2, r3};
+        block_reduce<4, 0>(vm, nullptr);
+        res4[0] = vm[0]; res4[1] = vm[1]; res4[2] = vm[2]; res4[3] = vm[3];
+    }
+
+    // ---------------------------------------------------------------- IPM: start point
+    // OCP_QP_INIT_VAR, var_init_scheme 1, cold start: HP/ocp_qp/x_ocp_qp_ipm.c:1435-1470,1581-1714 (ns = 0)
+    MDEV void ipm_init()
+    {
+        const double thr0 = 1e-1, mu0 = 1.0;
+        for (int k = tid; k <= N; k += T)
+        {
+            double* v = ux + k * NV; double* pk = pi + k * NX; double* l = lam + k * s2; double* tt = t + k * s2;
+            const double* dk = d + k * s2;
+            for (int i = 0; i < NV; i++) v[i] = 0.0;
+            for (int i = 0; i < NX; i++) pk[i] = 0.0;
+            for (int j = 0; j < s2; j++) { l[j] = 0.0; tt[j] = 1.0; }
+            {
+                // the first passA applies a zero step: the step starts at zero
+                double* a = dux + k * NV; double* bq = dpi + k * NX; double* c = dlam + k * s2; double* e = dt + k * s2;
+                for (int i = 0; i < NV; i++) a[i] = 0.0;
+                for (int i = 0; i < NX; i++) bq[i] = 0.0;
+                for (int j = 0; j < s2; j++) { c[j] = 0.0; e[j] = 0.0; }
+            }
+            if (k >= N) continue;
+            for (int j = 0; j < nbq; j++)
+            {
+                if (!row_active(k, j)) continue;
+                const int id = srvar[j];
+                double tl = v[id] - dk[j], tu = -v[id] - dk[ncq + j];
+                if (tl < thr0)
+                {
+                    if (tu < thr0) { v[id] = 0.5 * (dk[j] - dk[ncq + j]); tl = thr0; tu = thr0; }
+                    else { tl = thr0; v[id] = dk[j] + thr0; }
+                }
+                else if (tu < thr0) { tu = thr0; v[id] = -dk[ncq + j] - thr0; }
+                tt[j] = tl; tt[ncq + j] = tu;
+            }
+            const double* gk = gxy + k * 2 * K;
+            for (int c = 0; c < K; c++)
+            {
+                const double vv = (k >= 1) ? gk[c] * v[HXV] + gk[K + c] * v[HYV] : 0.0;
+                const double tl = vv - dk[nbq + c], tu = -vv - dk[ncq + nbq + c];
+                tt[nbq + c] = thr0 > tl ? thr0 : tl;
+                tt[ncq + nbq + c] = thr0 > tu ? thr0 : tu;
+            }
+            for (int j = 0; j < ncq; j++)
+                if (row_active(k, j)) { l[j] = mu0 / tt[j]; l[ncq + j] = mu0 / tt[ncq + j]; }
+        }
+        syncthreads();
+    }
+
+    // ---------------------------------------------------------------- IPM: passes
+    // passA: UPDATE_VAR_QP (x_core_qp_ipm_aux.c:220-325, split_step = 0) + OCP_QP_RES_COMPUTE (x_ocp_qp_res.c:336-466)
+    // + COMPUTE_GAMMA_GAMMA_QP (x_core_qp_ipm_aux.c:38-86) for res_m = lam*t - tau + assembly of the matrix to factorise
+    // (H + Gamma terms, gradient row) in the M field of every stage.
+    MDEV void passA(double a, double tau, double* n4)
+    {
+        const double lam_min = 1e-16, t_min = 1e-16;
+        // ---- A1: variable update, element-parallel
+        for (int e = tid; e < (N + 1) * NV; e += T) ux[e] += a * dux[e];
+        for (int e = tid; e < N * NX; e += T) pi[e] += a * dpi[e];
+        for (int e = tid; e < N * s2; e += T)
+        {
+            const int k = dq.div(e) >> 1;          // e / (2 ncq)
+            int j = e - k * s2; if (j >= ncq) j -= ncq;
+            if (!row_active(k, j)) continue;
+            double x = lam[e] + a * dlam[e];
+            lam[e] = x <= lam_min ? lam_min : x;
+            x = t[e] + a * dt[e];
+            t[e] = x <= t_min ? t_min : x;
+        }
+        syncthreads();
+        // ---- A2: inequality rows, one (stage, row pair) per thread: res_d, res_m norms, mu, 1/t, and the row's
+        // contributions (lam_u - lam_l, Gamma_l + Gamma_u, gamma_l - gamma_u) for A3, parked in the (dead) step arrays
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
+        for (int it = tid; it < N * ncq; it += T)
+        {
+            const int k = dq.div(it), j = it - k * ncq;
+            const int r0 = k * s2 + j, r1 = r0 + ncq;
+            if (!row_active(k, j)) { dlam[r0] = 0.0; dlam[r1] = 0.0; dt[r0] = 0.0; continue; }
+            const double* v = ux + k * NV;
+            double vv;
+            if (j < nbq) vv = v[srvar[j]];
+            else vv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+            const double l0 = lam[r0], l1 = lam[r1], t0 = t[r0], t1 = t[r1];
+            const double rd0 = d[r0] + t0 - vv, rd1 = d[r1] + t1 + vv;
+            rd[r0] = rd0; rd[r1] = rd1;
+            const double m0 = l0 * t0, m1 = l1 * t1;
+            musum += m0; musum += m1;
+            double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
+            q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
+            const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
+            ti[r0] = ti0; ti[r1] = ti1;
+            dlam[r0] = l1 - l0;
+            dlam[r1] = ti0 * l0 + ti1 * l1;
+            dt[r0] = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+        }
+        // ---- res_b = b + [B A] ux - x_{k+1}, one (stage, state) per thread
+        for (int it = tid; it < N * NX; it += T)
+        {
+            const int k = dnx.div(it), j = it - k * NX;
+            const double* v = ux + k * NV;
+            const double* Gk = G + k * (NV * NX) + NV * j;
+            double acc = b[it] - ux[(k + 1) * NV + NU + j];
+#pragma unroll
+            for (int i = 0; i < NV; i++) acc += Gk[i] * v[i];  // stage 0: the x rows of G are zero
+            rb[it] = acc;
+            const double q = dabs(acc);
+            n1 = q > n1 ? q : n1;
+        }
+        // ---- template of the matrix to factorise (off-diagonal entries), four-entry chunks
+        for (int it = tid; it < (N + 1) * NE; it += T)
+        {
+            const int k = it / NE, e = it - k * NE;
+            Mx[it] = Tp[stage_class(k) * NE + e];
+        }
+        syncthreads();
+        // ---- A3: stationarity residual, diagonal and gradient row, one (stage, variable) per thread
+        for (int it = tid; it < (N + 1) * NV; it += T)
+        {
+            const int k = dnv.div(it), i = it - k * NV;
+            const double* v = ux + k * NV;
+            const double* H = Hk(k);
+            double g = rq[it], dg = 0.0, gg = 0.0;
+#pragma unroll
+            for (int j = 0; j < NV; j++) g += H[i + NV * j] * v[j];
+            if (k > 0 && i >= NU) g -= pi[(k - 1) * NX + i - NU];
+            if (k < N)
+            {
+                const double* Gk = G + k * (NV * NX) + i;
+                const double* pk = pi + k * NX;
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; j++) acc += Gk[NV * j] * pk[j];
+                g += acc;
+                const int row = vrow(k, i);
+                if (row >= 0)
+                {
+                    const int r0 = k * s2 + row;
+                    g += dlam[r0]; dg += dlam[r0 + ncq]; gg += dt[r0];
+                }
+                if ((i == HXV || i == HYV) && k >= 1)
+                {
+                    const double* gk = gxy + k * 2 * K;
+                    const double* gi = i == HXV ? gk : gk + K;
+                    double aYX = 0.0;
+                    for (int c = 0; c < K; c++)
+                    {
+                        const int r0 = k * s2 + nbq + c;
+                        const double Gs = dlam[r0 + ncq];
+                        g += gi[c] * dlam[r0];
+                        dg += (gi[c] * Gs) * gi[c];
+                        gg += dt[r0] * gi[c];
+                        if (i == HYV) aYX += (gk[K + c] * Gs) * gk[c];
+                    }
+                    if (i == HYV) Mx[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
+                }
+            }
+            const double gi = var_active(k, i) ? g : 0.0;
+            rg[it] = gi;
+            Mx[k * NE + MI(i, i)] += dg;
+            Mx[k * NE + MI(NV, i)] = gi + gg;
+            const double q = dabs(gi);
+            n0 = q > n0 ? q : n0;
+        }
+        double vm[4] = {n0, n1, n2, n3}, vs[1] = {musum};
+        block_reduce<4, 1>(vm, vs);
+        n4[0] = vm[0]; n4[1] = vm[1]; n4[2] = vm[2]; n4[3] = vm[3];
+        mu = nct > 0 ? vs[0] / nct : 0.0;
+    }
+
+    // ---------------------------------------------------------------- IPM: the serial recursions (warp 0)
+    // chainA: Riccati factorisation, backward.  On entry the M field of every stage holds H + Gamma terms with the
+    // gradient row (passA); on exit, per stage: columns < NU = the Cholesky columns of the input block (rows NU.. = Lxu,
+    // row NV = l_u), the rest = P_k (lower, packed) and p_k (row NV); dinv = 1 / diag(Luu); Pb = P_{k+1} res_b.
+    MDEV void chainA()
+    {
+        if (wid != 0) return;
+        // the lower-trapezoid entries this lane owns: e = lane + 32 q  ->  (row, column)
+        constexpr int NQ = (NE + 31) / 32;
+        int er[NQ], ec[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+        {
+            const int e = lane + 32 * q;
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= e && r < NV) r++;
+            er[q] = r; ec[q] = e - r * (r + 1) / 2;
+        }
+#pragma unroll 1
+        for (int k = N; k >= 0; k--)
+        {
+            double* Mk = Mx + k * NE;
+            if (k < N)
+            {
+                // sW = P_{k+1} [G' | res_b]   (NX x (NV+1)): column i < NV = P G(i,:)', column NV = Pb
+                const double* Gk = G + k * (NV * NX);
+                const double* rbk = rb + k * NX;
+#pragma unroll 1
+                for (int e = lane; e < NX * NR; e += 32)
+                {
+                    const int i = e / NX, m = e - i * NX;
+                    const double* ga = i < NV ? Gk + i : rbk;
+                    const int sa = i < NV ? NV : 1;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int n = 0; n < NX; n++) acc += sP[m * NX + n] * ga[n * sa];
+                    sW[e] = acc;
+                    if (i == NV) Pb[k * NX + m] = acc;
+                }
+                syncwarp();
+                // M += G P G' on the lower triangle; gradient row += G (Pb + p_{k+1})
+                const double* Mn = Mx + (k + 1) * NE;
+#pragma unroll
+                for (int q = 0; q < NQ; q++)
+                {
+                    const int e = lane + 32 * q, r = er[q], c = ec[q];
+                    if (e >= NE) continue;
+                    double acc = 0.0;
+                    if (r < NV)
+                    {
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += Gk[r + NV * m] * sW[c * NX + m];
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += Gk[c + NV * m] * (sW[NV * NX + m] + Mn[MI(NV, NU + m)]);
+                    }
+                    Mk[e] += acc;
+                }
+                syncwarp();
+            }
+            // eliminate the NU input columns: Cholesky columns with the non-positive-pivot rule of dpotrf_l_mn
+            // (BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710: that column becomes zero)
+#pragma unroll
+            for (int j = 0; j < NU; j++)
+            {
+                const double piv = Mk[MI(j, j)];
+                double inv = 0.0;
+                if (piv > 0.0) inv = drsqrt(piv);
+                double upd[NQ];
+                bool wr[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; q++)
+                {
+                    const int e = lane + 32 * q, r = er[q], c = ec[q];
+                    wr[q] = false;
+                    if (e >= NE || c < j) continue;
+                    wr[q] = true;
+                    if (c == j) upd[q] = r == j ? piv * inv : Mk[e] * inv;
+                    else upd[q] = Mk[e] - (Mk[MI(r, j)] * inv) * (Mk[MI(c, j)] * inv);
+                }
+                syncwarp();
+#pragma unroll
+                for (int q = 0; q < NQ; q++) if (wr[q]) Mk[lane + 32 * q] = upd[q];
+                if (lane == 0) dinv[k * NU + j] = inv;
+                syncwarp();
+            }
+            // P_k as a full symmetric matrix for the next stage's products
+#pragma unroll 1
+            for (int e = lane; e < NX * NX; e += 32)
+            {
+                const int i = e / NX, jj = e - i * NX;
+                sP[e] = i >= jj ? Mk[MI(NU + i, NU + jj)] : Mk[MI(NU + jj, NU + i)];
+            }
+            syncwarp();
+        }
+    }
+
+    // chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> x part of `out` (stage stride NV)
+    MDEV void chainF(double* out)
+    {
+        if (wid != 0) return;
+        double xc[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xc[i] = 0.0;
+        if (lane < NX) out[NU + lane] = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < N; k++)
+        {
+            double x1 = 0.0;
+            if (lane < NX)
+            {
+                const double* Ar = Acl + k * (NX * NX) + lane * NX;
+                double a0 = cc[k * NX + lane], a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; j += 2) { a0 += Ar[j] * xc[j]; if (j + 1 < NX) a1 += Ar[j + 1] * xc[j + 1]; }
+                x1 = a0 + a1;
+                out[(k + 1) * NV + NU + lane] = x1;
+            }
+#pragma unroll
+            for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+        }
+    }
+
+    // chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> x part of zv
+    MDEV void chainC()
+    {
+        if (wid != 0) return;
+        double pn[NX];
+        {
+            const double e = lane < NX ? ee[N * NX + lane] : 0.0;
+            if (lane < NX) zv[N * NV + NU + lane] = e;
+#pragma unroll
+            for (int m = 0; m < NX; m++) pn[m] = shfl(e, m);
+        }
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; k--)
+        {
+            double p1 = 0.0;
+            if (lane < NX)
+            {
+                const double* Ac = Acl + k * (NX * NX) + lane;
+                double a0 = ee[k * NX + lane], a1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < NX; m += 2) { a0 += Ac[m * NX] * pn[m]; if (m + 1 < NX) a1 += Ac[(m + 1) * NX] * pn[m + 1]; }
+                p1 = a0 + a1;
+                zv[k * NV + NU + lane] = p1;
+            }
+#pragma unroll
+            for (int m = 0; m < NX; m++) pn[m] = shfl(p1, m);
+        }
+    }
+
+    // ---------------------------------------------------------------- IPM: passes around the chains
+    // gains after chainA: K_k = -Luu^-T Lxu', Acl_k = A_k + B_k K_k
+    MDEV void gains_pass()
+    {
+        for (int it = tid; it < (N + 1) * NX; it += T)
+        {
+            const int k = dnx.div(it), j = it - k * NX;
+            const double* Mk = Mx + k * NE;
+            double kg[NU];
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--)
+            {
+                double acc = -Mk[MI(NU + j, i)];
+#pragma unroll
+                for (int m = i + 1; m < NU; m++) acc -= Mk[MI(m, i)] * kg[m];
+                kg[i] = acc * dinv[k * NU + i];
+                Kg[k * (NU * NX) + i * NX + j] = kg[i];
+            }
+        }
+        syncthreads();
+        for (int it = tid; it < N * NX * NX; it += T)
+        {
+            const int k = it / (NX * NX), e = it - k * (NX * NX), i = e / NX, j = e - i * NX;
+            const double* Gk = G + k * (NV * NX) + NV * i;
+            double acc = Gk[NU + j];
+#pragma unroll
+            for (int m = 0; m < NU; m++) acc += Gk[m] * Kg[k * (NU * NX) + m * NX + j];
+            Acl[it] = acc;
+        }
+    }
+
+    // feed-forward terms: kk_k = -Luu^-T l_u,k and c_k = rhs_b,k + B_k kk_k.  from_factor: l_u = row NV of the factor
+    // (factorise+solve sweep); else l_u = Luu^-1 (z0_u + B'(p_{k+1} + Pb_k)) with p in the x part of zv.
+    MDEV void feedforward_pass(bool from_factor, const double* rbp)
+    {
+        for (int k = tid; k <= N; k += T)
+        {
+            const double* Mk = Mx + k * NE;
+            const double* Gk = G + k * (NV * NX);
+            double lu[NU], kv[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++)
+            {
+                double acc;
+                if (from_factor) acc = Mk[MI(NV, i)];
+                else
+                {
+                    acc = zv[k * NV + i];
+                    if (k < N)
+                    {
+#pragma unroll
+                        for (int m = 0; m < NX; m++) acc += Gk[i + NV * m] * (zv[(k + 1) * NV + NU + m] + Pb[k * NX + m]);
+                    }
+#pragma unroll
+                    for (int m = 0; m < i; m++) acc -= Mk[MI(i, m)] * lu[m];
+                    acc *= dinv[k * NU + i];
+                }
+                lu[i] = acc;
+            }
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--)
+            {
+                double acc = -lu[i];
+#pragma unroll
+                for (int m = i + 1; m < NU; m++) acc -= Mk[MI(m, i)] * kv[m];
+                kv[i] = acc * dinv[k * NU + i];
+                kk[k * NU + i] = kv[i];
+            }
+            if (k < N)
+            {
+#pragma unroll
+                for (int m = 0; m < NX; m++)
+                {
+                    double acc = rbp[k * NX + m];
+#pragma unroll
+                    for (int i = 0; i < NU; i++) acc += Gk[i + NV * m] * kv[i];
+                    cc[k * NX + m] = acc;
+                }
+            }
+        }
+        syncthreads();
+    }
+
+    // right-hand side of a solve with the existing factorisation (OCP_QP_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:1096-1242):
+    // gamma rows (COMPUTE_GAMMA_QP, x_core_qp_ipm_aux.c:89-113) -> z0 = rhs_g + J'(gamma_l - gamma_u) -> e_k.
+    //   mode 0: corrector, res_m = lam*t + dt_aff*dlam_aff - sigma_mu -> rmc      (x_ocp_qp_ipm.c:2138-2160)
+    //   mode 1: centering only, res_m = lam*t - sigma_mu -> rmc                    (:2175-2200)
+    //   mode 2: iterative refinement, right-hand side (rg2, rb2, rd2, rm2)          (:2221-2311)
+    // gsc: a dead array with the stride of the row arrays that receives gamma_l - gamma_u.
+    MDEV void rhs_pass(int mode, double sigma_mu)
+    {
+        const double* rgp = mode == 2 ? rg2 : rg;
+        const double* rdp = mode == 2 ? rd2 : rd;
+        double* gsc = mode == 2 ? dlam2 : dlam;
+        for (int it = tid; it < N * ncq; it += T)
+        {
+            const int k = dq.div(it), j = it - k * ncq;
+            const int r0 = k * s2 + j, r1 = r0 + ncq;
+            if (!row_active(k, j)) { if (mode != 2) { rmc[r0] = 0.0; rmc[r1] = 0.0; } gsc[r0] = 0.0; continue; }
+            const double l0 = lam[r0], l1 = lam[r1];
+            double m0, m1;
+            if (mode == 2) { m0 = rm2[r0]; m1 = rm2[r1]; }
+            else
+            {
+                m0 = l0 * t[r0]; m1 = l1 * t[r1];
+                if (mode == 0) { m0 += dt[r0] * dlam[r0]; m1 += dt[r1] * dlam[r1]; }
+                m0 -= sigma_mu; m1 -= sigma_mu;
+                rmc[r0] = m0; rmc[r1] = m1;
+            }
+            gsc[r0] = ti[r0] * (m0 - l0 * rdp[r0]) - ti[r1] * (m1 - l1 * rdp[r1]);
+        }
+        syncthreads();
+        for (int it = tid; it < (N + 1) * NV; it += T)
+        {
+            const int k = dnv.div(it), i = it - k * NV;
+            double z = rgp[it];
+            const int row = vrow(k, i);
+            if (row >= 0) z += gsc[k * s2 + row];
+            if ((i == HXV || i == HYV) && k >= 1 && k < N)
+            {
+                const double* gi = gxy + k * 2 * K + (i == HXV ? 0 : K);
+                for (int c = 0; c < K; c++) z += gi[c] * gsc[k * s2 + nbq + c];
+            }
+            zv[it] = var_active(k, i) ? z : 0.0;
+        }
+        if (mode == 2)
+        {
+            // Pb = P_{k+1} rhs_b for the new right-hand side (the factor's Pb belongs to res_b)
+            for (int it = tid; it < N * NX; it += T)
+            {
+                const int k = dnx.div(it), m = it - k * NX;
+                const double* Mn = Mx + (k + 1) * NE;
+                double acc = 0.0;
+#pragma unroll
+                for (int n = 0; n < NX; n++) acc += (m >= n ? Mn[MI(NU + m, NU + n)] : Mn[MI(NU + n, NU + m)]) * rb2[k * NX + n];
+                Pb[it] = acc;
+            }
+        }
+        syncthreads();
+        // e_k = Acl_k' Pb_k + z0_x + K_k' z0_u   (e_N = z0_x)
+        for (int it = tid; it < (N + 1) * NX; it += T)
+        {
+            const int k = dnx.div(it), j = it - k * NX;
+            double acc = zv[k * NV + NU + j];
+#pragma unroll
+            for (int m = 0; m < NU; m++) acc += Kg[k * (NU * NX) + m * NX + j] * zv[k * NV + m];
+            if (k < N)
+            {
+#pragma unroll
+                for (int m = 0; m < NX; m++) acc += Acl[k * (NX * NX) + m * NX + j] * Pb[k * NX + m];
+            }
+            ee[it] = acc;
+        }
+        syncthreads();
+    }
+
+    // expand_pass: du = K dx + kk; dt, dlam from the primal step (x_ocp_qp_kkt.c:748-764 + COMPUTE_LAM_T_QP,
+    // x_core_qp_ipm_aux.c:117-142), COMPUTE_ALPHA_QP (:146-216), the sums COMPUTE_MU_AFF_QP (:329-357) needs, the
+    // inequality / complementarity rows of OCP_QP_RES_COMPUTE_LIN (x_ocp_qp_res.c:560-633) of this very step, and
+    // dpi_k = P_{k+1} dx_{k+1} + p_{k+1} (x_ocp_qp_kkt.c:560-575 | 1270-1290).
+    //   mode 0: affine step (res_m = lam*t - tau, p = row NV of the factor); 1: rhs rmc, p = x part of zv;
+    //   mode 2: refinement (rd2, rm2 -> dux2, dpi2, dlam2, dt2), no step length
+    MDEV void expand_pass(int mode, double tau)
+    {
+        double* vo = mode == 2 ? dux2 : dux;
+        double* dlo = mode == 2 ? dlam2 : dlam;
+        double* dto = mode == 2 ? dt2 : dt;
+        double* dpo = mode == 2 ? dpi2 : dpi;
+        const double* rdp = mode == 2 ? rd2 : rd;
+        const double* rmp = mode == 2 ? rm2 : rmc;
+        for (int it = tid; it < (N + 1) * NU; it += T)
+        {
+            const int k = it / NU, m = it - k * NU;
+            double acc = kk[it];
+            const double* Kr = Kg + k * (NU * NX) + m * NX;
+            const double* dx = vo + k * NV + NU;
+#pragma unroll
+            for (int j = 0; j < NX; j++) acc += Kr[j] * dx[j];
+            vo[k * NV + m] = k < N ? acc : 0.0;
+        }
+        syncthreads();
+        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2s = 0.0, nd = 0.0, nm = 0.0;
+        for (int it = tid; it < N * ncq; it += T)
+        {
+            const int k = dq.div(it), j = it - k * ncq;
+            if (!row_active(k, j)) continue;
+            const double* v = vo + k * NV;
+            double dv;
+            if (j < nbq) dv = v[srvar[j]];
+            else dv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+#pragma unroll
+            for (int side = 0; side < 2; side++)
+            {
+                const int r = k * s2 + j + side * ncq;
+                double dtr = side ? -dv : dv;
+                const double lam0 = lam[r], t0 = t[r], e0 = rdp[r];
+                const double m = mode == 0 ? lam0 * t0 - tau : rmp[r];
+                const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * e0));
+                dtr -= e0;
+                dlo[r] = dlr; dto[r] = dtr;
+                // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best is
+                // kept as (numerator, denominator) and compared by cross-multiplication: one division per thread
+                if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
+                if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
+                s1 += lam0 * dtr + t0 * dlr;
+                s2s += dlr * dtr;
+                const double e = side ? e0 + dtr + dv : e0 + dtr - dv;
+                const double mm = m + lam0 * dtr + dlr * t0;
+                double q = dabs(e); nd = q > nd ? q : nd;
+                q = dabs(mm); nm = q > nm ? q : nm;
+            }
+        }
+        // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
+        for (int it = tid; it < N * NX; it += T)
+        {
+            const int k = dnx.div(it), i = it - k * NX;
+            const double* Mn = Mx + (k + 1) * NE;
+            const double* xn = vo + (k + 1) * NV + NU;
+            double acc = mode == 0 ? Mn[MI(NV, NU + i)] : zv[(k + 1) * NV + NU + i];
+#pragma unroll
+            for (int n = 0; n < NX; n++) acc += (i >= n ? Mn[MI(NU + i, NU + n)] : Mn[MI(NU + n, NU + i)]) * xn[n];
+            dpo[it] = acc;
+        }
+        if (mode != 2)
+        {
+            double vm[4] = {bpn / bpd, bdn / bdd, nd, nm}, vs[2] = {s1, s2s};
+            block_reduce<4, 2>(vm, vs);
+            alpha = -(vm[0] > vm[1] ? vm[0] : vm[1]);
+            lin_d = vm[2]; lin_m = vm[3];
+            S1 = vs[0]; S2 = vs[1];
+        }
+        else syncthreads();
+    }
+
+    // OCP_QP_RES_COMPUTE_LIN (HP/ocp_qp/x_ocp_qp_res.c:468-633): residual of the Newton system with right-hand side
+    // (rg, rb, rd, rmc) at the step (dux, dpi, dlam, dt); norms into out4.  WRITE: also store it (rg2, rb2, rd2, rm2) as
+    // the right-hand side of an iterative-refinement solve and compute all four norms from scratch; without WRITE the
+    // step is expand_pass's and so are the norms of the inequality / complementarity rows (lin_d, lin_m).
+    template <bool WRITE>
+    MDEV void res_pass(double* out4)
+    {
+        double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        for (int it = tid; it < (N + 1) * NV; it += T)
+        {
+            const int k = dnv.div(it), i = it - k * NV;
+            const double* v = dux + k * NV;
+            const double* H = Hk(k);
+            double g = rg[it];
+#pragma unroll
+            for (int j = 0; j < NV; j++) g += H[i + NV * j] * v[j];
+            if (k > 0 && i >= NU) g -= dpi[(k - 1) * NX + i - NU];
+            if (k < N)
+            {
+                const double* Gk = G + k * (NV * NX) + i;
+                const double* pk = dpi + k * NX;
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; j++) acc += Gk[NV * j] * pk[j];
+                g += acc;
+                const int row = vrow(k, i);
+                if (row >= 0) g += dlam[k * s2 + ncq + row] - dlam[k * s2 + row];
+                if ((i == HXV || i == HYV) && k >= 1)
+                {
+                    const double* gi = gxy + k * 2 * K + (i == HXV ? 0 : K);
+                    for (int c = 0; c < K; c++) g += gi[c] * (dlam[k * s2 + ncq + nbq + c] - dlam[k * s2 + nbq + c]);
+                }
+            }
+            const double gi = var_active(k, i) ? g : 0.0;
+            if (WRITE) rg2[it] = gi;
+            const double q = dabs(gi);
+            n0 = q > n0 ? q : n0;
+        }
+        for (int it = tid; it < N * NX; it += T)
+        {
+            const int k = dnx.div(it), j = it - k * NX;
+            const double* v = dux + k * NV;
+            const double* Gk = G + k * (NV * NX) + NV * j;
+            double acc = rb[it] - dux[(k + 1) * NV + NU + j];
+#pragma unroll
+            for (int i = 0; i < NV; i++) acc += Gk[i] * v[i];
+            if (WRITE) rb2[it] = acc;
+            const double q = dabs(acc);
+            n1 = q > n1 ? q : n1;
+        }
+        if (WRITE)
+        {
+            for (int it = tid; it < N * ncq; it += T)
+            {
+                const int k = dq.div(it), j = it - k * ncq;
+                const int r0 = k * s2 + j, r1 = r0 + ncq;
+                if (!row_active(k, j)) { rd2[r0] = 0.0; rd2[r1] = 0.0; rm2[r0] = 0.0; rm2[r1] = 0.0; continue; }
+                const double* v = dux + k * NV;
+                double vv;
+                if (j < nbq) vv = v[srvar[j]];
+                else vv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+                const double e0 = rd[r0] + dt[r0] - vv, e1 = rd[r1] + dt[r1] + vv;
+                rd2[r0] = e0; rd2[r1] = e1;
+                double q = dabs(e0); n2 = q > n2 ? q : n2; q = dabs(e1); n2 = q > n2 ? q : n2;
+                const double m0 = rmc[r0] + lam[r0] * dt[r0] + dlam[r0] * t[r0];
+                const double m1 = rmc[r1] + lam[r1] * dt[r1] + dlam[r1] * t[r1];
+                rm2[r0] = m0; rm2[r1] = m1;
+                q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
+            }
+        }
+        double vm[4] = {n0, n1, n2, n3};
+        block_reduce<4, 0>(vm, nullptr);
+        out4[0] = vm[0]; out4[1] = vm[1]; out4[2] = WRITE ? vm[2] : lin_d; out4[3] = WRITE ? vm[3] : lin_m;
+    }
+
+    // COMPUTE_ALPHA_QP on the current step (after iterative refinement changed it)
+    MDEV void alpha_pass()
+    {
+        double a_prim = -1.0, a_dual = -1.0;
+        for (int it = tid; it < N * s2; it += T)
+        {
+            const int k = dq.div(it) >> 1;
+            int j = it - k * s2; if (j >= ncq) j -= ncq;
+            if (!row_active(k, j)) continue;
+            if (a_dual * dlam[it] > lam[it]) a_dual = lam[it] / dlam[it];
+            if (a_prim * dt[it] > t[it]) a_prim = t[it] / dt[it];
+        }
+        double vm[2] = {a_prim, a_dual};
+        block_reduce<2, 0>(vm, nullptr);
+        alpha = -(vm[0] > vm[1] ? vm[0] : vm[1]);
+    }
+
+    // step += refinement step
+    MDEV void add_refinement()
+    {
+        for (int e = tid; e < (N + 1) * NV; e += T) dux[e] += dux2[e];
+        for (int e = tid; e < N * NX; e += T) dpi[e] += dpi2[e];
+        for (int e = tid; e < N * s2; e += T)
+        {
+            const int k = dq.div(e) >> 1;
+            int j = e - k * s2; if (j >= ncq) j -= ncq;
+            if (row_active(k, j)) { dlam[e] += dlam2[e]; dt[e] += dt2[e]; }
+        }
+        syncthreads();
+    }
+
+    MDEV bool itref_ok(const double* n) const
+    {
+        return (n[0] < tol_stat || n[0] < 1e-3 * res_max[0]) && (n[1] < tol_eq || n[1] < 1e-3 * res_max[1]) &&
+               (n[2] < tol_ineq || n[2] < 1e-3 * res_max[2]) && (n[3] < tol_comp || n[3] < 1e-3 * res_max[3]);
+    }
+
+    // solve with the existing factorisation for the right-hand side prepared by rhs_pass(mode)
+    MDEV void solve_kkt(int mode)
+    {
+        chainC();
+        syncthreads();
+        feedforward_pass(false, mode == 2 ? rb2 : rb);
+        chainF(mode == 2 ? dux2 : dux);
+        syncthreads();
+        solve_calls++;
+    }
+
+    // OCP_QP_IPM_SOLVE + OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683, 1888-2350 (pred_corr,
+    // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
+    MDEV int ipm_solve(int* iters)
+    {
+        const double tau_min = 1e-16, alpha_min = 1e-8;
+        ipm_init();
+        PROF(10)
+        alpha = 1.0;
+        double a = 0.0;  // the first passA applies no step
+        int it = 0;
+        if (nct == 0)
+        {
+            // no inequality rows at all: one direct solve of the equality-constrained QP, status 0
+            // (OCP_QP_FACT_SOLVE_KKT_UNCONSTR, HP/ocp_qp/x_ocp_qp_ipm.c:2444-2478)
+            passA(0.0, 0.0, res_max);
+            chainA(); syncthreads();
+            gains_pass(); syncthreads();
+            feedforward_pass(true, rb);
+            chainF(dux); syncthreads();
+            expand_pass(0, 0.0);
+            passA(1.0, 0.0, res_max);
+            *iters = 0;
+            return 0;
+        }
+        for (;;)
+        {
+            passA(a, tau_min, res_max);
+            PROF(0)
+            if (!(it < iter_max && alpha > alpha_min &&
+                  (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
+                   dabs(res_max[3] - tau_min) > tol_comp)))
+                break;
+            chainA();
+            syncthreads();
+            PROF(1)
+            gains_pass();
+            syncthreads();
+            feedforward_pass(true, rb);
+            PROF(2)
+            chainF(dux);
+            syncthreads();
+            PROF(3)
+            expand_pass(0, tau_min);
+            PROF(4)
+            // accuracy test of the factorisation at the affine step (lq_fact = 1, x_ocp_qp_ipm.c:1941-1974): HPIPM switches
+            // to its LQ-based factorisation when the linear-system residual exceeds 1e-5; counted, see DESIGN.md
+            {
+                double nl[4];
+                res_pass_affine(nl);
+                if (!(nl[0] <= 1e-5 && nl[1] <= 1e-5 && nl[2] <= 1e-5 && nl[3] <= 1e-5)) lq_count++;
+            }
+            PROF(5)
+            double sigma_mu = 0.0, mu_aff0 = 0.0;
+            {
+                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
+                const double tmp = mu_aff / mu;
+                sigma = tmp * tmp * tmp;
+                sigma_mu = sigma * mu;
+                sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
+            }
+            for (int pass = 1; pass < 3; pass++)
+            {
+                // pass 1: corrector; pass 2: centering only (conditional)
+                rhs_pass(pass == 1 ? 0 : 1, sigma_mu);
+                PROF(6)
+                solve_kkt(1);
+                PROF(7)
+                expand_pass(1, tau_min);
+                PROF(8)
+                const double ma = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+                if (pass == 1)
+                {
+                    mu_aff0 = mu_aff;
+                    mu_aff = ma;
+                    if (!(mu_aff > 2.0 * mu_aff0)) break;
+                }
+            }
+            // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN); iterative refinement is rare
+            double nlin[4];
+            res_pass<false>(nlin);
+            PROF(9)
+            bool refined = false;
+            for (int r = 0; r < 2; r++)
+            {
+                if (itref_ok(nlin)) break;
+                res_pass<true>(nlin);
+                rhs_pass(2, 0.0);
+                solve_kkt(2);
+                expand_pass(2, 0.0);
+                add_refinement();
+                refined = true;
+                itref_count++;
+                res_pass<true>(nlin);
+            }
+            if (refined) alpha_pass();
+            PROF(11)
+            a = alpha;
+            if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+            it++;
+        }
+        *iters = it;
+        if (it == iter_max) return 1;
+        if (alpha <= alpha_min) return 2;
+        if (disnan(mu)) return 3;
+        return 0;
+    }
+
+    // linear-system residual at the AFFINE step: right-hand side (rg, rb, rd, lam*t - tau) -- stationarity and dynamics
+    // rows from the arrays, inequality / complementarity rows from expand_pass(0)
+    MDEV void res_pass_affine(double* out4) { res_pass<false>(out4); }
+
+    // ---------------------------------------------------------------- after the QP
+    // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step
+    // (AC/acados/ocp_nlp/ocp_nlp_common.c:2401-2448): ux += step; pi, lam, t <- QP values.
+    MDEV void update_nlp()
+    {
+        for (int k = tid; k <= N; k += T)
+        {
+            double* z = Z(P.lay.zux, k); double* zl = Z(P.lay.zlam, k); double* zt = Z(P.lay.zt, k);
+            const double* v = ux + k * NV; const double* l = lam + k * s2; const double* tt = t + k * s2;
+            if (k < N)
+            {
+                double* zp = Z(P.lay.zpi, k);
+                for (int i = 0; i < NX; i++) zp[i] = pi[k * NX + i];
+                for (int j = 0; j < nbu; j++) { zl[j] = l[j]; zl[ncz + j] = l[ncq + j]; zt[j] = tt[j]; zt[ncz + j] = tt[ncq + j]; }
+                for (int c = 0; c < K; c++)
+                {
+                    const int a = nbu + NX + c, bq = nbq + c;
+                    zl[a] = l[bq]; zl[ncz + a] = l[ncq + bq]; zt[a] = tt[bq]; zt[ncz + a] = tt[ncq + bq];
+                }
+            }
+            if (k == 0)
+            {
+                // recover the eliminated x0 step and the multipliers of its bounds from stationarity
+                const double* zf = Z(P.lay.zfun, 0);
+                double s[NV], tmp[NV];
+                for (int i = 0; i < NU; i++) s[i] = v[i];
+                for (int i = 0; i < NX; i++) s[NU + i] = zf[nbu + i];  // dx0 = x0 - x_0
+                for (int i = 0; i < NX; i++)
+                {
+                    const int iv = NU + i;
+                    double acc = rq[iv];
+                    double hs = 0.0;
+                    for (int j = 0; j < NV; j++) hs += Hs[iv + NV * j] * s[j];
+                    acc += hs;
+                    if (N > 0) for (int j = 0; j < NX; j++) acc += sA0[iv + NV * j] * pi[j];
+                    if (iv == HXV || iv == HYV)
+                        for (int c = 0; c < K; c++)
+                        {
+                            const double dl = l[ncq + nbq + c] - l[nbq + c];
+                            acc += (iv == HXV ? gxy[c] : gxy[K + c]) * dl;
+                        }
+                    tmp[iv] = acc;
+                }
+                for (int j = 0; j < NX; j++)
+                {
+                    const int r = nbu + j;
+                    const double vv = tmp[NU + j];
+                    zl[r] = 1e-16; zl[ncz + r] = 1e-16; zt[r] = 1e-16; zt[ncz + r] = 1e-16;
+                    if (vv >= 0) zl[r] = vv; else zl[ncz + r] = -vv;
+                }
+                for (int i = 0; i < NV; i++) z[i] += s[i];
+            }
+            else
+            {
+                for (int j = 0; j < nbx; j++)
+                {
+                    const int a = nbu + j;
+                    if (k < N) { zl[a] = l[a]; zl[ncz + a] = l[ncq + a]; zt[a] = tt[a]; zt[ncz + a] = tt[ncq + a]; }
+                }
+                for (int i = 0; i < NV; i++) if (var_active(k, i)) z[i] += v[i];
+            }
+        }
+        syncthreads();
+    }
+
+    // residuals ocp_nlp_eval_residuals reports after an SQP_RTI step: stale linearisation, new lam / t
+    // (AC/interfaces/acados_c/ocp_nlp_interface.c:909-916)
+    MDEV void rti_residuals(double* res4)
+    {
+        double r2 = 0, r3 = 0;
+        for (int k = tid; k < N; k += T)
+        {
+            const double* zl = Z(P.lay.zlam, k); const double* zt = Z(P.lay.zt, k); const double* zf = Z(P.lay.zfun, k);
+            for (int j = 0; j < 2 * ncz; j++)
+            {
+                const int jj = j % ncz;
+                const bool act = jj < nbu || jj >= nbu + NX || (k == 0 ? true : jj - nbu < nbx);
+                if (!act) continue;
+                const double a = dabs(zf[j] + zt[j]), c = dabs(zl[j] * zt[j]);
+                r2 = a > r2 ? a : r2; r3 = c > r3 ? c : r3;
+            }
+        }
+        double vm[2] = {r2, r3};
+        block_reduce<2, 0>(vm, nullptr);
+        res4[2] = vm[0]; res4[3] = vm[1];
+    }
+
+    // ---------------------------------------------------------------- the solve
+    MDEV void run(int inst)
+    {
+        w = P.ws + (long) inst * P.ws_stride;
+        const double* x0 = P.x0 + (long) inst * NX;
+        const double* pg = P.p + (long) inst * (P.p_per_stage ? (N + 1) : 1) * 2 * K;
+        const double* lhg = P.lh + (long) inst * (P.lh_per_stage ? N : 1) * K;
+        const double* yrg = P.yref + (long) inst * (P.yref_per_stage ? N : 1) * NY;
+        const double* yre = P.yref_e + (long) inst * NX;
+        if (P.cold_start) cold_start(x0);
+        solve_calls = 0; lq_count = 0; itref_count = 0;
+#ifdef USVMPC_PROFILE
+        for (int i = 0; i < 24; i++) prof[i] = 0;
+        tprev = clock_now();
+#endif
+        const long long t_start = clock_now();
+        long long t_lin = 0, t_qp = 0;
+        int status = 2, sqp_iter = 0, qp_total = 0, qp_status = 0, qp_iter = 0;
+        double res[4] = {0, 0, 0, 0};
+        const int max_iter = P.nlp_type == 0 ? P.max_iter : 1;
+        for (sqp_iter = 0; sqp_iter < max_iter; sqp_iter++)
+        {
+            long long t0 = clock_now();
+            linearize(x0, pg, lhg, yrg, yre, res);
+            t_lin += clock_now() - t0;
+            PROF(12)
+            if (P.nlp_type == 0 && res[0] < P.tol[0] && res[1] < P.tol[1] && res[2] < P.tol[2] && res[3] < P.tol[3])
+            {
+                status = 0;  // ACADOS_SUCCESS, ocp_nlp_sqp.c:641-672
+                break;
+            }
+            t0 = clock_now();
+            qp_status = ipm_solve(&qp_iter);
+            t_qp += clock_now() - t0;
+            qp_total += qp_iter;
+            if (qp_status != 0 && qp_status != 1)
+            {
+                status = 4;  // ACADOS_QP_FAILURE, ocp_nlp_sqp.c:736-773
+                break;
+            }
+            update_nlp();
+            PROF(13)
+            if (P.nlp_type == 1)
+            {
+                status = 0;  // ocp_nlp_sqp_rti.c:810-817
+                rti_residuals(res);
+                sqp_iter = 1;
+                break;
+            }
+        }
+        if (tid == 0)
+        {
+            double* st = P.stats + (long) inst * NSTAT;
+            st[0] = status; st[1] = sqp_iter; st[2] = qp_total;
+            st[3] = res[0]; st[4] = res[1]; st[5] = res[2]; st[6] = res[3];
+            st[7] = lq_count; st[8] = solve_calls; st[9] = qp_status; st[10] = qp_iter; st[11] = itref_count;
+            st[12] = (double) (clock_now() - t_start); st[13] = (double) t_lin; st[14] = (double) t_qp; st[15] = 0;
+#ifdef USVMPC_PROFILE
+            if (qp_total >= USVMPC_PROFILE)
+                printf("PROF inst %d sqp %d qp %d | passA %lld chainA %lld gains+ff %lld chainF %lld expand0 %lld reslin0 %lld rhs %lld "
+                       "solve %lld expand1 %lld res %lld init %lld refine %lld lin %lld upd %lld\n", inst, sqp_iter, qp_total,
+                       prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11],
+                       prof[12], prof[13]);
+#endif
+        }
+        syncthreads();
+    }
+};
+
+// The persistent block: pull instances until the queue is drained.
+template <class M>
+MDEV void cta_main(const Params& P, double* smem, int block_id)
+{
+    CtaSolver<M> s(P, smem, P.scratch ? P.scratch + (long) block_id * P.plan.scratch_doubles : nullptr);
+    s.load_constants();
+    int* slot = (int*) (smem + P.plan.red_off);  // first reduction buffer doubles as the broadcast slot between solves
+    for (;;)
+    {
+        if (s.tid == 0) slot[0] = atomic_fetch_add(P.queue, 1);
+        syncthreads();
+        const int inst = slot[0];
+        syncthreads();
+        if (inst >= P.B) break;
+        s.run(inst);
+    }
+}
+
+}  // namespace usvmpc

@@ -13,7 +13,7 @@
 //
 // Jacobians are returned dense, column-major: Jx[i + NX*j] = d f_i / d x_j.
 #pragma once
-#include "warp_compat.h"
+#include "cta_compat.h"
 
 namespace usvmpc {
 

@@ -1,6 +1,7 @@
-// usvmpc_api.cu -- C ABI (include/usvmpc.h) over the warp-per-instance NMPC kernel.
-// Host side: owns the HBM working set of B instances, moves caller data in and out with the reference's
-// field names, launches ONE persistent kernel per solve (one warp per instance, csrc/nmpc_kernel.cuh).
+// usvmpc_api.cu -- C ABI (include/usvmpc.h) over the CTA-per-instance NMPC kernel.
+// Host side: owns the per-instance NLP iterates in HBM and the inputs of B instances, moves caller data in and out
+// with the reference's field names, and launches ONE persistent kernel per solve: thread blocks pull instances from a
+// device-side queue and solve each of them out of shared memory (csrc/cta_kernel.cuh).
 // Built by mpc_collisionavoidance_b200/build.py:  nvcc -gencode arch=compute_100a,code=sm_100a -shared ...
 #include <cuda_runtime.h>
 
@@ -10,19 +11,20 @@
 #include <cstring>
 
 #include "../../include/usvmpc.h"
-#include "nmpc_kernel.cuh"
+#include "cta_kernel.cuh"
 
 using namespace usvmpc;
 
 namespace {
 
-#ifndef USVMPC_WPC
-#define USVMPC_WPC 4
+#ifndef USVMPC_THREADS
+#define USVMPC_THREADS 256  // threads of one block (= one instance at a time)
 #endif
-constexpr int WPC = USVMPC_WPC;  // warps (= instances) per CTA
 #ifndef USVMPC_MIN_CTAS
-#define USVMPC_MIN_CTAS 4  // resident CTAs per SM the register allocation must allow (4 x 4 = 16 warps/SM)
+#define USVMPC_MIN_CTAS 2   // resident blocks per SM the register allocation must allow
 #endif
+constexpr int THREADS = USVMPC_THREADS;
+constexpr long SMEM_PER_SM = 227 * 1024, SMEM_RESERVED_PER_CTA = 1024;
 
 thread_local char g_err[512] = "";
 
@@ -42,14 +44,10 @@ int fail(int code, const char* fmt, ...)
     } while (0)
 
 template <class M>
-__global__ void __launch_bounds__(WPC * 32, USVMPC_MIN_CTAS) nmpc_solve_kernel(const __grid_constant__ Params P, int smem_per_warp)
+__global__ void __launch_bounds__(THREADS, USVMPC_MIN_CTAS) nmpc_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5;
-    const int inst = blockIdx.x * WPC + warp;
-    if (inst >= P.B) return;
-    WarpSolver<M> s(P, inst, smem + (size_t) warp * smem_per_warp);
-    s.run(inst);
+    cta_main<M>(P, smem, blockIdx.x);
 }
 
 // buf[b][k][i] <-> ws[b*stride + off + (k0+k)*fstride + c0 + i]
@@ -188,12 +186,17 @@ struct usvmpc_solver
     usvmpc_config cfg;
     int B, device, nx, nu, nv;
     Params P;
-    double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e;
+    double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e, *d_scratch;
+    double *d_bnd;                         // per-stage bounds shared by the batch: lbu | ubu | lbx | ubx | uh
+    double *h_bnd;                         // host mirror of d_bnd
+    int o_lbu, o_ubu, o_lbx, o_ubx, o_uh, n_bnd;
+    int* d_queue;
     double *d_p[2], *d_lh[2], *d_yref[2];  // [0] one row per instance, [1] one row per instance and stage
     double* d_stage;
     size_t stage_bytes;
     long launches;
-    int smem_per_warp;
+    int grid, ctas_per_sm, num_sms;
+    double sm_clock_hz;
 };
 
 namespace {
@@ -216,20 +219,36 @@ int upload_constants(usvmpc_solver* s, cudaStream_t st)
     return 0;
 }
 
+int upload_bounds(usvmpc_solver* s, cudaStream_t st)
+{
+    CU(cudaMemcpyAsync(s->d_bnd, s->h_bnd, sizeof(double) * s->n_bnd, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 void refresh_params(usvmpc_solver* s)
 {
     Params& P = s->P;
     const usvmpc_config& c = s->cfg;
     P.B = s->B; P.N = c.N; P.K = c.K; P.num_steps = c.num_steps; P.num_stages = c.num_stages; P.nlp_type = c.nlp_type;
     P.max_iter = c.max_iter; P.qp_iter_max = c.qp_iter_max; P.nbx = c.nbx; P.nbu = c.nbu;
-    for (int i = 0; i < NBXMAX; i++) { P.idxbx[i] = c.idxbx[i]; P.lbx[i] = c.lbx[i]; P.ubx[i] = c.ubx[i]; }
-    for (int i = 0; i < NBUMAX; i++) { P.lbu[i] = c.lbu[i]; P.ubu[i] = c.ubu[i]; }
+    for (int i = 0; i < NBXMAX; i++) P.idxbx[i] = c.idxbx[i];
     P.ncq = c.nbu + c.nbx + c.K; P.ncz = c.nbu + s->nx + c.K;
-    P.dt = c.dt; P.uh = c.uh;
+    P.dt = c.dt;
     for (int i = 0; i < 4; i++) P.tol[i] = c.tol[i];
+    P.lbu = s->d_bnd + s->o_lbu; P.ubu = s->d_bnd + s->o_ubu; P.lbx = s->d_bnd + s->o_lbx; P.ubx = s->d_bnd + s->o_ubx;
+    P.uh = s->d_bnd + s->o_uh;
     P.cst = s->d_cst; P.x0 = s->d_x0; P.yref_e = s->d_yref_e;
     P.p = s->d_p[P.p_per_stage]; P.lh = s->d_lh[P.lh_per_stage]; P.yref = s->d_yref[P.yref_per_stage];
-    P.ws = s->d_ws; P.stats = s->d_stats;
+    P.ws = s->d_ws; P.stats = s->d_stats; P.scratch = s->d_scratch; P.queue = s->d_queue;
+}
+
+// `value` as the caller gave it -> host pointer (values shared by the batch are kept on the host)
+int to_host(const double* value, int n, int on_device, double* tmp)
+{
+    if (on_device) CU(cudaMemcpy(tmp, value, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    else memcpy(tmp, value, sizeof(double) * n);
+    return 0;
 }
 
 // make sure the per-stage copy of an input exists and is current before a single stage of it is written
@@ -247,7 +266,8 @@ int want_per_stage(usvmpc_solver* s, double** pair, int* flag, int nst, int dim,
     return 0;
 }
 
-// write value [B][dim] (stage >= 0), [B][nst][dim] (ALL_STAGES) or [B][dim] for every stage (EVERY_STAGE)
+// write value [B][dim] (stage >= 0), [B][nst][dim] (ALL_STAGES) or [B][dim] for every stage (EVERY_STAGE); the copy kind
+// is inferred from the pointers (unified addressing), `on_device` only decides whether the call waits for the copy
 int set_input(usvmpc_solver* s, double** pair, int* flag, int nst, int dim, int stage, const double* value, cudaStream_t st)
 {
     if (dim == 0) return 0;
@@ -357,12 +377,115 @@ int out_copy(usvmpc_solver* s, int stage, const char* field, double* value, int 
     return fail(USVMPC_E_FIELD, "unknown field '%s' (x, u, pi, lam, t, sl, su, z)", field);
 }
 
+static int create_impl(usvmpc_solver* s)
+{
+    const usvmpc_config* cfg = &s->cfg;
+    const int nx = s->nx, nu = s->nu, N = cfg->N, K = cfg->K, B = s->B, ny = nx + nu;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, s->device));
+    s->num_sms = prop.multiProcessorCount;
+    int khz = 0;
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->device));
+    s->sm_clock_hz = 1e3 * khz;
+    s->P.lay = make_layout(nx, nu, N, K);
+    s->P.ws_stride = s->P.lay.total;
+    // placement of the working set: as many resident blocks per SM as the chain fields allow (at most USVMPC_MIN_CTAS,
+    // which bounds the registers), everything else that fits goes to shared memory too, the rest to the L2-resident
+    // block scratch.  USVMPC_CTAS_PER_SM overrides (diagnostics).
+    int want = USVMPC_MIN_CTAS;
+    if (const char* e = getenv("USVMPC_CTAS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+    if (want > USVMPC_MIN_CTAS) want = USVMPC_MIN_CTAS;
+    const long max_optin = (long) prop.sharedMemPerBlockOptin;
+    bool ok = false;
+    for (int c = want; c >= 1 && !ok; c--)
+    {
+        long budget = SMEM_PER_SM / c - SMEM_RESERVED_PER_CTA;
+        if (budget > max_optin) budget = max_optin;
+        if (make_plan(nx, nu, N, K, cfg->nbx, cfg->nbu, THREADS / 32, budget, &s->P.plan)) { ok = true; s->ctas_per_sm = c; }
+    }
+    if (!ok) return fail(USVMPC_E_INVALID, "N=%d, K=%d: the Riccati working set does not fit the shared memory of one SM", N, K);
+    s->grid = s->ctas_per_sm * s->num_sms;
+    if (s->grid > B) s->grid = B;
+    const int kk = K > 0 ? K : 1;
+    CU(cudaMalloc(&s->d_ws, sizeof(double) * (size_t) s->P.ws_stride * B));
+    CU(cudaMemset(s->d_ws, 0, sizeof(double) * (size_t) s->P.ws_stride * B));
+    CU(cudaMalloc(&s->d_stats, sizeof(double) * (size_t) B * NSTAT));
+    CU(cudaMemset(s->d_stats, 0, sizeof(double) * (size_t) B * NSTAT));
+    CU(cudaMalloc(&s->d_cst, sizeof(double) * (ny * ny + nx * nx)));
+    CU(cudaMalloc(&s->d_x0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMemset(s->d_x0, 0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMalloc(&s->d_yref_e, sizeof(double) * (size_t) B * nx));
+    CU(cudaMemset(s->d_yref_e, 0, sizeof(double) * (size_t) B * nx));
+    CU(cudaMalloc(&s->d_p[0], sizeof(double) * (size_t) B * 2 * kk));
+    CU(cudaMemset(s->d_p[0], 0, sizeof(double) * (size_t) B * 2 * kk));
+    CU(cudaMalloc(&s->d_lh[0], sizeof(double) * (size_t) B * kk));
+    CU(cudaMemset(s->d_lh[0], 0, sizeof(double) * (size_t) B * kk));
+    CU(cudaMalloc(&s->d_yref[0], sizeof(double) * (size_t) B * ny));
+    CU(cudaMemset(s->d_yref[0], 0, sizeof(double) * (size_t) B * ny));
+    if (s->P.plan.scratch_doubles)
+    {
+        CU(cudaMalloc(&s->d_scratch, sizeof(double) * (size_t) s->P.plan.scratch_doubles * s->grid));
+        CU(cudaMemset(s->d_scratch, 0, sizeof(double) * (size_t) s->P.plan.scratch_doubles * s->grid));
+    }
+    CU(cudaMalloc(&s->d_queue, sizeof(int) * 8));
+    CU(cudaMemset(s->d_queue, 0, sizeof(int) * 8));
+    // per-stage bounds shared by the batch, initialised from the description like acados_create() does
+    // (acados_solver.in.c:1028-1449: the same lbx/ubx/lbu/ubu/lh/uh on every stage)
+    const int nbu = cfg->nbu, nbx = cfg->nbx;
+    s->o_lbu = 0; s->o_ubu = s->o_lbu + N * nbu; s->o_lbx = s->o_ubu + N * nbu; s->o_ubx = s->o_lbx + N * nbx;
+    s->o_uh = s->o_ubx + N * nbx; s->n_bnd = s->o_uh + N * K + 1;
+    s->h_bnd = (double*) calloc(s->n_bnd, sizeof(double));
+    if (!s->h_bnd) return fail(USVMPC_E_INVALID, "out of host memory");
+    for (int k = 0; k < N; k++)
+    {
+        for (int i = 0; i < nbu; i++) { s->h_bnd[s->o_lbu + k * nbu + i] = cfg->lbu[i]; s->h_bnd[s->o_ubu + k * nbu + i] = cfg->ubu[i]; }
+        for (int i = 0; i < nbx; i++) { s->h_bnd[s->o_lbx + k * nbx + i] = cfg->lbx[i]; s->h_bnd[s->o_ubx + k * nbx + i] = cfg->ubx[i]; }
+        for (int i = 0; i < K; i++) s->h_bnd[s->o_uh + k * K + i] = cfg->uh;
+    }
+    CU(cudaMalloc(&s->d_bnd, sizeof(double) * s->n_bnd));
+    int rc = upload_bounds(s, 0);
+    if (rc) return rc;
+    refresh_params(s);
+    return upload_constants(s, 0);
+}
+
+template <class M>
+static int launch_solve(usvmpc_solver* s, cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * (size_t) s->P.plan.smem_doubles;
+    // the attribute is per function and process: set it for THIS solver's size right before its launch
+    CU(cudaFuncSetAttribute(nmpc_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CU(cudaMemsetAsync(s->d_queue, 0, sizeof(int) * 8, st));
+    nmpc_solve_kernel<M><<<s->grid, THREADS, smem, st>>>(s->P);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// bounds shared by the batch: one row per stage like the reference's nlp_in (ocp_nlp_constraints_bgh.c:630-822);
+// stage = USVMPC_EVERY_STAGE writes the row of every stage
+static int set_shared_bound(usvmpc_solver* s, int off, int dim, int k_first, int stage, const double* value, int on_device,
+                            cudaStream_t st)
+{
+    const int N = s->cfg.N;
+    if (dim == 0) return 0;
+    double tmp[KMAX > NBXMAX ? KMAX : NBXMAX];
+    int rc = to_host(value, dim, on_device, tmp);
+    if (rc) return rc;
+    if (stage == USVMPC_EVERY_STAGE) { for (int k = 0; k < N; k++) memcpy(s->h_bnd + off + k * dim, tmp, sizeof(double) * dim); }
+    else
+    {
+        if (stage < k_first || stage >= N) return fail(USVMPC_E_INVALID, "no such bound at stage %d", stage);
+        memcpy(s->h_bnd + off + stage * dim, tmp, sizeof(double) * dim);
+    }
+    return upload_bounds(s, st);
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* usvmpc_last_error(void) { return g_err; }
-const char* usvmpc_version(void) { return "usvmpc 0.1 (sm_100a, warp-per-instance fp64)"; }
+const char* usvmpc_version(void) { return "usvmpc 0.2 (sm_100a, block-per-instance fp64, shared-memory resident IPM)"; }
 
 int usvmpc_config_default(usvmpc_config* c, int model)
 {
@@ -382,12 +505,14 @@ int usvmpc_config_default(usvmpc_config* c, int model)
 int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver** out)
 {
     if (!cfg || !out) return fail(USVMPC_E_INVALID, "null argument");
+    *out = nullptr;
     int nx, nu;
     if (model_dims(cfg->model, &nx, &nu)) return fail(USVMPC_E_INVALID, "unknown model %d", cfg->model);
     if (batch < 1 || cfg->N < 1) return fail(USVMPC_E_INVALID, "batch and N must be >= 1");
-    if (cfg->N + 1 > NSPC) return fail(USVMPC_E_INVALID, "N=%d: the engine is built for horizons up to %d", cfg->N, NSPC - 1);
+    if (cfg->N > NMAX) return fail(USVMPC_E_INVALID, "N=%d: the engine is built for horizons up to %d", cfg->N, NMAX);
     if (cfg->K < 0 || cfg->K > KMAX) return fail(USVMPC_E_INVALID, "K=%d outside [0,%d]", cfg->K, KMAX);
-    if (cfg->nbx < 0 || cfg->nbx > nx || cfg->nbu < 0 || cfg->nbu > nu) return fail(USVMPC_E_INVALID, "nbx/nbu out of range");
+    if (cfg->nbx < 0 || cfg->nbx > nx || cfg->nbx > NBXMAX || cfg->nbu < 0 || cfg->nbu > nu || cfg->nbu > NBUMAX)
+        return fail(USVMPC_E_INVALID, "nbx/nbu out of range");
     if (cfg->num_stages != 1 && cfg->num_stages != 2 && cfg->num_stages != 4) return fail(USVMPC_E_INVALID, "ERK num_stages must be 1, 2 or 4");
     if (cfg->num_steps < 1) return fail(USVMPC_E_INVALID, "num_steps must be >= 1");
     for (int j = 0; j < cfg->nbx; j++)
@@ -397,42 +522,11 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
     if (device < 0 || device >= ndev) return fail(USVMPC_E_CUDA, "no CUDA device %d (found %d): the engine has no CPU path", device, ndev);
     CU(cudaSetDevice(device));
     usvmpc_solver* s = (usvmpc_solver*) calloc(1, sizeof(usvmpc_solver));
+    if (!s) return fail(USVMPC_E_INVALID, "out of host memory");
     s->cfg = *cfg; s->B = batch; s->device = device; s->nx = nx; s->nu = nu; s->nv = nx + nu;
-    const int N = cfg->N, K = cfg->K, B = batch, ny = nx + nu;
-    s->P.lay = make_layout(nx, nu, N, K, cfg->nbx, cfg->nbu);
-    s->P.ws_stride = s->P.lay.total;
-    if (!(cfg->model == USVMPC_MODEL_PENDULUM ? WarpSolver<Pendulum>::layout_matches(s->P.lay) : WarpSolver<Usv3>::layout_matches(s->P.lay)))
-        return fail(USVMPC_E_INVALID, "internal: layout.h and the kernel's compile-time offsets disagree");
-    s->smem_per_warp = warp_smem_doubles(nx, nu, N, K, cfg->nbx, cfg->nbu);
-    const int kk = K > 0 ? K : 1;
-    CU(cudaMalloc(&s->d_ws, sizeof(double) * (size_t) s->P.ws_stride * B));
-    CU(cudaMemset(s->d_ws, 0, sizeof(double) * (size_t) s->P.ws_stride * B));
-    CU(cudaMalloc(&s->d_stats, sizeof(double) * (size_t) B * NSTAT));
-    CU(cudaMemset(s->d_stats, 0, sizeof(double) * (size_t) B * NSTAT));
-    CU(cudaMalloc(&s->d_cst, sizeof(double) * (ny * ny + nx * nx)));
-    CU(cudaMalloc(&s->d_x0, sizeof(double) * (size_t) B * nx));
-    CU(cudaMemset(s->d_x0, 0, sizeof(double) * (size_t) B * nx));
-    CU(cudaMalloc(&s->d_yref_e, sizeof(double) * (size_t) B * nx));
-    CU(cudaMemset(s->d_yref_e, 0, sizeof(double) * (size_t) B * nx));
-    CU(cudaMalloc(&s->d_p[0], sizeof(double) * (size_t) B * 2 * kk));
-    CU(cudaMemset(s->d_p[0], 0, sizeof(double) * (size_t) B * 2 * kk));
-    CU(cudaMalloc(&s->d_lh[0], sizeof(double) * (size_t) B * kk));
-    CU(cudaMemset(s->d_lh[0], 0, sizeof(double) * (size_t) B * kk));
-    CU(cudaMalloc(&s->d_yref[0], sizeof(double) * (size_t) B * ny));
-    CU(cudaMemset(s->d_yref[0], 0, sizeof(double) * (size_t) B * ny));
-    refresh_params(s);
-    int rc = upload_constants(s, 0);
-    if (rc) return rc;
-    const size_t smem = sizeof(double) * (size_t) s->smem_per_warp * WPC;
-    if (cfg->model == USVMPC_MODEL_PENDULUM)
-        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Pendulum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    else
-        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Usv3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    if (const char* e = getenv("USVMPC_CARVEOUT"))  // diagnostic: shared-memory carve-out in percent (the rest is L1)
-    {
-        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Pendulum>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-        CU(cudaFuncSetAttribute(nmpc_solve_kernel<Usv3>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-    }
+    s->P.slice_iter = 0;
+    const int rc = create_impl(s);
+    if (rc) { usvmpc_free(s); return rc; }  // one cleanup path: everything allocated so far is released
     *out = s;
     return 0;
 }
@@ -442,8 +536,10 @@ int usvmpc_free(usvmpc_solver* s)
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->d_ws); cudaFree(s->d_stats); cudaFree(s->d_cst); cudaFree(s->d_x0); cudaFree(s->d_yref_e);
+    cudaFree(s->d_scratch); cudaFree(s->d_bnd); cudaFree(s->d_queue);
     for (int i = 0; i < 2; i++) { cudaFree(s->d_p[i]); cudaFree(s->d_lh[i]); cudaFree(s->d_yref[i]); }
     cudaFree(s->d_stage);
+    free(s->h_bnd);
     free(s);
     return 0;
 }
@@ -453,13 +549,8 @@ int usvmpc_solve(usvmpc_solver* s, void* stream)
     if (!s) return fail(USVMPC_E_INVALID, "null solver");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t) stream;
-    const int grid = (s->B + WPC - 1) / WPC;
-    const size_t smem = sizeof(double) * (size_t) s->smem_per_warp * WPC;
-    if (s->cfg.model == USVMPC_MODEL_PENDULUM)
-        nmpc_solve_kernel<Pendulum><<<grid, WPC * 32, smem, st>>>(s->P, s->smem_per_warp);
-    else
-        nmpc_solve_kernel<Usv3><<<grid, WPC * 32, smem, st>>>(s->P, s->smem_per_warp);
-    CU(cudaGetLastError());
+    const int rc = s->cfg.model == USVMPC_MODEL_PENDULUM ? launch_solve<Pendulum>(s, st) : launch_solve<Usv3>(s, st);
+    if (rc) return rc;
     s->launches++;
     return 0;
 }
@@ -467,16 +558,15 @@ int usvmpc_solve(usvmpc_solver* s, void* stream)
 int usvmpc_update_params(usvmpc_solver* s, int stage, const double* value, int np, int on_device, void* stream)
 {
     if (!s || !value) return fail(USVMPC_E_INVALID, "null argument");
-    (void) on_device;
     if (np != 2 * s->cfg.K) return fail(USVMPC_E_SIZE, "np=%d but the model has np=%d", np, 2 * s->cfg.K);  // tpl :1746-1751
     CU(cudaSetDevice(s->device));
+    (void) on_device;  // per-instance values: the copy kind is inferred from the pointer (unified addressing)
     return set_input(s, s->d_p, &s->P.p_per_stage, s->cfg.N + 1, 2 * s->cfg.K, stage, value, (cudaStream_t) stream);
 }
 
 int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
 {
     if (!s || !field || !value) return fail(USVMPC_E_INVALID, "null argument");
-    (void) on_device;
     CU(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t) stream;
     const int N = s->cfg.N, ny = s->nv, nx = s->nx;
@@ -491,9 +581,12 @@ int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const 
     }
     if (!strcmp(field, "W"))
     {
-        // shared by the batch and by all path stages; host pointer, column-major like the reference (tpl :854)
-        if (stage == N) memcpy(s->cfg.W_e, value, sizeof(double) * nx * nx);
-        else memcpy(s->cfg.W, value, sizeof(double) * ny * ny);
+        // shared by the batch and by all path stages; column-major like the reference (tpl :854)
+        double tmp[16 * 16];
+        const int n = stage == N ? nx * nx : ny * ny;
+        int rc = to_host(value, n, on_device, tmp);
+        if (rc) return rc;
+        memcpy(stage == N ? s->cfg.W_e : s->cfg.W, tmp, sizeof(double) * n);
         return upload_constants(s, st);
     }
     return fail(USVMPC_E_FIELD, "unknown cost field '%s' (yref, y_ref, W)", field);
@@ -502,7 +595,6 @@ int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const 
 int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
 {
     if (!s || !field || !value) return fail(USVMPC_E_INVALID, "null argument");
-    (void) on_device;
     CU(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t) stream;
     const int N = s->cfg.N;
@@ -513,24 +605,15 @@ int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field,
             CU(cudaMemcpyAsync(s->d_x0, value, sizeof(double) * (size_t) s->B * s->nx, cudaMemcpyDefault, st));
             return 0;
         }
-        if (stage < 0 || stage >= N) return fail(USVMPC_E_INVALID, "no state bounds at stage %d", stage);
-        memcpy(field[0] == 'l' ? s->cfg.lbx : s->cfg.ubx, value, sizeof(double) * s->cfg.nbx);
-        refresh_params(s);
-        return 0;
+        return set_shared_bound(s, field[0] == 'l' ? s->o_lbx : s->o_ubx, s->cfg.nbx, 1, stage, value, on_device, st);
     }
     if (!strcmp(field, "lbu") || !strcmp(field, "ubu"))
+        return set_shared_bound(s, field[0] == 'l' ? s->o_lbu : s->o_ubu, s->cfg.nbu, 0, stage, value, on_device, st);
+    if (!strcmp(field, "lh"))
     {
-        memcpy(field[0] == 'l' ? s->cfg.lbu : s->cfg.ubu, value, sizeof(double) * s->cfg.nbu);
-        refresh_params(s);
-        return 0;
+        return set_input(s, s->d_lh, &s->P.lh_per_stage, N, s->cfg.K, stage, value, st);
     }
-    if (!strcmp(field, "lh")) return set_input(s, s->d_lh, &s->P.lh_per_stage, N, s->cfg.K, stage, value, st);
-    if (!strcmp(field, "uh"))
-    {
-        if (s->cfg.K > 0) s->cfg.uh = value[0];
-        refresh_params(s);
-        return 0;
-    }
+    if (!strcmp(field, "uh")) return set_shared_bound(s, s->o_uh, s->cfg.K, 0, stage, value, on_device, st);
     return fail(USVMPC_E_FIELD, "unknown constraint field '%s' (lbx, ubx, lbu, ubu, lh, uh)", field);
 }
 
@@ -635,9 +718,12 @@ int usvmpc_info(usvmpc_solver* s, const char* what, double* value)
     else if (!strcmp(what, "workspace_bytes")) *value = (double) sizeof(double) * s->P.ws_stride * s->B;
     else if (!strcmp(what, "workspace_doubles_per_instance")) *value = (double) s->P.ws_stride;
     else if (!strcmp(what, "batch")) *value = s->B;
-    else if (!strcmp(what, "warps_per_cta")) *value = WPC;
-    else if (!strcmp(what, "smem_bytes_per_cta")) *value = (double) sizeof(double) * s->smem_per_warp * WPC;
-    else if (!strcmp(what, "grid")) *value = (s->B + WPC - 1) / WPC;
+    else if (!strcmp(what, "threads_per_cta")) *value = THREADS;
+    else if (!strcmp(what, "ctas_per_sm")) *value = s->ctas_per_sm;
+    else if (!strcmp(what, "smem_bytes_per_cta")) *value = (double) sizeof(double) * s->P.plan.smem_doubles;
+    else if (!strcmp(what, "scratch_bytes_per_cta")) *value = (double) sizeof(double) * s->P.plan.scratch_doubles;
+    else if (!strcmp(what, "grid")) *value = s->grid;
+    else if (!strcmp(what, "sm_clock_hz")) *value = s->sm_clock_hz;
     else return fail(USVMPC_E_FIELD, "unknown info '%s'", what);
     return 0;
 }

@@ -1,11 +1,11 @@
 // tests/emu/emu_solver.cpp -- TEST INFRASTRUCTURE ONLY.
 //
-// Builds the product's warp-per-instance kernel source (mpc_collisionavoidance_b200/csrc/nmpc_kernel.cuh)
-// for the CPU with -DUSVMPC_EMULATE: the 32 lanes of a warp become 32 cooperative fibers that switch at
-// every shuffle / __syncwarp (csrc/warp_compat.h).  This lets the CPU test-suite (-m "not gpu") check the
-// kernel's host-visible logic -- indexing, masks, the IPM control flow -- against the oracle, and lets
-// AddressSanitizer watch the shared-memory / workspace accesses, on a machine without a GPU.
-// Nothing in the product loads this library.
+// Builds the product's CTA-per-instance kernel source (mpc_collisionavoidance_b200/csrc/cta_kernel.cuh) for the
+// CPU with -DUSVMPC_EMULATE: the threads of a thread block become cooperative fibers with real warp / block
+// barriers (csrc/cta_compat.h); every OS worker thread plays one persistent block pulling instances from the same
+// work queue the device uses.  This lets the CPU test-suite (-m "not gpu") check the kernel's logic -- indexing,
+// masks, barriers, the IPM control flow -- against the oracle, and lets AddressSanitizer watch the shared-memory /
+// workspace accesses, on a machine without a GPU.  Nothing in the product loads this library.
 #include <pthread.h>
 #include <time.h>
 
@@ -14,13 +14,14 @@
 #include <cstring>
 #include <vector>
 
-#include "nmpc_kernel.cuh"
+#include "cta_kernel.cuh"
 
 namespace usvmpc {
 namespace emu {
 
-thread_local Warp* g_warp = nullptr;
+thread_local Block* g_blk = nullptr;
 
+extern "C" void usvmpc_fiber_switch(void** save_sp, void* new_sp);
 asm(".text\n"
     ".globl usvmpc_fiber_switch\n"
     ".type usvmpc_fiber_switch,@function\n"
@@ -32,38 +33,87 @@ asm(".text\n"
     "  ret\n"
     ".size usvmpc_fiber_switch, .-usvmpc_fiber_switch\n");
 
+static inline bool runnable(const Fiber& f) { return !f.done && (f.wait == nullptr || f.wait->gen != f.wait_gen); }
+
+// hand the processor to the next runnable fiber (same warp first); if every fiber is finished, back to the caller of
+// run_block; if fibers remain but none can run, the kernel has a divergent barrier
+static void switch_next()
+{
+    Block* b = g_blk;
+    const int me = b->cur, T = b->T, W = T / WARP, w0 = me / WARP, l0 = me % WARP;
+    int next = -1;
+    for (int i = 1; i <= WARP && next < 0; i++)
+    {
+        const int j = w0 * WARP + (l0 + i) % WARP;
+        if (j != me && runnable(b->f[j])) next = j;
+    }
+    for (int dw = 1; dw < W && next < 0; dw++)
+    {
+        const int wq = (w0 + dw) % W;
+        for (int l = 0; l < WARP; l++)
+            if (runnable(b->f[wq * WARP + l])) { next = wq * WARP + l; break; }
+    }
+    if (next < 0 && runnable(b->f[me])) return;
+    if (next < 0)
+    {
+        bool all_done = true;
+        for (int i = 0; i < T; i++) all_done = all_done && b->f[i].done;
+        if (!all_done)
+        {
+            fprintf(stderr, "usvmpc emu: deadlock -- some threads wait on a barrier the others never reach\n");
+            abort();
+        }
+        usvmpc_fiber_switch(&b->f[me].sp, b->main_sp);
+        abort();
+    }
+    b->cur = next;
+    usvmpc_fiber_switch(&b->f[me].sp, b->f[next].sp);
+}
+
+void arrive(Barrier* bar)
+{
+    Block* b = g_blk;
+    if (++bar->count == bar->need) { bar->count = 0; bar->gen++; return; }
+    Fiber& me = b->f[b->cur];
+    me.wait = bar; me.wait_gen = bar->gen;
+    while (bar->gen == me.wait_gen) switch_next();
+    me.wait = nullptr;
+}
+
 static void fiber_entry()
 {
-    Warp* w = g_warp;
-    w->body(w->arg);
-    const int me = w->cur;
-    if (me + 1 < WARP) { w->cur = me + 1; usvmpc_fiber_switch(&w->sp[me], w->sp[me + 1]); }
-    else usvmpc_fiber_switch(&w->sp[me], w->main_sp);
-    fprintf(stderr, "usvmpc emu: a finished lane was resumed (non-uniform sync point in the kernel)\n");
+    Block* b = g_blk;
+    b->body(b->arg);
+    b->f[b->cur].done = true;
+    switch_next();
+    fprintf(stderr, "usvmpc emu: a finished thread was resumed\n");
     abort();
 }
 
-void run_warp(void (*body)(void*), void* arg)
+void run_block(int T, void (*body)(void*), void* arg)
 {
-    const size_t STACK = 512 * 1024;
-    Warp w;
-    memset(&w, 0, sizeof(w));
-    w.stacks = (char*) aligned_alloc(64, STACK * WARP);
-    w.body = body; w.arg = arg;
-    for (int i = 0; i < WARP; i++)
+    const size_t STACK = 256 * 1024;
+    if (T % WARP || T > MAXT) abort();
+    Block* b = (Block*) calloc(1, sizeof(Block));
+    b->T = T; b->body = body; b->arg = arg;
+    b->stacks = (char*) aligned_alloc(64, STACK * T);
+    b->cta.need = T;
+    for (int w = 0; w < T / WARP; w++) b->warp[w].need = WARP;
+    for (int i = 0; i < T; i++)
     {
-        uint64_t* sp = (uint64_t*) (w.stacks + STACK * (i + 1));
+        uint64_t* sp = (uint64_t*) (b->stacks + STACK * (i + 1));
         *(--sp) = 0;
         *(--sp) = (uint64_t) (uintptr_t) &fiber_entry;
         for (int r = 0; r < 6; r++) *(--sp) = 0;
-        w.sp[i] = sp;
+        b->f[i].sp = sp;
     }
-    Warp* saved = g_warp;
-    g_warp = &w;
-    w.cur = 0;
-    usvmpc_fiber_switch(&w.main_sp, w.sp[0]);
-    g_warp = saved;
-    free(w.stacks);
+    Block* saved = g_blk;
+    g_blk = b;
+    b->cur = 0;
+    usvmpc_fiber_switch(&b->main_sp, b->f[0].sp);
+    g_blk = saved;
+    free(b->stacks);
+    free(b);
 }
 
 }  // namespace emu
@@ -75,32 +125,27 @@ namespace {
 
 struct Job {
     const Params* P;
-    int model;
-    int* next;
-    int smem_doubles;
+    int model, threads;
+    int next_block;
 };
 
-struct LaneArg { const Params* P; int inst; double* sm; int model; };
+struct BlockArg { const Params* P; int model; double* sm; int block; };
 
-void lane_body(void* a)
+void block_body(void* a)
 {
-    LaneArg* la = (LaneArg*) a;
-    if (la->model == 1) { WarpSolver<Pendulum> s(*la->P, la->inst, la->sm); s.run(la->inst); }
-    else { WarpSolver<Usv3> s(*la->P, la->inst, la->sm); s.run(la->inst); }
+    BlockArg* ba = (BlockArg*) a;
+    if (ba->model == 1) cta_main<Pendulum>(*ba->P, ba->sm, ba->block);
+    else cta_main<Usv3>(*ba->P, ba->sm, ba->block);
 }
 
 void* worker(void* arg)
 {
     Job* j = (Job*) arg;
-    std::vector<double> sm(j->smem_doubles + 16);
-    for (;;)
-    {
-        int i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
-        if (i >= j->P->B) break;
-        for (auto& v : sm) v = 0.0 / 0.0;  // poison: uninitialised shared memory must not be consumed
-        LaneArg la{j->P, i, sm.data(), j->model};
-        emu::run_warp(lane_body, &la);
-    }
+    const int block = __atomic_fetch_add(&j->next_block, 1, __ATOMIC_RELAXED);
+    std::vector<double> sm(j->P->plan.smem_doubles + 16);
+    for (auto& v : sm) v = 0.0 / 0.0;  // poison: uninitialised shared memory must not be consumed
+    BlockArg ba{j->P, j->model, sm.data(), block};
+    emu::run_block(j->threads, block_body, &ba);
     return nullptr;
 }
 
@@ -109,6 +154,15 @@ enum { ICFG_MODEL, ICFG_N, ICFG_K, ICFG_NUM_STEPS, ICFG_NUM_STAGES, ICFG_NLP_TYP
 enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_UH };
 
 }  // namespace
+
+// Emulation knobs (tests only): shared-memory budget in bytes (forces fields into the global scratch), threads per block
+extern "C" void usvemu_configure(long smem_budget, int block_threads);
+static long g_smem_budget = 227 * 1024;
+static int g_block_threads = 256;
+extern "C" void usvemu_configure(long smem_budget, int block_threads)
+{
+    g_smem_budget = smem_budget; g_block_threads = block_threads;
+}
 
 // same calling convention as oracle/usv_oracle.c:usvo_solve_batch so the tests can swap one for the other;
 // optional initial guess (xinit [B][N+1][nx], uinit [B][N][nu], piinit [B][N][nx]) and full multiplier output.
@@ -127,33 +181,49 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
     P.B = B; P.N = icfg[ICFG_N]; P.K = icfg[ICFG_K]; P.num_steps = icfg[ICFG_NUM_STEPS];
     P.num_stages = icfg[ICFG_NUM_STAGES]; P.nlp_type = icfg[ICFG_NLP_TYPE]; P.max_iter = icfg[ICFG_MAX_ITER];
     P.qp_iter_max = icfg[ICFG_QP_ITER_MAX]; P.nbx = icfg[ICFG_NBX]; P.nbu = icfg[ICFG_NBU];
-    for (int i = 0; i < P.nbx; i++) { P.idxbx[i] = idxbx[i]; P.lbx[i] = lbx[i]; P.ubx[i] = ubx[i]; }
-    for (int i = 0; i < P.nbu; i++) { P.lbu[i] = lbu[i]; P.ubu[i] = ubu[i]; }
+    const int N = P.N, K = P.K;
+    for (int i = 0; i < P.nbx; i++) P.idxbx[i] = idxbx[i];
+    std::vector<double> vlbu((size_t) N * P.nbu + 1), vubu((size_t) N * P.nbu + 1), vlbx((size_t) N * P.nbx + 1),
+        vubx((size_t) N * P.nbx + 1), vuh((size_t) N * K + 1);
+    for (int k = 0; k < N; k++)
+    {
+        for (int i = 0; i < P.nbu; i++) { vlbu[k * P.nbu + i] = lbu[i]; vubu[k * P.nbu + i] = ubu[i]; }
+        for (int i = 0; i < P.nbx; i++) { vlbx[k * P.nbx + i] = lbx[i]; vubx[k * P.nbx + i] = ubx[i]; }
+        for (int i = 0; i < K; i++) vuh[k * K + i] = dcfg[DCFG_UH];
+    }
+    P.lbu = vlbu.data(); P.ubu = vubu.data(); P.lbx = vlbx.data(); P.ubx = vubx.data(); P.uh = vuh.data();
     P.p_per_stage = p_per_stage; P.lh_per_stage = lh_per_stage; P.yref_per_stage = yref_per_stage;
     P.cold_start = xinit ? 0 : 1;
-    P.ncq = P.nbu + P.nbx + P.K; P.ncz = P.nbu + nx + P.K;
-    P.dt = dcfg[DCFG_DT]; P.uh = dcfg[DCFG_UH];
+    P.ncq = P.nbu + P.nbx + K; P.ncz = P.nbu + nx + K;
+    P.dt = dcfg[DCFG_DT];
     for (int i = 0; i < 4; i++) P.tol[i] = dcfg[DCFG_TOL_STAT + i];
     std::vector<double> cst(nv * nv + nx * nx);
     memcpy(cst.data(), W, sizeof(double) * nv * nv);
     memcpy(cst.data() + nv * nv, We, sizeof(double) * nx * nx);
     P.cst = cst.data();
     P.x0 = x0; P.p = p; P.lh = lh; P.yref = yref; P.yref_e = yref_e;
-    P.lay = make_layout(nx, nu, P.N, P.K, P.nbx, P.nbu);
+    P.lay = make_layout(nx, nu, N, K);
     P.ws_stride = P.lay.total;
-    if (!(model == 1 ? WarpSolver<Pendulum>::layout_matches(P.lay) : WarpSolver<Usv3>::layout_matches(P.lay)))
+    if (!make_plan(nx, nu, N, K, P.nbx, P.nbu, g_block_threads / 32, g_smem_budget, &P.plan))
     {
-        fprintf(stderr, "usvmpc emu: layout.h and the kernel's compile-time offsets disagree\n");
+        fprintf(stderr, "usvmpc emu: the chain fields do not fit the shared-memory budget\n");
         abort();
     }
-    // exact-size heap block (so a sanitizer sees overruns), poisoned with NaN
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if (nthreads > B) nthreads = B;
+    // exact-size heap blocks (so a sanitizer sees overruns), poisoned with NaN
     double* ws = (double*) malloc(sizeof(double) * P.ws_stride * B);
     for (long i = 0; i < (long) P.ws_stride * B; i++) ws[i] = 0.0 / 0.0;
     P.ws = ws;
+    std::vector<double> scratch((size_t) P.plan.scratch_doubles * nthreads + 1, 0.0 / 0.0);
+    P.scratch = P.plan.scratch_doubles ? scratch.data() : nullptr;
+    std::vector<int> queue(8, 0);
+    P.queue = queue.data();
     std::vector<double> st((size_t) B * NSTAT, 0.0);
     P.stats = st.data();
     const Layout& Y = P.lay;
-    const int N = P.N, ncz = P.ncz;
+    const int ncz = P.ncz;
     for (int b = 0; b < B; b++)
     {
         double* w = ws + (long) b * P.ws_stride;
@@ -170,10 +240,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
         }
     }
     Job job;
-    int next = 0;
-    job.P = &P; job.model = model; job.next = &next; job.smem_doubles = warp_smem_doubles(nx, nu, P.N, P.K, P.nbx, P.nbu);
-    if (nthreads < 1) nthreads = 1;
-    if (nthreads > 64) nthreads = 64;
+    job.P = &P; job.model = model; job.threads = g_block_threads; job.next_block = 0;
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     pthread_t th[64];
@@ -195,7 +262,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
             if (lam_out) for (int j = 0; j < 2 * ncz; j++) lam_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zlam.off + k * Y.zlam.stride + j];
             if (t_out) for (int j = 0; j < 2 * ncz; j++) t_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zt.off + k * Y.zt.stride + j];
         }
-        for (int i = 0; i < 9; i++) stats[(long) b * 9 + i] = st[(size_t) b * NSTAT + i];
+        for (int i = 0; i < 12; i++) stats[(long) b * 12 + i] = st[(size_t) b * NSTAT + i];
     }
     free(ws);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
