@@ -14,6 +14,8 @@
 #define DEV __device__ __forceinline__
 #define MDEV __device__ __forceinline__
 #define MDEVNI __device__ __noinline__
+// address-space hint: the pointer is known to point into shared memory (lets the compiler emit LDS / STS)
+#define ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 
 namespace usvmpc {
 DEV int thread_id() { return threadIdx.x; }
@@ -26,6 +28,8 @@ DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m)
 DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV void syncwarp() { __syncwarp(); }
 DEV void syncthreads() { __syncthreads(); }
+// barrier `id` (1..15) among the first `count` threads of the block (count a multiple of 32)
+DEV void named_barrier_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 DEV double dsqrt(double a) { return sqrt(a); }
 DEV double drsqrt(double a) { return rsqrt(a); }
 DEV float drsqrt(float a) { return rsqrtf(a); }
@@ -50,6 +54,7 @@ DEV long long clock_now() { return clock64(); }
 #define DEV static inline
 #define MDEV inline
 #define MDEVNI inline
+#define ASSUME_SHARED(p) ((void) 0)
 
 namespace usvmpc {
 namespace emu {
@@ -65,7 +70,7 @@ struct Fiber {
 struct Block {
     int T, cur;
     Fiber f[MAXT];
-    Barrier cta, warp[MAXT / WARP];
+    Barrier cta, warp[MAXT / WARP], named[16];
     double slot_d[MAXT];
     long slot_i[MAXT];
     void* main_sp;
@@ -83,6 +88,12 @@ DEV int block_threads() { return emu::g_blk->T; }
 DEV int lane_id() { return emu::g_blk->cur & 31; }
 DEV void syncwarp() { emu::Block* b = emu::g_blk; emu::arrive(&b->warp[b->cur >> 5]); }
 DEV void syncthreads() { emu::arrive(&emu::g_blk->cta); }
+DEV void named_barrier_sync(int id, int count)
+{
+    emu::Barrier* b = &emu::g_blk->named[id];
+    if (b->need != count) { if (b->count != 0) abort(); b->need = count; }
+    emu::arrive(b);
+}
 DEV double shfl(double v, int src)
 {
     emu::Block* b = emu::g_blk;

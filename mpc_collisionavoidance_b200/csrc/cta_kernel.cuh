@@ -46,6 +46,244 @@ struct FastDiv {
     MDEV int div(int x) const { return d == 1 ? x : (int) (((unsigned long long) (unsigned) x * magic) >> 32); }
 };
 
+// ---------------------------------------------------------------- the serial recursions
+#ifndef USVMPC_CHAIN_WARPS
+#define USVMPC_CHAIN_WARPS 2
+#endif
+constexpr int CHAIN_WARPS = USVMPC_CHAIN_WARPS;  // warps that share one stage step of the factorisation
+template <int CT>
+DEV void chain_sync()
+{
+    if (CT == 32) syncwarp(); else named_barrier_sync(1, CT);
+}
+
+// chainA: Riccati factorisation, backward (x_ocp_qp_kkt.c:455-535).  On entry the M field of every stage holds
+// H + Gamma terms with the gradient row (passA); on exit, per stage: columns < NU = the Cholesky columns of the input
+// block (rows NU.. = Lxu, row NV = l_u), the rest = P_k (lower, packed) and p_k (row NV); dinv = 1 / diag(Luu);
+// Pb = P_{k+1} res_b.  Per stage three steps, each spread over the 32 lanes, with one __syncwarp between them:
+//   1. sW = P_{k+1} [G' | res_b]  (NX x (NV+1); the last column + p_{k+1} is what the gradient row needs)
+//   2. sM = M + G sW              (lower trapezoid, NE entries)
+//   3. eliminate the NU input columns: every lane redoes the NU x NU Cholesky of the input block (2 dependent
+//      reciprocal square roots for NU = 2) and finishes its own entries; the Schur complement goes to M and, as a full
+//      symmetric matrix, to sP for the next stage.  Non-positive pivot => that column becomes zero (dpotrf_l_mn,
+//      BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).
+template <class M>
+MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sW, double* sP,
+                        int N)
+{
+    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NE = NV * (NV + 1) / 2 + NV;
+    constexpr int CT = 32 * CHAIN_WARPS;  // threads that share the items of a step (warps 0 .. CHAIN_WARPS-1)
+    constexpr int NQ = (NE + CT - 1) / CT, NWQ = (NX * NR + CT - 1) / CT;
+    ASSUME_SHARED(G); ASSUME_SHARED(Mx); ASSUME_SHARED(rb); ASSUME_SHARED(Pb); ASSUME_SHARED(dinv);
+    ASSUME_SHARED(sW); ASSUME_SHARED(sP);
+    double* sM = sW + NX * NR;  // scratch copy of the matrix between steps 2 and 3
+    const int lane = thread_id();  // index among the CT chain threads
+    // Uniform control flow: every lane runs every step on clamped item indices (a surplus lane recomputes the last item
+    // and stores the same value to the same address), so there is no divergent branch between the __syncwarps.
+    // step 1 items: e -> output (m, i) of sW = P [G' | rb]; source vector = row i of G (stride NV) or rb (stride 1)
+    int w_e[NWQ], w_m[NWQ], w_src[NWQ], w_str[NWQ];
+    bool w_last[NWQ];
+#pragma unroll
+    for (int q = 0; q < NWQ; q++)
+    {
+        int e = lane + CT * q;
+        e = e < NX * NR ? e : NX * NR - 1;
+        const int i = e / NX;
+        w_e[q] = e; w_m[q] = e - i * NX; w_last[q] = i == NV;
+        w_src[q] = i < NV ? i : 0; w_str[q] = i < NV ? NV : 1;
+    }
+    // step 2 / 3 items: e -> entry (r, c) of the lower trapezoid
+    int m_e[NQ], m_r[NQ], m_c[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+    {
+        int e = lane + CT * q;
+        e = e < NE ? e : NE - 1;
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= e && r < NV) r++;
+        m_e[q] = e; m_r[q] = r; m_c[q] = e - r * (r + 1) / 2;
+    }
+#pragma unroll 1
+    for (int k = N; k >= 0; k--)
+    {
+        double* Mk = Mx + k * NE;
+        if (k < N)
+        {
+            const double* Gk = G + k * (NV * NX);
+            const double* rbk = rb + k * NX;
+            const double* pn = Mk + NE + (NV * (NV + 1)) / 2 + NU;  // p_{k+1}: x part of row NV of stage k+1
+#pragma unroll
+            for (int q = 0; q < NWQ; q++)
+            {
+                const double* ga = w_last[q] ? rbk : Gk + w_src[q];
+                const double* pr = sP + w_m[q] * NX;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int n = 0; n < NX; n += 2)
+                {
+                    a0 += pr[n] * ga[n * w_str[q]];
+                    if (n + 1 < NX) a1 += pr[n + 1] * ga[(n + 1) * w_str[q]];
+                }
+                const double acc = a0 + a1;
+                if (w_last[q]) Pb[k * NX + w_m[q]] = acc;
+                sW[w_e[q]] = w_last[q] ? acc + pn[w_m[q]] : acc;
+            }
+            chain_sync<CT>();
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+            {
+                const int r = m_r[q], c = m_c[q];
+                const double* gr = Gk + (r < NV ? r : c);
+                const double* wc = sW + (r < NV ? c : NV) * NX;
+                double a0 = Mk[m_e[q]], a1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < NX; m += 2)
+                {
+                    a0 += gr[NV * m] * wc[m];
+                    if (m + 1 < NX) a1 += gr[NV * (m + 1)] * wc[m + 1];
+                }
+                sM[m_e[q]] = a0 + a1;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) sM[m_e[q]] = Mk[m_e[q]];
+        }
+        chain_sync<CT>();
+        // Cholesky of the NU x NU input block, redundantly on every lane
+        double Lt[NU][NU], inv[NU];
+#pragma unroll
+        for (int j = 0; j < NU; j++)
+        {
+            double piv = sM[j * (j + 1) / 2 + j];
+#pragma unroll
+            for (int i = 0; i < j; i++) piv -= Lt[j][i] * Lt[j][i];
+            inv[j] = piv > 0.0 ? drsqrt(piv) : 0.0;
+            Lt[j][j] = piv * inv[j];
+#pragma unroll
+            for (int jj = j + 1; jj < NU; jj++)
+            {
+                double v = sM[jj * (jj + 1) / 2 + j];
+#pragma unroll
+                for (int i = 0; i < j; i++) v -= Lt[jj][i] * Lt[j][i];
+                Lt[jj][j] = v * inv[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NU; j++) if (lane == j) dinv[k * NU + j] = inv[j];
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+        {
+            const int r = m_r[q], c = m_c[q];
+            // first NU entries of rows r and c of the factor by substitution.  For a row of the input block itself the
+            // same formula gives its entries up to the diagonal (what lies beyond is not used); row c is only used for
+            // c >= NU.
+            const double* rr = sM + r * (r + 1) / 2;
+            const double* rc = sM + c * (c + 1) / 2;
+            double v[NU], u[NU];
+#pragma unroll
+            for (int j = 0; j < NU; j++)
+            {
+                double x = rr[j], y = rc[j];
+#pragma unroll
+                for (int i = 0; i < j; i++) { x -= v[i] * Lt[j][i]; y -= u[i] * Lt[j][i]; }
+                v[j] = x * inv[j]; u[j] = y * inv[j];
+            }
+            double out = sM[m_e[q]];
+#pragma unroll
+            for (int j = 0; j < NU; j++) out -= v[j] * u[j];
+#pragma unroll
+            for (int j = 0; j < NU; j++) out = c == j ? v[j] : out;
+            Mk[m_e[q]] = out;
+            if (c >= NU && r < NV)
+            {
+                sP[(r - NU) * NX + (c - NU)] = out;
+                sP[(c - NU) * NX + (r - NU)] = out;
+            }
+        }
+        chain_sync<CT>();
+    }
+}
+
+// chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> x part of `out` (stage stride NV)      (x_ocp_qp_kkt.c:537-575)
+template <class M>
+MDEVNI void chainF_impl(const double* Acl, const double* cc, double* out, int N)
+{
+    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU;
+    ASSUME_SHARED(Acl); ASSUME_SHARED(cc);
+    const int lane = lane_id();
+    const int l = lane < NX ? lane : 0;
+    double xc[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) xc[i] = 0.0;
+    if (lane < NX) out[NU + lane] = 0.0;
+    // the rows of Acl_k and c_k do not depend on the recursion: fetch stage k+1 while stage k is being multiplied
+    double ar[NX], cv;
+#pragma unroll
+    for (int j = 0; j < NX; j++) ar[j] = N > 0 ? Acl[l * NX + j] : 0.0;
+    cv = N > 0 ? cc[l] : 0.0;
+#pragma unroll 1
+    for (int k = 0; k < N; k++)
+    {
+        double an[NX], cn = 0.0;
+        const int kn = k + 1 < N ? k + 1 : k;
+#pragma unroll
+        for (int j = 0; j < NX; j++) an[j] = Acl[kn * (NX * NX) + l * NX + j];
+        cn = cc[kn * NX + l];
+        double a0 = cv, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j += 2) { a0 += ar[j] * xc[j]; if (j + 1 < NX) a1 += ar[j + 1] * xc[j + 1]; }
+        const double x1 = a0 + a1;
+        if (lane < NX) out[(k + 1) * NV + NU + lane] = x1;
+#pragma unroll
+        for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+#pragma unroll
+        for (int j = 0; j < NX; j++) ar[j] = an[j];
+        cv = cn;
+    }
+}
+
+// chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> x part of zv                           (x_ocp_qp_kkt.c:1096-1242)
+template <class M>
+MDEVNI void chainC_impl(const double* Acl, const double* ee, double* zv, int N)
+{
+    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU;
+    ASSUME_SHARED(Acl); ASSUME_SHARED(ee); ASSUME_SHARED(zv);
+    const int lane = lane_id();
+    const int l = lane < NX ? lane : 0;
+    double pn[NX];
+    {
+        const double e = ee[N * NX + l];
+        if (lane < NX) zv[N * NV + NU + lane] = e;
+#pragma unroll
+        for (int m = 0; m < NX; m++) pn[m] = shfl(e, m);
+    }
+    double ac[NX], ev;
+#pragma unroll
+    for (int m = 0; m < NX; m++) ac[m] = N > 0 ? Acl[(N - 1) * (NX * NX) + m * NX + l] : 0.0;
+    ev = N > 0 ? ee[(N - 1) * NX + l] : 0.0;
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; k--)
+    {
+        double an[NX], en;
+        const int kn = k > 0 ? k - 1 : 0;
+#pragma unroll
+        for (int m = 0; m < NX; m++) an[m] = Acl[kn * (NX * NX) + m * NX + l];
+        en = ee[kn * NX + l];
+        double a0 = ev, a1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NX; m += 2) { a0 += ac[m] * pn[m]; if (m + 1 < NX) a1 += ac[m + 1] * pn[m + 1]; }
+        const double p1 = a0 + a1;
+        if (lane < NX) zv[k * NV + NU + lane] = p1;
+#pragma unroll
+        for (int m = 0; m < NX; m++) pn[m] = shfl(p1, m);
+#pragma unroll
+        for (int m = 0; m < NX; m++) ac[m] = an[m];
+        ev = en;
+    }
+}
+
 template <class M>
 struct CtaSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
@@ -84,7 +322,12 @@ struct CtaSolver {
 #define PROF(i)
 #endif
 
-    MDEV double* fld(int id) const { const SField& f = P.plan.f[id]; return (f.space ? gs : sm) + f.off; }
+    MDEV double* fld(int id) const
+    {
+        const SField& f = P.plan.f[id];
+        if (id < F_FIRST_FLEX) return sm + f.off;  // the chain fields are always in shared memory
+        return (f.space ? gs : sm) + f.off;
+    }
 
     MDEV CtaSolver(const Params& p, double* smem, double* gscratch) : P(p), sm(smem), gs(gscratch)
     {
@@ -97,7 +340,7 @@ struct CtaSolver {
         red = sm + P.plan.red_off;
         redbuf = 0;
         double* m = sm + P.plan.misc_off;
-        sA0 = m; m += NV * NX; sW = m; m += NX * NR; sP = m; m += NX * NX + 2;
+        sA0 = m; m += NV * NX; sW = m; m += NX * NR + NE + (NE & 1); sP = m; m += NX * NX + 2;  // sW = [P G' | scratch matrix]
         sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
         G = fld(F_G); Mx = fld(F_M); Acl = fld(F_ACL); Kg = fld(F_KG); cc = fld(F_CC); ee = fld(F_EE); Pb = fld(F_PB);
         rb = fld(F_RB); zv = fld(F_ZV); dux = fld(F_DUX); kk = fld(F_KK); dinv = fld(F_DINV);
@@ -106,6 +349,11 @@ struct CtaSolver {
         b = fld(F_B);
         rg2 = fld(F_RG2); rb2 = fld(F_RB2); rd2 = fld(F_RD2); rm2 = fld(F_RM2); dux2 = fld(F_DUX2); dpi2 = fld(F_DPI2);
         dlam2 = fld(F_DLAM2); dt2 = fld(F_DT2);
+        // address-space hints: these always point into shared memory
+        ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Ws); ASSUME_SHARED(Wes); ASSUME_SHARED(Tp);
+        ASSUME_SHARED(red); ASSUME_SHARED(sA0); ASSUME_SHARED(sW); ASSUME_SHARED(sP); ASSUME_SHARED(sxrow); ASSUME_SHARED(srvar);
+        ASSUME_SHARED(G); ASSUME_SHARED(Mx); ASSUME_SHARED(Acl); ASSUME_SHARED(Kg); ASSUME_SHARED(cc); ASSUME_SHARED(ee);
+        ASSUME_SHARED(Pb); ASSUME_SHARED(rb); ASSUME_SHARED(zv); ASSUME_SHARED(dux); ASSUME_SHARED(kk); ASSUME_SHARED(dinv);
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
@@ -663,158 +911,11 @@ struct CtaSolver {
     }
 
     // ---------------------------------------------------------------- IPM: the serial recursions (warp 0)
-    // chainA: Riccati factorisation, backward.  On entry the M field of every stage holds H + Gamma terms with the
-    // gradient row (passA); on exit, per stage: columns < NU = the Cholesky columns of the input block (rows NU.. = Lxu,
-    // row NV = l_u), the rest = P_k (lower, packed) and p_k (row NV); dinv = 1 / diag(Luu); Pb = P_{k+1} res_b.
-    MDEV void chainA()
-    {
-        if (wid != 0) return;
-        // the lower-trapezoid entries this lane owns: e = lane + 32 q  ->  (row, column)
-        constexpr int NQ = (NE + 31) / 32;
-        int er[NQ], ec[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; q++)
-        {
-            const int e = lane + 32 * q;
-            int r = 0;
-            while ((r + 1) * (r + 2) / 2 <= e && r < NV) r++;
-            er[q] = r; ec[q] = e - r * (r + 1) / 2;
-        }
-#pragma unroll 1
-        for (int k = N; k >= 0; k--)
-        {
-            double* Mk = Mx + k * NE;
-            if (k < N)
-            {
-                // sW = P_{k+1} [G' | res_b]   (NX x (NV+1)): column i < NV = P G(i,:)', column NV = Pb
-                const double* Gk = G + k * (NV * NX);
-                const double* rbk = rb + k * NX;
-#pragma unroll 1
-                for (int e = lane; e < NX * NR; e += 32)
-                {
-                    const int i = e / NX, m = e - i * NX;
-                    const double* ga = i < NV ? Gk + i : rbk;
-                    const int sa = i < NV ? NV : 1;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int n = 0; n < NX; n++) acc += sP[m * NX + n] * ga[n * sa];
-                    sW[e] = acc;
-                    if (i == NV) Pb[k * NX + m] = acc;
-                }
-                syncwarp();
-                // M += G P G' on the lower triangle; gradient row += G (Pb + p_{k+1})
-                const double* Mn = Mx + (k + 1) * NE;
-#pragma unroll
-                for (int q = 0; q < NQ; q++)
-                {
-                    const int e = lane + 32 * q, r = er[q], c = ec[q];
-                    if (e >= NE) continue;
-                    double acc = 0.0;
-                    if (r < NV)
-                    {
-#pragma unroll
-                        for (int m = 0; m < NX; m++) acc += Gk[r + NV * m] * sW[c * NX + m];
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int m = 0; m < NX; m++) acc += Gk[c + NV * m] * (sW[NV * NX + m] + Mn[MI(NV, NU + m)]);
-                    }
-                    Mk[e] += acc;
-                }
-                syncwarp();
-            }
-            // eliminate the NU input columns: Cholesky columns with the non-positive-pivot rule of dpotrf_l_mn
-            // (BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710: that column becomes zero)
-#pragma unroll
-            for (int j = 0; j < NU; j++)
-            {
-                const double piv = Mk[MI(j, j)];
-                double inv = 0.0;
-                if (piv > 0.0) inv = drsqrt(piv);
-                double upd[NQ];
-                bool wr[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; q++)
-                {
-                    const int e = lane + 32 * q, r = er[q], c = ec[q];
-                    wr[q] = false;
-                    if (e >= NE || c < j) continue;
-                    wr[q] = true;
-                    if (c == j) upd[q] = r == j ? piv * inv : Mk[e] * inv;
-                    else upd[q] = Mk[e] - (Mk[MI(r, j)] * inv) * (Mk[MI(c, j)] * inv);
-                }
-                syncwarp();
-#pragma unroll
-                for (int q = 0; q < NQ; q++) if (wr[q]) Mk[lane + 32 * q] = upd[q];
-                if (lane == 0) dinv[k * NU + j] = inv;
-                syncwarp();
-            }
-            // P_k as a full symmetric matrix for the next stage's products
-#pragma unroll 1
-            for (int e = lane; e < NX * NX; e += 32)
-            {
-                const int i = e / NX, jj = e - i * NX;
-                sP[e] = i >= jj ? Mk[MI(NU + i, NU + jj)] : Mk[MI(NU + jj, NU + i)];
-            }
-            syncwarp();
-        }
-    }
-
-    // chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> x part of `out` (stage stride NV)
-    MDEV void chainF(double* out)
-    {
-        if (wid != 0) return;
-        double xc[NX];
-#pragma unroll
-        for (int i = 0; i < NX; i++) xc[i] = 0.0;
-        if (lane < NX) out[NU + lane] = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < N; k++)
-        {
-            double x1 = 0.0;
-            if (lane < NX)
-            {
-                const double* Ar = Acl + k * (NX * NX) + lane * NX;
-                double a0 = cc[k * NX + lane], a1 = 0.0;
-#pragma unroll
-                for (int j = 0; j < NX; j += 2) { a0 += Ar[j] * xc[j]; if (j + 1 < NX) a1 += Ar[j + 1] * xc[j + 1]; }
-                x1 = a0 + a1;
-                out[(k + 1) * NV + NU + lane] = x1;
-            }
-#pragma unroll
-            for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
-        }
-    }
-
-    // chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> x part of zv
-    MDEV void chainC()
-    {
-        if (wid != 0) return;
-        double pn[NX];
-        {
-            const double e = lane < NX ? ee[N * NX + lane] : 0.0;
-            if (lane < NX) zv[N * NV + NU + lane] = e;
-#pragma unroll
-            for (int m = 0; m < NX; m++) pn[m] = shfl(e, m);
-        }
-#pragma unroll 1
-        for (int k = N - 1; k >= 0; k--)
-        {
-            double p1 = 0.0;
-            if (lane < NX)
-            {
-                const double* Ac = Acl + k * (NX * NX) + lane;
-                double a0 = ee[k * NX + lane], a1 = 0.0;
-#pragma unroll
-                for (int m = 0; m < NX; m += 2) { a0 += Ac[m * NX] * pn[m]; if (m + 1 < NX) a1 += Ac[(m + 1) * NX] * pn[m + 1]; }
-                p1 = a0 + a1;
-                zv[k * NV + NU + lane] = p1;
-            }
-#pragma unroll
-            for (int m = 0; m < NX; m++) pn[m] = shfl(p1, m);
-        }
-    }
+    // The recursions are free functions (chain_*_impl below, not inlined: their own register allocation and compact
+    // code, whatever the state of the surrounding solver) called by warp 0 only.
+    MDEV void chainA() { if (wid < CHAIN_WARPS) chainA_impl<M>(G, Mx, rb, Pb, dinv, sW, sP, N); }
+    MDEV void chainF(double* out) { if (wid == 0) chainF_impl<M>(Acl, cc, out, N); }
+    MDEV void chainC() { if (wid == 0) chainC_impl<M>(Acl, ee, zv, N); }
 
     // ---------------------------------------------------------------- IPM: passes around the chains
     // gains after chainA: K_k = -Luu^-T Lxu', Acl_k = A_k + B_k K_k
@@ -848,11 +949,14 @@ struct CtaSolver {
     }
 
     // feed-forward terms: kk_k = -Luu^-T l_u,k and c_k = rhs_b,k + B_k kk_k.  from_factor: l_u = row NV of the factor
-    // (factorise+solve sweep); else l_u = Luu^-1 (z0_u + B'(p_{k+1} + Pb_k)) with p in the x part of zv.
+    // (factorise+solve sweep); else l_u = Luu^-1 (z0_u + B'(p_{k+1} + Pb_k)) with p in the x part of zv.  One
+    // (stage, state) item per thread; the NU-vector kk is recomputed by each of the stage's NX items (cheaper than a
+    // barrier).
     MDEV void feedforward_pass(bool from_factor, const double* rbp)
     {
-        for (int k = tid; k <= N; k += T)
+        for (int it = tid; it < N * NX; it += T)
         {
+            const int k = dnx.div(it), mm = it - k * NX;
             const double* Mk = Mx + k * NE;
             const double* Gk = G + k * (NV * NX);
             double lu[NU], kv[NU];
@@ -864,11 +968,8 @@ struct CtaSolver {
                 else
                 {
                     acc = zv[k * NV + i];
-                    if (k < N)
-                    {
 #pragma unroll
-                        for (int m = 0; m < NX; m++) acc += Gk[i + NV * m] * (zv[(k + 1) * NV + NU + m] + Pb[k * NX + m]);
-                    }
+                    for (int m = 0; m < NX; m++) acc += Gk[i + NV * m] * (zv[(k + 1) * NV + NU + m] + Pb[k * NX + m]);
 #pragma unroll
                     for (int m = 0; m < i; m++) acc -= Mk[MI(i, m)] * lu[m];
                     acc *= dinv[k * NU + i];
@@ -882,20 +983,14 @@ struct CtaSolver {
 #pragma unroll
                 for (int m = i + 1; m < NU; m++) acc -= Mk[MI(m, i)] * kv[m];
                 kv[i] = acc * dinv[k * NU + i];
-                kk[k * NU + i] = kv[i];
+                if (mm == 0) kk[k * NU + i] = kv[i];
             }
-            if (k < N)
-            {
+            double acc = rbp[it];
 #pragma unroll
-                for (int m = 0; m < NX; m++)
-                {
-                    double acc = rbp[k * NX + m];
-#pragma unroll
-                    for (int i = 0; i < NU; i++) acc += Gk[i + NV * m] * kv[i];
-                    cc[k * NX + m] = acc;
-                }
-            }
+            for (int i = 0; i < NU; i++) acc += Gk[i + NV * mm] * kv[i];
+            cc[it] = acc;
         }
+        if (tid < NU) kk[N * NU + tid] = 0.0;  // no inputs at the terminal stage
         syncthreads();
     }
 
@@ -1054,8 +1149,7 @@ struct CtaSolver {
     // (rg, rb, rd, rmc) at the step (dux, dpi, dlam, dt); norms into out4.  WRITE: also store it (rg2, rb2, rd2, rm2) as
     // the right-hand side of an iterative-refinement solve and compute all four norms from scratch; without WRITE the
     // step is expand_pass's and so are the norms of the inequality / complementarity rows (lin_d, lin_m).
-    template <bool WRITE>
-    MDEV void res_pass(double* out4)
+    MDEV void res_pass(const bool WRITE, double* out4)
     {
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         for (int it = tid; it < (N + 1) * NV; it += T)
@@ -1162,110 +1256,95 @@ struct CtaSolver {
                (n[2] < tol_ineq || n[2] < 1e-3 * res_max[2]) && (n[3] < tol_comp || n[3] < 1e-3 * res_max[3]);
     }
 
-    // solve with the existing factorisation for the right-hand side prepared by rhs_pass(mode)
-    MDEV void solve_kkt(int mode)
-    {
-        chainC();
-        syncthreads();
-        feedforward_pass(false, mode == 2 ? rb2 : rb);
-        chainF(mode == 2 ? dux2 : dux);
-        syncthreads();
-        solve_calls++;
-    }
-
     // OCP_QP_IPM_SOLVE + OCP_QP_IPM_DELTA_STEP: HP/ocp_qp/x_ocp_qp_ipm.c:2354-2683, 1888-2350 (pred_corr,
     // cond_pred_corr, itref_corr_max = 2); returns HPIPM status 0 ok / 1 max iter / 2 min step / 3 NaN.
+    // One IPM iteration is a sequence of linear solves with the same matrix -- AFF (factorise + affine step), COR
+    // (corrector), CEN (centering only, conditional), REF (iterative refinement, rare) -- written as ONE loop over
+    // solve rounds so that every pass and chain has a single call site (compact code: the whole iteration stays in
+    // the instruction cache).
     MDEV int ipm_solve(int* iters)
     {
+        enum { AFF, COR, CEN, REF };
         const double tau_min = 1e-16, alpha_min = 1e-8;
         ipm_init();
         PROF(10)
         alpha = 1.0;
         double a = 0.0;  // the first passA applies no step
         int it = 0;
-        if (nct == 0)
-        {
-            // no inequality rows at all: one direct solve of the equality-constrained QP, status 0
-            // (OCP_QP_FACT_SOLVE_KKT_UNCONSTR, HP/ocp_qp/x_ocp_qp_ipm.c:2444-2478)
-            passA(0.0, 0.0, res_max);
-            chainA(); syncthreads();
-            gains_pass(); syncthreads();
-            feedforward_pass(true, rb);
-            chainF(dux); syncthreads();
-            expand_pass(0, 0.0);
-            passA(1.0, 0.0, res_max);
-            *iters = 0;
-            return 0;
-        }
         for (;;)
         {
-            passA(a, tau_min, res_max);
+            passA(a, nct > 0 ? tau_min : 0.0, res_max);
             PROF(0)
+            if (nct == 0 && it == 1) { it = 0; break; }  // no inequality rows: one direct solve (x_ocp_qp_ipm.c:2444-2478)
             if (!(it < iter_max && alpha > alpha_min &&
                   (res_max[0] > tol_stat || res_max[1] > tol_eq || res_max[2] > tol_ineq ||
                    dabs(res_max[3] - tau_min) > tol_comp)))
                 break;
-            chainA();
-            syncthreads();
-            PROF(1)
-            gains_pass();
-            syncthreads();
-            feedforward_pass(true, rb);
-            PROF(2)
-            chainF(dux);
-            syncthreads();
-            PROF(3)
-            expand_pass(0, tau_min);
-            PROF(4)
-            // accuracy test of the factorisation at the affine step (lq_fact = 1, x_ocp_qp_ipm.c:1941-1974): HPIPM switches
-            // to its LQ-based factorisation when the linear-system residual exceeds 1e-5; counted, see DESIGN.md
-            {
-                double nl[4];
-                res_pass_affine(nl);
-                if (!(nl[0] <= 1e-5 && nl[1] <= 1e-5 && nl[2] <= 1e-5 && nl[3] <= 1e-5)) lq_count++;
-            }
-            PROF(5)
-            double sigma_mu = 0.0, mu_aff0 = 0.0;
-            {
-                mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
-                const double tmp = mu_aff / mu;
-                sigma = tmp * tmp * tmp;
-                sigma_mu = sigma * mu;
-                sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
-            }
-            for (int pass = 1; pass < 3; pass++)
-            {
-                // pass 1: corrector; pass 2: centering only (conditional)
-                rhs_pass(pass == 1 ? 0 : 1, sigma_mu);
-                PROF(6)
-                solve_kkt(1);
-                PROF(7)
-                expand_pass(1, tau_min);
-                PROF(8)
-                const double ma = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
-                if (pass == 1)
-                {
-                    mu_aff0 = mu_aff;
-                    mu_aff = ma;
-                    if (!(mu_aff > 2.0 * mu_aff0)) break;
-                }
-            }
-            // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN); iterative refinement is rare
-            double nlin[4];
-            res_pass<false>(nlin);
-            PROF(9)
+            int kind = AFF, nref = 0;
             bool refined = false;
-            for (int r = 0; r < 2; r++)
+            double sigma_mu = 0.0;
+            for (;;)
             {
-                if (itref_ok(nlin)) break;
-                res_pass<true>(nlin);
-                rhs_pass(2, 0.0);
-                solve_kkt(2);
-                expand_pass(2, 0.0);
-                add_refinement();
-                refined = true;
-                itref_count++;
-                res_pass<true>(nlin);
+                if (kind == AFF)
+                {
+                    chainA();
+                    syncthreads();
+                    PROF(1)
+                    gains_pass();
+                    syncthreads();
+                }
+                else
+                {
+                    rhs_pass(kind == COR ? 0 : (kind == CEN ? 1 : 2), sigma_mu);
+                    PROF(6)
+                    chainC();
+                    syncthreads();
+                    solve_calls++;
+                    PROF(7)
+                }
+                feedforward_pass(kind == AFF, kind == REF ? rb2 : rb);
+                PROF(2)
+                chainF(kind == REF ? dux2 : dux);
+                syncthreads();
+                PROF(3)
+                expand_pass(kind == AFF ? 0 : (kind == REF ? 2 : 1), tau_min);
+                PROF(4)
+                if (kind == REF) { add_refinement(); refined = true; itref_count++; }
+                if (kind == COR)
+                {
+                    const double mu_aff0 = mu_aff;
+                    mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;  // COMPUTE_MU_AFF_QP
+                    if (mu_aff > 2.0 * mu_aff0) { kind = CEN; continue; }
+                }
+                // residual of the linear system at the step (OCP_QP_RES_COMPUTE_LIN): accuracy test of the factorisation
+                // after AFF, iterative-refinement test after COR / CEN / REF
+                double nlin[4];
+                bool wr = kind == REF, more = false;
+                for (;;)
+                {
+                    res_pass(wr, nlin);
+                    if (kind == AFF || nct == 0) break;
+                    if (itref_ok(nlin) || nref >= 2) break;
+                    if (wr) { more = true; break; }
+                    wr = true;  // once more, storing the residual as the right-hand side of the refinement solve
+                }
+                PROF(9)
+                if (nct == 0) break;
+                if (kind == AFF)
+                {
+                    // lq_fact = 1 (x_ocp_qp_ipm.c:1941-1974): HPIPM re-factorises with its LQ-based routine when the residual
+                    // of the Cholesky-based solve exceeds 1e-5; counted, see DESIGN.md
+                    if (!(nlin[0] <= 1e-5 && nlin[1] <= 1e-5 && nlin[2] <= 1e-5 && nlin[3] <= 1e-5)) lq_count++;
+                    mu_aff = (mu * nct + alpha * S1 + alpha * alpha * S2) / nct;
+                    const double tmp = mu_aff / mu;
+                    sigma = tmp * tmp * tmp;
+                    sigma_mu = sigma * mu;
+                    sigma_mu = sigma_mu > tau_min ? sigma_mu : tau_min;
+                    kind = COR;
+                    continue;
+                }
+                if (more) { kind = REF; nref++; continue; }
+                break;
             }
             if (refined) alpha_pass();
             PROF(11)
@@ -1279,10 +1358,6 @@ struct CtaSolver {
         if (disnan(mu)) return 3;
         return 0;
     }
-
-    // linear-system residual at the AFFINE step: right-hand side (rg, rb, rd, lam*t - tau) -- stationarity and dynamics
-    // rows from the arrays, inequality / complementarity rows from expand_pass(0)
-    MDEV void res_pass_affine(double* out4) { res_pass<false>(out4); }
 
     // ---------------------------------------------------------------- after the QP
     // d_ocp_qp_restore_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:723-871) + ocp_nlp_update_variables_sqp, full step
@@ -1430,8 +1505,8 @@ struct CtaSolver {
             st[12] = (double) (clock_now() - t_start); st[13] = (double) t_lin; st[14] = (double) t_qp; st[15] = 0;
 #ifdef USVMPC_PROFILE
             if (qp_total >= USVMPC_PROFILE)
-                printf("PROF inst %d sqp %d qp %d | passA %lld chainA %lld gains+ff %lld chainF %lld expand0 %lld reslin0 %lld rhs %lld "
-                       "solve %lld expand1 %lld res %lld init %lld refine %lld lin %lld upd %lld\n", inst, sqp_iter, qp_total,
+                printf("PROF inst %d sqp %d qp %d | passA %lld chainA %lld gains+ff %lld chainF %lld expand %lld - %lld rhs %lld "
+                       "chainC %lld - %lld res %lld init %lld alpha %lld lin %lld upd %lld\n", inst, sqp_iter, qp_total,
                        prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11],
                        prof[12], prof[13]);
 #endif
@@ -1449,11 +1524,15 @@ MDEV void cta_main(const Params& P, double* smem, int block_id)
     int* slot = (int*) (smem + P.plan.red_off);  // first reduction buffer doubles as the broadcast slot between solves
     for (;;)
     {
-        if (s.tid == 0) slot[0] = atomic_fetch_add(P.queue, 1);
+        if (s.tid == 0)
+        {
+            const int ticket = atomic_fetch_add(P.queue, 1);
+            slot[0] = ticket < P.B ? (P.order ? P.order[ticket] : ticket) : -1;
+        }
         syncthreads();
         const int inst = slot[0];
         syncthreads();
-        if (inst >= P.B) break;
+        if (inst < 0) break;
         s.run(inst);
     }
 }

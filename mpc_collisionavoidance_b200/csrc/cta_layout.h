@@ -61,7 +61,6 @@ struct Params {
     int p_per_stage, lh_per_stage, yref_per_stage, cold_start;
     int ncq, ncz;
     int rti_phase;          // 0: prepare + feedback, 1: prepare only, 2: feedback only (ocp_nlp_sqp_rti.c:459-488)
-    int slice_iter;         // SQP iterations one block spends on an instance before it goes back to the queue
     double dt, tol[4];
     const double* lbu;      // [N][nbu]   (shared by the batch, per stage like the reference's nlp_in)
     const double* ubu;      // [N][nbu]
@@ -78,8 +77,8 @@ struct Params {
     long ws_stride;
     double* stats;          // [B][NSTAT]
     double* scratch;        // [grid][plan.scratch_doubles]
-    int* queue;             // work queue: [0] head, [1] tail, [2] finished instances, [4...] instance ids (-1: not yet published)
-    int queue_cap;
+    int* queue;             // work queue: [0] next ticket
+    const int* order;       // ticket -> instance (longest-first order from the previous solve's iteration counts) or null
     Layout lay;
     Plan plan;
 };
@@ -128,7 +127,7 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int warps,
     P.red_off = (int) o;
     o += 2 * warps * 8;                                  // two reduction buffers of 8 values per warp
     P.misc_off = (int) o;
-    o += nv * nx + 2 * nx + 8 + (nx + 2 * (nu + nx + K) + 8) / 2 + warps * (nx * (nv + 1) + nx * nx + 4);
+    o += nv * nx + (nx * (nv + 1) + ne + 1) + (nx * nx + 2) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
     o = round_up((int) o, 2);
     for (int i = 0; i < F_FIRST_FLEX; i++)
     {

@@ -50,6 +50,37 @@ __global__ void __launch_bounds__(THREADS, USVMPC_MIN_CTAS) nmpc_solve_kernel(co
     cta_main<M>(P, smem, blockIdx.x);
 }
 
+// Longest-processing-time-first order of the work queue: instances sorted by decreasing IPM iteration count of the
+// PREVIOUS solve of this solver (statistics record, column 2).  In closed-loop / Monte-Carlo use consecutive solves of
+// an instance cost about the same, so the expensive instances start first and the launch does not end with a few
+// blocks finishing instances they picked up late.  One block, counting sort on min(iterations, NBIN-1).
+constexpr int LPT_BINS = 4096;
+__global__ void lpt_order_kernel(const double* stats, int B, int* order)
+{
+    __shared__ int hist[LPT_BINS];
+    for (int i = threadIdx.x; i < LPT_BINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+    {
+        int key = (int) stats[(long) b * NSTAT + 2];
+        key = key < 0 ? 0 : (key > LPT_BINS - 1 ? LPT_BINS - 1 : key);
+        atomicAdd(&hist[key], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int run = 0;
+        for (int i = LPT_BINS - 1; i >= 0; i--) { const int c = hist[i]; hist[i] = run; run += c; }  // descending keys
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+    {
+        int key = (int) stats[(long) b * NSTAT + 2];
+        key = key < 0 ? 0 : (key > LPT_BINS - 1 ? LPT_BINS - 1 : key);
+        order[atomicAdd(&hist[key], 1)] = b;
+    }
+}
+
 // buf[b][k][i] <-> ws[b*stride + off + (k0+k)*fstride + c0 + i]
 __global__ void ws_copy_kernel(double* ws, long stride, int off, int fstride, int c0, int dim, int k0, int nst, int B,
                                double* buf, int to_ws)
@@ -191,6 +222,8 @@ struct usvmpc_solver
     double *h_bnd;                         // host mirror of d_bnd
     int o_lbu, o_ubu, o_lbx, o_ubx, o_uh, n_bnd;
     int* d_queue;
+    int* d_order;                          // longest-first queue order from the previous solve
+    int have_history, lpt;
     double *d_p[2], *d_lh[2], *d_yref[2];  // [0] one row per instance, [1] one row per instance and stage
     double* d_stage;
     size_t stage_bytes;
@@ -241,6 +274,7 @@ void refresh_params(usvmpc_solver* s)
     P.cst = s->d_cst; P.x0 = s->d_x0; P.yref_e = s->d_yref_e;
     P.p = s->d_p[P.p_per_stage]; P.lh = s->d_lh[P.lh_per_stage]; P.yref = s->d_yref[P.yref_per_stage];
     P.ws = s->d_ws; P.stats = s->d_stats; P.scratch = s->d_scratch; P.queue = s->d_queue;
+    P.order = (s->lpt && s->have_history) ? s->d_order : nullptr;
 }
 
 // `value` as the caller gave it -> host pointer (values shared by the batch are kept on the host)
@@ -429,6 +463,8 @@ static int create_impl(usvmpc_solver* s)
     }
     CU(cudaMalloc(&s->d_queue, sizeof(int) * 8));
     CU(cudaMemset(s->d_queue, 0, sizeof(int) * 8));
+    CU(cudaMalloc(&s->d_order, sizeof(int) * (size_t) B));
+    s->lpt = 1; s->have_history = 0;
     // per-stage bounds shared by the batch, initialised from the description like acados_create() does
     // (acados_solver.in.c:1028-1449: the same lbx/ubx/lbu/ubu/lh/uh on every stage)
     const int nbu = cfg->nbu, nbx = cfg->nbx;
@@ -456,8 +492,17 @@ static int launch_solve(usvmpc_solver* s, cudaStream_t st)
     // the attribute is per function and process: set it for THIS solver's size right before its launch
     CU(cudaFuncSetAttribute(nmpc_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     CU(cudaMemsetAsync(s->d_queue, 0, sizeof(int) * 8, st));
+    if (s->lpt && s->have_history && s->B > s->grid)
+    {
+        lpt_order_kernel<<<1, 1024, 0, st>>>(s->d_stats, s->B, s->d_order);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    refresh_params(s);
+    if (s->B <= s->grid) s->P.order = nullptr;
     nmpc_solve_kernel<M><<<s->grid, THREADS, smem, st>>>(s->P);
     CU(cudaGetLastError());
+    s->have_history = 1;
     return 0;
 }
 
@@ -524,7 +569,6 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
     usvmpc_solver* s = (usvmpc_solver*) calloc(1, sizeof(usvmpc_solver));
     if (!s) return fail(USVMPC_E_INVALID, "out of host memory");
     s->cfg = *cfg; s->B = batch; s->device = device; s->nx = nx; s->nu = nu; s->nv = nx + nu;
-    s->P.slice_iter = 0;
     const int rc = create_impl(s);
     if (rc) { usvmpc_free(s); return rc; }  // one cleanup path: everything allocated so far is released
     *out = s;
@@ -536,7 +580,7 @@ int usvmpc_free(usvmpc_solver* s)
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->d_ws); cudaFree(s->d_stats); cudaFree(s->d_cst); cudaFree(s->d_x0); cudaFree(s->d_yref_e);
-    cudaFree(s->d_scratch); cudaFree(s->d_bnd); cudaFree(s->d_queue);
+    cudaFree(s->d_scratch); cudaFree(s->d_bnd); cudaFree(s->d_queue); cudaFree(s->d_order);
     for (int i = 0; i < 2; i++) { cudaFree(s->d_p[i]); cudaFree(s->d_lh[i]); cudaFree(s->d_yref[i]); }
     cudaFree(s->d_stage);
     free(s->h_bnd);
@@ -693,6 +737,7 @@ int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value)
     else if (!strcmp(field, "nlp_solver_type")) c.nlp_type = (int) value ? USVMPC_SQP_RTI : USVMPC_SQP;
     else if (!strcmp(field, "cold_start")) s->P.cold_start = value != 0.0;
     else if (!strcmp(field, "print_level")) {}
+    else if (!strcmp(field, "lpt_schedule")) s->lpt = value != 0.0;
     else if (!strcmp(field, "rti_phase")) { if (value != 0.0) return fail(USVMPC_E_INVALID, "rti_phase %g: only 0 (prepare+feedback in one call) is implemented", value); }
     else if (!strcmp(field, "step_length")) { if (value != 1.0) return fail(USVMPC_E_INVALID, "step_length %g: the engine takes full SQP steps like the reference scripts", value); }
     else return fail(USVMPC_E_FIELD, "unknown option '%s'", field);
