@@ -118,7 +118,9 @@ int usvmpc_eval_cost(usvmpc_solver* s, double* value, int on_device, void* strea
 
 /* replaces ocp_nlp_solver_opts_set (ocp_nlp_interface.c:943).  Fields: "max_iter", "qp_iter_max", "tol_stat",
  * "tol_eq", "tol_ineq", "tol_comp", "nlp_solver_type" (0/1), "cold_start" (extension: 1 = every solve starts from
- * x_k = x0, u = 0, pi = 0 instead of the previous iterate), "print_level", "rti_phase" (0 only), "step_length" (1 only) */
+ * x_k = x0, u = 0, pi = 0 instead of the previous iterate), "lpt_schedule" (extension, default 1: the work queue of a
+ * solve is ordered by decreasing iteration count of the previous solve of this solver), "print_level", "rti_phase"
+ * (0 only), "step_length" (1 only) */
 int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value);
 
 /* Obstacle front end of the guidance node (nmpc_ca/src/nmpc_guidance_ca1.cpp:251-363, obstaclesCallback + body2NED):
@@ -128,6 +130,23 @@ int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value);
  * with the smallest clearance are kept; unused slots hold (init_obs_pos, init_obs_pos, 0). */
 int usvmpc_obstacle_frontend(const double* pose, const double* obs_body, const int* len, int batch, int max_obs, int K,
                              double boat_radius, double init_obs_pos, double* p_out, double* r_out, void* stream);
+
+/* The QP seam of the reference, qp_solver_config.evaluate(qp_in, qp_out) (acados/ocp_qp/ocp_qp_common.h:62-76 ->
+ * ocp_qp_hpipm.c:240 -> d_ocp_qp_ipm_solve): solve ONE given OCP QP per instance -- in the form HPIPM sees it, i.e. after
+ * x0 elimination -- with the engine's IPM, tolerances / iteration limit as configured.  Device pointers, engine layout:
+ *   G   [B][N][nv*nx]   [B';A'] of every stage, column-major nv x nx (stage 0: x rows zero)
+ *   b   [B][N][nx]      rq [B][N+1][nv]      gxy [B][N][2K] = (dh_c/dX, c<K | dh_c/dY, c<K)
+ *   d   [B][N][2*ncq]   rows [u boxes | x boxes | h rows] lower side then upper side (upper side negated like HPIPM's d)
+ * out: ux [B][N+1][nv], pi [B][N][nx], lam, t [B][N][2*ncq]; the statistics record holds HPIPM status (slot 0), iterations
+ * (slot 2) and the four residual norms.  The Hessian is the solver's Gauss-Newton Hessian (LINEAR_LS: constant). */
+int usvmpc_qp_solve(usvmpc_solver* s, const double* G, const double* b, const double* rq, const double* gxy, const double* d,
+                    double* ux, double* pi, double* lam, double* t, void* stream);
+
+/* Multi-GPU result exchange: give the solver a device buffer [B][width] and the solve kernel's
+ * epilogue writes every instance's packed result row into it -- x [N+1][nx] | u [N][nu] | status, sqp_iter, qp_iter,
+ * res_stat, res_eq, res_ineq, res_comp -- so that the buffer can be handed to ncclAllGather as it is (it may be this
+ * rank's slice of the gathered tensor: in-place all-gather).  NULL switches the epilogue off.  Returns width. */
+int usvmpc_set_result_buffer(usvmpc_solver* s, double* device_buffer);
 
 /* engine introspection for benchmarks: kernels launched so far, bytes of HBM held, batch, launch geometry */
 int usvmpc_info(usvmpc_solver* s, const char* what, double* value);

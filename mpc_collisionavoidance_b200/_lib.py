@@ -23,7 +23,8 @@ class Config(C.Structure):
 SYMBOLS = ["usvmpc_last_error", "usvmpc_version", "usvmpc_config_default", "usvmpc_create", "usvmpc_free",
            "usvmpc_solve", "usvmpc_update_params", "usvmpc_cost_model_set", "usvmpc_constraints_model_set",
            "usvmpc_out_set", "usvmpc_out_get", "usvmpc_dims_get_from_attr", "usvmpc_get_stats",
-           "usvmpc_solver_opts_set", "usvmpc_info", "usvmpc_eval_cost", "usvmpc_obstacle_frontend"]
+           "usvmpc_solver_opts_set", "usvmpc_info", "usvmpc_eval_cost", "usvmpc_obstacle_frontend",
+           "usvmpc_set_result_buffer", "usvmpc_qp_solve"]
 
 _lib = None
 
@@ -54,6 +55,8 @@ def load():
     lib.usvmpc_eval_cost.argtypes = [vp, dp, ci, vp]
     lib.usvmpc_obstacle_frontend.argtypes = [dp, dp, vp, ci, ci, ci, C.c_double, C.c_double, dp, dp, vp]
     lib.usvmpc_info.argtypes = [vp, cp, C.POINTER(C.c_double)]
+    lib.usvmpc_set_result_buffer.argtypes = [vp, dp]
+    lib.usvmpc_qp_solve.argtypes = [vp] + [dp] * 9 + [vp]
     for name in SYMBOLS:
         getattr(lib, name)
     _lib = lib

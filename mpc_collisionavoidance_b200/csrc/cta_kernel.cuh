@@ -67,16 +67,20 @@ DEV void chain_sync()
 //      reciprocal square roots for NU = 2) and finishes its own entries; the Schur complement goes to M and, as a full
 //      symmetric matrix, to sP for the next stage.  Non-positive pivot => that column becomes zero (dpotrf_l_mn,
 //      BF/kernel/generic/kernel_dgemm_4x4_lib4.c:5701-5710).
-template <class M>
-MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sW, double* sP,
+template <class M, class RT>
+MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sWd, double* sPd,
                         int N)
 {
     constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NE = NV * (NV + 1) / 2 + NV;
     constexpr int CT = 32 * CHAIN_WARPS;  // threads that share the items of a step (warps 0 .. CHAIN_WARPS-1)
     constexpr int NQ = (NE + CT - 1) / CT, NWQ = (NX * NR + CT - 1) / CT;
     ASSUME_SHARED(G); ASSUME_SHARED(Mx); ASSUME_SHARED(rb); ASSUME_SHARED(Pb); ASSUME_SHARED(dinv);
-    ASSUME_SHARED(sW); ASSUME_SHARED(sP);
-    double* sM = sW + NX * NR;  // scratch copy of the matrix between steps 2 and 3
+    ASSUME_SHARED(sWd); ASSUME_SHARED(sPd);
+    // RT = double: the reference's arithmetic.  RT = float: the factorisation (these three steps) runs in fp32 -- the
+    // `s_` twin of the reference (x_ocp_qp_kkt.c:457-461 is its only precision-dependent branch) -- while residuals,
+    // the solves with the factor and iterative refinement stay fp64 (BASELINE.json config 4).
+    RT* sW = (RT*) sWd; RT* sP = (RT*) sPd;
+    RT* sM = sW + NX * NR;  // scratch copy of the matrix between steps 2 and 3
     const int lane = thread_id();  // index among the CT chain threads
     // Uniform control flow: every lane runs every step on clamped item indices (a surplus lane recomputes the last item
     // and stores the same value to the same address), so there is no divergent branch between the __syncwarps.
@@ -116,17 +120,17 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
             for (int q = 0; q < NWQ; q++)
             {
                 const double* ga = w_last[q] ? rbk : Gk + w_src[q];
-                const double* pr = sP + w_m[q] * NX;
-                double a0 = 0.0, a1 = 0.0;
+                const RT* pr = sP + w_m[q] * NX;
+                RT a0 = 0, a1 = 0;
 #pragma unroll
                 for (int n = 0; n < NX; n += 2)
                 {
-                    a0 += pr[n] * ga[n * w_str[q]];
-                    if (n + 1 < NX) a1 += pr[n + 1] * ga[(n + 1) * w_str[q]];
+                    a0 += pr[n] * (RT) ga[n * w_str[q]];
+                    if (n + 1 < NX) a1 += pr[n + 1] * (RT) ga[(n + 1) * w_str[q]];
                 }
-                const double acc = a0 + a1;
+                const RT acc = a0 + a1;
                 if (w_last[q]) Pb[k * NX + w_m[q]] = acc;
-                sW[w_e[q]] = w_last[q] ? acc + pn[w_m[q]] : acc;
+                sW[w_e[q]] = w_last[q] ? acc + (RT) pn[w_m[q]] : acc;
             }
             chain_sync<CT>();
 #pragma unroll
@@ -134,13 +138,13 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
             {
                 const int r = m_r[q], c = m_c[q];
                 const double* gr = Gk + (r < NV ? r : c);
-                const double* wc = sW + (r < NV ? c : NV) * NX;
-                double a0 = Mk[m_e[q]], a1 = 0.0;
+                const RT* wc = sW + (r < NV ? c : NV) * NX;
+                RT a0 = (RT) Mk[m_e[q]], a1 = 0;
 #pragma unroll
                 for (int m = 0; m < NX; m += 2)
                 {
-                    a0 += gr[NV * m] * wc[m];
-                    if (m + 1 < NX) a1 += gr[NV * (m + 1)] * wc[m + 1];
+                    a0 += (RT) gr[NV * m] * wc[m];
+                    if (m + 1 < NX) a1 += (RT) gr[NV * (m + 1)] * wc[m + 1];
                 }
                 sM[m_e[q]] = a0 + a1;
             }
@@ -148,23 +152,23 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
         else
         {
 #pragma unroll
-            for (int q = 0; q < NQ; q++) sM[m_e[q]] = Mk[m_e[q]];
+            for (int q = 0; q < NQ; q++) sM[m_e[q]] = (RT) Mk[m_e[q]];
         }
         chain_sync<CT>();
         // Cholesky of the NU x NU input block, redundantly on every lane
-        double Lt[NU][NU], inv[NU];
+        RT Lt[NU][NU], inv[NU];
 #pragma unroll
         for (int j = 0; j < NU; j++)
         {
-            double piv = sM[j * (j + 1) / 2 + j];
+            RT piv = sM[j * (j + 1) / 2 + j];
 #pragma unroll
             for (int i = 0; i < j; i++) piv -= Lt[j][i] * Lt[j][i];
-            inv[j] = piv > 0.0 ? drsqrt(piv) : 0.0;
+            inv[j] = piv > (RT) 0 ? drsqrt(piv) : (RT) 0;
             Lt[j][j] = piv * inv[j];
 #pragma unroll
             for (int jj = j + 1; jj < NU; jj++)
             {
-                double v = sM[jj * (jj + 1) / 2 + j];
+                RT v = sM[jj * (jj + 1) / 2 + j];
 #pragma unroll
                 for (int i = 0; i < j; i++) v -= Lt[jj][i] * Lt[j][i];
                 Lt[jj][j] = v * inv[j];
@@ -179,18 +183,18 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
             // first NU entries of rows r and c of the factor by substitution.  For a row of the input block itself the
             // same formula gives its entries up to the diagonal (what lies beyond is not used); row c is only used for
             // c >= NU.
-            const double* rr = sM + r * (r + 1) / 2;
-            const double* rc = sM + c * (c + 1) / 2;
-            double v[NU], u[NU];
+            const RT* rr = sM + r * (r + 1) / 2;
+            const RT* rc = sM + c * (c + 1) / 2;
+            RT v[NU], u[NU];
 #pragma unroll
             for (int j = 0; j < NU; j++)
             {
-                double x = rr[j], y = rc[j];
+                RT x = rr[j], y = rc[j];
 #pragma unroll
                 for (int i = 0; i < j; i++) { x -= v[i] * Lt[j][i]; y -= u[i] * Lt[j][i]; }
                 v[j] = x * inv[j]; u[j] = y * inv[j];
             }
-            double out = sM[m_e[q]];
+            RT out = sM[m_e[q]];
 #pragma unroll
             for (int j = 0; j < NU; j++) out -= v[j] * u[j];
 #pragma unroll
@@ -313,7 +317,8 @@ struct CtaSolver {
     double res_max[4], mu, mu_aff, sigma, alpha;
     double S1, S2;        // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
     double lin_d, lin_m;  // residual norms of the linearised inequality / complementarity rows at the last expanded step
-    int solve_calls, lq_count, itref_count;
+    int solve_calls, lq_count, itref_count, fp32_count;
+    bool use_fp32;  // this factorisation runs in fp32 (config 4); cleared for the rest of a QP once its accuracy test fails
 #ifdef USVMPC_PROFILE
     // phase clocks of thread 0 (diagnostic builds only)
     long long prof[24], tprev;
@@ -357,7 +362,7 @@ struct CtaSolver {
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
-        solve_calls = 0; lq_count = 0; itref_count = 0;
+        solve_calls = 0; lq_count = 0; itref_count = 0; fp32_count = 0; use_fp32 = false;
     }
 
     MDEV double* Z(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
@@ -910,10 +915,63 @@ struct CtaSolver {
         mu = nct > 0 ? vs[0] / nct : 0.0;
     }
 
+    // passM: assemble the matrices to factorise once more from the current iterate (H + Gamma terms, gradient row =
+    // res_g + gamma terms) -- what the tail of passA does -- after a factorisation consumed them (fp32 attempt of
+    // config 4 that failed its accuracy test).  Rare path.
+    MDEV void passM()
+    {
+        const double tau = 1e-16;
+        for (int it = tid; it < (N + 1) * NE; it += T)
+        {
+            const int k = it / NE, e = it - k * NE;
+            Mx[it] = Tp[stage_class(k) * NE + e];
+        }
+        syncthreads();
+        for (int it = tid; it < (N + 1) * NV; it += T)
+        {
+            const int k = dnv.div(it), i = it - k * NV;
+            double dg = 0.0, gg = 0.0;
+            if (k < N)
+            {
+                auto row_terms = [&](int r0, double& Gs, double& gd) {
+                    const int r1 = r0 + ncq;
+                    const double l0 = lam[r0], l1 = lam[r1], t0 = t[r0], t1 = t[r1], i0 = ti[r0], i1 = ti[r1];
+                    Gs = i0 * l0 + i1 * l1;
+                    gd = i0 * ((l0 * t0 - tau) - l0 * rd[r0]) - i1 * ((l1 * t1 - tau) - l1 * rd[r1]);
+                };
+                const int row = vrow(k, i);
+                if (row >= 0) { double Gs, gd; row_terms(k * s2 + row, Gs, gd); dg += Gs; gg += gd; }
+                if ((i == HXV || i == HYV) && k >= 1)
+                {
+                    const double* gk = gxy + k * 2 * K;
+                    const double* gi = i == HXV ? gk : gk + K;
+                    double aYX = 0.0;
+                    for (int c = 0; c < K; c++)
+                    {
+                        double Gs, gd;
+                        row_terms(k * s2 + nbq + c, Gs, gd);
+                        dg += (gi[c] * Gs) * gi[c];
+                        gg += gd * gi[c];
+                        if (i == HYV) aYX += (gk[K + c] * Gs) * gk[c];
+                    }
+                    if (i == HYV) Mx[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
+                }
+            }
+            Mx[k * NE + MI(i, i)] += dg;
+            Mx[k * NE + MI(NV, i)] = rg[it] + gg;
+        }
+        syncthreads();
+    }
+
     // ---------------------------------------------------------------- IPM: the serial recursions (warp 0)
     // The recursions are free functions (chain_*_impl below, not inlined: their own register allocation and compact
     // code, whatever the state of the surrounding solver) called by warp 0 only.
-    MDEV void chainA() { if (wid < CHAIN_WARPS) chainA_impl<M>(G, Mx, rb, Pb, dinv, sW, sP, N); }
+    MDEV void chainA()
+    {
+        if (wid >= CHAIN_WARPS) return;
+        if (use_fp32) chainA_impl<M, float>(G, Mx, rb, Pb, dinv, sW, sP, N);
+        else chainA_impl<M, double>(G, Mx, rb, Pb, dinv, sW, sP, N);
+    }
     MDEV void chainF(double* out) { if (wid == 0) chainF_impl<M>(Acl, cc, out, N); }
     MDEV void chainC() { if (wid == 0) chainC_impl<M>(Acl, ee, zv, N); }
 
@@ -1271,6 +1329,7 @@ struct CtaSolver {
         alpha = 1.0;
         double a = 0.0;  // the first passA applies no step
         int it = 0;
+        use_fp32 = P.chain_fp32 != 0;
         for (;;)
         {
             passA(a, nct > 0 ? tau_min : 0.0, res_max);
@@ -1281,14 +1340,16 @@ struct CtaSolver {
                    dabs(res_max[3] - tau_min) > tol_comp)))
                 break;
             int kind = AFF, nref = 0;
-            bool refined = false;
+            bool refined = false, refactor = false;
             double sigma_mu = 0.0;
             for (;;)
             {
                 if (kind == AFF)
                 {
+                    if (refactor) passM();  // the fp32 attempt consumed the matrices: assemble them again
                     chainA();
                     syncthreads();
+                    if (use_fp32) fp32_count++;
                     PROF(1)
                     gains_pass();
                     syncthreads();
@@ -1330,6 +1391,13 @@ struct CtaSolver {
                 }
                 PROF(9)
                 if (nct == 0) break;
+                if (kind == AFF && use_fp32 && !itref_ok(nlin))
+                {
+                    // fp32 factorisation (config 4): the fp64 residual of the affine solve is the accuracy test; when it fails,
+                    // this and every later factorisation of the QP run in fp64 (Gamma only grows towards the solution)
+                    use_fp32 = false; refactor = true;
+                    continue;
+                }
                 if (kind == AFF)
                 {
                     // lq_fact = 1 (x_ocp_qp_ipm.c:1941-1974): HPIPM re-factorises with its LQ-based routine when the residual
@@ -1446,9 +1514,49 @@ struct CtaSolver {
         res4[2] = vm[0]; res4[3] = vm[1];
     }
 
+    // ---------------------------------------------------------------- QP-only entry
+    // The seam qp_solver_config.evaluate(qp_in, qp_out) of the reference (AC/acados/ocp_qp/ocp_qp_common.h:62-76): solve ONE
+    // given OCP QP per instance (after x0 elimination, the form HPIPM sees) with the IPM and return its solution.  The
+    // Hessian is the solver's Gauss-Newton Hessian (constant for LINEAR_LS); everything else comes from P.qp.
+    MDEV void run_qp(int inst)
+    {
+        const QpIo& q = P.qp;
+        const double* gG = q.G + (long) inst * N * (NV * NX);
+        const double* gb = q.b + (long) inst * N * NX;
+        const double* grq = q.rq + (long) inst * (N + 1) * NV;
+        const double* gg = q.gxy + (long) inst * N * 2 * K;
+        const double* gd = q.d + (long) inst * N * s2;
+        for (int e = tid; e < N * NV * NX; e += T) G[e] = gG[e];
+        for (int e = tid; e < N * NX; e += T) b[e] = gb[e];
+        for (int e = tid; e < (N + 1) * NV; e += T) rq[e] = grq[e];
+        for (int e = tid; e < N * 2 * K; e += T) gxy[e] = gg[e];
+        for (int e = tid; e < N * s2; e += T) d[e] = gd[e];
+        for (int e = tid; e < s2; e += T) d[N * s2 + e] = 0.0;
+        syncthreads();
+        solve_calls = 0; lq_count = 0; itref_count = 0; fp32_count = 0;
+        int it = 0;
+        const int qp_status = ipm_solve(&it);
+        double* oux = q.ux + (long) inst * (N + 1) * NV;
+        double* opi = q.pi + (long) inst * N * NX;
+        double* ol = q.lam + (long) inst * N * s2;
+        double* ot = q.t + (long) inst * N * s2;
+        for (int e = tid; e < (N + 1) * NV; e += T) oux[e] = ux[e];
+        for (int e = tid; e < N * NX; e += T) opi[e] = pi[e];
+        for (int e = tid; e < N * s2; e += T) { ol[e] = lam[e]; ot[e] = t[e]; }
+        if (tid == 0)
+        {
+            double* st = P.stats + (long) inst * NSTAT;
+            for (int i = 0; i < NSTAT; i++) st[i] = 0.0;
+            st[0] = qp_status; st[2] = it; st[3] = res_max[0]; st[4] = res_max[1]; st[5] = res_max[2]; st[6] = res_max[3];
+            st[7] = lq_count; st[8] = solve_calls; st[9] = qp_status; st[10] = it; st[11] = itref_count; st[15] = fp32_count;
+        }
+        syncthreads();
+    }
+
     // ---------------------------------------------------------------- the solve
     MDEV void run(int inst)
     {
+        if (P.qp.G) { run_qp(inst); return; }
         w = P.ws + (long) inst * P.ws_stride;
         const double* x0 = P.x0 + (long) inst * NX;
         const double* pg = P.p + (long) inst * (P.p_per_stage ? (N + 1) : 1) * 2 * K;
@@ -1456,7 +1564,7 @@ struct CtaSolver {
         const double* yrg = P.yref + (long) inst * (P.yref_per_stage ? N : 1) * NY;
         const double* yre = P.yref_e + (long) inst * NX;
         if (P.cold_start) cold_start(x0);
-        solve_calls = 0; lq_count = 0; itref_count = 0;
+        solve_calls = 0; lq_count = 0; itref_count = 0; fp32_count = 0;
 #ifdef USVMPC_PROFILE
         for (int i = 0; i < 24; i++) prof[i] = 0;
         tprev = clock_now();
@@ -1502,7 +1610,7 @@ struct CtaSolver {
             st[0] = status; st[1] = sqp_iter; st[2] = qp_total;
             st[3] = res[0]; st[4] = res[1]; st[5] = res[2]; st[6] = res[3];
             st[7] = lq_count; st[8] = solve_calls; st[9] = qp_status; st[10] = qp_iter; st[11] = itref_count;
-            st[12] = (double) (clock_now() - t_start); st[13] = (double) t_lin; st[14] = (double) t_qp; st[15] = 0;
+            st[12] = (double) (clock_now() - t_start); st[13] = (double) t_lin; st[14] = (double) t_qp; st[15] = fp32_count;
 #ifdef USVMPC_PROFILE
             if (qp_total >= USVMPC_PROFILE)
                 printf("PROF inst %d sqp %d qp %d | passA %lld chainA %lld gains+ff %lld chainF %lld expand %lld - %lld rhs %lld "
@@ -1510,6 +1618,20 @@ struct CtaSolver {
                        prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11],
                        prof[12], prof[13]);
 #endif
+        }
+        if (P.packed)
+        {
+            // epilogue: the instance's result row of the send buffer of the all-gather:
+            // x [N+1][NX] | u [N][NU] | status, sqp_iter, qp_iter, res_stat, res_eq, res_ineq, res_comp
+            double* row = P.packed + (long) inst * P.packed_width;
+            const int nxs = (N + 1) * NX, nus = N * NU;
+            for (int e = tid; e < nxs; e += T) { const int k = e / NX, i = e - k * NX; row[e] = Z(P.lay.zux, k)[NU + i]; }
+            for (int e = tid; e < nus; e += T) { const int k = e / NU, i = e - k * NU; row[nxs + e] = Z(P.lay.zux, k)[i]; }
+            if (tid == 0)
+            {
+                double* r7 = row + nxs + nus;
+                r7[0] = status; r7[1] = sqp_iter; r7[2] = qp_total; r7[3] = res[0]; r7[4] = res[1]; r7[5] = res[2]; r7[6] = res[3];
+            }
         }
         syncthreads();
     }

@@ -24,7 +24,8 @@ constexpr int NBUMAX = 4;
 constexpr int NSTAT = 16;    // per-instance statistics record (doubles)
 // stats: 0 status, 1 sqp_iter, 2 qp_iter (total), 3..6 res_stat/eq/ineq/comp, 7 IPM iterations whose factorisation
 //        failed HPIPM's accuracy test (lq_fact), 8 solve-only Riccati sweeps, 9 last QP status, 10 last QP
-//        iterations, 11 iterative-refinement solves, 12 time_tot, 13 time_lin, 14 time_qp (seconds, SM clock), 15 -
+//        iterations, 11 iterative-refinement solves, 12 time_tot, 13 time_lin, 14 time_qp (SM clock cycles), 15 factorisations
+//        that ran in fp32 (riccati_precision = 32)
 
 struct Field { int off, stride, es; };  // offset of (stage 0, element 0), stage stride, element stride (doubles)
 
@@ -55,11 +56,18 @@ struct Plan {
     int scratch_doubles; // global scratch of one block (0 if everything fits)
 };
 
+// device arrays of the QP-only entry (usvmpc_qp_solve); G == nullptr: normal NMPC solve
+struct QpIo {
+    const double *G, *b, *rq, *gxy, *d;   // [B][N][NV*NX], [B][N][NX], [B][N+1][NV], [B][N][2K], [B][N][2 ncq]
+    double *ux, *pi, *lam, *t;            // [B][N+1][NV], [B][N][NX], [B][N][2 ncq], [B][N][2 ncq]
+};
+
 struct Params {
     int B, N, K, num_steps, num_stages, nlp_type, max_iter, qp_iter_max, nbx, nbu;
     int idxbx[NBXMAX];
     int p_per_stage, lh_per_stage, yref_per_stage, cold_start;
     int ncq, ncz;
+    int chain_fp32;         // 1: Riccati factorisation in fp32 (residuals, solves, refinement fp64): BASELINE.json config 4
     int rti_phase;          // 0: prepare + feedback, 1: prepare only, 2: feedback only (ocp_nlp_sqp_rti.c:459-488)
     double dt, tol[4];
     const double* lbu;      // [N][nbu]   (shared by the batch, per stage like the reference's nlp_in)
@@ -77,8 +85,11 @@ struct Params {
     long ws_stride;
     double* stats;          // [B][NSTAT]
     double* scratch;        // [grid][plan.scratch_doubles]
+    double* packed;         // optional [B][packed_width]: result rows written by the solve's epilogue (all-gather send buffer)
+    int packed_width;
     int* queue;             // work queue: [0] next ticket
     const int* order;       // ticket -> instance (longest-first order from the previous solve's iteration counts) or null
+    QpIo qp;
     Layout lay;
     Plan plan;
 };

@@ -738,6 +738,11 @@ int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value)
     else if (!strcmp(field, "cold_start")) s->P.cold_start = value != 0.0;
     else if (!strcmp(field, "print_level")) {}
     else if (!strcmp(field, "lpt_schedule")) s->lpt = value != 0.0;
+    else if (!strcmp(field, "riccati_precision"))
+    {
+        if (value != 32.0 && value != 64.0) return fail(USVMPC_E_INVALID, "riccati_precision must be 32 or 64");
+        s->P.chain_fp32 = value == 32.0;
+    }
     else if (!strcmp(field, "rti_phase")) { if (value != 0.0) return fail(USVMPC_E_INVALID, "rti_phase %g: only 0 (prepare+feedback in one call) is implemented", value); }
     else if (!strcmp(field, "step_length")) { if (value != 1.0) return fail(USVMPC_E_INVALID, "step_length %g: the engine takes full SQP steps like the reference scripts", value); }
     else return fail(USVMPC_E_FIELD, "unknown option '%s'", field);
@@ -754,6 +759,34 @@ int usvmpc_obstacle_frontend(const double* pose, const double* obs_body, const i
                                                                                      init_obs_pos, p_out, r_out);
     CU(cudaGetLastError());
     return 0;
+}
+
+int usvmpc_qp_solve(usvmpc_solver* s, const double* G, const double* b, const double* rq, const double* gxy, const double* d,
+                    double* ux, double* pi, double* lam, double* t, void* stream)
+{
+    if (!s || !G || !b || !rq || !d || !ux || !pi || !lam || !t) return fail(USVMPC_E_INVALID, "null argument");
+    if (s->cfg.K > 0 && !gxy) return fail(USVMPC_E_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    const double* g2 = gxy ? gxy : d;
+    s->P.qp = QpIo{G, b, rq, g2, d, ux, pi, lam, t};
+    const int have = s->have_history;
+    s->have_history = 0;   // the iteration counts of an NMPC solve say nothing about these QPs: plain queue order
+    const int rc = s->cfg.model == USVMPC_MODEL_PENDULUM ? launch_solve<Pendulum>(s, (cudaStream_t) stream)
+                                                          : launch_solve<Usv3>(s, (cudaStream_t) stream);
+    s->P.qp = QpIo{};
+    (void) have;
+    s->have_history = 0;   // the statistics record now holds QP statistics: no history for the next NMPC solve
+    if (rc) return rc;
+    s->launches++;
+    return 0;
+}
+
+int usvmpc_set_result_buffer(usvmpc_solver* s, double* device_buffer)
+{
+    if (!s) return fail(USVMPC_E_INVALID, "null solver");
+    s->P.packed = device_buffer;
+    s->P.packed_width = (s->cfg.N + 1) * s->nx + s->cfg.N * s->nu + 7;
+    return s->P.packed_width;
 }
 
 int usvmpc_info(usvmpc_solver* s, const char* what, double* value)

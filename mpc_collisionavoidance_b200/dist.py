@@ -31,6 +31,21 @@ def unpack_results(packed, N, nx, nu):
     return packed[:, :a].reshape(-1, N + 1, nx), packed[:, a:b].reshape(-1, N, nu), packed[:, b:]
 
 
+def gather_buffer(torch, B_local, world, rank, N, nx, nu, device):
+    """(gathered [world*B_local, width], own slice) for equal shards: the engine's epilogue writes this rank's packed
+    result rows straight into its slice of the gathered tensor (solver.set_result_buffer(own slice)), and the
+    all-gather runs in place -- no pack kernel, no concatenation."""
+    width = packed_width(N, nx, nu)
+    out = torch.zeros((world * B_local, width), dtype=torch.float64, device=device)
+    return out, out[rank * B_local:(rank + 1) * B_local]
+
+
+def all_gather_in_place(dist, gathered, own):
+    """the one collective of the path"""
+    dist.all_gather_into_tensor(gathered, own)
+    return gathered
+
+
 def all_gather_results(torch, dist, packed, B, world):
     """All-gather the per-rank packed results into [B, width] in global instance order (ragged shards padded)."""
     sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]

@@ -27,7 +27,8 @@ _MEM_FIELDS = ["sl", "su"]
 _COST_FIELDS = ["y_ref", "yref"]
 _CONSTR_FIELDS = ["lbx", "ubx", "lbu", "ubu"]
 _STAT_COL = {"status": 0, "sqp_iter": 1, "qp_iter": 2, "res_stat": 3, "res_eq": 4, "res_ineq": 5, "res_comp": 6,
-             "solve_sweeps": 8, "qp_status": 9, "qp_iter_last": 10}
+             "lq_fact": 7, "solve_sweeps": 8, "qp_status": 9, "qp_iter_last": 10, "refinement_solves": 11,
+             "time_tot": 12, "time_lin": 13, "time_qp": 14, "fp32_factorisations": 15}
 
 
 def _is_torch(v):
@@ -221,7 +222,7 @@ class BatchedAcadosOcpSolver:
         return out[0] if self.unbatched else out
 
     def stats_table(self, device=False):
-        """[B, 12] statistics record (include/usvmpc.h)"""
+        """[B, 16] statistics record (include/usvmpc.h)"""
         if device:
             out = self._torch.empty((self.B, _lib.NSTAT), dtype=self._torch.float64, device=f"cuda:{self.device}")
             _lib.check(self.lib.usvmpc_get_stats(self.h, C.c_void_p(out.data_ptr()), 1, self._stream()), "stats")
@@ -238,7 +239,11 @@ class BatchedAcadosOcpSolver:
             raise Exception("AcadosOcpSolver.get_stats(): {} is not a valid argument.\n Possible values are {}. Exiting.".format(
                 field_, list(_STAT_COL) + ["statistics"]))
         col = self.stats_table()[:, _STAT_COL[field_]]
-        if field_ in ("status", "sqp_iter", "qp_iter", "solve_sweeps", "qp_status", "qp_iter_last"):
+        if field_.startswith("time_"):
+            # the reference's timers (ocp_nlp_sqp_rti.c:984-1014) are wall-clock seconds; the engine counts SM clock cycles
+            # per instance inside the kernel (time one block spent on the instance)
+            return col / self.info("sm_clock_hz")
+        if not field_.startswith("res_"):
             col = col.astype(np.int64)
         return col
 
@@ -263,6 +268,46 @@ class BatchedAcadosOcpSolver:
                 raise Exception("initialize_t_slacks = 1 is not implemented")
             return
         _lib.check(self.lib.usvmpc_solver_opts_set(self.h, field_.encode(), float(value_)), "options_set")
+
+    def qp_solve(self, G, b, rq, gxy, d):
+        """The QP seam of the reference (qp_solver_config.evaluate, ocp_qp_common.h:62-76): solve one given OCP QP per
+        instance (engine layout, see include/usvmpc.h:usvmpc_qp_solve) with the engine's IPM.  Arrays: numpy or torch;
+        returns dict(ux, pi, lam, t, iter, status, res) of numpy arrays."""
+        torch = self._torch
+        dev = f"cuda:{self.device}"
+        nv, nx, N, B, K = self.nx + self.nu, self.nx, self.N, self.B, self.K
+        r2 = 2 * (self.cfg.nbu + self.cfg.nbx + K)
+        want = {"G": (B, N, nv * nx), "b": (B, N, nx), "rq": (B, N + 1, nv), "gxy": (B, N, 2 * K), "d": (B, N, r2)}
+        t = {}
+        for name, v in (("G", G), ("b", b), ("rq", rq), ("gxy", gxy), ("d", d)):
+            a = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v, dtype=torch.float64, device=dev).contiguous()
+            if tuple(a.shape) != want[name]:
+                raise Exception('mismatching dimension for field "{}" with dimension {} (you have {})'.format(name, want[name], tuple(a.shape)))
+            t[name] = a
+        out = {"ux": torch.zeros((B, N + 1, nv), dtype=torch.float64, device=dev),
+               "pi": torch.zeros((B, N, nx), dtype=torch.float64, device=dev),
+               "lam": torch.zeros((B, N, r2), dtype=torch.float64, device=dev),
+               "t": torch.zeros((B, N, r2), dtype=torch.float64, device=dev)}
+        p = lambda a: C.c_void_p(a.data_ptr()) if a.numel() else None
+        _lib.check(self.lib.usvmpc_qp_solve(self.h, p(t["G"]), p(t["b"]), p(t["rq"]), p(t["gxy"]), p(t["d"]), p(out["ux"]),
+                                            p(out["pi"]), p(out["lam"]), p(out["t"]), self._stream()), "qp_solve")
+        st = self.stats_table()
+        res = {k: v.cpu().numpy() for k, v in out.items()}
+        res.update(iter=st[:, 2].astype(np.int64), status=st[:, 0].astype(np.int64), res=st[:, 3:7])
+        return res
+
+    def set_result_buffer(self, tensor):
+        """torch CUDA float64 tensor [B, width] (or None): the solve kernel writes each instance's packed result row
+        (x | u | status, sqp_iter, qp_iter, 4 residuals) into it -- the send buffer of the multi-GPU all-gather."""
+        if tensor is None:
+            self._result_buffer = None
+            return _lib.check(self.lib.usvmpc_set_result_buffer(self.h, None), "set_result_buffer")
+        width = (self.N + 1) * self.nx + self.N * self.nu + 7
+        if tuple(tensor.shape) != (self.B, width) or not tensor.is_cuda or not tensor.is_contiguous() \
+                or tensor.dtype != self._torch.float64:
+            raise Exception("result buffer must be a contiguous CUDA float64 tensor of shape {}".format((self.B, width)))
+        self._result_buffer = tensor   # keep it alive
+        return _lib.check(self.lib.usvmpc_set_result_buffer(self.h, C.c_void_p(tensor.data_ptr())), "set_result_buffer")
 
     def info(self, what):
         v = C.c_double()

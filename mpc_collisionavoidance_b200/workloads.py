@@ -10,6 +10,13 @@ import numpy as np
 U_REF = 0.9
 DT = 0.05
 
+# Position reference: X_ref = X_0 + XREF_FACTOR * u_ref * dt * N.  The survey's 1.5 asks for more distance than the
+# horizon can cover at u_ref; at N = 100 that drives the surge speed across the model's non-smooth drag switch
+# (u > 1.25, usv_model.py: if_else) and the reference's full-step SQP then cycles on every scene (0/64 converged).  With
+# 0.8 the reference converges on 81 % of the N = 100 scenes (52/64, same seed); SURVEY.md section 8(d) lets the builder
+# tune the ranges and asks for them to be recorded: this is the only range that differs from the survey's, config 4 only.
+XREF_FACTOR = {4: 0.8}
+
 # BASELINE.json configs: (N, K, batch, num_steps)
 CONFIGS = {
     1: dict(N=20, K=3, B=1, num_steps=1),
@@ -38,21 +45,21 @@ def make_batch(config_id: int, B: int = None, N: int = None, K: int = None, seed
     if config_id == 5:
         # Monte-Carlo disturbance scenarios: 128 base scenes x draws of x0 += N(0, diag(...)^2)
         nbase = min(128, B)
-        base = _scenes(rng, nbase, N, K)
+        base = _scenes(rng, nbase, N, K, XREF_FACTOR.get(config_id, 1.5))
         reps = -(-B // nbase)
         idx = np.tile(np.arange(nbase), reps)[:B]
         sig = np.array([0.05, 0.05, 0.02, 0.05, 0.01, 0.02])
         x0 = base.x0[idx] + rng.standard_normal((B, 6)) * sig
         return Batch(x0, base.p[idx].copy(), base.lh[idx].copy(), base.yref[idx].copy(), base.yref_e[idx].copy())
-    return _scenes(rng, B, N, K)
+    return _scenes(rng, B, N, K, XREF_FACTOR.get(config_id, 1.5))
 
 
-def _scenes(rng, B, N, K) -> Batch:
+def _scenes(rng, B, N, K, xref_factor=1.5) -> Batch:
     x0 = np.stack([np.zeros(B), rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), rng.uniform(0.4, 1.0, B),
                    rng.uniform(-0.02, 0.02, B), rng.uniform(-0.05, 0.05, B)], axis=1)
     span = U_REF * DT * N
     yref = np.zeros((B, 8))
-    yref[:, 0] = x0[:, 0] + span * 1.5
+    yref[:, 0] = x0[:, 0] + span * xref_factor
     yref[:, 3] = U_REF
     p = np.zeros((B, 2 * K))
     lh = np.zeros((B, K))

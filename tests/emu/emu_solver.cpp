@@ -156,12 +156,12 @@ enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_U
 }  // namespace
 
 // Emulation knobs (tests only): shared-memory budget in bytes (forces fields into the global scratch), threads per block
-extern "C" void usvemu_configure(long smem_budget, int block_threads);
+extern "C" void usvemu_configure(long smem_budget, int block_threads, int chain_fp32);
 static long g_smem_budget = 227 * 1024;
-static int g_block_threads = 256;
-extern "C" void usvemu_configure(long smem_budget, int block_threads)
+static int g_block_threads = 256, g_chain_fp32 = 0;
+extern "C" void usvemu_configure(long smem_budget, int block_threads, int chain_fp32)
 {
-    g_smem_budget = smem_budget; g_block_threads = block_threads;
+    g_smem_budget = smem_budget; g_block_threads = block_threads; g_chain_fp32 = chain_fp32;
 }
 
 // same calling convention as oracle/usv_oracle.c:usvo_solve_batch so the tests can swap one for the other;
@@ -194,6 +194,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
     P.lbu = vlbu.data(); P.ubu = vubu.data(); P.lbx = vlbx.data(); P.ubx = vubx.data(); P.uh = vuh.data();
     P.p_per_stage = p_per_stage; P.lh_per_stage = lh_per_stage; P.yref_per_stage = yref_per_stage;
     P.cold_start = xinit ? 0 : 1;
+    P.chain_fp32 = g_chain_fp32;
     P.ncq = P.nbu + P.nbx + K; P.ncz = P.nbu + nx + K;
     P.dt = dcfg[DCFG_DT];
     for (int i = 0; i < 4; i++) P.tol[i] = dcfg[DCFG_TOL_STAT + i];
@@ -262,7 +263,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
             if (lam_out) for (int j = 0; j < 2 * ncz; j++) lam_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zlam.off + k * Y.zlam.stride + j];
             if (t_out) for (int j = 0; j < 2 * ncz; j++) t_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zt.off + k * Y.zt.stride + j];
         }
-        for (int i = 0; i < 12; i++) stats[(long) b * 12 + i] = st[(size_t) b * NSTAT + i];
+        for (int i = 0; i < 12; i++) stats[(long) b * 12 + i] = st[(size_t) b * NSTAT + (i == 9 ? 15 : i)];  // slot 9: fp32 factorisations
     }
     free(ws);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);

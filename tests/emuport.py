@@ -26,9 +26,9 @@ def build(force=False):
 
 
 def solve_batch(prob: RefProblem, x0, p, lh, yref, yref_e, xinit=None, uinit=None, piinit=None, nthreads=8,
-                smem_budget=227 * 1024, block_threads=256):
+                smem_budget=227 * 1024, block_threads=256, chain_fp32=False):
     lib = C.CDLL(build())
-    lib.usvemu_configure(C.c_long(smem_budget), block_threads)
+    lib.usvemu_configure(C.c_long(smem_budget), block_threads, int(chain_fp32))
     lib.usvemu_solve_batch.restype = C.c_double
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     x0, p, lh, yref, yref_e, xinit, uinit, piinit = map(c, (x0, p, lh, yref, yref_e, xinit, uinit, piinit))
@@ -47,4 +47,4 @@ def solve_batch(prob: RefProblem, x0, p, lh, yref, yref_e, xinit=None, uinit=Non
                                   _d(uinit), _d(piinit), _d(x), _d(u), _d(pi), _d(lam), _d(t), _d(stats), nthreads)
     return dict(x=x, u=u, pi=pi, lam=lam, t=t, status=stats[:, 0].astype(int), sqp_iter=stats[:, 1].astype(int),
                 qp_iter=stats[:, 2].astype(int), res=stats[:, 3:7], lq_calls=stats[:, 7].astype(int), solve_calls=stats[:, 8].astype(int),
-                itref=stats[:, 11].astype(int), seconds=secs)
+                itref=stats[:, 11].astype(int), fp32_facts=stats[:, 9].astype(int), seconds=secs)

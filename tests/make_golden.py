@@ -5,6 +5,9 @@ from /root/reference).  Run here (the reference does not exist on the GPU box):
 
 Fixtures:
   usv_cfg{1,2,3}_solve.npz  inputs + reference outputs (x, u, status, sqp_iter, qp_iter, res) of full SQP solves
+  usv_cfg4_solve.npz        64 instances of config 4 (N = 100; scene ranges of workloads.XREF_FACTOR)
+  usv_cfg5_solve.npz        256 Monte-Carlo draws of config 5 (128 base scenes x 2 draws of the x0 disturbance)
+  usv_cfg2_lq.npz           the instances of the headline batch on which the reference takes its LQ path
   usv_cfg1_rti.npz          one SQP_RTI step (known answer 2 of SURVEY.md appendix B)
   usv_cfg2_qp.npz           QPs captured at HPIPM's door (after x0 elimination) with HPIPM's solution and
                             iteration count, for QP-level parity of the IPM/Riccati kernels
@@ -31,8 +34,23 @@ def solve_fixture(cfg_id, B, name):
     o = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=8)
     np.savez_compressed(os.path.join(G, name), cfg_id=cfg_id, N=c["N"], K=c["K"], num_steps=c["num_steps"], x0=b.x0, p=b.p,
                         lh=b.lh, yref=b.yref, yref_e=b.yref_e, x=o["x"], u=o["u"], status=o["status"],
-                        sqp_iter=o["sqp_iter"], qp_iter=o["qp_iter"], res=o["res"])
+                        sqp_iter=o["sqp_iter"], qp_iter=o["qp_iter"], res=o["res"], lq_calls=o["lq_calls"])
     print(name, "status", np.bincount(o["status"]), "sqp_iter", o["sqp_iter"])
+
+
+def lq_fixture():
+    """instances of the headline batch on which the reference's IPM takes its LQ path (lq_fact = 1) + their neighbours"""
+    c = CONFIGS[2]
+    b = make_batch(2)
+    P = rh.RefProblem(N=c["N"], K=c["K"], num_steps=c["num_steps"])
+    o = rh.solve_batch(P, b.x0, b.p, b.lh, b.yref, b.yref_e, nthreads=8)
+    hit = np.flatnonzero(o["lq_calls"] > 0)
+    sel = sorted(set(int(i + dlt) for i in hit for dlt in (0, 1) if i + dlt < len(b.x0)))
+    sel = np.array(sel[:32])
+    np.savez_compressed(os.path.join(G, "usv_cfg2_lq.npz"), index=sel, x0=b.x0[sel], p=b.p[sel], lh=b.lh[sel], yref=b.yref[sel],
+                        yref_e=b.yref_e[sel], x=o["x"][sel], u=o["u"][sel], status=o["status"][sel], sqp_iter=o["sqp_iter"][sel],
+                        qp_iter=o["qp_iter"][sel], res=o["res"][sel], lq_calls=o["lq_calls"][sel])
+    print("lq fixture: instances", hit, "status", o["status"][hit], "lq_calls", o["lq_calls"][hit])
 
 
 def known_answer_fixture():
@@ -75,4 +93,7 @@ if __name__ == "__main__":
     solve_fixture(1, 16, "usv_cfg1_solve.npz")
     solve_fixture(2, 32, "usv_cfg2_solve.npz")
     solve_fixture(3, 8, "usv_cfg3_solve.npz")
+    solve_fixture(4, 64, "usv_cfg4_solve.npz")
+    solve_fixture(5, 256, "usv_cfg5_solve.npz")
     qp_fixture()
+    lq_fixture()

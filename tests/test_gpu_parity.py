@@ -282,3 +282,120 @@ def test_obstacle_frontend_against_oracle():
     # float32 arithmetic in both; the device cos/sin may differ from libm in the last bit before the float rounding
     np.testing.assert_allclose(p.cpu().numpy(), p_ref, rtol=2e-6, atol=2e-6)
     np.testing.assert_array_equal(r.cpu().numpy(), r_ref)
+
+
+def _engine_cfg(cfg_id, B, nlp_type=0):
+    from mpc_collisionavoidance_b200.workloads import CONFIGS
+    c = CONFIGS[cfg_id]
+    return rh.RefProblem(N=c["N"], K=c["K"], num_steps=c["num_steps"], nlp_type=nlp_type)
+
+
+def _check_against_fixture(r, f, n, sqp_slack=1):
+    """status identical; SQP iteration counts within `sqp_slack` (reported); converged trajectories within 1e-6;
+    own fp64 KKT residuals <= 1e-6"""
+    np.testing.assert_array_equal(r["status"], f["status"][:n])
+    ok = f["status"][:n] == 0
+    dsqp = np.abs(r["sqp_iter"] - f["sqp_iter"][:n])
+    assert (dsqp[ok] <= sqp_slack).all(), dsqp[ok].max()
+    for k in ("x", "u"):
+        good, worst = _close(r[k], f[k][:n], ok)
+        assert good, (k, worst)
+    assert (r["res"][ok] < 1e-6).all()
+    return int((dsqp[ok] != 0).sum()), int(ok.sum())
+
+
+@pytest.mark.gpu
+def test_config4_full_solve_fp64_and_fp32_riccati(golden_dir):
+    # BASELINE.json config 4: N = 100, 5 obstacles (scene ranges: workloads.XREF_FACTOR).  Full solves of 64 instances
+    # against the reference fixture in fp64, then with the Riccati factorisation in fp32 and fp64 residuals /
+    # refinement / fallback ("fp32 Riccati with fp64 KKT check"): same statuses, trajectories within 1e-6, own fp64
+    # KKT residuals <= 1e-6.
+    f = np.load(os.path.join(golden_dir, "usv_cfg4_solve.npz"))
+    n = 64
+    P = _engine_cfg(4, n)
+    r = engine_solve(P, f["x0"][:n], f["p"][:n], f["lh"][:n], f["yref"][:n], f["yref_e"][:n])
+    differ, conv = _check_against_fixture(r, f, n)
+    assert conv >= 40
+    s = r["solver"]
+    assert s.get_stats("fp32_factorisations").sum() == 0
+    s.options_set("riccati_precision", 32)
+    r32 = engine_solve(P, f["x0"][:n], f["p"][:n], f["lh"][:n], f["yref"][:n], f["yref_e"][:n], solver=s)
+    _check_against_fixture(r32, f, n, sqp_slack=2)
+    n32 = s.get_stats("fp32_factorisations").sum()
+    assert n32 > 0.5 * r32["qp_iter"].sum(), (n32, r32["qp_iter"].sum())   # most factorisations really ran in fp32
+    print(f"config 4: {conv}/64 converged, {differ} instances differ by one SQP iteration (fp64); "
+          f"fp32: {n32} of {r32['qp_iter'].sum()} factorisations in fp32")
+
+
+@pytest.mark.gpu
+def test_config5_monte_carlo_fixture(golden_dir):
+    # BASELINE.json config 5: Monte-Carlo disturbance scenarios (128 base scenes x draws of x0); 256 draws against the
+    # reference fixture
+    f = np.load(os.path.join(golden_dir, "usv_cfg5_solve.npz"))
+    n = 256
+    r = engine_solve(_engine_cfg(5, n), f["x0"][:n], f["p"][:n], f["lh"][:n], f["yref"][:n], f["yref_e"][:n])
+    differ, conv = _check_against_fixture(r, f, n)
+    assert conv >= 200
+    print(f"config 5: {conv}/256 converged, {differ} instances differ by one SQP iteration")
+
+
+@pytest.mark.gpu
+def test_lq_fact_instances(golden_dir):
+    # Instances on which the reference's IPM switches to its LQ factorisation (lq_fact = 1, x_ocp_qp_ipm.c:1941-2006).
+    # The engine detects the same condition (statistics slot 7) but keeps the Cholesky-based factor: status and SQP
+    # iteration counts must still equal the reference's on every such instance of the fixture.
+    f = np.load(os.path.join(golden_dir, "usv_cfg2_lq.npz"))
+    n = len(f["x0"])
+    assert (f["lq_calls"] > 0).sum() >= 1
+    r = engine_solve(_engine_cfg(2, n), f["x0"], f["p"], f["lh"], f["yref"], f["yref_e"])
+    np.testing.assert_array_equal(r["status"], f["status"])
+    sel = (f["lq_calls"] > 0) & (f["status"] == 0)   # (a QP that breaks down with NaNs is a QP failure in both, not counted here)
+    assert sel.any() and (r["solver"].get_stats("lq_fact")[sel] > 0).all()
+    ok = f["status"] == 0
+    assert (np.abs(r["sqp_iter"] - f["sqp_iter"])[ok] <= 1).all()
+
+
+@pytest.mark.gpu
+def test_qp_level_on_device_matches_hpipm_fixture(golden_dir):
+    # QPs captured at HPIPM's door (after x0 elimination) solved by the device IPM through the QP seam of the C ABI
+    # (usvmpc_qp_solve): HPIPM's iteration count, status and solution.
+    from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
+    from enginehelper import ocp_from_problem
+    f = np.load(os.path.join(golden_dir, "usv_cfg2_qp.npz"))
+    nq = int(f["n"])
+    N, K, nv, nx, nu = 40, 5, 8, 6, 2
+    nbu, nbx = 2, 3
+    ncq = nbu + nbx + K
+    G = np.zeros((nq, N, nv * nx)); b = np.zeros((nq, N, nx)); rq = np.zeros((nq, N + 1, nv)); gxy = np.zeros((nq, N, 2 * K))
+    d = np.zeros((nq, N, 2 * ncq))
+    rows0 = [0, 1] + [nbu + nbx + c for c in range(K)]          # stage 0: [lbu | lh] (no x boxes after x0 elimination)
+    for i in range(nq):
+        q = {k: f[f"q{i}_{k}"] for k in ("BAbt", "b", "rqz", "DCt", "d")}
+        G[i, 0].reshape(nx, nv)[:, :nu] = q["BAbt"][0][:nu * nx].reshape(nx, nu)
+        G[i, 1:] = q["BAbt"][1:]
+        b[i] = q["b"]
+        rq[i, 0, :nu] = q["rqz"][0][:nu]
+        rq[i, 1:N] = q["rqz"][1:N]
+        rq[i, N, nu:] = q["rqz"][N][:nx]
+        for k in range(1, N):
+            D = q["DCt"][k].reshape(K, nv)
+            gxy[i, k, :K], gxy[i, k, K:] = D[:, nu + 0], D[:, nu + 1]
+            d[i, k] = q["d"][k][:2 * ncq]
+        nc0 = nbu + K
+        d[i, 0][rows0] = q["d"][0][:nc0]
+        d[i, 0][[ncq + r for r in rows0]] = q["d"][0][nc0:2 * nc0]
+    s = BatchedAcadosOcpSolver(ocp_from_problem(rh.RefProblem(N=N, K=K, num_steps=4)), batch=nq)
+    o = s.qp_solve(G, b, rq, gxy, d)
+    for i in range(nq):
+        it, st = f[f"q{i}_info"]
+        assert (o["iter"][i], o["status"][i]) == (it, st), (i, o["iter"][i], it)
+        ux, pi, lam, t = f[f"q{i}_ux"], f[f"q{i}_pi"], f[f"q{i}_lam"], f[f"q{i}_t"]
+        np.testing.assert_allclose(o["ux"][i, 0, :nu], ux[0][:nu], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(o["ux"][i, 1:N], ux[1:N], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(o["ux"][i, N, nu:], ux[N][:nx], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(o["pi"][i], pi, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(o["lam"][i, 1:N], lam[1:N, :2 * ncq], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(o["t"][i, 1:N], t[1:N, :2 * ncq], rtol=1e-6, atol=1e-7)
+        nc0 = nbu + K
+        np.testing.assert_allclose(o["lam"][i, 0][rows0], lam[0][:nc0], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(o["t"][i, 0][rows0], t[0][:nc0], rtol=1e-6, atol=1e-7)
