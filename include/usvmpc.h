@@ -119,8 +119,9 @@ int usvmpc_eval_cost(usvmpc_solver* s, double* value, int on_device, void* strea
 /* replaces ocp_nlp_solver_opts_set (ocp_nlp_interface.c:943).  Fields: "max_iter", "qp_iter_max", "tol_stat",
  * "tol_eq", "tol_ineq", "tol_comp", "nlp_solver_type" (0/1), "cold_start" (extension: 1 = every solve starts from
  * x_k = x0, u = 0, pi = 0 instead of the previous iterate), "lpt_schedule" (extension, default 1: the work queue of a
- * solve is ordered by decreasing iteration count of the previous solve of this solver), "print_level", "rti_phase"
- * (0 only), "step_length" (1 only) */
+ * solve is ordered by decreasing iteration count of the previous solve of this solver), "riccati_precision" (extension: 32 = Riccati factorisation in fp32 with an fp64 accuracy test and fallback, BASELINE
+ * config 4; 64 = default), "print_level", "rti_phase" (0 preparation + feedback, 1 preparation, 2 feedback:
+ * ocp_nlp_sqp_rti.c:459-488), "step_length" (1 only) */
 int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value);
 
 /* Obstacle front end of the guidance node (nmpc_ca/src/nmpc_guidance_ca1.cpp:251-363, obstaclesCallback + body2NED):

@@ -157,6 +157,23 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
         chain_sync<CT>();
         // Cholesky of the NU x NU input block, redundantly on every lane
         RT Lt[NU][NU], inv[NU];
+        if (NU == 2)
+        {
+            // both reciprocal square roots of the 2 x 2 block at once: piv_1 = M11 - M10^2 / M00 = det / M00, so
+            // 1 / sqrt(piv_1) = sqrt(M00) / sqrt(det) and rsqrt(M00), rsqrt(det) do not depend on each other (half the
+            // dependent chain of the two-column Cholesky).  Pivot rule unchanged: piv_1 > 0 <=> det > 0 when M00 > 0.
+            const RT m00 = sM[0], m10 = sM[1], m11 = sM[2];
+            const RT det = m00 * m11 - m10 * m10;
+            const RT i0 = m00 > (RT) 0 ? drsqrt(m00) : (RT) 0;
+            RT i1;
+            if (m00 > (RT) 0) i1 = det > (RT) 0 ? drsqrt(det) * (m00 * i0) : (RT) 0;
+            else i1 = m11 > (RT) 0 ? drsqrt(m11) : (RT) 0;  // zero first column: the second pivot is M11 itself
+            const RT l10 = m10 * i0;
+            inv[0] = i0; inv[NU - 1] = i1;
+            Lt[0][0] = m00 * i0; Lt[NU - 1][0] = l10;
+            Lt[NU - 1][NU - 1] = (m11 - l10 * l10) * i1;
+        }
+        else
 #pragma unroll
         for (int j = 0; j < NU; j++)
         {
@@ -210,11 +227,12 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
     }
 }
 
-// chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> x part of `out` (stage stride NV)      (x_ocp_qp_kkt.c:537-575)
+// chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> out[(k+1) * NV + NU + i]                  (x_ocp_qp_kkt.c:537-575)
+// (used on the BLOCK maps of the horizon, see CtaSolver::chainF: N = number of blocks, NV = NX, NU = 0)
 template <class M>
-MDEVNI void chainF_impl(const double* Acl, const double* cc, double* out, int N)
+MDEVNI void chainF_impl(const double* Acl, const double* cc, double* out, int N, int NV, int NU)
 {
-    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU;
+    constexpr int NX = M::NX;
     ASSUME_SHARED(Acl); ASSUME_SHARED(cc);
     const int lane = lane_id();
     const int l = lane < NX ? lane : 0;
@@ -248,11 +266,11 @@ MDEVNI void chainF_impl(const double* Acl, const double* cc, double* out, int N)
     }
 }
 
-// chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> x part of zv                           (x_ocp_qp_kkt.c:1096-1242)
+// chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> zv[k * NV + NU + i]                          (x_ocp_qp_kkt.c:1096-1242)
 template <class M>
-MDEVNI void chainC_impl(const double* Acl, const double* ee, double* zv, int N)
+MDEVNI void chainC_impl(const double* Acl, const double* ee, double* zv, int N, int NV, int NU)
 {
-    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU;
+    constexpr int NX = M::NX;
     ASSUME_SHARED(Acl); ASSUME_SHARED(ee); ASSUME_SHARED(zv);
     const int lane = lane_id();
     const int l = lane < NX ? lane : 0;
@@ -302,13 +320,11 @@ struct CtaSolver {
     FastDiv dq, dnv, dnx;
     double *sm, *gs, *w;
     // constants in shared memory
-    double *Hs, *Hes, *Ws, *Wes, *Tp, *red, *sA0, *sW, *sP;
+    double *Hs, *Hes, *Ws, *Wes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
     int *sxrow, *srvar;
     int redbuf;
-    // working-set fields
-    double *G, *Mx, *Acl, *Kg, *cc, *ee, *Pb, *rb, *zv, *dux, *kk, *dinv;
-    double *ux, *pi, *lam, *t, *dlam, *dt, *rd, *rmc, *rg, *dpi, *gxy, *ti, *d, *rq, *b;
-    double *rg2, *rb2, *rd2, *rm2, *dux2, *dpi2, *dlam2, *dt2;
+    // working-set fields: no pointer is kept in registers; every access forms the address from the block's shared-memory
+    // base (or its global scratch) and the offset in the kernel parameters (constant bank), see the accessors below
     // IPM arguments (HP/ocp_qp/x_ocp_qp_ipm.c:133-161 overridden by AC/acados/ocp_qp/ocp_qp_hpipm.c:106-116 and, in SQP
     // mode, by AC/acados/ocp_nlp/ocp_nlp_sqp.c:201-227)
     double tol_stat, tol_eq, tol_ineq, tol_comp;
@@ -333,6 +349,41 @@ struct CtaSolver {
         if (id < F_FIRST_FLEX) return sm + f.off;  // the chain fields are always in shared memory
         return (f.space ? gs : sm) + f.off;
     }
+    MDEV double* G_() const { double* p_ = sm + P.plan.f[F_G].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* Mx_() const { double* p_ = sm + P.plan.f[F_M].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* Acl_() const { double* p_ = sm + P.plan.f[F_ACL].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* Kg_() const { double* p_ = sm + P.plan.f[F_KG].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* cc_() const { double* p_ = sm + P.plan.f[F_CC].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* ee_() const { double* p_ = sm + P.plan.f[F_EE].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* Pb_() const { double* p_ = sm + P.plan.f[F_PB].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* rb_() const { double* p_ = sm + P.plan.f[F_RB].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* zv_() const { double* p_ = sm + P.plan.f[F_ZV].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* dux_() const { double* p_ = sm + P.plan.f[F_DUX].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* kk_() const { double* p_ = sm + P.plan.f[F_KK].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* dinv_() const { double* p_ = sm + P.plan.f[F_DINV].off; ASSUME_SHARED(p_); return p_; }
+    MDEV double* ux_() const { return fld(F_UX); }
+    MDEV double* pi_() const { return fld(F_PI); }
+    MDEV double* lam_() const { return fld(F_LAM); }
+    MDEV double* t_() const { return fld(F_T); }
+    MDEV double* dlam_() const { return fld(F_DLAM); }
+    MDEV double* dt_() const { return fld(F_DT); }
+    MDEV double* rd_() const { return fld(F_RD); }
+    MDEV double* rmc_() const { return fld(F_RMC); }
+    MDEV double* rg_() const { return fld(F_RG); }
+    MDEV double* dpi_() const { return fld(F_DPI); }
+    MDEV double* gxy_() const { return fld(F_GXY); }
+    MDEV double* ti_() const { return fld(F_TI); }
+    MDEV double* d_() const { return fld(F_D); }
+    MDEV double* rq_() const { return fld(F_RQ); }
+    MDEV double* b_() const { return fld(F_B); }
+    MDEV double* rg2_() const { return fld(F_RG2); }
+    MDEV double* rb2_() const { return fld(F_RB2); }
+    MDEV double* rd2_() const { return fld(F_RD2); }
+    MDEV double* rm2_() const { return fld(F_RM2); }
+    MDEV double* dux2_() const { return fld(F_DUX2); }
+    MDEV double* dpi2_() const { return fld(F_DPI2); }
+    MDEV double* dlam2_() const { return fld(F_DLAM2); }
+    MDEV double* dt2_() const { return fld(F_DT2); }
 
     MDEV CtaSolver(const Params& p, double* smem, double* gscratch) : P(p), sm(smem), gs(gscratch)
     {
@@ -346,19 +397,15 @@ struct CtaSolver {
         redbuf = 0;
         double* m = sm + P.plan.misc_off;
         sA0 = m; m += NV * NX; sW = m; m += NX * NR + NE + (NE & 1); sP = m; m += NX * NX + 2;  // sW = [P G' | scratch matrix]
+        {
+            const int nb1 = (N + BS - 1) / BS + 1;
+            Phi = m; m += nb1 * NX * NX; phi = m; m += nb1 * NX; Xb = m; m += nb1 * NX;
+        }
         sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
-        G = fld(F_G); Mx = fld(F_M); Acl = fld(F_ACL); Kg = fld(F_KG); cc = fld(F_CC); ee = fld(F_EE); Pb = fld(F_PB);
-        rb = fld(F_RB); zv = fld(F_ZV); dux = fld(F_DUX); kk = fld(F_KK); dinv = fld(F_DINV);
-        ux = fld(F_UX); pi = fld(F_PI); lam = fld(F_LAM); t = fld(F_T); dlam = fld(F_DLAM); dt = fld(F_DT); rd = fld(F_RD);
-        rmc = fld(F_RMC); rg = fld(F_RG); dpi = fld(F_DPI); gxy = fld(F_GXY); ti = fld(F_TI); d = fld(F_D); rq = fld(F_RQ);
-        b = fld(F_B);
-        rg2 = fld(F_RG2); rb2 = fld(F_RB2); rd2 = fld(F_RD2); rm2 = fld(F_RM2); dux2 = fld(F_DUX2); dpi2 = fld(F_DPI2);
-        dlam2 = fld(F_DLAM2); dt2 = fld(F_DT2);
         // address-space hints: these always point into shared memory
         ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Ws); ASSUME_SHARED(Wes); ASSUME_SHARED(Tp);
         ASSUME_SHARED(red); ASSUME_SHARED(sA0); ASSUME_SHARED(sW); ASSUME_SHARED(sP); ASSUME_SHARED(sxrow); ASSUME_SHARED(srvar);
-        ASSUME_SHARED(G); ASSUME_SHARED(Mx); ASSUME_SHARED(Acl); ASSUME_SHARED(Kg); ASSUME_SHARED(cc); ASSUME_SHARED(ee);
-        ASSUME_SHARED(Pb); ASSUME_SHARED(rb); ASSUME_SHARED(zv); ASSUME_SHARED(dux); ASSUME_SHARED(kk); ASSUME_SHARED(dinv);
+        ASSUME_SHARED(Phi); ASSUME_SHARED(phi); ASSUME_SHARED(Xb);
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
@@ -536,7 +583,7 @@ struct CtaSolver {
                 for (int i = 0; i < NX; i++) { x[i] = xa[i]; s[i] = sa[i]; }
             }
             // G = [B'; A'] (nv x nx, column-major): ocp_nlp_dynamics_cont.c:801-804
-            double* Gk = G + k * (NV * NX);
+            double* Gk = G_() + k * (NV * NX);
             const int row = col < NX ? NU + col : col - NX;
 #pragma unroll
             for (int i = 0; i < NX; i++) Gk[row + NV * i] = s[i];
@@ -549,7 +596,7 @@ struct CtaSolver {
                     for (int i = 0; i < NX; i++) Gk[NU + c + NV * i] = (i == c) ? 1.0 : 0.0;
                 }
                 const double* zn = Z(P.lay.zux, k + 1);
-                double* bk = b + k * NX;
+                double* bk = b_() + k * NX;
 #pragma unroll
                 for (int i = 0; i < NX; i++) bk[i] = x[i] - zn[NU + i];  // dyn_fun = phi(x,u) - x_next
             }
@@ -560,10 +607,29 @@ struct CtaSolver {
     // cost / constraints / adjoints / NLP residuals / QP vectors, one thread per stage.
     // ocp_nlp_approximate_qp_matrices + _vectors_sqp (ocp_nlp_common.c:1926-2084), ocp_nlp_res_compute (:2549-2603),
     // x0 elimination d_ocp_qp_reduce_eq_dof (HP/ocp_qp/x_ocp_qp_red.c:268-454).  res4 = (stat, eq, ineq, comp).
-    MDEV void linearize(const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
+    // SQP_RTI with rti_phase 1 / 2 (ocp_nlp_sqp_rti.c:459-488): the preparation phase runs the integrator with its
+    // sensitivities -- the expensive part of the linearisation -- and parks [B';A'] and phi(x,u) - x_next in the
+    // instance's HBM block; the feedback phase picks them up, evaluates cost / constraints / x0 embedding with the x0
+    // that has arrived meanwhile, solves the QP and updates.
+    MDEV void prep_store(int inst)
+    {
+        double* g = P.prep + (long) inst * N * (NV * NX + NX);
+        for (int e = tid; e < N * NV * NX; e += T) g[e] = G_()[e];
+        for (int e = tid; e < N * NX; e += T) g[N * NV * NX + e] = b_()[e];
+        syncthreads();
+    }
+    MDEV void prep_load(int inst)
+    {
+        const double* g = P.prep + (long) inst * N * (NV * NX + NX);
+        for (int e = tid; e < N * NV * NX; e += T) G_()[e] = g[e];
+        for (int e = tid; e < N * NX; e += T) b_()[e] = g[N * NV * NX + e];
+        syncthreads();
+    }
+
+    MDEV void linearize(int inst, const double* x0, const double* pg, const double* lhg, const double* yrg, const double* yre,
                        double* res4)
     {
-        integrate_all();
+        if (P.nlp_type == 1 && P.rti_phase == 2) prep_load(inst); else integrate_all();
         double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
         for (int k = tid; k <= N; k += T)
         {
@@ -571,8 +637,8 @@ struct CtaSolver {
             const double* zl = Z(P.lay.zlam, k);
             const double* zt = Z(P.lay.zt, k);
             double* zf = Z(P.lay.zfun, k);
-            double* rqk = rq + k * NV;
-            double* dk = d + k * s2;
+            double* rqk = rq_() + k * NV;
+            double* dk = d_() + k * s2;
             double cg[NV], adj[NV];
             // ---- LINEAR_LS cost gradient (ocp_nlp_cost_ls.c:749-843)
             if (k < N)
@@ -666,7 +732,7 @@ struct CtaSolver {
                 // obstacle distances h_c = ||(X,Y) - (ox_c, oy_c)||, dh/d(X,Y) = ((X,Y) - o_c)/h_c
                 const double* pk = pg + (P.p_per_stage ? k * 2 * K : 0);
                 const double* lhk = lhg + (P.lh_per_stage ? k * K : 0);
-                double* gk = gxy + k * 2 * K;
+                double* gk = gxy_() + k * 2 * K;
                 for (int c = 0; c < K; c++)
                 {
                     const double ddx = z[HXV] - pk[2 * c], ddy = z[HYV] - pk[2 * c + 1];
@@ -688,7 +754,7 @@ struct CtaSolver {
                 }
             }
             // ---- dynamics adjoint -[B';A'] pi_k (+ pi_{k-1} on x): ocp_nlp_common.c:2001-2019 ; stationarity residual
-            const double* Gk = G + k * (NV * NX);
+            const double* Gk = G_() + k * (NV * NX);
             const double* pik = Z(P.lay.zpi, k);
 #pragma unroll
             for (int i = 0; i < NV; i++)
@@ -708,7 +774,7 @@ struct CtaSolver {
             }
             if (k < N)
             {
-                const double* bk = b + k * NX;
+                const double* bk = b_() + k * NX;
 #pragma unroll
                 for (int i = 0; i < NX; i++) { const double a = dabs(bk[i]); r1 = a > r1 ? a : r1; }
             }
@@ -717,7 +783,7 @@ struct CtaSolver {
             for (int i = 0; i < NV; i++) rqk[i] = cg[i];
             if (k == 0 && N > 0)
             {
-                double* bk = b;
+                double* bk = b_();
 #pragma unroll
                 for (int j = 0; j < NX; j++)
                 {
@@ -739,7 +805,7 @@ struct CtaSolver {
                 for (int e = 0; e < NV * NX; e++)
                 {
                     sA0[e] = Gk[e];
-                    if (e % NV >= NU) G[e] = 0.0;
+                    if (e % NV >= NU) G_()[e] = 0.0;
                 }
             }
         }
@@ -755,14 +821,14 @@ struct CtaSolver {
         const double thr0 = 1e-1, mu0 = 1.0;
         for (int k = tid; k <= N; k += T)
         {
-            double* v = ux + k * NV; double* pk = pi + k * NX; double* l = lam + k * s2; double* tt = t + k * s2;
-            const double* dk = d + k * s2;
+            double* v = ux_() + k * NV; double* pk = pi_() + k * NX; double* l = lam_() + k * s2; double* tt = t_() + k * s2;
+            const double* dk = d_() + k * s2;
             for (int i = 0; i < NV; i++) v[i] = 0.0;
             for (int i = 0; i < NX; i++) pk[i] = 0.0;
             for (int j = 0; j < s2; j++) { l[j] = 0.0; tt[j] = 1.0; }
             {
                 // the first passA applies a zero step: the step starts at zero
-                double* a = dux + k * NV; double* bq = dpi + k * NX; double* c = dlam + k * s2; double* e = dt + k * s2;
+                double* a = dux_() + k * NV; double* bq = dpi_() + k * NX; double* c = dlam_() + k * s2; double* e = dt_() + k * s2;
                 for (int i = 0; i < NV; i++) a[i] = 0.0;
                 for (int i = 0; i < NX; i++) bq[i] = 0.0;
                 for (int j = 0; j < s2; j++) { c[j] = 0.0; e[j] = 0.0; }
@@ -781,7 +847,7 @@ struct CtaSolver {
                 else if (tu < thr0) { tu = thr0; v[id] = -dk[ncq + j] - thr0; }
                 tt[j] = tl; tt[ncq + j] = tu;
             }
-            const double* gk = gxy + k * 2 * K;
+            const double* gk = gxy_() + k * 2 * K;
             for (int c = 0; c < K; c++)
             {
                 const double vv = (k >= 1) ? gk[c] * v[HXV] + gk[K + c] * v[HYV] : 0.0;
@@ -803,17 +869,17 @@ struct CtaSolver {
     {
         const double lam_min = 1e-16, t_min = 1e-16;
         // ---- A1: variable update, element-parallel
-        for (int e = tid; e < (N + 1) * NV; e += T) ux[e] += a * dux[e];
-        for (int e = tid; e < N * NX; e += T) pi[e] += a * dpi[e];
+        for (int e = tid; e < (N + 1) * NV; e += T) ux_()[e] += a * dux_()[e];
+        for (int e = tid; e < N * NX; e += T) pi_()[e] += a * dpi_()[e];
         for (int e = tid; e < N * s2; e += T)
         {
             const int k = dq.div(e) >> 1;          // e / (2 ncq)
             int j = e - k * s2; if (j >= ncq) j -= ncq;
             if (!row_active(k, j)) continue;
-            double x = lam[e] + a * dlam[e];
-            lam[e] = x <= lam_min ? lam_min : x;
-            x = t[e] + a * dt[e];
-            t[e] = x <= t_min ? t_min : x;
+            double x = lam_()[e] + a * dlam_()[e];
+            lam_()[e] = x <= lam_min ? lam_min : x;
+            x = t_()[e] + a * dt_()[e];
+            t_()[e] = x <= t_min ? t_min : x;
         }
         syncthreads();
         // ---- A2: inequality rows, one (stage, row pair) per thread: res_d, res_m norms, mu, 1/t, and the row's
@@ -823,34 +889,34 @@ struct CtaSolver {
         {
             const int k = dq.div(it), j = it - k * ncq;
             const int r0 = k * s2 + j, r1 = r0 + ncq;
-            if (!row_active(k, j)) { dlam[r0] = 0.0; dlam[r1] = 0.0; dt[r0] = 0.0; continue; }
-            const double* v = ux + k * NV;
+            if (!row_active(k, j)) { dlam_()[r0] = 0.0; dlam_()[r1] = 0.0; dt_()[r0] = 0.0; continue; }
+            const double* v = ux_() + k * NV;
             double vv;
             if (j < nbq) vv = v[srvar[j]];
-            else vv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
-            const double l0 = lam[r0], l1 = lam[r1], t0 = t[r0], t1 = t[r1];
-            const double rd0 = d[r0] + t0 - vv, rd1 = d[r1] + t1 + vv;
-            rd[r0] = rd0; rd[r1] = rd1;
+            else vv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+            const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1];
+            const double rd0 = d_()[r0] + t0 - vv, rd1 = d_()[r1] + t1 + vv;
+            rd_()[r0] = rd0; rd_()[r1] = rd1;
             const double m0 = l0 * t0, m1 = l1 * t1;
             musum += m0; musum += m1;
             double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
             q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
             const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
-            ti[r0] = ti0; ti[r1] = ti1;
-            dlam[r0] = l1 - l0;
-            dlam[r1] = ti0 * l0 + ti1 * l1;
-            dt[r0] = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+            ti_()[r0] = ti0; ti_()[r1] = ti1;
+            dlam_()[r0] = l1 - l0;
+            dlam_()[r1] = ti0 * l0 + ti1 * l1;
+            dt_()[r0] = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
         }
         // ---- res_b = b + [B A] ux - x_{k+1}, one (stage, state) per thread
         for (int it = tid; it < N * NX; it += T)
         {
             const int k = dnx.div(it), j = it - k * NX;
-            const double* v = ux + k * NV;
-            const double* Gk = G + k * (NV * NX) + NV * j;
-            double acc = b[it] - ux[(k + 1) * NV + NU + j];
+            const double* v = ux_() + k * NV;
+            const double* Gk = G_() + k * (NV * NX) + NV * j;
+            double acc = b_()[it] - ux_()[(k + 1) * NV + NU + j];
 #pragma unroll
             for (int i = 0; i < NV; i++) acc += Gk[i] * v[i];  // stage 0: the x rows of G are zero
-            rb[it] = acc;
+            rb_()[it] = acc;
             const double q = dabs(acc);
             n1 = q > n1 ? q : n1;
         }
@@ -858,23 +924,23 @@ struct CtaSolver {
         for (int it = tid; it < (N + 1) * NE; it += T)
         {
             const int k = it / NE, e = it - k * NE;
-            Mx[it] = Tp[stage_class(k) * NE + e];
+            Mx_()[it] = Tp[stage_class(k) * NE + e];
         }
         syncthreads();
         // ---- A3: stationarity residual, diagonal and gradient row, one (stage, variable) per thread
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
             const int k = dnv.div(it), i = it - k * NV;
-            const double* v = ux + k * NV;
+            const double* v = ux_() + k * NV;
             const double* H = Hk(k);
-            double g = rq[it], dg = 0.0, gg = 0.0;
+            double g = rq_()[it], dg = 0.0, gg = 0.0;
 #pragma unroll
             for (int j = 0; j < NV; j++) g += H[i + NV * j] * v[j];
-            if (k > 0 && i >= NU) g -= pi[(k - 1) * NX + i - NU];
+            if (k > 0 && i >= NU) g -= pi_()[(k - 1) * NX + i - NU];
             if (k < N)
             {
-                const double* Gk = G + k * (NV * NX) + i;
-                const double* pk = pi + k * NX;
+                const double* Gk = G_() + k * (NV * NX) + i;
+                const double* pk = pi_() + k * NX;
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < NX; j++) acc += Gk[NV * j] * pk[j];
@@ -883,29 +949,29 @@ struct CtaSolver {
                 if (row >= 0)
                 {
                     const int r0 = k * s2 + row;
-                    g += dlam[r0]; dg += dlam[r0 + ncq]; gg += dt[r0];
+                    g += dlam_()[r0]; dg += dlam_()[r0 + ncq]; gg += dt_()[r0];
                 }
                 if ((i == HXV || i == HYV) && k >= 1)
                 {
-                    const double* gk = gxy + k * 2 * K;
+                    const double* gk = gxy_() + k * 2 * K;
                     const double* gi = i == HXV ? gk : gk + K;
                     double aYX = 0.0;
                     for (int c = 0; c < K; c++)
                     {
                         const int r0 = k * s2 + nbq + c;
-                        const double Gs = dlam[r0 + ncq];
-                        g += gi[c] * dlam[r0];
+                        const double Gs = dlam_()[r0 + ncq];
+                        g += gi[c] * dlam_()[r0];
                         dg += (gi[c] * Gs) * gi[c];
-                        gg += dt[r0] * gi[c];
+                        gg += dt_()[r0] * gi[c];
                         if (i == HYV) aYX += (gk[K + c] * Gs) * gk[c];
                     }
-                    if (i == HYV) Mx[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
+                    if (i == HYV) Mx_()[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
                 }
             }
             const double gi = var_active(k, i) ? g : 0.0;
-            rg[it] = gi;
-            Mx[k * NE + MI(i, i)] += dg;
-            Mx[k * NE + MI(NV, i)] = gi + gg;
+            rg_()[it] = gi;
+            Mx_()[k * NE + MI(i, i)] += dg;
+            Mx_()[k * NE + MI(NV, i)] = gi + gg;
             const double q = dabs(gi);
             n0 = q > n0 ? q : n0;
         }
@@ -924,7 +990,7 @@ struct CtaSolver {
         for (int it = tid; it < (N + 1) * NE; it += T)
         {
             const int k = it / NE, e = it - k * NE;
-            Mx[it] = Tp[stage_class(k) * NE + e];
+            Mx_()[it] = Tp[stage_class(k) * NE + e];
         }
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
@@ -935,15 +1001,15 @@ struct CtaSolver {
             {
                 auto row_terms = [&](int r0, double& Gs, double& gd) {
                     const int r1 = r0 + ncq;
-                    const double l0 = lam[r0], l1 = lam[r1], t0 = t[r0], t1 = t[r1], i0 = ti[r0], i1 = ti[r1];
+                    const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1], i0 = ti_()[r0], i1 = ti_()[r1];
                     Gs = i0 * l0 + i1 * l1;
-                    gd = i0 * ((l0 * t0 - tau) - l0 * rd[r0]) - i1 * ((l1 * t1 - tau) - l1 * rd[r1]);
+                    gd = i0 * ((l0 * t0 - tau) - l0 * rd_()[r0]) - i1 * ((l1 * t1 - tau) - l1 * rd_()[r1]);
                 };
                 const int row = vrow(k, i);
                 if (row >= 0) { double Gs, gd; row_terms(k * s2 + row, Gs, gd); dg += Gs; gg += gd; }
                 if ((i == HXV || i == HYV) && k >= 1)
                 {
-                    const double* gk = gxy + k * 2 * K;
+                    const double* gk = gxy_() + k * 2 * K;
                     const double* gi = i == HXV ? gk : gk + K;
                     double aYX = 0.0;
                     for (int c = 0; c < K; c++)
@@ -954,11 +1020,11 @@ struct CtaSolver {
                         gg += gd * gi[c];
                         if (i == HYV) aYX += (gk[K + c] * Gs) * gk[c];
                     }
-                    if (i == HYV) Mx[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
+                    if (i == HYV) Mx_()[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
                 }
             }
-            Mx[k * NE + MI(i, i)] += dg;
-            Mx[k * NE + MI(NV, i)] = rg[it] + gg;
+            Mx_()[k * NE + MI(i, i)] += dg;
+            Mx_()[k * NE + MI(NV, i)] = rg_()[it] + gg;
         }
         syncthreads();
     }
@@ -969,11 +1035,117 @@ struct CtaSolver {
     MDEV void chainA()
     {
         if (wid >= CHAIN_WARPS) return;
-        if (use_fp32) chainA_impl<M, float>(G, Mx, rb, Pb, dinv, sW, sP, N);
-        else chainA_impl<M, double>(G, Mx, rb, Pb, dinv, sW, sP, N);
+        if (use_fp32) chainA_impl<M, float>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
+        else chainA_impl<M, double>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
     }
-    MDEV void chainF(double* out) { if (wid == 0) chainF_impl<M>(Acl, cc, out, N); }
-    MDEV void chainC() { if (wid == 0) chainC_impl<M>(Acl, ee, zv, N); }
+    // The two vector recursions dx_{k+1} = Acl_k dx_k + c_k and p_k = Acl_k' p_{k+1} + e_k are affine maps, so BS of them
+    // compose into one: Phi_j = Acl_{e-1} ... Acl_s for block j = stages [s, e).  The block products are formed once per
+    // factorisation (block_products), then every solve runs
+    //   1. the affine term of every block map          (all blocks in parallel, BS dependent mat-vecs)
+    //   2. the recursion over the nb = N / BS blocks    (warp 0, nb dependent mat-vecs instead of N)
+    //   3. the stages inside every block                (all blocks in parallel, BS - 1 dependent mat-vecs)
+    // i.e. 2 BS + N / BS dependent mat-vecs instead of N.  A block is handled by a group of GS lanes (lane r = row r of the
+    // mat-vec, the vector travels by shuffle).
+    static constexpr int BS = 4, GS = NX <= 8 ? 8 : 16;
+    // steps of block j applied to the vector whose component r this lane holds.  FWD: k = s .. e-1, v <- Acl_k v + aff_k,
+    // else k = e-1 .. s, v <- Acl_k' v + aff_k.  out != nullptr: every intermediate vector is stored (stage stride NV,
+    // offset NU; FWD: at stage k+1, else at stage k).
+    template <bool FWD, bool AFFINE>
+    MDEV double group_steps(int j, double vr, const double* aff, double* out) const
+    {
+        const int r = lane % GS, base = lane - r, rr = r < NX ? r : NX - 1;
+        const int s = j * BS, e = s + BS < N ? s + BS : N;
+        const double* A = Acl_();
+#pragma unroll 1
+        for (int q = 0; q < BS; q++)
+        {
+            const int k = FWD ? s + q : e - 1 - q;
+            const bool live = FWD ? k < e : k >= s;
+            const int kc = live ? k : (FWD ? e - 1 : s);
+            const double* Ak = A + kc * (NX * NX);
+            double a0 = AFFINE ? aff[kc * NX + rr] : 0.0, a1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m += 2)
+            {
+                a0 += (FWD ? Ak[rr * NX + m] : Ak[m * NX + rr]) * shfl(vr, base + m);
+                if (m + 1 < NX) a1 += (FWD ? Ak[rr * NX + m + 1] : Ak[(m + 1) * NX + rr]) * shfl(vr, base + m + 1);
+            }
+            const double nv_ = a0 + a1;
+            if (live)
+            {
+                vr = nv_;
+                if (out && r < NX) out[(FWD ? kc + 1 : kc) * NV + NU + r] = vr;
+            }
+        }
+        return vr;
+    }
+    MDEV int num_blocks() const { return (N + BS - 1) / BS; }
+    // Phi_j, column by column: the block's steps applied to the unit vectors
+    MDEV void block_products()
+    {
+        const int nb = num_blocks(), ngrp = T / GS;
+        for (int it0 = 0; it0 < nb * NX; it0 += ngrp)
+        {
+            const int it = it0 + tid / GS, r = lane % GS;
+            const bool act = it < nb * NX;
+            const int itc = act ? it : nb * NX - 1;
+            const int j = itc / NX, c = itc - j * NX;
+            const double v = group_steps<true, false>(j, r == c ? 1.0 : 0.0, nullptr, nullptr);
+            if (act && r < NX) Phi[j * (NX * NX) + r * NX + c] = v;
+        }
+        syncthreads();
+    }
+    // dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k -> x part of `out` (stage stride NV)
+    MDEV void chainF(double* out)
+    {
+        const int nb = num_blocks(), ngrp = T / GS;
+        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        {
+            const int j = j0 + tid / GS, r = lane % GS;
+            const bool act = j < nb;
+            const double v = group_steps<true, true>(act ? j : nb - 1, 0.0, cc_(), nullptr);
+            if (act && r < NX) phi[j * NX + r] = v;
+        }
+        syncthreads();
+        if (wid == 0) chainF_impl<M>(Phi, phi, Xb, nb, NX, 0);
+        syncthreads();
+        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        {
+            const int j = j0 + tid / GS, r = lane % GS;
+            const bool act = j < nb;
+            const int jc = act ? j : nb - 1;
+            const double x0 = Xb[jc * NX + (r < NX ? r : NX - 1)];
+            if (act && r < NX) out[jc * BS * NV + NU + r] = x0;
+            group_steps<true, true>(jc, x0, cc_(), act ? out : nullptr);
+        }
+    }
+    // p_N = e_N, p_k = Acl_k' p_{k+1} + e_k -> x part of zv
+    MDEV void chainC()
+    {
+        const int nb = num_blocks(), ngrp = T / GS;
+        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        {
+            const int j = j0 + tid / GS, r = lane % GS;
+            const bool act = j < nb;
+            const double v = group_steps<false, true>(act ? j : nb - 1, 0.0, ee_(), nullptr);
+            if (act && r < NX) phi[j * NX + r] = v;
+        }
+        if (tid < NX) phi[nb * NX + tid] = ee_()[N * NX + tid];
+        syncthreads();
+        if (wid == 0) chainC_impl<M>(Phi, phi, Xb, nb, NX, 0);
+        syncthreads();
+        double* z = zv_();
+        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        {
+            const int j = j0 + tid / GS, r = lane % GS;
+            const bool act = j < nb;
+            const int jc = act ? j : nb - 1;
+            const int e = jc * BS + BS < N ? jc * BS + BS : N;
+            const double p0 = Xb[(jc + 1) * NX + (r < NX ? r : NX - 1)];
+            if (act && r < NX) z[e * NV + NU + r] = p0;
+            group_steps<false, true>(jc, p0, ee_(), act ? z : nullptr);
+        }
+    }
 
     // ---------------------------------------------------------------- IPM: passes around the chains
     // gains after chainA: K_k = -Luu^-T Lxu', Acl_k = A_k + B_k K_k
@@ -982,7 +1154,7 @@ struct CtaSolver {
         for (int it = tid; it < (N + 1) * NX; it += T)
         {
             const int k = dnx.div(it), j = it - k * NX;
-            const double* Mk = Mx + k * NE;
+            const double* Mk = Mx_() + k * NE;
             double kg[NU];
 #pragma unroll
             for (int i = NU - 1; i >= 0; i--)
@@ -990,19 +1162,19 @@ struct CtaSolver {
                 double acc = -Mk[MI(NU + j, i)];
 #pragma unroll
                 for (int m = i + 1; m < NU; m++) acc -= Mk[MI(m, i)] * kg[m];
-                kg[i] = acc * dinv[k * NU + i];
-                Kg[k * (NU * NX) + i * NX + j] = kg[i];
+                kg[i] = acc * dinv_()[k * NU + i];
+                Kg_()[k * (NU * NX) + i * NX + j] = kg[i];
             }
         }
         syncthreads();
         for (int it = tid; it < N * NX * NX; it += T)
         {
             const int k = it / (NX * NX), e = it - k * (NX * NX), i = e / NX, j = e - i * NX;
-            const double* Gk = G + k * (NV * NX) + NV * i;
+            const double* Gk = G_() + k * (NV * NX) + NV * i;
             double acc = Gk[NU + j];
 #pragma unroll
-            for (int m = 0; m < NU; m++) acc += Gk[m] * Kg[k * (NU * NX) + m * NX + j];
-            Acl[it] = acc;
+            for (int m = 0; m < NU; m++) acc += Gk[m] * Kg_()[k * (NU * NX) + m * NX + j];
+            Acl_()[it] = acc;
         }
     }
 
@@ -1015,8 +1187,8 @@ struct CtaSolver {
         for (int it = tid; it < N * NX; it += T)
         {
             const int k = dnx.div(it), mm = it - k * NX;
-            const double* Mk = Mx + k * NE;
-            const double* Gk = G + k * (NV * NX);
+            const double* Mk = Mx_() + k * NE;
+            const double* Gk = G_() + k * (NV * NX);
             double lu[NU], kv[NU];
 #pragma unroll
             for (int i = 0; i < NU; i++)
@@ -1025,12 +1197,12 @@ struct CtaSolver {
                 if (from_factor) acc = Mk[MI(NV, i)];
                 else
                 {
-                    acc = zv[k * NV + i];
+                    acc = zv_()[k * NV + i];
 #pragma unroll
-                    for (int m = 0; m < NX; m++) acc += Gk[i + NV * m] * (zv[(k + 1) * NV + NU + m] + Pb[k * NX + m]);
+                    for (int m = 0; m < NX; m++) acc += Gk[i + NV * m] * (zv_()[(k + 1) * NV + NU + m] + Pb_()[k * NX + m]);
 #pragma unroll
                     for (int m = 0; m < i; m++) acc -= Mk[MI(i, m)] * lu[m];
-                    acc *= dinv[k * NU + i];
+                    acc *= dinv_()[k * NU + i];
                 }
                 lu[i] = acc;
             }
@@ -1040,15 +1212,15 @@ struct CtaSolver {
                 double acc = -lu[i];
 #pragma unroll
                 for (int m = i + 1; m < NU; m++) acc -= Mk[MI(m, i)] * kv[m];
-                kv[i] = acc * dinv[k * NU + i];
-                if (mm == 0) kk[k * NU + i] = kv[i];
+                kv[i] = acc * dinv_()[k * NU + i];
+                if (mm == 0) kk_()[k * NU + i] = kv[i];
             }
             double acc = rbp[it];
 #pragma unroll
             for (int i = 0; i < NU; i++) acc += Gk[i + NV * mm] * kv[i];
-            cc[it] = acc;
+            cc_()[it] = acc;
         }
-        if (tid < NU) kk[N * NU + tid] = 0.0;  // no inputs at the terminal stage
+        if (tid < NU) kk_()[N * NU + tid] = 0.0;  // no inputs at the terminal stage
         syncthreads();
     }
 
@@ -1060,25 +1232,25 @@ struct CtaSolver {
     // gsc: a dead array with the stride of the row arrays that receives gamma_l - gamma_u.
     MDEV void rhs_pass(int mode, double sigma_mu)
     {
-        const double* rgp = mode == 2 ? rg2 : rg;
-        const double* rdp = mode == 2 ? rd2 : rd;
-        double* gsc = mode == 2 ? dlam2 : dlam;
+        const double* rgp = mode == 2 ? rg2_() : rg_();
+        const double* rdp = mode == 2 ? rd2_() : rd_();
+        double* gsc = mode == 2 ? dlam2_() : dlam_();
         for (int it = tid; it < N * ncq; it += T)
         {
             const int k = dq.div(it), j = it - k * ncq;
             const int r0 = k * s2 + j, r1 = r0 + ncq;
-            if (!row_active(k, j)) { if (mode != 2) { rmc[r0] = 0.0; rmc[r1] = 0.0; } gsc[r0] = 0.0; continue; }
-            const double l0 = lam[r0], l1 = lam[r1];
+            if (!row_active(k, j)) { if (mode != 2) { rmc_()[r0] = 0.0; rmc_()[r1] = 0.0; } gsc[r0] = 0.0; continue; }
+            const double l0 = lam_()[r0], l1 = lam_()[r1];
             double m0, m1;
-            if (mode == 2) { m0 = rm2[r0]; m1 = rm2[r1]; }
+            if (mode == 2) { m0 = rm2_()[r0]; m1 = rm2_()[r1]; }
             else
             {
-                m0 = l0 * t[r0]; m1 = l1 * t[r1];
-                if (mode == 0) { m0 += dt[r0] * dlam[r0]; m1 += dt[r1] * dlam[r1]; }
+                m0 = l0 * t_()[r0]; m1 = l1 * t_()[r1];
+                if (mode == 0) { m0 += dt_()[r0] * dlam_()[r0]; m1 += dt_()[r1] * dlam_()[r1]; }
                 m0 -= sigma_mu; m1 -= sigma_mu;
-                rmc[r0] = m0; rmc[r1] = m1;
+                rmc_()[r0] = m0; rmc_()[r1] = m1;
             }
-            gsc[r0] = ti[r0] * (m0 - l0 * rdp[r0]) - ti[r1] * (m1 - l1 * rdp[r1]);
+            gsc[r0] = ti_()[r0] * (m0 - l0 * rdp[r0]) - ti_()[r1] * (m1 - l1 * rdp[r1]);
         }
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
@@ -1089,10 +1261,10 @@ struct CtaSolver {
             if (row >= 0) z += gsc[k * s2 + row];
             if ((i == HXV || i == HYV) && k >= 1 && k < N)
             {
-                const double* gi = gxy + k * 2 * K + (i == HXV ? 0 : K);
+                const double* gi = gxy_() + k * 2 * K + (i == HXV ? 0 : K);
                 for (int c = 0; c < K; c++) z += gi[c] * gsc[k * s2 + nbq + c];
             }
-            zv[it] = var_active(k, i) ? z : 0.0;
+            zv_()[it] = var_active(k, i) ? z : 0.0;
         }
         if (mode == 2)
         {
@@ -1100,11 +1272,11 @@ struct CtaSolver {
             for (int it = tid; it < N * NX; it += T)
             {
                 const int k = dnx.div(it), m = it - k * NX;
-                const double* Mn = Mx + (k + 1) * NE;
+                const double* Mn = Mx_() + (k + 1) * NE;
                 double acc = 0.0;
 #pragma unroll
-                for (int n = 0; n < NX; n++) acc += (m >= n ? Mn[MI(NU + m, NU + n)] : Mn[MI(NU + n, NU + m)]) * rb2[k * NX + n];
-                Pb[it] = acc;
+                for (int n = 0; n < NX; n++) acc += (m >= n ? Mn[MI(NU + m, NU + n)] : Mn[MI(NU + n, NU + m)]) * rb2_()[k * NX + n];
+                Pb_()[it] = acc;
             }
         }
         syncthreads();
@@ -1112,15 +1284,15 @@ struct CtaSolver {
         for (int it = tid; it < (N + 1) * NX; it += T)
         {
             const int k = dnx.div(it), j = it - k * NX;
-            double acc = zv[k * NV + NU + j];
+            double acc = zv_()[k * NV + NU + j];
 #pragma unroll
-            for (int m = 0; m < NU; m++) acc += Kg[k * (NU * NX) + m * NX + j] * zv[k * NV + m];
+            for (int m = 0; m < NU; m++) acc += Kg_()[k * (NU * NX) + m * NX + j] * zv_()[k * NV + m];
             if (k < N)
             {
 #pragma unroll
-                for (int m = 0; m < NX; m++) acc += Acl[k * (NX * NX) + m * NX + j] * Pb[k * NX + m];
+                for (int m = 0; m < NX; m++) acc += Acl_()[k * (NX * NX) + m * NX + j] * Pb_()[k * NX + m];
             }
-            ee[it] = acc;
+            ee_()[it] = acc;
         }
         syncthreads();
     }
@@ -1133,17 +1305,17 @@ struct CtaSolver {
     //   mode 2: refinement (rd2, rm2 -> dux2, dpi2, dlam2, dt2), no step length
     MDEV void expand_pass(int mode, double tau)
     {
-        double* vo = mode == 2 ? dux2 : dux;
-        double* dlo = mode == 2 ? dlam2 : dlam;
-        double* dto = mode == 2 ? dt2 : dt;
-        double* dpo = mode == 2 ? dpi2 : dpi;
-        const double* rdp = mode == 2 ? rd2 : rd;
-        const double* rmp = mode == 2 ? rm2 : rmc;
+        double* vo = mode == 2 ? dux2_() : dux_();
+        double* dlo = mode == 2 ? dlam2_() : dlam_();
+        double* dto = mode == 2 ? dt2_() : dt_();
+        double* dpo = mode == 2 ? dpi2_() : dpi_();
+        const double* rdp = mode == 2 ? rd2_() : rd_();
+        const double* rmp = mode == 2 ? rm2_() : rmc_();
         for (int it = tid; it < (N + 1) * NU; it += T)
         {
             const int k = it / NU, m = it - k * NU;
-            double acc = kk[it];
-            const double* Kr = Kg + k * (NU * NX) + m * NX;
+            double acc = kk_()[it];
+            const double* Kr = Kg_() + k * (NU * NX) + m * NX;
             const double* dx = vo + k * NV + NU;
 #pragma unroll
             for (int j = 0; j < NX; j++) acc += Kr[j] * dx[j];
@@ -1158,15 +1330,15 @@ struct CtaSolver {
             const double* v = vo + k * NV;
             double dv;
             if (j < nbq) dv = v[srvar[j]];
-            else dv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+            else dv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
 #pragma unroll
             for (int side = 0; side < 2; side++)
             {
                 const int r = k * s2 + j + side * ncq;
                 double dtr = side ? -dv : dv;
-                const double lam0 = lam[r], t0 = t[r], e0 = rdp[r];
+                const double lam0 = lam_()[r], t0 = t_()[r], e0 = rdp[r];
                 const double m = mode == 0 ? lam0 * t0 - tau : rmp[r];
-                const double dlr = -ti[r] * (m + (lam0 * dtr) - (lam0 * e0));
+                const double dlr = -ti_()[r] * (m + (lam0 * dtr) - (lam0 * e0));
                 dtr -= e0;
                 dlo[r] = dlr; dto[r] = dtr;
                 // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best is
@@ -1185,9 +1357,9 @@ struct CtaSolver {
         for (int it = tid; it < N * NX; it += T)
         {
             const int k = dnx.div(it), i = it - k * NX;
-            const double* Mn = Mx + (k + 1) * NE;
+            const double* Mn = Mx_() + (k + 1) * NE;
             const double* xn = vo + (k + 1) * NV + NU;
-            double acc = mode == 0 ? Mn[MI(NV, NU + i)] : zv[(k + 1) * NV + NU + i];
+            double acc = mode == 0 ? Mn[MI(NV, NU + i)] : zv_()[(k + 1) * NV + NU + i];
 #pragma unroll
             for (int n = 0; n < NX; n++) acc += (i >= n ? Mn[MI(NU + i, NU + n)] : Mn[MI(NU + n, NU + i)]) * xn[n];
             dpo[it] = acc;
@@ -1213,42 +1385,42 @@ struct CtaSolver {
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
             const int k = dnv.div(it), i = it - k * NV;
-            const double* v = dux + k * NV;
+            const double* v = dux_() + k * NV;
             const double* H = Hk(k);
-            double g = rg[it];
+            double g = rg_()[it];
 #pragma unroll
             for (int j = 0; j < NV; j++) g += H[i + NV * j] * v[j];
-            if (k > 0 && i >= NU) g -= dpi[(k - 1) * NX + i - NU];
+            if (k > 0 && i >= NU) g -= dpi_()[(k - 1) * NX + i - NU];
             if (k < N)
             {
-                const double* Gk = G + k * (NV * NX) + i;
-                const double* pk = dpi + k * NX;
+                const double* Gk = G_() + k * (NV * NX) + i;
+                const double* pk = dpi_() + k * NX;
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < NX; j++) acc += Gk[NV * j] * pk[j];
                 g += acc;
                 const int row = vrow(k, i);
-                if (row >= 0) g += dlam[k * s2 + ncq + row] - dlam[k * s2 + row];
+                if (row >= 0) g += dlam_()[k * s2 + ncq + row] - dlam_()[k * s2 + row];
                 if ((i == HXV || i == HYV) && k >= 1)
                 {
-                    const double* gi = gxy + k * 2 * K + (i == HXV ? 0 : K);
-                    for (int c = 0; c < K; c++) g += gi[c] * (dlam[k * s2 + ncq + nbq + c] - dlam[k * s2 + nbq + c]);
+                    const double* gi = gxy_() + k * 2 * K + (i == HXV ? 0 : K);
+                    for (int c = 0; c < K; c++) g += gi[c] * (dlam_()[k * s2 + ncq + nbq + c] - dlam_()[k * s2 + nbq + c]);
                 }
             }
             const double gi = var_active(k, i) ? g : 0.0;
-            if (WRITE) rg2[it] = gi;
+            if (WRITE) rg2_()[it] = gi;
             const double q = dabs(gi);
             n0 = q > n0 ? q : n0;
         }
         for (int it = tid; it < N * NX; it += T)
         {
             const int k = dnx.div(it), j = it - k * NX;
-            const double* v = dux + k * NV;
-            const double* Gk = G + k * (NV * NX) + NV * j;
-            double acc = rb[it] - dux[(k + 1) * NV + NU + j];
+            const double* v = dux_() + k * NV;
+            const double* Gk = G_() + k * (NV * NX) + NV * j;
+            double acc = rb_()[it] - dux_()[(k + 1) * NV + NU + j];
 #pragma unroll
             for (int i = 0; i < NV; i++) acc += Gk[i] * v[i];
-            if (WRITE) rb2[it] = acc;
+            if (WRITE) rb2_()[it] = acc;
             const double q = dabs(acc);
             n1 = q > n1 ? q : n1;
         }
@@ -1258,17 +1430,17 @@ struct CtaSolver {
             {
                 const int k = dq.div(it), j = it - k * ncq;
                 const int r0 = k * s2 + j, r1 = r0 + ncq;
-                if (!row_active(k, j)) { rd2[r0] = 0.0; rd2[r1] = 0.0; rm2[r0] = 0.0; rm2[r1] = 0.0; continue; }
-                const double* v = dux + k * NV;
+                if (!row_active(k, j)) { rd2_()[r0] = 0.0; rd2_()[r1] = 0.0; rm2_()[r0] = 0.0; rm2_()[r1] = 0.0; continue; }
+                const double* v = dux_() + k * NV;
                 double vv;
                 if (j < nbq) vv = v[srvar[j]];
-                else vv = k >= 1 ? gxy[k * 2 * K + j - nbq] * v[HXV] + gxy[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
-                const double e0 = rd[r0] + dt[r0] - vv, e1 = rd[r1] + dt[r1] + vv;
-                rd2[r0] = e0; rd2[r1] = e1;
+                else vv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
+                const double e0 = rd_()[r0] + dt_()[r0] - vv, e1 = rd_()[r1] + dt_()[r1] + vv;
+                rd2_()[r0] = e0; rd2_()[r1] = e1;
                 double q = dabs(e0); n2 = q > n2 ? q : n2; q = dabs(e1); n2 = q > n2 ? q : n2;
-                const double m0 = rmc[r0] + lam[r0] * dt[r0] + dlam[r0] * t[r0];
-                const double m1 = rmc[r1] + lam[r1] * dt[r1] + dlam[r1] * t[r1];
-                rm2[r0] = m0; rm2[r1] = m1;
+                const double m0 = rmc_()[r0] + lam_()[r0] * dt_()[r0] + dlam_()[r0] * t_()[r0];
+                const double m1 = rmc_()[r1] + lam_()[r1] * dt_()[r1] + dlam_()[r1] * t_()[r1];
+                rm2_()[r0] = m0; rm2_()[r1] = m1;
                 q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
             }
         }
@@ -1286,8 +1458,8 @@ struct CtaSolver {
             const int k = dq.div(it) >> 1;
             int j = it - k * s2; if (j >= ncq) j -= ncq;
             if (!row_active(k, j)) continue;
-            if (a_dual * dlam[it] > lam[it]) a_dual = lam[it] / dlam[it];
-            if (a_prim * dt[it] > t[it]) a_prim = t[it] / dt[it];
+            if (a_dual * dlam_()[it] > lam_()[it]) a_dual = lam_()[it] / dlam_()[it];
+            if (a_prim * dt_()[it] > t_()[it]) a_prim = t_()[it] / dt_()[it];
         }
         double vm[2] = {a_prim, a_dual};
         block_reduce<2, 0>(vm, nullptr);
@@ -1297,13 +1469,13 @@ struct CtaSolver {
     // step += refinement step
     MDEV void add_refinement()
     {
-        for (int e = tid; e < (N + 1) * NV; e += T) dux[e] += dux2[e];
-        for (int e = tid; e < N * NX; e += T) dpi[e] += dpi2[e];
+        for (int e = tid; e < (N + 1) * NV; e += T) dux_()[e] += dux2_()[e];
+        for (int e = tid; e < N * NX; e += T) dpi_()[e] += dpi2_()[e];
         for (int e = tid; e < N * s2; e += T)
         {
             const int k = dq.div(e) >> 1;
             int j = e - k * s2; if (j >= ncq) j -= ncq;
-            if (row_active(k, j)) { dlam[e] += dlam2[e]; dt[e] += dt2[e]; }
+            if (row_active(k, j)) { dlam_()[e] += dlam2_()[e]; dt_()[e] += dt2_()[e]; }
         }
         syncthreads();
     }
@@ -1353,6 +1525,7 @@ struct CtaSolver {
                     PROF(1)
                     gains_pass();
                     syncthreads();
+                    block_products();
                 }
                 else
                 {
@@ -1363,9 +1536,9 @@ struct CtaSolver {
                     solve_calls++;
                     PROF(7)
                 }
-                feedforward_pass(kind == AFF, kind == REF ? rb2 : rb);
+                feedforward_pass(kind == AFF, kind == REF ? rb2_() : rb_());
                 PROF(2)
-                chainF(kind == REF ? dux2 : dux);
+                chainF(kind == REF ? dux2_() : dux_());
                 syncthreads();
                 PROF(3)
                 expand_pass(kind == AFF ? 0 : (kind == REF ? 2 : 1), tau_min);
@@ -1435,11 +1608,11 @@ struct CtaSolver {
         for (int k = tid; k <= N; k += T)
         {
             double* z = Z(P.lay.zux, k); double* zl = Z(P.lay.zlam, k); double* zt = Z(P.lay.zt, k);
-            const double* v = ux + k * NV; const double* l = lam + k * s2; const double* tt = t + k * s2;
+            const double* v = ux_() + k * NV; const double* l = lam_() + k * s2; const double* tt = t_() + k * s2;
             if (k < N)
             {
                 double* zp = Z(P.lay.zpi, k);
-                for (int i = 0; i < NX; i++) zp[i] = pi[k * NX + i];
+                for (int i = 0; i < NX; i++) zp[i] = pi_()[k * NX + i];
                 for (int j = 0; j < nbu; j++) { zl[j] = l[j]; zl[ncz + j] = l[ncq + j]; zt[j] = tt[j]; zt[ncz + j] = tt[ncq + j]; }
                 for (int c = 0; c < K; c++)
                 {
@@ -1457,16 +1630,16 @@ struct CtaSolver {
                 for (int i = 0; i < NX; i++)
                 {
                     const int iv = NU + i;
-                    double acc = rq[iv];
+                    double acc = rq_()[iv];
                     double hs = 0.0;
                     for (int j = 0; j < NV; j++) hs += Hs[iv + NV * j] * s[j];
                     acc += hs;
-                    if (N > 0) for (int j = 0; j < NX; j++) acc += sA0[iv + NV * j] * pi[j];
+                    if (N > 0) for (int j = 0; j < NX; j++) acc += sA0[iv + NV * j] * pi_()[j];
                     if (iv == HXV || iv == HYV)
                         for (int c = 0; c < K; c++)
                         {
                             const double dl = l[ncq + nbq + c] - l[nbq + c];
-                            acc += (iv == HXV ? gxy[c] : gxy[K + c]) * dl;
+                            acc += (iv == HXV ? gxy_()[c] : gxy_()[K + c]) * dl;
                         }
                     tmp[iv] = acc;
                 }
@@ -1526,12 +1699,12 @@ struct CtaSolver {
         const double* grq = q.rq + (long) inst * (N + 1) * NV;
         const double* gg = q.gxy + (long) inst * N * 2 * K;
         const double* gd = q.d + (long) inst * N * s2;
-        for (int e = tid; e < N * NV * NX; e += T) G[e] = gG[e];
-        for (int e = tid; e < N * NX; e += T) b[e] = gb[e];
-        for (int e = tid; e < (N + 1) * NV; e += T) rq[e] = grq[e];
-        for (int e = tid; e < N * 2 * K; e += T) gxy[e] = gg[e];
-        for (int e = tid; e < N * s2; e += T) d[e] = gd[e];
-        for (int e = tid; e < s2; e += T) d[N * s2 + e] = 0.0;
+        for (int e = tid; e < N * NV * NX; e += T) G_()[e] = gG[e];
+        for (int e = tid; e < N * NX; e += T) b_()[e] = gb[e];
+        for (int e = tid; e < (N + 1) * NV; e += T) rq_()[e] = grq[e];
+        for (int e = tid; e < N * 2 * K; e += T) gxy_()[e] = gg[e];
+        for (int e = tid; e < N * s2; e += T) d_()[e] = gd[e];
+        for (int e = tid; e < s2; e += T) d_()[N * s2 + e] = 0.0;
         syncthreads();
         solve_calls = 0; lq_count = 0; itref_count = 0; fp32_count = 0;
         int it = 0;
@@ -1540,9 +1713,9 @@ struct CtaSolver {
         double* opi = q.pi + (long) inst * N * NX;
         double* ol = q.lam + (long) inst * N * s2;
         double* ot = q.t + (long) inst * N * s2;
-        for (int e = tid; e < (N + 1) * NV; e += T) oux[e] = ux[e];
-        for (int e = tid; e < N * NX; e += T) opi[e] = pi[e];
-        for (int e = tid; e < N * s2; e += T) { ol[e] = lam[e]; ot[e] = t[e]; }
+        for (int e = tid; e < (N + 1) * NV; e += T) oux[e] = ux_()[e];
+        for (int e = tid; e < N * NX; e += T) opi[e] = pi_()[e];
+        for (int e = tid; e < N * s2; e += T) { ol[e] = lam_()[e]; ot[e] = t_()[e]; }
         if (tid == 0)
         {
             double* st = P.stats + (long) inst * NSTAT;
@@ -1574,10 +1747,17 @@ struct CtaSolver {
         int status = 2, sqp_iter = 0, qp_total = 0, qp_status = 0, qp_iter = 0;
         double res[4] = {0, 0, 0, 0};
         const int max_iter = P.nlp_type == 0 ? P.max_iter : 1;
+        if (P.nlp_type == 1 && P.rti_phase == 1)
+        {
+            // preparation phase only: no QP, the iterate and the statistics of the last feedback step stay
+            integrate_all();
+            prep_store(inst);
+            return;
+        }
         for (sqp_iter = 0; sqp_iter < max_iter; sqp_iter++)
         {
             long long t0 = clock_now();
-            linearize(x0, pg, lhg, yrg, yre, res);
+            linearize(inst, x0, pg, lhg, yrg, yre, res);
             t_lin += clock_now() - t0;
             PROF(12)
             if (P.nlp_type == 0 && res[0] < P.tol[0] && res[1] < P.tol[1] && res[2] < P.tol[2] && res[3] < P.tol[3])

@@ -85,6 +85,7 @@ struct Params {
     long ws_stride;
     double* stats;          // [B][NSTAT]
     double* scratch;        // [grid][plan.scratch_doubles]
+    double* prep;           // [B][N][NV*NX + NX]: linearisation parked between the RTI preparation and feedback phases (or null)
     double* packed;         // optional [B][packed_width]: result rows written by the solve's epilogue (all-gather send buffer)
     int packed_width;
     int* queue;             // work queue: [0] next ticket
@@ -139,6 +140,7 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int warps,
     o += 2 * warps * 8;                                  // two reduction buffers of 8 values per warp
     P.misc_off = (int) o;
     o += nv * nx + (nx * (nv + 1) + ne + 1) + (nx * nx + 2) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
+    o += ((N + 3) / 4 + 1) * (nx * nx + 2 * nx);         // block maps of the vector recursions (blocks of 4 stages)
     o = round_up((int) o, 2);
     for (int i = 0; i < F_FIRST_FLEX; i++)
     {

@@ -217,7 +217,7 @@ struct usvmpc_solver
     usvmpc_config cfg;
     int B, device, nx, nu, nv;
     Params P;
-    double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e, *d_scratch;
+    double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e, *d_scratch, *d_prep;
     double *d_bnd;                         // per-stage bounds shared by the batch: lbu | ubu | lbx | ubx | uh
     double *h_bnd;                         // host mirror of d_bnd
     int o_lbu, o_ubu, o_lbx, o_ubx, o_uh, n_bnd;
@@ -273,7 +273,7 @@ void refresh_params(usvmpc_solver* s)
     P.uh = s->d_bnd + s->o_uh;
     P.cst = s->d_cst; P.x0 = s->d_x0; P.yref_e = s->d_yref_e;
     P.p = s->d_p[P.p_per_stage]; P.lh = s->d_lh[P.lh_per_stage]; P.yref = s->d_yref[P.yref_per_stage];
-    P.ws = s->d_ws; P.stats = s->d_stats; P.scratch = s->d_scratch; P.queue = s->d_queue;
+    P.ws = s->d_ws; P.stats = s->d_stats; P.scratch = s->d_scratch; P.queue = s->d_queue; P.prep = s->d_prep;
     P.order = (s->lpt && s->have_history) ? s->d_order : nullptr;
 }
 
@@ -580,7 +580,7 @@ int usvmpc_free(usvmpc_solver* s)
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->d_ws); cudaFree(s->d_stats); cudaFree(s->d_cst); cudaFree(s->d_x0); cudaFree(s->d_yref_e);
-    cudaFree(s->d_scratch); cudaFree(s->d_bnd); cudaFree(s->d_queue); cudaFree(s->d_order);
+    cudaFree(s->d_scratch); cudaFree(s->d_prep); cudaFree(s->d_bnd); cudaFree(s->d_queue); cudaFree(s->d_order);
     for (int i = 0; i < 2; i++) { cudaFree(s->d_p[i]); cudaFree(s->d_lh[i]); cudaFree(s->d_yref[i]); }
     cudaFree(s->d_stage);
     free(s->h_bnd);
@@ -743,7 +743,19 @@ int usvmpc_solver_opts_set(usvmpc_solver* s, const char* field, double value)
         if (value != 32.0 && value != 64.0) return fail(USVMPC_E_INVALID, "riccati_precision must be 32 or 64");
         s->P.chain_fp32 = value == 32.0;
     }
-    else if (!strcmp(field, "rti_phase")) { if (value != 0.0) return fail(USVMPC_E_INVALID, "rti_phase %g: only 0 (prepare+feedback in one call) is implemented", value); }
+    else if (!strcmp(field, "rti_phase"))
+    {
+        // 0: preparation + feedback, 1: preparation, 2: feedback (ocp_nlp_sqp_rti.c:459-488)
+        if (value != 0.0 && value != 1.0 && value != 2.0) return fail(USVMPC_E_INVALID, "rti_phase must be 0, 1 or 2");
+        if (value != 0.0 && !s->d_prep)
+        {
+            const size_t n = (size_t) s->B * c.N * (s->nv * s->nx + s->nx);
+            CU(cudaSetDevice(s->device));
+            CU(cudaMalloc(&s->d_prep, sizeof(double) * n));
+            CU(cudaMemset(s->d_prep, 0, sizeof(double) * n));
+        }
+        s->P.rti_phase = (int) value;
+    }
     else if (!strcmp(field, "step_length")) { if (value != 1.0) return fail(USVMPC_E_INVALID, "step_length %g: the engine takes full SQP steps like the reference scripts", value); }
     else return fail(USVMPC_E_FIELD, "unknown option '%s'", field);
     refresh_params(s);
