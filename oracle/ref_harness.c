@@ -43,7 +43,7 @@ void ocp_nlp_eval_residuals(ocp_nlp_solver *solver, ocp_nlp_in *nlp_in, ocp_nlp_
  * process-wide model configuration (CasADi-ABI sparsity callbacks carry no context pointer;
  * the reference's generated library is global state too, acados_solver.in.c:101-107)
  * ---------------------------------------------------------------------------------------- */
-static int g_model = 0, g_nx = 6, g_nu = 2, g_K = 0;
+static int g_model = 0, g_nx = 6, g_nu = 2, g_K = 0, g_hx = 0, g_hy = 1;
 
 #define MAXNX 8
 #define MAXK 64
@@ -116,19 +116,19 @@ static int vde_n_out(void) { return 3; }
 /* ---- <model>_constr_h_fun : (x,u,z,p) -> h ;  _constr_h_fun_jac_uxt_zt -> (h, (dh/d[u;x])^T, (dh/dz)) ---- */
 static int h_fun(const double **arg, double **res, int *iw, double *w, void *mem)
 {
-    usvm_obstacle_h(g_K, arg[0], arg[3], res[0], NULL, NULL);
+    usvm_obstacle_h_at(g_hx, g_hy, g_K, arg[0], arg[3], res[0], NULL, NULL);
     return 0;
 }
 static int hjac_fun(const double **arg, double **res, int *iw, double *w, void *mem)
 {
     double gX[MAXK], gY[MAXK];
     const int nv = g_nu + g_nx;
-    usvm_obstacle_h(g_K, arg[0], arg[3], res[0], gX, gY);
+    usvm_obstacle_h_at(g_hx, g_hy, g_K, arg[0], arg[3], res[0], gX, gY);
     for (int i = 0; i < g_K; i++)
     {
         for (int r = 0; r < nv; r++) res[1][r + nv * i] = 0.0;
-        res[1][g_nu + 0 + nv * i] = gX[i];
-        res[1][g_nu + 1 + nv * i] = gY[i];
+        res[1][g_nu + g_hx + nv * i] = gX[i];
+        res[1][g_nu + g_hy + nv * i] = gY[i];
     }
     return 0;
 }
@@ -247,13 +247,16 @@ void d_ocp_qp_solve_kkt_step(struct d_ocp_qp *qp, struct d_ocp_qp_sol *qp_sol, s
 /* ------------------------------------------------------------------------------------------
  * solver context == what acados_create() builds (one per thread)
  * ---------------------------------------------------------------------------------------- */
+/* icfg[ICFG_NSH] soft obstacle rows (the first nsh rows of h: idxsh = 0..nsh-1) with the slack data dcfg[DCFG_LSH..]:
+ * lsh, ush, zl, zu, Zl, Zu, one value for all soft rows (usv_guidance_ca1/acados_settings.py:105-178) */
 enum { ICFG_MODEL, ICFG_N, ICFG_K, ICFG_NUM_STEPS, ICFG_NUM_STAGES, ICFG_NLP_TYPE, ICFG_MAX_ITER,
-       ICFG_QP_ITER_MAX, ICFG_COND_N, ICFG_NBX, ICFG_NBU, ICFG_PRINT, ICFG_LEN };
-enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_UH, DCFG_LEN };
+       ICFG_QP_ITER_MAX, ICFG_COND_N, ICFG_NBX, ICFG_NBU, ICFG_PRINT, ICFG_NSH, ICFG_LEN };
+enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_UH, DCFG_LSH, DCFG_USH, DCFG_ZL, DCFG_ZU,
+       DCFG_ZZL, DCFG_ZZU, DCFG_LEN };
 
 typedef struct
 {
-    int model, N, K, nx, nu, ny, nye, np, nbx, nbu, nlp_type;
+    int model, N, K, nx, nu, ny, nye, np, nbx, nbu, nlp_type, nsh;
     ocp_nlp_plan *plan;
     ocp_nlp_config *config;
     ocp_nlp_dims *dims;
@@ -285,6 +288,9 @@ void *usvref_create(const int *icfg, const double *dcfg, const double *W, const 
     const int nxm = c->nx, num = c->nu;
     c->ny = nxm + num; c->nye = nxm; c->np = 2 * K; c->nbx = icfg[ICFG_NBX]; c->nbu = icfg[ICFG_NBU];
     g_model = c->model; g_nx = nxm; g_nu = num; g_K = K;   /* contexts are created serially */
+    usvm_pos_states(c->model, &g_hx, &g_hy);
+    c->nsh = icfg[ICFG_NSH];
+    const int nsh = c->nsh;
 
     /* plan & config (template :186-239) */
     c->plan = ocp_nlp_plan_create(N);
@@ -304,7 +310,7 @@ void *usvref_create(const int *icfg, const double *dcfg, const double *W, const 
         nbxe[N + 1], zero = 0;
     for (int i = 0; i <= N; i++)
     {
-        nx[i] = nxm; nu[i] = num; nz[i] = 0; ns[i] = 0; ny[i] = c->ny;
+        nx[i] = nxm; nu[i] = num; nz[i] = 0; ns[i] = i < N ? nsh : 0; ny[i] = c->ny;
         nbx[i] = c->nbx; nbu[i] = c->nbu; ng[i] = 0; nh[i] = K; nbxe[i] = 0;
     }
     nbx[0] = nxm; nbxe[0] = nxm;
@@ -329,7 +335,7 @@ void *usvref_create(const int *icfg, const double *dcfg, const double *W, const 
         if (K > 0)
         {
             ocp_nlp_dims_set_constraints(c->config, c->dims, i, "nh", &nh[i]);
-            ocp_nlp_dims_set_constraints(c->config, c->dims, i, "nsh", &zero);
+            ocp_nlp_dims_set_constraints(c->config, c->dims, i, "nsh", (void *) &nsh);
         }
         ocp_nlp_dims_set_cost(c->config, c->dims, i, "ny", &ny[i]);
     }
@@ -385,6 +391,19 @@ void *usvref_create(const int *icfg, const double *dcfg, const double *W, const 
     ocp_nlp_cost_model_set(c->config, c->dims, c->in, N, "W", (void *) We);
     ocp_nlp_cost_model_set(c->config, c->dims, c->in, N, "Vx", Vxe);
     free(Vx); free(Vu); free(Vxe); free(yref0);
+    if (nsh > 0)
+    {
+        /* slack penalties (template :880-930): zl, zu, Zl, Zu per stage */
+        double zl[MAXK], zu[MAXK], Zl[MAXK], Zu[MAXK];
+        for (int j = 0; j < nsh; j++) { zl[j] = dcfg[DCFG_ZL]; zu[j] = dcfg[DCFG_ZU]; Zl[j] = dcfg[DCFG_ZZL]; Zu[j] = dcfg[DCFG_ZZU]; }
+        for (int i = 0; i < N; i++)
+        {
+            ocp_nlp_cost_model_set(c->config, c->dims, c->in, i, "Zl", Zl);
+            ocp_nlp_cost_model_set(c->config, c->dims, c->in, i, "Zu", Zu);
+            ocp_nlp_cost_model_set(c->config, c->dims, c->in, i, "zl", zl);
+            ocp_nlp_cost_model_set(c->config, c->dims, c->in, i, "zu", zu);
+        }
+    }
 
     /* constraints */
     int idxbx0[MAXNX], idxbu[MAXNX];
@@ -419,6 +438,19 @@ void *usvref_create(const int *icfg, const double *dcfg, const double *W, const 
             ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "nl_constr_h_fun", &c->hfun[i]);
             ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "lh", lh);
             ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "uh", uh);
+        }
+        if (nsh > 0)
+        {
+            /* soft nonlinear rows (template :1395-1449): idxsh, lsh, ush */
+            int idxsh[MAXK];
+            double lsh[MAXK], ush[MAXK];
+            for (int j = 0; j < nsh; j++) { idxsh[j] = j; lsh[j] = dcfg[DCFG_LSH]; ush[j] = dcfg[DCFG_USH]; }
+            for (int i = 0; i < N; i++)
+            {
+                ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "idxsh", idxsh);
+                ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "lsh", lsh);
+                ocp_nlp_constraints_model_set(c->config, c->dims, c->in, i, "ush", ush);
+            }
         }
     }
 
@@ -529,6 +561,7 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
         }
         ocp_nlp_out_set(c->config, c->dims, c->out, i, "lam", (void *) zeros_ineq);
         ocp_nlp_out_set(c->config, c->dims, c->out, i, "t", (void *) zeros_ineq);
+        if (c->nsh > 0 && i < N) blasfeo_dvecse(2 * c->nsh, 0.0, c->out->ux + i, nu + nx);  /* slack values sl, su */
     }
     g_tap.ipm_iters = 0; g_tap.lq_calls = 0; g_tap.solve_calls = 0; g_tap.calls = 0; g_tap.got = 0;
     int status = ocp_nlp_solve(c->solver, c->in, c->out);
@@ -551,12 +584,12 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
     }
     if (lam_out || t_out)
     {
-        /* caller lays stages out with stride 2*(nbx_max+nbu+K), nbx_max = max(nx, nbx) */
+        /* caller lays stages out with stride 2*(nbx_max+nbu+K) + 2*nsh, nbx_max = max(nx, nbx) */
         int nbm = (c->nbx > nx ? c->nbx : nx) + c->nbu + K;
         for (int i = 0; i <= N; i++)
         {
-            if (lam_out) ocp_nlp_out_get(c->config, c->dims, c->out, i, "lam", lam_out + i * 2 * nbm);
-            if (t_out) ocp_nlp_out_get(c->config, c->dims, c->out, i, "t", t_out + i * 2 * nbm);
+            if (lam_out) ocp_nlp_out_get(c->config, c->dims, c->out, i, "lam", lam_out + i * (2 * nbm + 2 * c->nsh));
+            if (t_out) ocp_nlp_out_get(c->config, c->dims, c->out, i, "t", t_out + i * (2 * nbm + 2 * c->nsh));
         }
     }
     if (stats)
@@ -565,6 +598,18 @@ int usvref_solve(void *h, const double *x0, const double *p, int p_per_stage, co
         stats[3] = r[0]; stats[4] = r[1]; stats[5] = r[2]; stats[6] = r[3]; stats[7] = (double) g_tap.lq_calls; stats[8] = (double) g_tap.solve_calls;
     }
     return status;
+}
+
+/* slack values of the last solve: sl, su [N][nsh] (ocp_nlp_get_at_stage "sl"/"su" of the Python wrapper,
+ * acados_ocp_solver.py:744-782 reads the same memory) */
+void usvref_get_slacks(void *h, double *sl, double *su)
+{
+    usvref_ctx *c = h;
+    for (int i = 0; i < c->N; i++)
+    {
+        blasfeo_unpack_dvec(c->nsh, c->out->ux + i, c->nu + c->nx, sl + i * c->nsh, 1);
+        blasfeo_unpack_dvec(c->nsh, c->out->ux + i, c->nu + c->nx + c->nsh, su + i * c->nsh, 1);
+    }
 }
 
 /* Arm the QP tap of the calling thread: capture the `want`-th QP (0-based) of the next solve.

@@ -11,6 +11,9 @@
  *                      (thrust-rate states removed)
  *  model 1  "pendulum" cart-pole, x=[x1,theta,v1,dtheta], u=[F]
  *                      AC/examples/acados_python/getting_started/common/export_pendulum_ode_model.py:37-94
+ *  model 2  "usv_model_guidance_ca1"  the guidance model of the deployed collision-avoidance node,
+ *                      x=[u,v,ye,chie,psied,xned,yned,psi], u=[Upsieddot]
+ *                      NM/scripts/usv_guidance_ca1/usv_model.py:65-128 (T1 = 1, beta = atan2(v, u + 0.001))
  *
  * CasADi differentiation conventions are mirrored: d|a|/da = sign(a) with sign(0)=0,
  * d(if_else(c,a,b))/dc = 0.
@@ -24,13 +27,22 @@
 
 #define USVM_MODEL_USV3 0
 #define USVM_MODEL_PENDULUM 1
+#define USVM_MODEL_GUIDANCE_CA1 2
 
 static inline double usvm_sign(double a) { return (a > 0.0) - (a < 0.0); }
 
 static inline void usvm_dims(int model, int *nx, int *nu)
 {
     if (model == USVM_MODEL_PENDULUM) { *nx = 4; *nu = 1; }
+    else if (model == USVM_MODEL_GUIDANCE_CA1) { *nx = 8; *nu = 1; }
     else { *nx = 6; *nu = 2; }
+}
+
+/* indices of the NED position states that enter the obstacle distance */
+static inline void usvm_pos_states(int model, int *hx, int *hy)
+{
+    if (model == USVM_MODEL_GUIDANCE_CA1) { *hx = 5; *hy = 6; }
+    else { *hx = 0; *hy = 1; }
 }
 
 /* f, Jx (6x6), Ju (6x2); Jx/Ju may be NULL */
@@ -116,14 +128,69 @@ static inline void usvm_pendulum(const double *x, const double *uc, double *f, d
     }
 }
 
+/* f, Jx (8x8), Ju (8x1): NM/scripts/usv_guidance_ca1/usv_model.py:117-128 */
+static inline void usvm_guidance_ca1(const double *x, const double *uc, double *f, double *Jx, double *Ju)
+{
+    const double T1 = 1.0;
+    const double u = x[0], v = x[1], chie = x[3], psied = x[4], psi = x[7];
+    const double ue = u + 0.001;
+    const double beta = atan2(v, ue);
+    const double psie = chie - beta;
+    const double se = sin(psie), ce = cos(psie), sp = sin(psi), cp = cos(psi);
+    f[0] = 0.0;
+    f[1] = 0.0;
+    f[2] = u * se + v * ce;
+    f[3] = (psied - psie) / T1;
+    f[4] = uc[0];
+    f[5] = u * cp - v * sp;
+    f[6] = u * sp + v * cp;
+    f[7] = (psied - psie) / T1;
+    if (Jx)
+    {
+        const double den = ue * ue + v * v;
+        const double db_du = -v / den, db_dv = ue / den;     /* d atan2(v, u + 0.001) */
+        const double w = u * ce - v * se;                    /* d f2 / d psie */
+        for (int i = 0; i < 64; i++) Jx[i] = 0.0;
+        Jx[2 + 8 * 0] = se - w * db_du;
+        Jx[2 + 8 * 1] = ce - w * db_dv;
+        Jx[2 + 8 * 3] = w;
+        Jx[3 + 8 * 0] = db_du / T1;
+        Jx[3 + 8 * 1] = db_dv / T1;
+        Jx[3 + 8 * 3] = -1.0 / T1;
+        Jx[3 + 8 * 4] = 1.0 / T1;
+        Jx[5 + 8 * 0] = cp;  Jx[5 + 8 * 1] = -sp;  Jx[5 + 8 * 7] = -u * sp - v * cp;
+        Jx[6 + 8 * 0] = sp;  Jx[6 + 8 * 1] = cp;   Jx[6 + 8 * 7] = u * cp - v * sp;
+        Jx[7 + 8 * 0] = db_du / T1;
+        Jx[7 + 8 * 1] = db_dv / T1;
+        Jx[7 + 8 * 3] = -1.0 / T1;
+        Jx[7 + 8 * 4] = 1.0 / T1;
+    }
+    if (Ju)
+    {
+        for (int i = 0; i < 8; i++) Ju[i] = 0.0;
+        Ju[4] = 1.0;
+    }
+}
+
 static inline void usvm_f_jac(int model, const double *x, const double *uc, double *f, double *Jx, double *Ju)
 {
     if (model == USVM_MODEL_PENDULUM) usvm_pendulum(x, uc, f, Jx, Ju);
+    else if (model == USVM_MODEL_GUIDANCE_CA1) usvm_guidance_ca1(x, uc, f, Jx, Ju);
     else usvm_usv3(x, uc, f, Jx, Ju);
 }
 
 /* obstacle distances h_i = ||(X,Y) - (ox_i, oy_i)||, i<K, p=[ox_1,oy_1,...]
  * (NM/scripts/usv_pf_ca/usv_model.py:165-168).  dh/dX, dh/dY returned in gX,gY (may be NULL). */
+static inline void usvm_obstacle_h_at(int hx, int hy, int K, const double *x, const double *p, double *h, double *gX, double *gY)
+{
+    for (int i = 0; i < K; i++)
+    {
+        const double dx = x[hx] - p[2 * i], dy = x[hy] - p[2 * i + 1];
+        const double d = sqrt(dx * dx + dy * dy);
+        h[i] = d;
+        if (gX) { gX[i] = dx / d; gY[i] = dy / d; }
+    }
+}
 static inline void usvm_obstacle_h(int K, const double *x, const double *p, double *h, double *gX, double *gY)
 {
     for (int i = 0; i < K; i++)

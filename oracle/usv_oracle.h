@@ -8,23 +8,29 @@
 #define USVO_NBM 16    /* max box rows per stage */
 #define USVO_NGM 32    /* max general / nonlinear rows per stage */
 #define USVO_NCM (USVO_NBM + USVO_NGM)
+#define USVO_NSM 16    /* max soft rows per stage (each has a lower and an upper slack variable) */
+#define USVO_NVT (USVO_NVM + 2 * USVO_NSM)  /* [u; x; sl; su] */
+#define USVO_NCT (2 * USVO_NCM + 2 * USVO_NSM) /* [lb lg | ub ug | ls | us] */
 
 /* ---- stage-wise OCP QP, HPIPM conventions (SURVEY.md section 3e "data conventions") ---- */
 typedef struct
 {
-    int nx, nu, nb, ng;                      /* this stage */
+    int nx, nu, nb, ng, ns;                  /* this stage; ns soft rows, slack variables sl, su follow [u;x] */
+    int idxs_rev[USVO_NCM];                  /* row -> slack index or -1 (HPIPM idxs_rev) */
+    double Z[2 * USVO_NSM];                  /* diagonal Hessian of the slacks [Zl; Zu] */
     int idxb[USVO_NBM];                      /* box rows index into [u;x] */
     double BAt[USVO_NVM * USVO_NXM];         /* (nu+nx) x nx_next, column-major, ld = nu+nx : [B';A'] */
     double b[USVO_NXM];
     double RSQ[USVO_NVM * USVO_NVM];         /* (nu+nx)^2 column-major, lower triangle read */
-    double rq[USVO_NVM];
+    double rq[USVO_NVT];                     /* gradient of [u;x] then of the slacks (z) */
     double DCt[USVO_NVM * USVO_NGM];         /* (nu+nx) x ng column-major */
-    double d[2 * USVO_NCM];                  /* [lb lg | -ub -ug]-style residuals: lower rows then upper rows */
+    double d[USVO_NCT];                      /* [lb lg | -ub -ug]-style residuals: lower rows then upper rows, then the
+                                                lower bounds of the slacks [ls | us] */
 } usvo_qp_stage;
 
 typedef struct
 {
-    double ux[USVO_NVM], pi[USVO_NXM], lam[2 * USVO_NCM], t[2 * USVO_NCM];
+    double ux[USVO_NVT], pi[USVO_NXM], lam[USVO_NCT], t[USVO_NCT];
 } usvo_qp_sol_stage;
 
 typedef struct
@@ -60,6 +66,10 @@ typedef struct
     double dt, tol[4], uh;
     double W[USVO_NVM * USVO_NVM], We[USVO_NXM * USVO_NXM];  /* column-major ny x ny, nx x nx */
     double lbu[USVO_NBM], ubu[USVO_NBM], lbx[USVO_NBM], ubx[USVO_NBM];
+    /* soft obstacle rows: the first nsh rows of h (idxsh = 0..nsh-1), one value of lsh, ush, zl, zu, Zl, Zu for all
+     * (usv_guidance_ca1/acados_settings.py:105-178) */
+    int nsh;
+    double lsh, ush, zl, zu, Zl, Zu;
 } usvo_problem;
 
 void usvo_problem_init(usvo_problem *P, const int *icfg, const double *dcfg, const double *W, const double *We,
@@ -72,6 +82,12 @@ int usvo_solve(const usvo_problem *P, const double *x0, const double *p, int p_p
                int lh_per_stage, const double *yref, int yref_per_stage, const double *yref_e, const double *xinit,
                const double *uinit, const double *piinit, double *x_out, double *u_out, double *pi_out,
                double *lam_out, double *t_out, double *stats);
+
+/* usvo_solve + the slack values sl, su [N][nsh] of the solution (may be NULL) */
+int usvo_solve_ex(const usvo_problem *P, const double *x0, const double *p, int p_per_stage, const double *lh,
+                  int lh_per_stage, const double *yref, int yref_per_stage, const double *yref_e, const double *xinit,
+                  const double *uinit, const double *piinit, double *x_out, double *u_out, double *pi_out,
+                  double *lam_out, double *t_out, double *stats, double *sl_out, double *su_out);
 
 double usvo_solve_batch(const int *icfg, const double *dcfg, const double *W, const double *We, const double *lbu,
                         const double *ubu, const int *idxbx, const double *lbx, const double *ubx, int B,

@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "..", "oracle", "libusv_oracle.so")
 
 
 class usvo_problem(C.Structure):
-    _fields_ = [("raw", C.c_char * 8192)]  # opaque, larger than sizeof(usvo_problem)
+    _fields_ = [("raw", C.c_char * 16384)]  # opaque, larger than sizeof(usvo_problem)
 
 
 def available():
@@ -44,12 +44,17 @@ class OracleSolver:
         if lh is None:
             lh = np.zeros(1)
         x = np.zeros((N + 1, nx)); u = np.zeros((N, nu)); pi = np.zeros((N, nx))
-        lam = np.zeros((N + 1, 2 * P.nbm)); t = np.zeros((N + 1, 2 * P.nbm)); stats = np.zeros(9)
-        self.lib.usvo_solve(C.byref(self.P), _d(x0), _d(p), int(p.ndim > 1), _d(lh), int(lh.ndim > 1), _d(yref),
-                            int(yref.ndim > 1), _d(yref_e), _d(xinit), _d(uinit), _d(piinit), _d(x), _d(u), _d(pi),
-                            _d(lam), _d(t), _d(stats))
-        return dict(x=x, u=u, pi=pi, lam=lam, t=t, status=int(stats[0]), sqp_iter=int(stats[1]),
-                    qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]), solve_calls=int(stats[8]))
+        w = 2 * P.nbm + 2 * P.nsh
+        lam = np.zeros((N + 1, w)); t = np.zeros((N + 1, w)); stats = np.zeros(9)
+        sl = np.zeros((N, max(P.nsh, 1))); su = np.zeros((N, max(P.nsh, 1)))
+        self.lib.usvo_solve_ex(C.byref(self.P), _d(x0), _d(p), int(p.ndim > 1), _d(lh), int(lh.ndim > 1), _d(yref),
+                               int(yref.ndim > 1), _d(yref_e), _d(xinit), _d(uinit), _d(piinit), _d(x), _d(u), _d(pi),
+                               _d(lam), _d(t), _d(stats), _d(sl), _d(su))
+        out = dict(x=x, u=u, pi=pi, lam=lam, t=t, status=int(stats[0]), sqp_iter=int(stats[1]),
+                   qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]), solve_calls=int(stats[8]))
+        if P.nsh:
+            out.update(sl=sl, su=su)
+        return out
 
 
 def qp_solve(buf, sqp_mode=True, tol4=(1e-6,) * 4, iter_max=50):

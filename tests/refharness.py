@@ -7,8 +7,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "..", "oracle", "_ref", "libusv_ref.so")
 
-ICFG = ["model", "N", "K", "num_steps", "num_stages", "nlp_type", "max_iter", "qp_iter_max", "cond_N", "nbx", "nbu", "print"]
-DCFG = ["dt", "tol_stat", "tol_eq", "tol_ineq", "tol_comp", "uh"]
+ICFG = ["model", "N", "K", "num_steps", "num_stages", "nlp_type", "max_iter", "qp_iter_max", "cond_N", "nbx", "nbu", "print", "nsh"]
+DCFG = ["dt", "tol_stat", "tol_eq", "tol_ineq", "tol_comp", "uh", "lsh", "ush", "zl", "zu", "Zl", "Zu"]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -31,10 +31,16 @@ class RefProblem:
 
     def __init__(self, model=0, N=20, K=3, num_steps=1, num_stages=4, nlp_type=0, max_iter=100, qp_iter_max=50,
                  cond_N=0, dt=0.05, tol=1e-6, uh=1e6, W=None, We=None, lbu=None, ubu=None, idxbx=None, lbx=None,
-                 ubx=None):
-        self.model, self.N, self.K = model, N, K
-        self.nx, self.nu = (4, 1) if model == 1 else (6, 2)
+                 ubx=None, nsh=0, lsh=0.0, ush=0.0, zl=0.0, zu=0.0, Zl=0.0, Zu=0.0):
+        self.model, self.N, self.K, self.nsh = model, N, K, nsh
+        self.nx, self.nu = {0: (6, 2), 1: (4, 1), 2: (8, 1)}[model]
         self.ny = self.nx + self.nu
+        if W is None and model == 2:
+            # the deployed CA solver: usv_guidance_ca1/acados_settings.py:70-118
+            W = np.diag([0, 0, 0.05, 0.01, 0, 0, 0, 0, 0.2])
+            We = np.diag([0, 0, 0.1, 0.05, 0, 0, 0, 0.0])
+            lbu, ubu = np.array([-0.5]), np.array([0.5])
+            idxbx, lbx, ubx = np.array([], dtype=np.int32), np.array([]), np.array([])
         if W is None:
             W = np.diag([1, 1, 0.1, 10, 0.1, 0.1, 1e-3, 1e-3])
             We = 5 * np.diag([1, 1, 0.1, 10, 0.1, 0.1])
@@ -48,11 +54,12 @@ class RefProblem:
         self.lbx = np.ascontiguousarray(lbx if lbx is not None else [], dtype=np.float64)
         self.ubx = np.ascontiguousarray(ubx if ubx is not None else [], dtype=np.float64)
         self.icfg = np.array([model, N, K, num_steps, num_stages, nlp_type, max_iter, qp_iter_max, cond_N,
-                              len(self.idxbx), len(self.lbu), 0], dtype=np.int32)
+                              len(self.idxbx), len(self.lbu), 0, nsh], dtype=np.int32)
         tols = tol if isinstance(tol, (list, tuple)) else [tol] * 4
-        self.dcfg = np.array([dt, *tols, uh], dtype=np.float64)
+        self.dcfg = np.array([dt, *tols, uh, lsh, ush, zl, zu, Zl, Zu], dtype=np.float64)
+        self.slack = dict(lsh=lsh, ush=ush, zl=zl, zu=zu, Zl=Zl, Zu=Zu)
         self.dt, self.uh = dt, uh
-        self.nbm = max(self.nx, len(self.idxbx)) + len(self.lbu) + K   # stage stride /2 of lam, t
+        self.nbm = max(self.nx, len(self.idxbx)) + len(self.lbu) + K   # stage stride /2 of lam, t (+ nsh slack-bound rows)
 
 
 class RefSolver:
@@ -80,12 +87,18 @@ class RefSolver:
         if lh is None:
             lh = np.zeros(1)
         x = np.zeros((N + 1, nx)); u = np.zeros((N, nu)); pi = np.zeros((N, nx))
-        lam = np.zeros((N + 1, 2 * P.nbm)); t = np.zeros((N + 1, 2 * P.nbm)); stats = np.zeros(9)
+        w = 2 * P.nbm + 2 * P.nsh
+        lam = np.zeros((N + 1, w)); t = np.zeros((N + 1, w)); stats = np.zeros(9)
         self.lib.usvref_solve(self.h, _d(x0), _d(p), int(p.ndim > 1), _d(lh), int(lh.ndim > 1), _d(yref),
                               int(yref.ndim > 1), _d(yref_e), _d(xinit), _d(uinit), _d(piinit), _d(x), _d(u), _d(pi),
                               _d(lam), _d(t), _d(stats))
-        return dict(x=x, u=u, pi=pi, lam=lam, t=t, status=int(stats[0]), sqp_iter=int(stats[1]),
-                    qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]), solve_calls=int(stats[8]))
+        out = dict(x=x, u=u, pi=pi, lam=lam, t=t, status=int(stats[0]), sqp_iter=int(stats[1]),
+                   qp_iter=int(stats[2]), res=stats[3:7].copy(), lq_calls=int(stats[7]), solve_calls=int(stats[8]))
+        if P.nsh:
+            sl = np.zeros((N, P.nsh)); su = np.zeros((N, P.nsh))
+            self.lib.usvref_get_slacks(self.h, _d(sl), _d(su))
+            out.update(sl=sl, su=su)
+        return out
 
     def solve_capture_qp(self, want, *args, **kw):
         """Solve while capturing the `want`-th QP HPIPM sees (after x0 elimination)."""
