@@ -29,6 +29,8 @@ extern "C" {
 
 #define USVMPC_MODEL_USV3 0      /* 3-DOF USV, nx=6 nu=2, h = obstacle distances  */
 #define USVMPC_MODEL_PENDULUM 1  /* cart-pole of the reference's golden-vector tests          */
+#define USVMPC_MODEL_GUIDANCE_CA1 2 /* the deployed CA guidance model "usv_model_guidance_ca1", nx=8 nu=1
+                                       (nmpc_ca/scripts/usv_guidance_ca1/usv_model.py:65-128)       */
 
 #define USVMPC_SQP 0
 #define USVMPC_SQP_RTI 1
@@ -71,6 +73,11 @@ typedef struct usvmpc_config
     double lbu[4], ubu[4], lbx[8], ubx[8];
     double W[16 * 16];         /* ny x ny, column-major, y = [x; u] (Vx=[I;0], Vu=[0;I])            */
     double W_e[16 * 16];       /* nx x nx, column-major                                             */
+    /* soft obstacle rows (dims.nsh, constraints.idxsh = 0..nsh-1: the first nsh rows of h), each with a lower and an
+     * upper slack variable: slack bounds lsh / ush, linear and quadratic penalties zl, zu, Zl, Zu
+     * (usv_guidance_ca1/acados_settings.py:105-178; acados_solver.in.c:880-930,1395-1449) */
+    int nsh;
+    double lsh[32], ush[32], zl[32], zu[32], Zl[32], Zu[32];
 } usvmpc_config;
 
 const char* usvmpc_last_error(void);
@@ -92,17 +99,19 @@ int usvmpc_solve(usvmpc_solver* s, void* stream);
 int usvmpc_update_params(usvmpc_solver* s, int stage, const double* value, int np, int on_device, void* stream);
 
 /* replaces ocp_nlp_cost_model_set (ocp_nlp_interface.c:402): "yref"/"y_ref" value [B][ny] (stage N: [B][nx]);
- * "W" value [ny*ny] column-major, shared by the batch (stage N: W_e [nx*nx]) */
+ * "W" value [ny*ny] column-major, shared by the batch (stage N: W_e [nx*nx]); "zl", "zu", "Zl", "Zu" value [nsh],
+ * shared by the batch and the stages */
 int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device,
                           void* stream);
 
 /* replaces ocp_nlp_constraints_model_set (ocp_nlp_interface.c:413; field map ocp_nlp_constraints_bgh.c:630-822):
  * stage 0 "lbx"/"ubx" = x0, value [B][nx]; "lh" value [B][K]; "lbu","ubu","uh" and "lbx","ubx" of stages >= 1 are
- * shared by the batch (value [nbu] / [K] / [nbx], host memory) */
+ * shared by the batch (value [nbu] / [K] / [nbx], host memory); so are "lsh", "ush" (value [nsh]) */
 int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field, const double* value,
                                  int on_device, void* stream);
 
-/* replace ocp_nlp_out_set / ocp_nlp_out_get (ocp_nlp_interface.c:452,489): fields x u pi lam t (+ sl su z: empty) */
+/* replace ocp_nlp_out_set / ocp_nlp_out_get (ocp_nlp_interface.c:452,489): fields x u pi lam t sl su (z: empty).
+ * lam / t of a stage: [lbu lbx lh | ubu ubx uh | lsh | ush] with the stage's own counts (acados_ocp_solver.py:732-735) */
 int usvmpc_out_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream);
 int usvmpc_out_get(usvmpc_solver* s, int stage, const char* field, double* value, int on_device, void* stream);
 

@@ -17,7 +17,9 @@ class Config(C.Structure):
                 ("nlp_type", C.c_int), ("max_iter", C.c_int), ("qp_iter_max", C.c_int), ("nbx", C.c_int),
                 ("nbu", C.c_int), ("idxbx", C.c_int * 8), ("dt", C.c_double), ("tol", C.c_double * 4),
                 ("uh", C.c_double), ("lbu", C.c_double * 4), ("ubu", C.c_double * 4), ("lbx", C.c_double * 8),
-                ("ubx", C.c_double * 8), ("W", C.c_double * 256), ("W_e", C.c_double * 256)]
+                ("ubx", C.c_double * 8), ("W", C.c_double * 256), ("W_e", C.c_double * 256), ("nsh", C.c_int),
+                ("lsh", C.c_double * 32), ("ush", C.c_double * 32), ("zl", C.c_double * 32), ("zu", C.c_double * 32),
+                ("Zl", C.c_double * 32), ("Zu", C.c_double * 32)]
 
 
 SYMBOLS = ["usvmpc_last_error", "usvmpc_version", "usvmpc_config_default", "usvmpc_create", "usvmpc_free",

@@ -306,7 +306,7 @@ MDEVNI void chainC_impl(const double* Acl, const double* ee, double* zv, int N, 
     }
 }
 
-template <class M>
+template <class M, bool SOFT>
 struct CtaSolver {
     static constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NY = NV;
     static constexpr int HXV = NU + M::HX, HYV = NU + M::HY;
@@ -316,8 +316,8 @@ struct CtaSolver {
 
     const Params& P;
     int tid, lane, wid, T, W;
-    int N, K, nbu, nbx, ncq, ncz, nbq, nct, s2;
-    FastDiv dq, dnv, dnx;
+    int N, K, nbu, nbx, ncq, ncz, nbq, nct, s2, ns;  // ns: soft rows (the first ns rows of h); 0 unless SOFT
+    FastDiv dq, dnv, dnx, ds2;
     double *sm, *gs, *w;
     // constants in shared memory
     double *Hs, *Hes, *Ws, *Wes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
@@ -332,7 +332,7 @@ struct CtaSolver {
     // IPM state (block-uniform)
     double res_max[4], mu, mu_aff, sigma, alpha;
     double S1, S2;        // sum(lam*dt + t*dlam), sum(dlam*dt) of the last expanded step
-    double lin_d, lin_m;  // residual norms of the linearised inequality / complementarity rows at the last expanded step
+    double lin_d, lin_m, lin_g;  // residual norms of the linearised inequality / complementarity / slack-stationarity rows at the last expanded step
     int solve_calls, lq_count, itref_count, fp32_count;
     bool use_fp32;  // this factorisation runs in fp32 (config 4); cleared for the rest of a QP once its accuracy test fails
 #ifdef USVMPC_PROFILE
@@ -376,6 +376,13 @@ struct CtaSolver {
     MDEV double* d_() const { return fld(F_D); }
     MDEV double* rq_() const { return fld(F_RQ); }
     MDEV double* b_() const { return fld(F_B); }
+    MDEV double* sv_() const { return fld(F_SV); }
+    MDEV double* dsv_() const { return fld(F_DSV); }
+    MDEV double* rgs_() const { return fld(F_RGS); }
+    MDEV double* zsi_() const { return fld(F_ZSI); }
+    MDEV double* rqs_() const { return fld(F_RQS); }
+    MDEV double* dsv2_() const { return fld(F_DSV2); }
+    MDEV double* rgs2_() const { return fld(F_RGS2); }
     MDEV double* rg2_() const { return fld(F_RG2); }
     MDEV double* rb2_() const { return fld(F_RB2); }
     MDEV double* rd2_() const { return fld(F_RD2); }
@@ -388,9 +395,11 @@ struct CtaSolver {
     MDEV CtaSolver(const Params& p, double* smem, double* gscratch) : P(p), sm(smem), gs(gscratch)
     {
         tid = thread_id(); lane = tid & 31; wid = tid >> 5; T = block_threads(); W = T >> 5;
-        N = P.N; K = P.K; nbu = P.nbu; nbx = P.nbx; ncq = P.ncq; ncz = P.ncz; nbq = nbu + nbx; s2 = 2 * ncq;
-        nct = N >= 1 ? 2 * ((nbu + K) + (N - 1) * (nbu + nbx + K)) : 0;
-        dq.set(ncq); dnv.set(NV); dnx.set(NX);
+        N = P.N; K = P.K; nbu = P.nbu; nbx = P.nbx; ncq = P.ncq; ncz = P.ncz; nbq = nbu + nbx;
+        ns = SOFT ? P.ns : 0;
+        s2 = 2 * ncq + 2 * ns;
+        nct = N >= 1 ? 2 * ((nbu + K + ns) + (N - 1) * (nbu + nbx + K + ns)) : 0;
+        dq.set(ncq); dnv.set(NV); dnx.set(NX); ds2.set(s2);
         double* c = sm + P.plan.const_off;
         Hs = c; c += NV * NV; Hes = c; c += NV * NV; Ws = c; c += NV * NV; Wes = c; c += NX * NX; Tp = c;
         red = sm + P.plan.red_off;
@@ -415,6 +424,20 @@ struct CtaSolver {
     MDEV double* Z(const Field& f, int k) const { return w + f.off + (long) k * f.stride; }
     MDEV bool var_active(int k, int i) const { return k == 0 ? (i < NU) : (k == N ? (i >= NU) : true); }
     MDEV bool row_active(int k, int j) const { return k < N && (j < nbu || j >= nbq || k >= 1); }
+    // element e of a row array -> stage k; is the row live?  (lower side | upper side | slack-bound rows)
+    MDEV bool elem_active(int e, int& k) const
+    {
+        k = ds2.div(e);
+        int j = e - k * s2;
+        if (j >= 2 * ncq) return k < N;
+        if (j >= ncq) j -= ncq;
+        return row_active(k, j);
+    }
+    // soft row?  (h row c = j - nbq < ns)  -> slack index or -1
+    MDEV int soft_index(int j) const { return (SOFT && j >= nbq && j - nbq < ns) ? j - nbq : -1; }
+    // slack penalties of slack `is`, scaled like the stage cost (ocp_nlp_cost_ls.c:733,826-841): side 0 lower, 1 upper
+    MDEV double zlin(int is, int side) const { return P.dt * P.zs[side * ns + is]; }
+    MDEV double zquad(int is, int side) const { return P.dt * P.zs[(2 + side) * ns + is]; }
     // IPM row of the box on variable c at stage k, or -1
     MDEV int vrow(int k, int c) const
     {
@@ -527,7 +550,8 @@ struct CtaSolver {
             double* p = Z(P.lay.zpi, k);
             for (int i = 0; i < NX; i++) p[i] = 0.0;
             double* l = Z(P.lay.zlam, k); double* tt = Z(P.lay.zt, k);
-            for (int j = 0; j < 2 * ncz; j++) { l[j] = 0.0; tt[j] = 0.0; }
+            for (int j = 0; j < 2 * ncz + 2 * ns; j++) { l[j] = 0.0; tt[j] = 0.0; }
+            if (SOFT) { double* zs = Z(P.lay.zsv, k); for (int j = 0; j < 2 * ns; j++) zs[j] = 0.0; }
         }
         syncthreads();
     }
@@ -677,7 +701,7 @@ struct CtaSolver {
 #pragma unroll
             for (int i = 0; i < NV; i++) adj[i] = 0.0;
             // ---- BGH constraints (ocp_nlp_constraints_bgh.c:1228-1430): fun = [lb - g ; g - ub], adj = J'(lam_l - lam_u)
-            for (int j = 0; j < 2 * ncz; j++) zf[j] = 0.0;
+            for (int j = 0; j < 2 * ncz + 2 * ns; j++) zf[j] = 0.0;
             for (int j = 0; j < s2; j++) dk[j] = 0.0;
             double dx0[NX];
 #pragma unroll
@@ -739,8 +763,30 @@ struct CtaSolver {
                     const double h = dsqrt(ddx * ddx + ddy * ddy);
                     const double gX = ddx / h, gY = ddy / h;
                     gk[c] = gX; gk[K + c] = gY;
-                    const double fl = lhk[c] - h, fu = h - P.uh[k * K + c];
+                    double fl = lhk[c] - h, fu = h - P.uh[k * K + c];
                     const int r = nbu + NX + c, rqp = nbq + c;
+                    if (SOFT && c < ns)
+                    {
+                        // soft row (ocp_nlp_constraints_bgh.c:1404-1427, ocp_nlp_cost_ls.c:826-841): the slacks enter the row, have
+                        // their own bound rows fun = bound - slack, cost gradient scaling (z + Z s) and adjoint lam_row + lam_bound
+                        const double* zs = Z(P.lay.zsv, k);
+#pragma unroll
+                        for (int side = 0; side < 2; side++)
+                        {
+                            const double sj = zs[side * ns + c];
+                            if (side) fu -= sj; else fl -= sj;
+                            const int rs = 2 * ncz + side * ns + c;
+                            const double fs = (side ? P.ush[k * ns + c] : P.lsh[k * ns + c]) - sj;
+                            zf[rs] = fs;
+                            dk[2 * ncq + side * ns + c] = fs;
+                            const double cgs = P.dt * (P.zs[side * ns + c] + P.zs[(2 + side) * ns + c] * sj);
+                            rqs_()[k * 2 * ns + side * ns + c] = cgs;
+                            const double adjs = zl[side * ncz + r] + zl[rs];
+                            double a = dabs(cgs - adjs); r0 = a > r0 ? a : r0;
+                            a = dabs(fs + zt[rs]); r2 = a > r2 ? a : r2;
+                            a = dabs(zl[rs] * zt[rs]); r3 = a > r3 ? a : r3;
+                        }
+                    }
                     zf[r] = fl; zf[ncz + r] = fu;
                     // stage 0: fold the eliminated x0 step into the bounds (x_ocp_qp_red.c:380-420)
                     const double v = (k == 0) ? gX * dx0[M::HX] + gY * dx0[M::HY] : 0.0;
@@ -833,6 +879,22 @@ struct CtaSolver {
                 for (int i = 0; i < NX; i++) bq[i] = 0.0;
                 for (int j = 0; j < s2; j++) { c[j] = 0.0; e[j] = 0.0; }
             }
+            if (SOFT)
+            {
+                // slack variables start at zero, lifted onto their lower bound + thr0 where needed (x_ocp_qp_ipm.c:1610-1626)
+                double* sv = sv_() + k * 2 * ns; double* dsv = dsv_() + k * 2 * ns;
+                for (int j = 0; j < 2 * ns; j++)
+                {
+                    double sj = 0.0;
+                    if (k < N)
+                    {
+                        double ts = sj - dk[2 * ncq + j];
+                        if (ts < thr0) { ts = thr0; sj = dk[2 * ncq + j] + ts; }
+                        tt[2 * ncq + j] = ts;
+                    }
+                    sv[j] = sj; dsv[j] = 0.0;
+                }
+            }
             if (k >= N) continue;
             for (int j = 0; j < nbq; j++)
             {
@@ -851,12 +913,15 @@ struct CtaSolver {
             for (int c = 0; c < K; c++)
             {
                 const double vv = (k >= 1) ? gk[c] * v[HXV] + gk[K + c] * v[HYV] : 0.0;
-                const double tl = vv - dk[nbq + c], tu = -vv - dk[ncq + nbq + c];
+                const int is = soft_index(nbq + c);
+                const double sl = is >= 0 ? sv_()[k * 2 * ns + is] : 0.0, su = is >= 0 ? sv_()[k * 2 * ns + ns + is] : 0.0;
+                const double tl = (vv + sl) - dk[nbq + c], tu = (-vv + su) - dk[ncq + nbq + c];
                 tt[nbq + c] = thr0 > tl ? thr0 : tl;
                 tt[ncq + nbq + c] = thr0 > tu ? thr0 : tu;
             }
             for (int j = 0; j < ncq; j++)
                 if (row_active(k, j)) { l[j] = mu0 / tt[j]; l[ncq + j] = mu0 / tt[ncq + j]; }
+            for (int j = 2 * ncq; j < s2; j++) l[j] = mu0 / tt[j];
         }
         syncthreads();
     }
@@ -871,11 +936,11 @@ struct CtaSolver {
         // ---- A1: variable update, element-parallel
         for (int e = tid; e < (N + 1) * NV; e += T) ux_()[e] += a * dux_()[e];
         for (int e = tid; e < N * NX; e += T) pi_()[e] += a * dpi_()[e];
+        if (SOFT) for (int e = tid; e < N * 2 * ns; e += T) sv_()[e] += a * dsv_()[e];
         for (int e = tid; e < N * s2; e += T)
         {
-            const int k = dq.div(e) >> 1;          // e / (2 ncq)
-            int j = e - k * s2; if (j >= ncq) j -= ncq;
-            if (!row_active(k, j)) continue;
+            int k;
+            if (!elem_active(e, k)) continue;
             double x = lam_()[e] + a * dlam_()[e];
             lam_()[e] = x <= lam_min ? lam_min : x;
             x = t_()[e] + a * dt_()[e];
@@ -895,7 +960,9 @@ struct CtaSolver {
             if (j < nbq) vv = v[srvar[j]];
             else vv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
             const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1];
-            const double rd0 = d_()[r0] + t0 - vv, rd1 = d_()[r1] + t1 + vv;
+            const int is = soft_index(j);
+            double rd0 = d_()[r0] + t0 - vv, rd1 = d_()[r1] + t1 + vv;
+            if (is >= 0) { rd0 -= sv_()[k * 2 * ns + is]; rd1 -= sv_()[k * 2 * ns + ns + is]; }  // soft row: the slack enters the row
             rd_()[r0] = rd0; rd_()[r1] = rd1;
             const double m0 = l0 * t0, m1 = l1 * t1;
             musum += m0; musum += m1;
@@ -903,9 +970,41 @@ struct CtaSolver {
             q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
             const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
             ti_()[r0] = ti0; ti_()[r1] = ti1;
+            double G0 = ti0 * l0, G1 = ti1 * l1;
+            double g0 = ti0 * ((m0 - tau) - l0 * rd0), g1 = ti1 * ((m1 - tau) - l1 * rd1);
+            if (is >= 0)
+            {
+                // the row's two slack variables and their bound rows: residuals (x_ocp_qp_res.c:416-438), Gamma / gamma, and
+                // the elimination of the slacks COND_SLACKS_FACT_SOLVE (x_ocp_qp_kkt.c:220-291)
+#pragma unroll
+                for (int side = 0; side < 2; side++)
+                {
+                    const int rs = k * s2 + 2 * ncq + side * ns + is, si = k * 2 * ns + side * ns + is;
+                    const double ls = lam_()[rs], ts = t_()[rs], sj = sv_()[si];
+                    const double rds = d_()[rs] + ts - sj, ms = ls * ts;
+                    rd_()[rs] = rds;
+                    musum += ms;
+                    q = dabs(ms); n3 = q > n3 ? q : n3;
+                    q = dabs(rds); n2 = q > n2 ? q : n2;
+                    const double tis = 1.0 / ts;
+                    ti_()[rs] = tis;
+                    const double Gsl = tis * ls, gsl = tis * ((ms - tau) - ls * rds);
+                    const double Z = zquad(is, side);
+                    const double rgs = Z * sj + rqs_()[si] - ls - (side ? l1 : l0);
+                    rgs_()[si] = rgs;
+                    q = dabs(rgs); n0 = q > n0 ? q : n0;
+                    const double Gr = side ? G1 : G0, gr = side ? g1 : g0;
+                    const double zi = 1.0 / (Z + 1e-15 + Gr + Gsl);
+                    zsi_()[si] = zi;
+                    const double rhs = rgs + gr + gsl;
+                    dsv_()[si] = rhs;
+                    const double tmp = rhs * zi;
+                    if (side) { G1 = Gr - Gr * zi * Gr; g1 = gr - Gr * tmp; } else { G0 = Gr - Gr * zi * Gr; g0 = gr - Gr * tmp; }
+                }
+            }
             dlam_()[r0] = l1 - l0;
-            dlam_()[r1] = ti0 * l0 + ti1 * l1;
-            dt_()[r0] = ti0 * ((m0 - tau) - l0 * rd0) - ti1 * ((m1 - tau) - l1 * rd1);
+            dlam_()[r1] = G0 + G1;
+            dt_()[r0] = g0 - g1;
         }
         // ---- res_b = b + [B A] ux - x_{k+1}, one (stage, state) per thread
         for (int it = tid; it < N * NX; it += T)
@@ -1002,8 +1101,25 @@ struct CtaSolver {
                 auto row_terms = [&](int r0, double& Gs, double& gd) {
                     const int r1 = r0 + ncq;
                     const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1], i0 = ti_()[r0], i1 = ti_()[r1];
-                    Gs = i0 * l0 + i1 * l1;
-                    gd = i0 * ((l0 * t0 - tau) - l0 * rd_()[r0]) - i1 * ((l1 * t1 - tau) - l1 * rd_()[r1]);
+                    double G[2] = {i0 * l0, i1 * l1};
+                    double g[2] = {i0 * ((l0 * t0 - tau) - l0 * rd_()[r0]), i1 * ((l1 * t1 - tau) - l1 * rd_()[r1])};
+                    const int is = soft_index(r0 - k * s2);
+                    if (is >= 0)
+                    {
+#pragma unroll
+                        for (int side = 0; side < 2; side++)
+                        {
+                            const int rs = k * s2 + 2 * ncq + side * ns + is, si = k * 2 * ns + side * ns + is;
+                            const double ls = lam_()[rs], ts = t_()[rs], tis = ti_()[rs];
+                            const double Gsl = tis * ls, gsl = tis * ((ls * ts - tau) - ls * rd_()[rs]);
+                            const double zi = zsi_()[si], tmp = (rgs_()[si] + g[side] + gsl) * zi, Gr = G[side];
+                            (void) Gsl;
+                            G[side] = Gr - Gr * zi * Gr;
+                            g[side] = g[side] - Gr * tmp;
+                        }
+                    }
+                    Gs = G[0] + G[1];
+                    gd = g[0] - g[1];
                 };
                 const int row = vrow(k, i);
                 if (row >= 0) { double Gs, gd; row_terms(k * s2 + row, Gs, gd); dg += Gs; gg += gd; }
@@ -1250,7 +1366,37 @@ struct CtaSolver {
                 m0 -= sigma_mu; m1 -= sigma_mu;
                 rmc_()[r0] = m0; rmc_()[r1] = m1;
             }
-            gsc[r0] = ti_()[r0] * (m0 - l0 * rdp[r0]) - ti_()[r1] * (m1 - l1 * rdp[r1]);
+            double g0 = ti_()[r0] * (m0 - l0 * rdp[r0]), g1 = ti_()[r1] * (m1 - l1 * rdp[r1]);
+            const int is = soft_index(j);
+            if (is >= 0)
+            {
+                // COND_SLACKS_SOLVE (x_ocp_qp_kkt.c:295-353): gamma of the slack-bound rows, right-hand side of the slack
+                // variables, gamma of the row with the slacks eliminated
+                const double* rgsp = mode == 2 ? rgs2_() : rgs_();
+                double* dso = mode == 2 ? dsv2_() : dsv_();
+#pragma unroll
+                for (int side = 0; side < 2; side++)
+                {
+                    const int rs = k * s2 + 2 * ncq + side * ns + is, si = k * 2 * ns + side * ns + is;
+                    const double ls = lam_()[rs];
+                    double ms;
+                    if (mode == 2) ms = rm2_()[rs];
+                    else
+                    {
+                        ms = ls * t_()[rs];
+                        if (mode == 0) ms += dt_()[rs] * dlam_()[rs];
+                        ms -= sigma_mu;
+                        rmc_()[rs] = ms;
+                    }
+                    const double gsl = ti_()[rs] * (ms - ls * rdp[rs]);
+                    const double gr = side ? g1 : g0, Gr = side ? ti_()[r1] * l1 : ti_()[r0] * l0;
+                    const double rhs = rgsp[si] + gr + gsl;
+                    dso[si] = rhs;
+                    const double tmp = rhs * zsi_()[si];
+                    if (side) g1 = gr - Gr * tmp; else g0 = gr - Gr * tmp;
+                }
+            }
+            gsc[r0] = g0 - g1;
         }
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
@@ -1322,7 +1468,27 @@ struct CtaSolver {
             vo[k * NV + m] = k < N ? acc : 0.0;
         }
         syncthreads();
-        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2s = 0.0, nd = 0.0, nm = 0.0;
+        double bdn = 1.0, bdd = -1.0, bpn = 1.0, bpd = -1.0, s1 = 0.0, s2s = 0.0, nd = 0.0, nm = 0.0, ng = 0.0;
+        // one inequality row: dlam, dt from the row's expanded step `dtr` (J dux, + slack step on a soft row), step-length
+        // candidates, mu_aff sums, linear-system residual of the row (`lin` = the part of the row's equation that is not dt)
+        auto do_row = [&](int r, double dtr, double lin) -> double {
+            const double lam0 = lam_()[r], t0 = t_()[r], e0 = rdp[r];
+            const double m = mode == 0 ? lam0 * t0 - tau : rmp[r];
+            const double dlr = -ti_()[r] * (m + (lam0 * dtr) - (lam0 * e0));
+            dtr -= e0;
+            dlo[r] = dlr; dto[r] = dtr;
+            // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best is
+            // kept as (numerator, denominator) and compared by cross-multiplication: one division per thread
+            if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
+            if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
+            s1 += lam0 * dtr + t0 * dlr;
+            s2s += dlr * dtr;
+            const double e = e0 + dtr - lin;
+            const double mm = m + lam0 * dtr + dlr * t0;
+            double q = dabs(e); nd = q > nd ? q : nd;
+            q = dabs(mm); nm = q > nm ? q : nm;
+            return dlr;
+        };
         for (int it = tid; it < N * ncq; it += T)
         {
             const int k = dq.div(it), j = it - k * ncq;
@@ -1331,26 +1497,29 @@ struct CtaSolver {
             double dv;
             if (j < nbq) dv = v[srvar[j]];
             else dv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
-#pragma unroll
-            for (int side = 0; side < 2; side++)
+            const int r0 = k * s2 + j, r1 = r0 + ncq;
+            const int is = soft_index(j);
+            if (is < 0)
             {
-                const int r = k * s2 + j + side * ncq;
-                double dtr = side ? -dv : dv;
-                const double lam0 = lam_()[r], t0 = t_()[r], e0 = rdp[r];
-                const double m = mode == 0 ? lam0 * t0 - tau : rmp[r];
-                const double dlr = -ti_()[r] * (m + (lam0 * dtr) - (lam0 * e0));
-                dtr -= e0;
-                dlo[r] = dlr; dto[r] = dtr;
-                // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best is
-                // kept as (numerator, denominator) and compared by cross-multiplication: one division per thread
-                if (dlr < 0.0 && bdn * dlr < lam0 * bdd) { bdn = lam0; bdd = dlr; }
-                if (dtr < 0.0 && bpn * dtr < t0 * bpd) { bpn = t0; bpd = dtr; }
-                s1 += lam0 * dtr + t0 * dlr;
-                s2s += dlr * dtr;
-                const double e = side ? e0 + dtr + dv : e0 + dtr - dv;
-                const double mm = m + lam0 * dtr + dlr * t0;
-                double q = dabs(e); nd = q > nd ? q : nd;
-                q = dabs(mm); nm = q > nm ? q : nm;
+                do_row(r0, dv, dv);
+                do_row(r1, -dv, -dv);
+            }
+            else
+            {
+                // EXPAND_SLACKS (x_ocp_qp_kkt.c:357-400): the slack steps from the row's J dux, then the four rows
+                double* dso = mode == 2 ? dsv2_() : dsv_();
+                const double* rgsp = mode == 2 ? rgs2_() : rgs_();
+                const int s0 = k * 2 * ns + is, s1i = s0 + ns, rs0 = k * s2 + 2 * ncq + is, rs1 = rs0 + ns;
+                const double ds0 = -zsi_()[s0] * (dso[s0] + dv * (ti_()[r0] * lam_()[r0]));
+                const double ds1 = -zsi_()[s1i] * (dso[s1i] + (-dv) * (ti_()[r1] * lam_()[r1]));
+                dso[s0] = ds0; dso[s1i] = ds1;
+                const double dl0 = do_row(r0, dv + ds0, dv + ds0);
+                const double dl1 = do_row(r1, -dv + ds1, -dv + ds1);
+                const double dls0 = do_row(rs0, ds0, ds0);
+                const double dls1 = do_row(rs1, ds1, ds1);
+                // stationarity rows of the slacks in the linear system (x_ocp_qp_res.c:540-556)
+                double q = dabs(zquad(is, 0) * ds0 + rgsp[s0] - dls0 - dl0); ng = q > ng ? q : ng;
+                q = dabs(zquad(is, 1) * ds1 + rgsp[s1i] - dls1 - dl1); ng = q > ng ? q : ng;
             }
         }
         // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
@@ -1366,10 +1535,10 @@ struct CtaSolver {
         }
         if (mode != 2)
         {
-            double vm[4] = {bpn / bpd, bdn / bdd, nd, nm}, vs[2] = {s1, s2s};
-            block_reduce<4, 2>(vm, vs);
+            double vm[5] = {bpn / bpd, bdn / bdd, nd, nm, ng}, vs[2] = {s1, s2s};
+            block_reduce<5, 2>(vm, vs);
             alpha = -(vm[0] > vm[1] ? vm[0] : vm[1]);
-            lin_d = vm[2]; lin_m = vm[3];
+            lin_d = vm[2]; lin_m = vm[3]; lin_g = vm[4];
             S1 = vs[0]; S2 = vs[1];
         }
         else syncthreads();
@@ -1435,7 +1604,28 @@ struct CtaSolver {
                 double vv;
                 if (j < nbq) vv = v[srvar[j]];
                 else vv = k >= 1 ? gxy_()[k * 2 * K + j - nbq] * v[HXV] + gxy_()[k * 2 * K + K + j - nbq] * v[HYV] : 0.0;
-                const double e0 = rd_()[r0] + dt_()[r0] - vv, e1 = rd_()[r1] + dt_()[r1] + vv;
+                double e0 = rd_()[r0] + dt_()[r0] - vv, e1 = rd_()[r1] + dt_()[r1] + vv;
+                const int is = soft_index(j);
+                if (is >= 0)
+                {
+                    // soft row: the slack step enters the row; rows of the slack bounds and of the slacks' stationarity
+#pragma unroll
+                    for (int side = 0; side < 2; side++)
+                    {
+                        const int rs = k * s2 + 2 * ncq + side * ns + is, si = k * 2 * ns + side * ns + is;
+                        const double ds = dsv_()[si];
+                        if (side) e1 -= ds; else e0 -= ds;
+                        const double es = rd_()[rs] + dt_()[rs] - ds;
+                        rd2_()[rs] = es;
+                        double q = dabs(es); n2 = q > n2 ? q : n2;
+                        const double ms = rmc_()[rs] + lam_()[rs] * dt_()[rs] + dlam_()[rs] * t_()[rs];
+                        rm2_()[rs] = ms;
+                        q = dabs(ms); n3 = q > n3 ? q : n3;
+                        const double gs = zquad(is, side) * ds + rgs_()[si] - dlam_()[rs] - dlam_()[side ? r1 : r0];
+                        rgs2_()[si] = gs;
+                        q = dabs(gs); n0 = q > n0 ? q : n0;
+                    }
+                }
                 rd2_()[r0] = e0; rd2_()[r1] = e1;
                 double q = dabs(e0); n2 = q > n2 ? q : n2; q = dabs(e1); n2 = q > n2 ? q : n2;
                 const double m0 = rmc_()[r0] + lam_()[r0] * dt_()[r0] + dlam_()[r0] * t_()[r0];
@@ -1446,7 +1636,8 @@ struct CtaSolver {
         }
         double vm[4] = {n0, n1, n2, n3};
         block_reduce<4, 0>(vm, nullptr);
-        out4[0] = vm[0]; out4[1] = vm[1]; out4[2] = WRITE ? vm[2] : lin_d; out4[3] = WRITE ? vm[3] : lin_m;
+        out4[0] = (WRITE || !SOFT) ? vm[0] : (vm[0] > lin_g ? vm[0] : lin_g);
+        out4[1] = vm[1]; out4[2] = WRITE ? vm[2] : lin_d; out4[3] = WRITE ? vm[3] : lin_m;
     }
 
     // COMPUTE_ALPHA_QP on the current step (after iterative refinement changed it)
@@ -1455,9 +1646,8 @@ struct CtaSolver {
         double a_prim = -1.0, a_dual = -1.0;
         for (int it = tid; it < N * s2; it += T)
         {
-            const int k = dq.div(it) >> 1;
-            int j = it - k * s2; if (j >= ncq) j -= ncq;
-            if (!row_active(k, j)) continue;
+            int k;
+            if (!elem_active(it, k)) continue;
             if (a_dual * dlam_()[it] > lam_()[it]) a_dual = lam_()[it] / dlam_()[it];
             if (a_prim * dt_()[it] > t_()[it]) a_prim = t_()[it] / dt_()[it];
         }
@@ -1471,11 +1661,11 @@ struct CtaSolver {
     {
         for (int e = tid; e < (N + 1) * NV; e += T) dux_()[e] += dux2_()[e];
         for (int e = tid; e < N * NX; e += T) dpi_()[e] += dpi2_()[e];
+        if (SOFT) for (int e = tid; e < N * 2 * ns; e += T) dsv_()[e] += dsv2_()[e];
         for (int e = tid; e < N * s2; e += T)
         {
-            const int k = dq.div(e) >> 1;
-            int j = e - k * s2; if (j >= ncq) j -= ncq;
-            if (row_active(k, j)) { dlam_()[e] += dlam2_()[e]; dt_()[e] += dt2_()[e]; }
+            int k;
+            if (elem_active(e, k)) { dlam_()[e] += dlam2_()[e]; dt_()[e] += dt2_()[e]; }
         }
         syncthreads();
     }
@@ -1619,6 +1809,16 @@ struct CtaSolver {
                     const int a = nbu + NX + c, bq = nbq + c;
                     zl[a] = l[bq]; zl[ncz + a] = l[ncq + bq]; zt[a] = tt[bq]; zt[ncz + a] = tt[ncq + bq];
                 }
+                if (SOFT)
+                {
+                    // the QP's slack values are a step like [u; x]; the multipliers / slacks of the slack bounds are the QP's
+                    double* zs = Z(P.lay.zsv, k);
+                    for (int j = 0; j < 2 * ns; j++)
+                    {
+                        zs[j] += sv_()[k * 2 * ns + j];
+                        zl[2 * ncz + j] = l[2 * ncq + j]; zt[2 * ncz + j] = tt[2 * ncq + j];
+                    }
+                }
             }
             if (k == 0)
             {
@@ -1673,10 +1873,10 @@ struct CtaSolver {
         for (int k = tid; k < N; k += T)
         {
             const double* zl = Z(P.lay.zlam, k); const double* zt = Z(P.lay.zt, k); const double* zf = Z(P.lay.zfun, k);
-            for (int j = 0; j < 2 * ncz; j++)
+            for (int j = 0; j < 2 * ncz + 2 * ns; j++)
             {
                 const int jj = j % ncz;
-                const bool act = jj < nbu || jj >= nbu + NX || (k == 0 ? true : jj - nbu < nbx);
+                const bool act = j >= 2 * ncz || jj < nbu || jj >= nbu + NX || (k == 0 ? true : jj - nbu < nbx);
                 if (!act) continue;
                 const double a = dabs(zf[j] + zt[j]), c = dabs(zl[j] * zt[j]);
                 r2 = a > r2 ? a : r2; r3 = c > r3 ? c : r3;
@@ -1818,10 +2018,10 @@ struct CtaSolver {
 };
 
 // The persistent block: pull instances until the queue is drained.
-template <class M>
+template <class M, bool SOFT>
 MDEV void cta_main(const Params& P, double* smem, int block_id)
 {
-    CtaSolver<M> s(P, smem, P.scratch ? P.scratch + (long) block_id * P.plan.scratch_doubles : nullptr);
+    CtaSolver<M, SOFT> s(P, smem, P.scratch ? P.scratch + (long) block_id * P.plan.scratch_doubles : nullptr);
     s.load_constants();
     int* slot = (int*) (smem + P.plan.red_off);  // first reduction buffer doubles as the broadcast slot between solves
     for (;;)

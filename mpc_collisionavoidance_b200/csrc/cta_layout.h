@@ -13,6 +13,8 @@
 //   IPM / QP level  (ncq = nbu + nbx + K): [ u boxes | x boxes (idxbx) | h rows ]
 //   NLP level       (ncz = nbu + NX  + K): [ u boxes | x boxes: NX slots (stage 0 holds the x0 embedding,
 //                                            stages 1..N-1 use the first nbx) | h rows ]
+// Soft rows (the first ns rows of h, each with a lower and an upper slack variable): the lower bounds of the slacks
+// follow both sides as rows [ ls (ns) | us (ns) ], like HPIPM's [lb lg | ub ug | ls | us].
 #pragma once
 
 namespace usvmpc {
@@ -31,7 +33,7 @@ struct Field { int off, stride, es; };  // offset of (stage 0, element 0), stage
 
 // per-instance block in HBM
 struct Layout {
-    Field zux, zpi, zlam, zt, zfun;
+    Field zux, zpi, zlam, zt, zfun, zsv;   // zsv: slack values [sl (ns) | su (ns)] of the NLP iterate
     long total;
 };
 
@@ -40,7 +42,8 @@ struct Layout {
 enum FieldId {
     F_G, F_M, F_ACL, F_KG, F_CC, F_EE, F_PB, F_RB, F_ZV, F_DUX, F_KK, F_DINV,
     F_UX, F_PI, F_LAM, F_T, F_DLAM, F_DT, F_RD, F_RMC, F_RG, F_DPI, F_GXY, F_TI, F_D, F_RQ, F_B,
-    F_RG2, F_RB2, F_RD2, F_RM2, F_DUX2, F_DPI2, F_DLAM2, F_DT2,
+    F_SV, F_DSV, F_RGS, F_ZSI, F_RQS,   // slack variables: values, step (/ condensation right-hand side), res_g, 1/(Z+Gamma..), gradient
+    F_RG2, F_RB2, F_RD2, F_RM2, F_DUX2, F_DPI2, F_DLAM2, F_DT2, F_DSV2, F_RGS2,
     F_COUNT
 };
 constexpr int F_FIRST_FLEX = F_UX;
@@ -67,6 +70,7 @@ struct Params {
     int idxbx[NBXMAX];
     int p_per_stage, lh_per_stage, yref_per_stage, cold_start;
     int ncq, ncz;
+    int ns;                 // soft rows: the first ns rows of h (0: all constraints hard)
     int chain_fp32;         // 1: Riccati factorisation in fp32 (residuals, solves, refinement fp64): BASELINE.json config 4
     int rti_phase;          // 0: prepare + feedback, 1: prepare only, 2: feedback only (ocp_nlp_sqp_rti.c:459-488)
     double dt, tol[4];
@@ -75,6 +79,9 @@ struct Params {
     const double* lbx;      // [N][nbx]   (row 0 unused: stage 0 holds the x0 embedding)
     const double* ubx;      // [N][nbx]
     const double* uh;       // [N][K]
+    const double* lsh;      // [N][ns] lower bounds of the lower / upper slacks (ocp_nlp_constraints_bgh.c:760-790)
+    const double* ush;      // [N][ns]
+    const double* zs;       // [4][ns]: zl, zu, Zl, Zu -- linear and quadratic slack penalties (ocp_nlp_cost_ls.c:826-841)
     const double* cst;      // [W (NY*NY col-major) | W_e (NX*NX col-major)]
     const double* x0;       // [B][NX]
     const double* p;        // [B][N+1][2K] or [B][2K]
@@ -97,28 +104,31 @@ struct Params {
 
 inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
 
-inline Layout make_layout(int nx, int nu, int N, int K)
+inline Layout make_layout(int nx, int nu, int N, int K, int ns = 0)
 {
     Layout L;
     const int N1 = N + 1, nv = nx + nu;
-    const int ncz = nu + nx + K;  // room for nbu <= nu input boxes
+    const int ncz = nu + nx + K + ns;  // room for nbu <= nu input boxes; + the slack-bound rows
     long o = 0;
     auto put = [&](Field& f, int stride) { f.off = (int) o; f.stride = stride; f.es = 1; o += (long) stride * N1; };
     put(L.zux, round_up(nv, 2)); put(L.zpi, round_up(nx, 2));
     put(L.zlam, round_up(2 * ncz, 2)); put(L.zt, round_up(2 * ncz, 2)); put(L.zfun, round_up(2 * ncz, 2));
+    put(L.zsv, round_up(2 * ns, 2) > 0 ? round_up(2 * ns, 2) : 2);
     L.total = (o + 15) / 16 * 16;  // 128-byte multiple
     return L;
 }
 
 // stage strides of the working-set fields
-inline void field_dims(int nx, int nu, int K, int nbx, int nbu, int* dim)
+inline void field_dims(int nx, int nu, int K, int nbx, int nbu, int ns, int* dim)
 {
-    const int nv = nx + nu, ne = nv * (nv + 1) / 2 + nv, r2 = 2 * (nbu + nbx + K);
+    const int nv = nx + nu, ne = nv * (nv + 1) / 2 + nv, r2 = 2 * (nbu + nbx + K) + 2 * ns;
     dim[F_G] = nv * nx; dim[F_M] = ne; dim[F_ACL] = nx * nx; dim[F_KG] = nu * nx; dim[F_CC] = nx; dim[F_EE] = nx;
     dim[F_PB] = nx; dim[F_RB] = nx; dim[F_ZV] = nv; dim[F_DUX] = nv; dim[F_KK] = nu; dim[F_DINV] = nu;
     dim[F_UX] = nv; dim[F_PI] = nx; dim[F_LAM] = r2; dim[F_T] = r2; dim[F_DLAM] = r2; dim[F_DT] = r2; dim[F_RD] = r2;
     dim[F_RMC] = r2; dim[F_RG] = nv; dim[F_DPI] = nx; dim[F_GXY] = 2 * K; dim[F_TI] = r2; dim[F_D] = r2; dim[F_RQ] = nv;
     dim[F_B] = nx;
+    dim[F_SV] = 2 * ns; dim[F_DSV] = 2 * ns; dim[F_RGS] = 2 * ns; dim[F_ZSI] = 2 * ns; dim[F_RQS] = 2 * ns;
+    dim[F_DSV2] = 2 * ns; dim[F_RGS2] = 2 * ns;
     dim[F_RG2] = nv; dim[F_RB2] = nx; dim[F_RD2] = r2; dim[F_RM2] = r2; dim[F_DUX2] = nv; dim[F_DPI2] = nx;
     dim[F_DLAM2] = r2; dim[F_DT2] = r2;
 }
@@ -126,12 +136,12 @@ inline void field_dims(int nx, int nu, int K, int nbx, int nbu, int* dim)
 // Place the working set: chain fields and constants in shared memory, then the pass fields in priority order while
 // they fit `smem_budget` bytes; the rest goes to the block's global scratch.  Returns false if even the chain fields
 // do not fit.
-inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int warps, long smem_budget, Plan* out)
+inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int ns, int warps, long smem_budget, Plan* out)
 {
     Plan P;
     const int N1 = N + 1, nv = nx + nu, ne = nv * (nv + 1) / 2 + nv;
     int dim[F_COUNT];
-    field_dims(nx, nu, K, nbx, nbu, dim);
+    field_dims(nx, nu, K, nbx, nbu, ns, dim);
     long o = 0;
     P.const_off = (int) o;
     o += 2 * nv * nv + nv * nv + nx * nx + 3 * ne;      // Hs, Hes, Ws, Wes, Tp

@@ -8,6 +8,9 @@
 //            NM/scripts/usv_position_control/usv_model.py:61-77,116-128 with the thrust-rate states
 //            removed; obstacle distance h_i = ||(X,Y)-(ox_i,oy_i)|| of
 //            NM/scripts/usv_pf_ca/usv_model.py:165-168.
+//  Usv8Ca1   guidance model of the deployed collision-avoidance node, x=[u,v,ye,chie,psied,xned,yned,psi],
+//            u=[Upsieddot]: NM/scripts/usv_guidance_ca1/usv_model.py:65-128 (T1 = 1, beta = atan2(v, u + 0.001)); the
+//            obstacle distances use (xned, yned).
 //  Pendulum  cart-pole of the reference's own golden-vector tests
 //            (AC/examples/acados_python/getting_started/common/export_pendulum_ode_model.py:37-94).
 //
@@ -115,6 +118,91 @@ struct Usv3 {
         ks[3] = ((b3 + J33 * s[3]) + J34 * s[4]) + J35 * s[5];
         ks[4] = ((J43 * s[3]) + J44 * s[4]) + J45 * s[5];
         ks[5] = ((b5 + J53 * s[3]) + J54 * s[4]) + J55 * s[5];
+    }
+};
+
+DEV double datan2(double y, double x) { return atan2(y, x); }
+
+struct Usv8Ca1 {
+    static constexpr int ID = 2;
+    static constexpr int NX = 8, NU = 1;
+    static constexpr int HX = 5, HY = 6;  // NED position states entering the obstacle distance
+    static constexpr int NKIN = 0;        // (states that do not enter the dynamics are not leading here: integrate every column)
+
+    MDEV static void f_jac(const double* x, const double* uc, double* f, double* Jx, double* Ju)
+    {
+        const double T1 = 1.0;
+        const double u = x[0], v = x[1], chie = x[3], psied = x[4], psi = x[7];
+        const double ue = u + 0.001;
+        const double beta = datan2(v, ue);
+        const double psie = chie - beta;
+        double se, ce, sp, cp;
+        dsincos(psie, &se, &ce);
+        dsincos(psi, &sp, &cp);
+        f[0] = 0.0;
+        f[1] = 0.0;
+        f[2] = u * se + v * ce;
+        f[3] = (psied - psie) / T1;
+        f[4] = uc[0];
+        f[5] = u * cp - v * sp;
+        f[6] = u * sp + v * cp;
+        f[7] = (psied - psie) / T1;
+        const double den = ue * ue + v * v;
+        const double db_du = -v / den, db_dv = ue / den;  // d atan2(v, u + 0.001)
+        const double w = u * ce - v * se;                 // d f2 / d psie
+#pragma unroll
+        for (int i = 0; i < 64; i++) Jx[i] = 0.0;
+        Jx[2 + 8 * 0] = se - w * db_du;
+        Jx[2 + 8 * 1] = ce - w * db_dv;
+        Jx[2 + 8 * 3] = w;
+        Jx[3 + 8 * 0] = db_du / T1;
+        Jx[3 + 8 * 1] = db_dv / T1;
+        Jx[3 + 8 * 3] = -1.0 / T1;
+        Jx[3 + 8 * 4] = 1.0 / T1;
+        Jx[5 + 8 * 0] = cp;  Jx[5 + 8 * 1] = -sp;  Jx[5 + 8 * 7] = -u * sp - v * cp;
+        Jx[6 + 8 * 0] = sp;  Jx[6 + 8 * 1] = cp;   Jx[6 + 8 * 7] = u * cp - v * sp;
+        Jx[7 + 8 * 0] = db_du / T1;
+        Jx[7 + 8 * 1] = db_dv / T1;
+        Jx[7 + 8 * 3] = -1.0 / T1;
+        Jx[7 + 8 * 4] = 1.0 / T1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) Ju[i] = 0.0;
+        Ju[4] = 1.0;
+    }
+
+    // one column of the variational equation (see Usv3::vde_col), using the sparsity of the Jacobian
+    MDEV static void vde_col(const double* x, const double* uc, const double* s, int ucol, double* f, double* ks)
+    {
+        const double T1 = 1.0;
+        const double u = x[0], v = x[1], chie = x[3], psied = x[4], psi = x[7];
+        const double ue = u + 0.001;
+        const double beta = datan2(v, ue);
+        const double psie = chie - beta;
+        double se, ce, sp, cp;
+        dsincos(psie, &se, &ce);
+        dsincos(psi, &sp, &cp);
+        f[0] = 0.0;
+        f[1] = 0.0;
+        f[2] = u * se + v * ce;
+        f[3] = (psied - psie) / T1;
+        f[4] = uc[0];
+        f[5] = u * cp - v * sp;
+        f[6] = u * sp + v * cp;
+        f[7] = (psied - psie) / T1;
+        const double den = ue * ue + v * v;
+        const double db_du = -v / den, db_dv = ue / den;
+        const double w = u * ce - v * se;
+        const double J20 = se - w * db_du, J21 = ce - w * db_dv, J30 = db_du / T1, J31 = db_dv / T1;
+        const double J57 = -u * sp - v * cp, J67 = u * cp - v * sp;
+        // the same terms in the same (column) order as the dense product Jx s (+ Ju)
+        ks[0] = 0.0;
+        ks[1] = 0.0;
+        ks[2] = (J20 * s[0] + J21 * s[1]) + w * s[3];
+        ks[3] = ((J30 * s[0] + J31 * s[1]) + (-1.0 / T1) * s[3]) + (1.0 / T1) * s[4];
+        ks[4] = ucol == 0 ? 1.0 : 0.0;
+        ks[5] = (cp * s[0] + (-sp) * s[1]) + J57 * s[7];
+        ks[6] = (sp * s[0] + cp * s[1]) + J67 * s[7];
+        ks[7] = ((J30 * s[0] + J31 * s[1]) + (-1.0 / T1) * s[3]) + (1.0 / T1) * s[4];
     }
 };
 

@@ -43,11 +43,11 @@ int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(USVMPC_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-template <class M>
+template <class M, bool SOFT>
 __global__ void __launch_bounds__(THREADS, USVMPC_MIN_CTAS) nmpc_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ double smem[];
-    cta_main<M>(P, smem, blockIdx.x);
+    cta_main<M, SOFT>(P, smem, blockIdx.x);
 }
 
 // Longest-processing-time-first order of the work queue: instances sorted by decreasing IPM iteration count of the
@@ -98,18 +98,23 @@ __global__ void ws_copy_kernel(double* ws, long stride, int off, int fstride, in
 
 // multipliers / slacks of one stage between the engine's NLP row layout (layout.h) and the reference's order
 // [lbu lbx lh | ubu ubx uh] with the stage's own counts (acados_template/acados_ocp_solver.py:732-735)
-__global__ void ws_rows_kernel(double* ws, long stride, int off, int ncz, int nbu, int nxslots, int nbxk, int K, int B,
+__global__ void ws_rows_kernel(double* ws, long stride, int off, int ncz, int nbu, int nxslots, int nbxk, int K, int ns, int B,
                                double* buf, int to_ws)
 {
-    const int nck = nbu + nbxk + K;
-    const long n = (long) B * 2 * nck;
+    const int nck = nbu + nbxk + K, w = 2 * nck + 2 * ns;   // [lbu lbx lh | ubu ubx uh | lsh | ush]
+    const long n = (long) B * w;
     for (long idx = blockIdx.x * (long) blockDim.x + threadIdx.x; idx < n; idx += (long) gridDim.x * blockDim.x)
     {
-        const int j = (int) (idx % (2 * nck));
-        const long b = idx / (2 * nck);
-        const int side = j / nck, jj = j % nck;
-        const int src = jj < nbu + nbxk ? jj : nbu + nxslots + (jj - nbu - nbxk);
-        double* a = ws + b * stride + off + side * ncz + src;
+        const int j = (int) (idx % w);
+        const long b = idx / w;
+        int pos;
+        if (j >= 2 * nck) pos = 2 * ncz + (j - 2 * nck);
+        else
+        {
+            const int side = j / nck, jj = j % nck;
+            pos = side * ncz + (jj < nbu + nbxk ? jj : nbu + nxslots + (jj - nbu - nbxk));
+        }
+        double* a = ws + b * stride + off + pos;
         if (to_ws) *a = buf[idx]; else buf[idx] = *a;
     }
 }
@@ -220,7 +225,7 @@ struct usvmpc_solver
     double *d_ws, *d_stats, *d_cst, *d_x0, *d_yref_e, *d_scratch, *d_prep;
     double *d_bnd;                         // per-stage bounds shared by the batch: lbu | ubu | lbx | ubx | uh
     double *h_bnd;                         // host mirror of d_bnd
-    int o_lbu, o_ubu, o_lbx, o_ubx, o_uh, n_bnd;
+    int o_lbu, o_ubu, o_lbx, o_ubx, o_uh, o_lsh, o_ush, o_zs, n_bnd;
     int* d_queue;
     int* d_order;                          // longest-first queue order from the previous solve
     int have_history, lpt;
@@ -238,6 +243,7 @@ int model_dims(int model, int* nx, int* nu)
 {
     if (model == USVMPC_MODEL_USV3) { *nx = Usv3::NX; *nu = Usv3::NU; return 0; }
     if (model == USVMPC_MODEL_PENDULUM) { *nx = Pendulum::NX; *nu = Pendulum::NU; return 0; }
+    if (model == USVMPC_MODEL_GUIDANCE_CA1) { *nx = Usv8Ca1::NX; *nu = Usv8Ca1::NU; return 0; }
     return -1;
 }
 
@@ -266,11 +272,11 @@ void refresh_params(usvmpc_solver* s)
     P.B = s->B; P.N = c.N; P.K = c.K; P.num_steps = c.num_steps; P.num_stages = c.num_stages; P.nlp_type = c.nlp_type;
     P.max_iter = c.max_iter; P.qp_iter_max = c.qp_iter_max; P.nbx = c.nbx; P.nbu = c.nbu;
     for (int i = 0; i < NBXMAX; i++) P.idxbx[i] = c.idxbx[i];
-    P.ncq = c.nbu + c.nbx + c.K; P.ncz = c.nbu + s->nx + c.K;
+    P.ncq = c.nbu + c.nbx + c.K; P.ncz = c.nbu + s->nx + c.K; P.ns = c.nsh;
     P.dt = c.dt;
     for (int i = 0; i < 4; i++) P.tol[i] = c.tol[i];
     P.lbu = s->d_bnd + s->o_lbu; P.ubu = s->d_bnd + s->o_ubu; P.lbx = s->d_bnd + s->o_lbx; P.ubx = s->d_bnd + s->o_ubx;
-    P.uh = s->d_bnd + s->o_uh;
+    P.uh = s->d_bnd + s->o_uh; P.lsh = s->d_bnd + s->o_lsh; P.ush = s->d_bnd + s->o_ush; P.zs = s->d_bnd + s->o_zs;
     P.cst = s->d_cst; P.x0 = s->d_x0; P.yref_e = s->d_yref_e;
     P.p = s->d_p[P.p_per_stage]; P.lh = s->d_lh[P.lh_per_stage]; P.yref = s->d_yref[P.yref_per_stage];
     P.ws = s->d_ws; P.stats = s->d_stats; P.scratch = s->d_scratch; P.queue = s->d_queue; P.prep = s->d_prep;
@@ -345,6 +351,8 @@ int out_field(usvmpc_solver* s, const char* field, Field* f, int* c0, int* dim, 
     if (!strcmp(field, "x")) { *f = Y.zux; *c0 = s->nu; *dim = s->nx; *nst = s->cfg.N + 1; return 0; }
     if (!strcmp(field, "u")) { *f = Y.zux; *c0 = 0; *dim = s->nu; *nst = s->cfg.N; return 0; }
     if (!strcmp(field, "pi")) { *f = Y.zpi; *c0 = 0; *dim = s->nx; *nst = s->cfg.N; return 0; }
+    if (s->cfg.nsh > 0 && !strcmp(field, "sl")) { *f = Y.zsv; *c0 = 0; *dim = s->cfg.nsh; *nst = s->cfg.N; return 0; }
+    if (s->cfg.nsh > 0 && !strcmp(field, "su")) { *f = Y.zsv; *c0 = s->cfg.nsh; *dim = s->cfg.nsh; *nst = s->cfg.N; return 0; }
     return -1;
 }
 
@@ -384,10 +392,10 @@ int out_copy(usvmpc_solver* s, int stage, const char* field, double* value, int 
         if (stage < 0 || stage > N) return fail(USVMPC_E_INVALID, "field %s needs a stage in [0,%d]", field, N);
         const int nbxk = stage == 0 ? s->nx : (stage < N ? s->cfg.nbx : 0);
         const int nbuk = stage < N ? s->cfg.nbu : 0, Kk = stage < N ? s->cfg.K : 0;
-        const int nck = nbuk + nbxk + Kk;
+        const int nck = nbuk + nbxk + Kk, nsk = stage < N ? s->cfg.nsh : 0;
         if (nck == 0) return 0;
         const Field& fl = !strcmp(field, "lam") ? s->P.lay.zlam : s->P.lay.zt;
-        const size_t bytes = sizeof(double) * (size_t) B * 2 * nck;
+        const size_t bytes = sizeof(double) * (size_t) B * (2 * nck + 2 * nsk);
         double* buf = value;
         if (!on_device)
         {
@@ -396,8 +404,8 @@ int out_copy(usvmpc_solver* s, int stage, const char* field, double* value, int 
             buf = s->d_stage;
             if (to_ws) CU(cudaMemcpyAsync(buf, value, bytes, cudaMemcpyHostToDevice, st));
         }
-        ws_rows_kernel<<<grid_for((long) B * 2 * nck), 256, 0, st>>>(s->d_ws, s->P.ws_stride, fl.off + stage * fl.stride, s->P.ncz,
-                                                                     s->cfg.nbu, s->nx, nbxk, s->cfg.K, B, buf, to_ws);
+        ws_rows_kernel<<<grid_for((long) B * (2 * nck + 2 * nsk)), 256, 0, st>>>(s->d_ws, s->P.ws_stride, fl.off + stage * fl.stride,
+                                                                                 s->P.ncz, s->cfg.nbu, s->nx, nbxk, s->cfg.K, nsk, B, buf, to_ws);
         CU(cudaGetLastError());
         s->launches++;
         if (!on_device)
@@ -421,7 +429,7 @@ static int create_impl(usvmpc_solver* s)
     int khz = 0;
     CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->device));
     s->sm_clock_hz = 1e3 * khz;
-    s->P.lay = make_layout(nx, nu, N, K);
+    s->P.lay = make_layout(nx, nu, N, K, cfg->nsh);
     s->P.ws_stride = s->P.lay.total;
     // placement of the working set: as many resident blocks per SM as the chain fields allow (at most USVMPC_MIN_CTAS,
     // which bounds the registers), everything else that fits goes to shared memory too, the rest to the L2-resident
@@ -435,7 +443,7 @@ static int create_impl(usvmpc_solver* s)
     {
         long budget = SMEM_PER_SM / c - SMEM_RESERVED_PER_CTA;
         if (budget > max_optin) budget = max_optin;
-        if (make_plan(nx, nu, N, K, cfg->nbx, cfg->nbu, THREADS / 32, budget, &s->P.plan)) { ok = true; s->ctas_per_sm = c; }
+        if (make_plan(nx, nu, N, K, cfg->nbx, cfg->nbu, cfg->nsh, THREADS / 32, budget, &s->P.plan)) { ok = true; s->ctas_per_sm = c; }
     }
     if (!ok) return fail(USVMPC_E_INVALID, "N=%d, K=%d: the Riccati working set does not fit the shared memory of one SM", N, K);
     s->grid = s->ctas_per_sm * s->num_sms;
@@ -469,7 +477,9 @@ static int create_impl(usvmpc_solver* s)
     // (acados_solver.in.c:1028-1449: the same lbx/ubx/lbu/ubu/lh/uh on every stage)
     const int nbu = cfg->nbu, nbx = cfg->nbx;
     s->o_lbu = 0; s->o_ubu = s->o_lbu + N * nbu; s->o_lbx = s->o_ubu + N * nbu; s->o_ubx = s->o_lbx + N * nbx;
-    s->o_uh = s->o_ubx + N * nbx; s->n_bnd = s->o_uh + N * K + 1;
+    const int ns = cfg->nsh;
+    s->o_uh = s->o_ubx + N * nbx; s->o_lsh = s->o_uh + N * K; s->o_ush = s->o_lsh + N * ns; s->o_zs = s->o_ush + N * ns;
+    s->n_bnd = s->o_zs + 4 * ns + 1;
     s->h_bnd = (double*) calloc(s->n_bnd, sizeof(double));
     if (!s->h_bnd) return fail(USVMPC_E_INVALID, "out of host memory");
     for (int k = 0; k < N; k++)
@@ -477,6 +487,12 @@ static int create_impl(usvmpc_solver* s)
         for (int i = 0; i < nbu; i++) { s->h_bnd[s->o_lbu + k * nbu + i] = cfg->lbu[i]; s->h_bnd[s->o_ubu + k * nbu + i] = cfg->ubu[i]; }
         for (int i = 0; i < nbx; i++) { s->h_bnd[s->o_lbx + k * nbx + i] = cfg->lbx[i]; s->h_bnd[s->o_ubx + k * nbx + i] = cfg->ubx[i]; }
         for (int i = 0; i < K; i++) s->h_bnd[s->o_uh + k * K + i] = cfg->uh;
+        for (int i = 0; i < ns; i++) { s->h_bnd[s->o_lsh + k * ns + i] = cfg->lsh[i]; s->h_bnd[s->o_ush + k * ns + i] = cfg->ush[i]; }
+    }
+    for (int i = 0; i < ns; i++)
+    {
+        s->h_bnd[s->o_zs + i] = cfg->zl[i]; s->h_bnd[s->o_zs + ns + i] = cfg->zu[i];
+        s->h_bnd[s->o_zs + 2 * ns + i] = cfg->Zl[i]; s->h_bnd[s->o_zs + 3 * ns + i] = cfg->Zu[i];
     }
     CU(cudaMalloc(&s->d_bnd, sizeof(double) * s->n_bnd));
     int rc = upload_bounds(s, 0);
@@ -485,12 +501,12 @@ static int create_impl(usvmpc_solver* s)
     return upload_constants(s, 0);
 }
 
-template <class M>
+template <class M, bool SOFT>
 static int launch_solve(usvmpc_solver* s, cudaStream_t st)
 {
     const size_t smem = sizeof(double) * (size_t) s->P.plan.smem_doubles;
     // the attribute is per function and process: set it for THIS solver's size right before its launch
-    CU(cudaFuncSetAttribute(nmpc_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CU(cudaFuncSetAttribute(nmpc_solve_kernel<M, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     CU(cudaMemsetAsync(s->d_queue, 0, sizeof(int) * 8, st));
     if (s->lpt && s->have_history && s->B > s->grid)
     {
@@ -500,7 +516,7 @@ static int launch_solve(usvmpc_solver* s, cudaStream_t st)
     }
     refresh_params(s);
     if (s->B <= s->grid) s->P.order = nullptr;
-    nmpc_solve_kernel<M><<<s->grid, THREADS, smem, st>>>(s->P);
+    nmpc_solve_kernel<M, SOFT><<<s->grid, THREADS, smem, st>>>(s->P);
     CU(cudaGetLastError());
     s->have_history = 1;
     return 0;
@@ -523,6 +539,18 @@ static int set_shared_bound(usvmpc_solver* s, int off, int dim, int k_first, int
         memcpy(s->h_bnd + off + stage * dim, tmp, sizeof(double) * dim);
     }
     return upload_bounds(s, st);
+}
+
+// the kernel instantiation of the solver's model / constraint kind
+static int launch_model(usvmpc_solver* s, cudaStream_t st)
+{
+    const bool soft = s->cfg.nsh > 0;
+    switch (s->cfg.model)
+    {
+    case USVMPC_MODEL_PENDULUM: return launch_solve<Pendulum, false>(s, st);
+    case USVMPC_MODEL_GUIDANCE_CA1: return soft ? launch_solve<Usv8Ca1, true>(s, st) : launch_solve<Usv8Ca1, false>(s, st);
+    default: return soft ? launch_solve<Usv3, true>(s, st) : launch_solve<Usv3, false>(s, st);
+    }
 }
 
 }  // namespace
@@ -556,6 +584,7 @@ int usvmpc_create(const usvmpc_config* cfg, int batch, int device, usvmpc_solver
     if (batch < 1 || cfg->N < 1) return fail(USVMPC_E_INVALID, "batch and N must be >= 1");
     if (cfg->N > NMAX) return fail(USVMPC_E_INVALID, "N=%d: the engine is built for horizons up to %d", cfg->N, NMAX);
     if (cfg->K < 0 || cfg->K > KMAX) return fail(USVMPC_E_INVALID, "K=%d outside [0,%d]", cfg->K, KMAX);
+    if (cfg->nsh < 0 || cfg->nsh > cfg->K) return fail(USVMPC_E_INVALID, "nsh=%d outside [0,K=%d]", cfg->nsh, cfg->K);
     if (cfg->nbx < 0 || cfg->nbx > nx || cfg->nbx > NBXMAX || cfg->nbu < 0 || cfg->nbu > nu || cfg->nbu > NBUMAX)
         return fail(USVMPC_E_INVALID, "nbx/nbu out of range");
     if (cfg->num_stages != 1 && cfg->num_stages != 2 && cfg->num_stages != 4) return fail(USVMPC_E_INVALID, "ERK num_stages must be 1, 2 or 4");
@@ -593,7 +622,7 @@ int usvmpc_solve(usvmpc_solver* s, void* stream)
     if (!s) return fail(USVMPC_E_INVALID, "null solver");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t) stream;
-    const int rc = s->cfg.model == USVMPC_MODEL_PENDULUM ? launch_solve<Pendulum>(s, st) : launch_solve<Usv3>(s, st);
+    const int rc = launch_model(s, st);
     if (rc) return rc;
     s->launches++;
     return 0;
@@ -633,7 +662,18 @@ int usvmpc_cost_model_set(usvmpc_solver* s, int stage, const char* field, const 
         memcpy(stage == N ? s->cfg.W_e : s->cfg.W, tmp, sizeof(double) * n);
         return upload_constants(s, st);
     }
-    return fail(USVMPC_E_FIELD, "unknown cost field '%s' (yref, y_ref, W)", field);
+    if (!strcmp(field, "zl") || !strcmp(field, "zu") || !strcmp(field, "Zl") || !strcmp(field, "Zu"))
+    {
+        // slack penalties: shared by the batch and by the stages (ocp_nlp_cost_ls.c:826-841)
+        const int ns = s->cfg.nsh, which = field[0] == 'z' ? (field[1] == 'l' ? 0 : 1) : (field[1] == 'l' ? 2 : 3);
+        if (ns == 0) return 0;
+        double tmp[KMAX];
+        int rc = to_host(value, ns, on_device, tmp);
+        if (rc) return rc;
+        memcpy(s->h_bnd + s->o_zs + which * ns, tmp, sizeof(double) * ns);
+        return upload_bounds(s, st);
+    }
+    return fail(USVMPC_E_FIELD, "unknown cost field '%s' (yref, y_ref, W, zl, zu, Zl, Zu)", field);
 }
 
 int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field, const double* value, int on_device, void* stream)
@@ -658,6 +698,8 @@ int usvmpc_constraints_model_set(usvmpc_solver* s, int stage, const char* field,
         return set_input(s, s->d_lh, &s->P.lh_per_stage, N, s->cfg.K, stage, value, st);
     }
     if (!strcmp(field, "uh")) return set_shared_bound(s, s->o_uh, s->cfg.K, 0, stage, value, on_device, st);
+    if (!strcmp(field, "lsh")) return set_shared_bound(s, s->o_lsh, s->cfg.nsh, 0, stage, value, on_device, st);
+    if (!strcmp(field, "ush")) return set_shared_bound(s, s->o_ush, s->cfg.nsh, 0, stage, value, on_device, st);
     return fail(USVMPC_E_FIELD, "unknown constraint field '%s' (lbx, ubx, lbu, ubu, lh, uh)", field);
 }
 
@@ -681,13 +723,17 @@ int usvmpc_dims_get_from_attr(usvmpc_solver* s, int stage, const char* field)
     if (!strcmp(field, "x")) return s->nx;
     if (!strcmp(field, "u")) return stage < N ? s->nu : 0;
     if (!strcmp(field, "pi")) return stage < N ? s->nx : 0;
-    if (!strcmp(field, "lam") || !strcmp(field, "t")) return 2 * (nbuk + nbxk + Kk);
+    const int nsk = stage < N ? s->cfg.nsh : 0;
+    if (!strcmp(field, "lam") || !strcmp(field, "t")) return 2 * (nbuk + nbxk + Kk) + 2 * nsk;
+    if (!strcmp(field, "sl") || !strcmp(field, "su") || !strcmp(field, "lsh") || !strcmp(field, "ush") || !strcmp(field, "zl") ||
+        !strcmp(field, "zu") || !strcmp(field, "Zl") || !strcmp(field, "Zu"))
+        return nsk;
     if (!strcmp(field, "p")) return 2 * s->cfg.K;
     if (!strcmp(field, "yref") || !strcmp(field, "y_ref")) return stage < N ? s->nv : s->nx;
     if (!strcmp(field, "lbx") || !strcmp(field, "ubx")) return nbxk;
     if (!strcmp(field, "lbu") || !strcmp(field, "ubu")) return nbuk;
     if (!strcmp(field, "lh") || !strcmp(field, "uh")) return Kk;
-    if (!strcmp(field, "sl") || !strcmp(field, "su") || !strcmp(field, "z")) return 0;
+    if (!strcmp(field, "z")) return 0;
     return fail(USVMPC_E_FIELD, "unknown field '%s'", field);
 }
 
@@ -783,8 +829,8 @@ int usvmpc_qp_solve(usvmpc_solver* s, const double* G, const double* b, const do
     s->P.qp = QpIo{G, b, rq, g2, d, ux, pi, lam, t};
     const int have = s->have_history;
     s->have_history = 0;   // the iteration counts of an NMPC solve say nothing about these QPs: plain queue order
-    const int rc = s->cfg.model == USVMPC_MODEL_PENDULUM ? launch_solve<Pendulum>(s, (cudaStream_t) stream)
-                                                          : launch_solve<Usv3>(s, (cudaStream_t) stream);
+    if (s->cfg.nsh > 0) return fail(USVMPC_E_INVALID, "usvmpc_qp_solve: soft rows are not part of the QP seam's layout");
+    const int rc = launch_model(s, (cudaStream_t) stream);
     s->P.qp = QpIo{};
     (void) have;
     s->have_history = 0;   // the statistics record now holds QP statistics: no history for the next NMPC solve

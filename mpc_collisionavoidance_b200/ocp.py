@@ -8,14 +8,20 @@ The reference's classes need CasADi (symbolic model) and a code generator; here 
 engine's built-in device models, selected by `model.name`, and no code is generated.  A genuine
 `acados_template.AcadosOcp` instance is accepted as well (duck typing) as long as it stays inside the path
 the engine implements: LINEAR_LS cost with Vx=[I;0], Vu=[0;I]; BGH constraints (input boxes, state boxes,
-h = obstacle distances); ERK; GAUSS_NEWTON; PARTIAL_CONDENSING_HPIPM; SQP or SQP_RTI.
+h = obstacle distances, hard or soft: idxsh / lsh / ush with the penalties zl, zu, Zl, Zu); ERK; GAUSS_NEWTON;
+PARTIAL_CONDENSING_HPIPM; SQP or SQP_RTI.  Anything outside that path (soft boxes, other cost / constraint /
+integrator / QP plugins, a step length != 1, Levenberg-Marquardt, qp_solver_cond_N != N) is refused with an
+Exception instead of being silently ignored.
 """
 import numpy as np
 
 from . import _lib
 
-MODELS = {"usv3": 0, "usv_model_ca": 0, "usv3_ca": 0, "pendulum": 1, "pendulum_ode": 1}
-MODEL_DIMS = {0: (6, 2), 1: (4, 1)}
+# model.name -> device model.  "usv_model_guidance_ca1" is the model the deployed CA node generates its solver from
+# (nmpc_ca/scripts/usv_guidance_ca1/usv_model.py:45).
+MODELS = {"usv3": 0, "usv_model_ca": 0, "usv3_ca": 0, "pendulum": 1, "pendulum_ode": 1, "usv_model_guidance_ca1": 2,
+          "usv_guidance_ca1": 2}
+MODEL_DIMS = {0: (6, 2), 1: (4, 1), 2: (8, 1)}
 
 
 class AcadosModel:
@@ -40,6 +46,8 @@ class AcadosOcpCost:
         self.Vx_e = None
         self.yref = None
         self.yref_e = None
+        # slack penalties of the soft rows (acados_ocp.py: zl, zu, Zl, Zu)
+        self.zl = np.array([]); self.zu = np.array([]); self.Zl = np.array([]); self.Zu = np.array([])
 
 
 class AcadosOcpConstraints:
@@ -49,6 +57,8 @@ class AcadosOcpConstraints:
         self.lbu = np.array([]); self.ubu = np.array([]); self.idxbu = np.array([], dtype=int)
         self.lbx = np.array([]); self.ubx = np.array([]); self.idxbx = np.array([], dtype=int)
         self.lh = np.array([]); self.uh = np.array([])
+        # soft nonlinear rows: bounds of the lower / upper slacks and the rows they belong to
+        self.lsh = np.array([]); self.ush = np.array([]); self.idxsh = np.array([], dtype=int)
 
 
 class AcadosOcpOptions:
@@ -143,6 +153,42 @@ def config_from_ocp(ocp):
         if len(uh) != K or not np.all(uh == uh[0]):
             raise Exception("uh must have one (common) value per obstacle row")
         cfg.uh = float(uh[0])
+    # ---- soft constraints: only soft h rows, and they must be the leading rows of h (every nmpc_ca script that uses
+    # slacks softens all of its h rows: usv_guidance_ca1/acados_settings.py:160-178)
+    for nm in ("idxsbx", "idxsbu", "idxsg", "idxsphi", "idxsbx_e", "idxsh_e", "idxsg_e", "idxsphi_e", "lsbx", "lsbu", "usbx", "usbu"):
+        v = getattr(k, nm, None)
+        if v is not None and np.size(v) > 0:
+            raise Exception(f"constraints.{nm}: only soft nonlinear rows (idxsh) are implemented")
+    idxsh = np.asarray(getattr(k, "idxsh", []), dtype=int).ravel()
+    nsh = len(idxsh)
+    if nsh:
+        if nsh > K or not np.array_equal(idxsh, np.arange(nsh)):
+            raise Exception("idxsh must be 0..nsh-1 (the leading rows of h)")
+
+        def per_row(v, name):
+            v = _arr(v)
+            if len(v) != nsh:
+                raise Exception(f"{name} must have one value per soft row (nsh = {nsh})")
+            return v
+        lsh, ush = per_row(getattr(k, "lsh", None), "lsh"), per_row(getattr(k, "ush", None), "ush")
+        z = [per_row(getattr(c, nm, None), nm)[:nsh] if len(_arr(getattr(c, nm, None))) == nsh
+             else per_row(_arr(getattr(c, nm, None))[:nsh], nm) for nm in ("zl", "zu", "Zl", "Zu")]
+        cfg.nsh = nsh
+        for i in range(nsh):
+            cfg.lsh[i], cfg.ush[i] = lsh[i], ush[i]
+            cfg.zl[i], cfg.zu[i], cfg.Zl[i], cfg.Zu[i] = z[0][i], z[1][i], z[2][i], z[3][i]
+    else:
+        for nm in ("zl", "zu", "Zl", "Zu"):
+            if np.size(_arr(getattr(c, nm, None))) > 0:
+                raise Exception(f"cost.{nm} given but no soft rows (idxsh) declared")
+    # ---- options the engine does not implement are refused, not dropped
+    if float(getattr(o, "nlp_solver_step_length", 1.0)) != 1.0:
+        raise Exception("nlp_solver_step_length != 1: the engine takes full SQP steps like the nmpc_ca scripts")
+    if float(getattr(o, "levenberg_marquardt", 0.0)) != 0.0:
+        raise Exception("levenberg_marquardt != 0 is not implemented")
+    cond_N = getattr(o, "qp_solver_cond_N", None)
+    if cond_N is not None and int(cond_N) != N:
+        raise Exception("qp_solver_cond_N != N: the engine solves the uncondensed QP (cond_N = N, the default of the template)")
     return cfg, model, nx, nu
 
 
@@ -151,9 +197,11 @@ def config_from_ocp(ocp):
 # ocp_formulation_json_dump (acados_template/acados_ocp_solver.py:416-444): one dict per description class, attribute
 # names without the class prefix, numpy arrays as nested lists; x0 appears as constraints.lbx_0 / ubx_0.
 _JSON_FIELDS = {
-    "cost": ["cost_type", "cost_type_e", "W", "W_e", "Vx", "Vu", "Vx_e", "yref", "yref_e"],
-    "constraints": ["constr_type", "lbu", "ubu", "idxbu", "lbx", "ubx", "idxbx", "lh", "uh"],
+    "cost": ["cost_type", "cost_type_e", "W", "W_e", "Vx", "Vu", "Vx_e", "yref", "yref_e", "zl", "zu", "Zl", "Zu"],
+    "constraints": ["constr_type", "lbu", "ubu", "idxbu", "lbx", "ubx", "idxbx", "lh", "uh", "lsh", "ush", "idxsh",
+                    "idxsbx", "idxsbu", "idxsg", "idxsphi", "lsbx", "lsbu", "usbx", "usbu"],
     "solver_options": ["qp_solver", "hessian_approx", "integrator_type", "tf", "nlp_solver_type", "nlp_solver_step_length",
+                       "levenberg_marquardt", "qp_solver_cond_N",
                        "sim_method_num_stages", "sim_method_num_steps", "qp_solver_iter_max", "nlp_solver_tol_stat",
                        "nlp_solver_tol_eq", "nlp_solver_tol_ineq", "nlp_solver_tol_comp", "nlp_solver_max_iter", "print_level"],
 }

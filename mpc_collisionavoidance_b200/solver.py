@@ -177,14 +177,25 @@ class BatchedAcadosOcpSolver:
             v = np.ascontiguousarray(v.flatten(order="F"))  # column-major like the reference (:1032-1062)
             _lib.check(self.lib.usvmpc_cost_model_set(self.h, stage, b"W", C.c_void_p(v.ctypes.data), 0, self._stream()), "cost_set W")
             return
+        if field_ in ("zl", "zu", "Zl", "Zu"):
+            # slack penalties: shared by the batch and the stages
+            v = np.ascontiguousarray(value_, dtype=np.float64).ravel()
+            if v.shape[0] != self.cfg.nsh:
+                raise Exception("AcadosOcpSolver.cost_set(): mismatching dimension for field {}: {} vs {}".format(field_, v.shape[0], self.cfg.nsh))
+            _lib.check(self.lib.usvmpc_cost_model_set(self.h, self._stage(stage_, allow_special=False), field_.encode(),
+                                                      C.c_void_p(v.ctypes.data), 0, self._stream()), "cost_set " + field_)
+            return
         if field_ not in _COST_FIELDS:
-            raise Exception("AcadosOcpSolver.cost_set(): {} is not a valid argument (yref, y_ref, W)".format(field_))
+            raise Exception("AcadosOcpSolver.cost_set(): {} is not a valid argument (yref, y_ref, W, zl, zu, Zl, Zu)".format(field_))
         self._call_set(stage_, field_, value_)
 
     def constraints_set(self, stage_, field_, value_, api="warn"):
-        if field_ == "uh":
+        if field_ in ("uh", "lsh", "ush"):
             v = np.ascontiguousarray(value_, dtype=np.float64).ravel()
-            _lib.check(self.lib.usvmpc_constraints_model_set(self.h, self._stage(stage_), b"uh", C.c_void_p(v.ctypes.data), 0, self._stream()), "uh")
+            want = self.K if field_ == "uh" else self.cfg.nsh
+            if v.shape[0] != want:
+                raise Exception('mismatching dimension for field "{}" with dimension {} (you have {})'.format(field_, want, v.shape[0]))
+            _lib.check(self.lib.usvmpc_constraints_model_set(self.h, self._stage(stage_), field_.encode(), C.c_void_p(v.ctypes.data), 0, self._stream()), field_)
             return
         if field_ not in _CONSTR_FIELDS + ["lh"]:
             raise Exception("AcadosOcpSolver.constraints_set(): {} is not a valid argument".format(field_))

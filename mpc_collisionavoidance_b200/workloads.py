@@ -77,6 +77,61 @@ def _scenes(rng, B, N, K, xref_factor=1.5) -> Batch:
     return Batch(x0, p, lh, yref, yref[:, :6].copy())
 
 
+@dataclass
+class GuidanceBatch:
+    x0: np.ndarray      # [B, 8]   u, v, ye, chie, psied, xned, yned, psi
+    p: np.ndarray       # [B, 16]  obstacle centres in NED
+    lh: np.ndarray      # [B, 8]   obstacle radii (lower bound of the distance rows)
+    yref: np.ndarray    # [B, 9]
+    yref_e: np.ndarray  # [B, 8]
+
+
+def make_guidance_batch(B: int, seed: int = 77) -> GuidanceBatch:
+    """Synthetic scenes for the deployed collision-avoidance OCP (usv_guidance_ca1): the vessel follows the path
+    (4,-5) -> (4,25) of the script (main.py:73-75,101-104) heading north; the obstacles of the script's list, jittered,
+    the unused slots parked at (100,100) like the node does (nmpc_guidance_ca1.cpp:330-363)."""
+    rng = np.random.default_rng(seed)
+    x0 = np.stack([rng.uniform(0.4, 1.0, B), rng.uniform(-0.05, 0.05, B), rng.uniform(-0.5, 0.5, B), rng.uniform(-0.3, 0.3, B),
+                   rng.uniform(-0.3, 0.3, B), 4.0 + rng.uniform(-0.5, 0.5, B), rng.uniform(-6.0, 6.0, B),
+                   np.pi / 2 + rng.uniform(-0.3, 0.3, B)], axis=1)
+    base = np.array([[4, 4], [4, 7], [4, 12], [4, 20]], dtype=float)
+    p = np.full((B, 8, 2), 100.0)
+    p[:, :4] = base[None] + rng.uniform(-1.0, 1.0, (B, 4, 2))
+    lh = np.full((B, 8), 1.5)
+    lh[:, :4] = rng.uniform(1.0, 2.0, (B, 4))
+    return GuidanceBatch(x0, p.reshape(B, 16), lh, np.zeros((B, 9)), np.zeros((B, 8)))
+
+
+def guidance_ca1_ocp(N: int = 100, Tf: float = 5.0, nlp_solver_type: str = "SQP_RTI", soft: bool = True):
+    """The OCP of the deployed CA node as an AcadosOcp-style description, numbers of
+    nmpc_ca/scripts/usv_guidance_ca1/acados_settings.py:70-208 (soft = False: the same rows as hard constraints)."""
+    from .ocp import AcadosOcp
+    nx, nu, K = 8, 1, 8
+    ocp = AcadosOcp()
+    ocp.model.name = "usv_model_guidance_ca1"
+    ocp.dims.N = N
+    Q = np.diag([0, 0, 0.05, 0.01, 0, 0, 0, 0.0])
+    ocp.cost.W = np.block([[Q, np.zeros((nx, nu))], [np.zeros((nu, nx)), np.array([[0.2]])]])
+    ocp.cost.W_e = np.diag([0, 0, 0.1, 0.05, 0, 0, 0, 0.0])
+    Vx = np.zeros((nx + nu, nx)); Vx[:nx, :nx] = np.eye(nx)
+    Vu = np.zeros((nx + nu, nu)); Vu[nx:, :] = np.eye(nu)
+    ocp.cost.Vx, ocp.cost.Vu, ocp.cost.Vx_e = Vx, Vu, np.eye(nx)
+    ocp.cost.yref, ocp.cost.yref_e = np.zeros(nx + nu), np.zeros(nx)
+    ocp.constraints.lbu, ocp.constraints.ubu, ocp.constraints.idxbu = np.array([-0.5]), np.array([0.5]), np.array([0])
+    ocp.constraints.lh, ocp.constraints.uh = np.full(K, 1.5), np.full(K, 1e6)
+    if soft:
+        ocp.cost.zl, ocp.cost.zu, ocp.cost.Zl, ocp.cost.Zu = np.ones(K), np.ones(K), np.zeros(K), np.zeros(K)
+        ocp.constraints.lsh, ocp.constraints.ush, ocp.constraints.idxsh = np.full(K, -0.2), np.zeros(K), np.arange(K)
+    ocp.constraints.x0 = np.zeros(nx)
+    ocp.parameter_values = np.full(2 * K, 100.0)
+    o = ocp.solver_options
+    o.tf = Tf
+    o.qp_solver, o.hessian_approx, o.integrator_type = "PARTIAL_CONDENSING_HPIPM", "GAUSS_NEWTON", "ERK"
+    o.nlp_solver_type = nlp_solver_type
+    o.sim_method_num_stages, o.sim_method_num_steps = 4, 1
+    return ocp
+
+
 def benchmark_ocp(config_id: int, nlp_solver_type: str = "SQP"):
     """The benchmark OCP of SURVEY.md section 8d as an AcadosOcp-style description (same attribute names as the
     nmpc_ca `acados_settings.py` scripts): 3-DOF USV, LINEAR_LS tracking cost, thrust and velocity boxes, K obstacle

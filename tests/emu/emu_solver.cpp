@@ -134,8 +134,11 @@ struct BlockArg { const Params* P; int model; double* sm; int block; };
 void block_body(void* a)
 {
     BlockArg* ba = (BlockArg*) a;
-    if (ba->model == 1) cta_main<Pendulum>(*ba->P, ba->sm, ba->block);
-    else cta_main<Usv3>(*ba->P, ba->sm, ba->block);
+    const bool soft = ba->P->ns > 0;
+    if (ba->model == 1) cta_main<Pendulum, false>(*ba->P, ba->sm, ba->block);
+    else if (ba->model == 2) { if (soft) cta_main<Usv8Ca1, true>(*ba->P, ba->sm, ba->block); else cta_main<Usv8Ca1, false>(*ba->P, ba->sm, ba->block); }
+    else if (soft) cta_main<Usv3, true>(*ba->P, ba->sm, ba->block);
+    else cta_main<Usv3, false>(*ba->P, ba->sm, ba->block);
 }
 
 void* worker(void* arg)
@@ -150,8 +153,9 @@ void* worker(void* arg)
 }
 
 enum { ICFG_MODEL, ICFG_N, ICFG_K, ICFG_NUM_STEPS, ICFG_NUM_STAGES, ICFG_NLP_TYPE, ICFG_MAX_ITER, ICFG_QP_ITER_MAX,
-       ICFG_COND_N, ICFG_NBX, ICFG_NBU, ICFG_PRINT };
-enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_UH };
+       ICFG_COND_N, ICFG_NBX, ICFG_NBU, ICFG_PRINT, ICFG_NSH };
+enum { DCFG_DT, DCFG_TOL_STAT, DCFG_TOL_EQ, DCFG_TOL_INEQ, DCFG_TOL_COMP, DCFG_UH, DCFG_LSH, DCFG_USH, DCFG_ZL, DCFG_ZU, DCFG_ZZL,
+       DCFG_ZZU };
 
 }  // namespace
 
@@ -163,6 +167,9 @@ extern "C" void usvemu_configure(long smem_budget, int block_threads, int chain_
 {
     g_smem_budget = smem_budget; g_block_threads = block_threads; g_chain_fp32 = chain_fp32;
 }
+// optional output of the slack values of the next solve: [B][N][2 nsh] = (sl | su) per stage
+static double* sv_out = nullptr;
+extern "C" void usvemu_slack_output(double* buf) { sv_out = buf; }
 
 // same calling convention as oracle/usv_oracle.c:usvo_solve_batch so the tests can swap one for the other;
 // optional initial guess (xinit [B][N+1][nx], uinit [B][N][nu], piinit [B][N][nx]) and full multiplier output.
@@ -175,7 +182,7 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
                                      double* lam_out, double* t_out, double* stats, int nthreads)
 {
     const int model = icfg[ICFG_MODEL];
-    const int nx = model == 1 ? 4 : 6, nu = model == 1 ? 1 : 2, nv = nx + nu;
+    const int nx = model == 1 ? 4 : (model == 2 ? 8 : 6), nu = model == 0 ? 2 : 1, nv = nx + nu;
     Params P;
     memset(&P, 0, sizeof(P));
     P.B = B; P.N = icfg[ICFG_N]; P.K = icfg[ICFG_K]; P.num_steps = icfg[ICFG_NUM_STEPS];
@@ -192,6 +199,12 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
         for (int i = 0; i < K; i++) vuh[k * K + i] = dcfg[DCFG_UH];
     }
     P.lbu = vlbu.data(); P.ubu = vubu.data(); P.lbx = vlbx.data(); P.ubx = vubx.data(); P.uh = vuh.data();
+    const int ns = icfg[ICFG_NSH];
+    P.ns = ns;
+    std::vector<double> vlsh((size_t) N * ns + 1), vush((size_t) N * ns + 1), vzs((size_t) 4 * ns + 1);
+    for (int k = 0; k < N; k++) for (int i = 0; i < ns; i++) { vlsh[k * ns + i] = dcfg[DCFG_LSH]; vush[k * ns + i] = dcfg[DCFG_USH]; }
+    for (int i = 0; i < ns; i++) { vzs[i] = dcfg[DCFG_ZL]; vzs[ns + i] = dcfg[DCFG_ZU]; vzs[2 * ns + i] = dcfg[DCFG_ZZL]; vzs[3 * ns + i] = dcfg[DCFG_ZZU]; }
+    P.lsh = vlsh.data(); P.ush = vush.data(); P.zs = vzs.data();
     P.p_per_stage = p_per_stage; P.lh_per_stage = lh_per_stage; P.yref_per_stage = yref_per_stage;
     P.cold_start = xinit ? 0 : 1;
     P.chain_fp32 = g_chain_fp32;
@@ -203,9 +216,9 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
     memcpy(cst.data() + nv * nv, We, sizeof(double) * nx * nx);
     P.cst = cst.data();
     P.x0 = x0; P.p = p; P.lh = lh; P.yref = yref; P.yref_e = yref_e;
-    P.lay = make_layout(nx, nu, N, K);
+    P.lay = make_layout(nx, nu, N, K, ns);
     P.ws_stride = P.lay.total;
-    if (!make_plan(nx, nu, N, K, P.nbx, P.nbu, g_block_threads / 32, g_smem_budget, &P.plan))
+    if (!make_plan(nx, nu, N, K, P.nbx, P.nbu, ns, g_block_threads / 32, g_smem_budget, &P.plan))
     {
         fprintf(stderr, "usvmpc emu: the chain fields do not fit the shared-memory budget\n");
         abort();
@@ -231,7 +244,8 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
         // a freshly created solver: multipliers zero (cold_start() does the same when no guess is given)
         for (int k = 0; k <= N; k++)
         {
-            for (int j = 0; j < 2 * ncz; j++) { w[Y.zlam.off + k * Y.zlam.stride + j] = 0.0; w[Y.zt.off + k * Y.zt.stride + j] = 0.0; }
+            for (int j = 0; j < 2 * ncz + 2 * ns; j++) { w[Y.zlam.off + k * Y.zlam.stride + j] = 0.0; w[Y.zt.off + k * Y.zt.stride + j] = 0.0; }
+            for (int j = 0; j < 2 * ns; j++) w[Y.zsv.off + k * Y.zsv.stride + j] = 0.0;
             if (xinit)
             {
                 for (int i = 0; i < nu; i++) w[Y.zux.off + k * Y.zux.stride + i] = (k < N && uinit) ? uinit[((long) b * N + k) * nu + i] : 0.0;
@@ -260,8 +274,10 @@ extern "C" double usvemu_solve_batch(const int* icfg, const double* dcfg, const 
                 for (int i = 0; i < nu; i++) u_out[((long) b * N + k) * nu + i] = w[Y.zux.off + k * Y.zux.stride + i];
                 if (pi_out) for (int i = 0; i < nx; i++) pi_out[((long) b * N + k) * nx + i] = w[Y.zpi.off + k * Y.zpi.stride + i];
             }
-            if (lam_out) for (int j = 0; j < 2 * ncz; j++) lam_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zlam.off + k * Y.zlam.stride + j];
-            if (t_out) for (int j = 0; j < 2 * ncz; j++) t_out[((long) b * (N + 1) + k) * 2 * ncz + j] = w[Y.zt.off + k * Y.zt.stride + j];
+            const int wl = 2 * ncz + 2 * ns;   // [lower | upper | slack bounds]
+            if (lam_out) for (int j = 0; j < wl; j++) lam_out[((long) b * (N + 1) + k) * wl + j] = w[Y.zlam.off + k * Y.zlam.stride + j];
+            if (t_out) for (int j = 0; j < wl; j++) t_out[((long) b * (N + 1) + k) * wl + j] = w[Y.zt.off + k * Y.zt.stride + j];
+            if (sv_out && k < N) for (int j = 0; j < 2 * ns; j++) sv_out[((long) b * N + k) * 2 * ns + j] = w[Y.zsv.off + k * Y.zsv.stride + j];
         }
         for (int i = 0; i < 12; i++) stats[(long) b * 12 + i] = st[(size_t) b * NSTAT + (i == 9 ? 15 : i)];  // slot 9: fp32 factorisations
     }

@@ -39,12 +39,17 @@ def solve_batch(prob: RefProblem, x0, p, lh, yref, yref_e, xinit=None, uinit=Non
     B = x0.shape[0]
     N, nx, nu = prob.N, prob.nx, prob.nu
     ncz = len(prob.lbu) + nx + prob.K
+    nsh = getattr(prob, "nsh", 0)
     x = np.zeros((B, N + 1, nx)); u = np.zeros((B, N, nu)); pi = np.zeros((B, N, nx))
-    lam = np.zeros((B, N + 1, 2 * ncz)); t = np.zeros((B, N + 1, 2 * ncz)); stats = np.zeros((B, 12))
+    wl = 2 * ncz + 2 * nsh
+    lam = np.zeros((B, N + 1, wl)); t = np.zeros((B, N + 1, wl)); stats = np.zeros((B, 12))
+    sv = np.zeros((B, N, max(2 * nsh, 1)))
+    lib.usvemu_slack_output(_d(sv) if nsh else None)
     secs = lib.usvemu_solve_batch(_i(prob.icfg), _d(prob.dcfg), _d(prob.W), _d(prob.We), _d(prob.lbu), _d(prob.ubu),
                                   _i(prob.idxbx), _d(prob.lbx), _d(prob.ubx), B, _d(x0), _d(p), int(p.ndim > 2),
                                   _d(lh), int(lh.ndim > 2), _d(yref), int(yref.ndim > 2), _d(yref_e), _d(xinit),
                                   _d(uinit), _d(piinit), _d(x), _d(u), _d(pi), _d(lam), _d(t), _d(stats), nthreads)
     return dict(x=x, u=u, pi=pi, lam=lam, t=t, status=stats[:, 0].astype(int), sqp_iter=stats[:, 1].astype(int),
                 qp_iter=stats[:, 2].astype(int), res=stats[:, 3:7], lq_calls=stats[:, 7].astype(int), solve_calls=stats[:, 8].astype(int),
-                itref=stats[:, 11].astype(int), fp32_facts=stats[:, 9].astype(int), seconds=secs)
+                itref=stats[:, 11].astype(int), fp32_facts=stats[:, 9].astype(int), seconds=secs,
+                sl=sv[:, :, :nsh], su=sv[:, :, nsh:2 * nsh])

@@ -8,6 +8,7 @@ Fixtures:
   usv_cfg4_solve.npz        64 instances of config 4 (N = 100; scene ranges of workloads.XREF_FACTOR)
   usv_cfg5_solve.npz        256 Monte-Carlo draws of config 5 (128 base scenes x 2 draws of the x0 disturbance)
   usv_cfg2_lq.npz           the instances of the headline batch on which the reference takes its LQ path
+  usv_guidance_ca1.npz      the deployed CA solver (nx = 8, nu = 1, N = 100, 8 soft obstacle rows): RTI step and SQP solve
   usv_cfg1_rti.npz          one SQP_RTI step (known answer 2 of SURVEY.md appendix B)
   usv_cfg2_qp.npz           QPs captured at HPIPM's door (after x0 elimination) with HPIPM's solution and
                             iteration count, for QP-level parity of the IPM/Riccati kernels
@@ -36,6 +37,24 @@ def solve_fixture(cfg_id, B, name):
                         lh=b.lh, yref=b.yref, yref_e=b.yref_e, x=o["x"], u=o["u"], status=o["status"],
                         sqp_iter=o["sqp_iter"], qp_iter=o["qp_iter"], res=o["res"], lq_calls=o["lq_calls"])
     print(name, "status", np.bincount(o["status"]), "sqp_iter", o["sqp_iter"])
+
+
+def guidance_fixture():
+    """the deployed CA solver (usv_guidance_ca1: nx = 8, nu = 1, N = 100, 8 SOFT obstacle rows): one SQP_RTI step and a
+    full SQP solve of 24 scenes, with the slack values"""
+    from mpc_collisionavoidance_b200.workloads import make_guidance_batch
+    b = make_guidance_batch(24)
+    out = dict(x0=b.x0, p=b.p, lh=b.lh, yref=b.yref, yref_e=b.yref_e)
+    for nlp_type, tag in ((1, "rti"), (0, "sqp")):
+        P = rh.RefProblem(model=2, N=100, K=8, num_steps=1, nlp_type=nlp_type, nsh=8, lsh=-0.2, ush=0.0, zl=1.0, zu=1.0, uh=1e6,
+                          max_iter=30)
+        s = rh.RefSolver(P)
+        rs = [s.solve(b.x0[i], b.p[i], b.lh[i], b.yref[i], b.yref_e[i]) for i in range(len(b.x0))]
+        for k in ("x", "u", "sl", "su", "res", "lam", "t"):
+            out[f"{tag}_{k}"] = np.stack([r[k] for r in rs])
+        out[f"{tag}_stat"] = np.array([[r["status"], r["sqp_iter"], r["qp_iter"]] for r in rs])
+        print("guidance", tag, out[f"{tag}_stat"].T)
+    np.savez_compressed(os.path.join(G, "usv_guidance_ca1.npz"), **out)
 
 
 def lq_fixture():
@@ -97,3 +116,4 @@ if __name__ == "__main__":
     solve_fixture(5, 256, "usv_cfg5_solve.npz")
     qp_fixture()
     lq_fixture()
+    guidance_fixture()

@@ -107,3 +107,23 @@ def test_long_horizon_four_pass_rounds():
     np.testing.assert_array_equal(a["status"], c["status"])
     np.testing.assert_array_equal(a["qp_iter"], c["qp_iter"])
     assert np.abs(a["x"] - c["x"]).max() < 1e-7 and np.abs(a["u"] - c["u"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("nlp_type,tag", [(1, "rti"), (0, "sqp")])
+def test_soft_constrained_guidance_ocp(golden_dir, nlp_type, tag):
+    # the kernel source (device model Usv8Ca1, SOFT instantiation) on the deployed CA OCP against the reference fixture
+    f = np.load(os.path.join(golden_dir, "usv_guidance_ca1.npz"))
+    n = 8
+    P = rh.RefProblem(model=2, N=100, K=8, num_steps=1, nlp_type=nlp_type, nsh=8, lsh=-0.2, ush=0.0, zl=1.0, zu=1.0, uh=1e6,
+                      max_iter=30)
+    r = ep.solve_batch(P, f["x0"][:n], f["p"][:n], f["lh"][:n], f["yref"][:n], f["yref_e"][:n], nthreads=8)
+    np.testing.assert_array_equal(np.stack([r["status"], r["sqp_iter"], r["qp_iter"]], 1), f[f"{tag}_stat"][:n])
+    for k in ("x", "u", "sl", "su"):
+        np.testing.assert_allclose(r[k], f[f"{tag}_{k}"][:n], rtol=1e-7, atol=1e-8, err_msg=f"{tag} {k}")
+    # multipliers: engine rows [u | x slots (8) | h] per side, then the slack bounds -> reference [lbu lbx lh | .. | lsh | ush]
+    ncz = 1 + 8 + 8
+    for k in (0, 1, 50):
+        nbx = 8 if k == 0 else 0
+        rows = list(range(1 + nbx)) + [1 + 8 + c for c in range(8)]
+        idx = rows + [ncz + j for j in rows] + [2 * ncz + j for j in range(16)]
+        np.testing.assert_allclose(r["lam"][:, k][:, idx], f[f"{tag}_lam"][:n, k, :len(idx)], rtol=1e-6, atol=1e-9)

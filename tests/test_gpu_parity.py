@@ -441,3 +441,95 @@ def test_rti_phase_split_equals_single_call():
     np.testing.assert_array_equal(outs[0][3], outs[1][3])
     np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=0, atol=1e-12)
     np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=0, atol=1e-10)
+
+
+def _guidance_solver(B, nlp_solver_type, soft=True, **over):
+    from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
+    from mpc_collisionavoidance_b200.workloads import guidance_ca1_ocp
+    ocp = guidance_ca1_ocp(nlp_solver_type=nlp_solver_type, soft=soft)
+    ocp.solver_options.nlp_solver_max_iter = 30
+    for k, v in over.items():
+        setattr(ocp.constraints if hasattr(ocp.constraints, k) else ocp.cost, k, v)
+    return BatchedAcadosOcpSolver(ocp, batch=B)
+
+
+def _guidance_solve(s, x0, p, lh, yref, yref_e):
+    N = 100
+    s.options_set("cold_start", 1)
+    s.set(0, "lbx", x0); s.set(0, "ubx", x0)
+    s.set("every", "p", p); s.constraints_set("every", "lh", lh)
+    s.set("every", "yref", yref); s.set(N, "yref", yref_e)
+    status = s.solve()
+    st = s.stats_table()
+    sl = np.stack([s.get(k, "sl") for k in range(N)], 1) if s.cfg.nsh else None
+    su = np.stack([s.get(k, "su") for k in range(N)], 1) if s.cfg.nsh else None
+    return dict(status=np.asarray(status), sqp_iter=st[:, 1].astype(int), qp_iter=st[:, 2].astype(int), res=st[:, 3:7],
+                x=s.get_all("x"), u=s.get_all("u"), sl=sl, su=su)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nlp,tag", [("SQP_RTI", "rti"), ("SQP", "sqp")])
+def test_deployed_guidance_ca1_soft_constraints(golden_dir, nlp, tag):
+    # the model the ROS node deploys (usv_guidance_ca1: nx = 8, nu = 1, N = 100, 8 SOFT obstacle
+    # rows, lsh = -0.2, zl = zu = 1) through the public API, against the unmodified reference (fixture): status,
+    # iteration counts, trajectories, slack values, multipliers in the reference's order
+    f = np.load(os.path.join(golden_dir, "usv_guidance_ca1.npz"))
+    n = 24
+    s = _guidance_solver(n, nlp)
+    r = _guidance_solve(s, f["x0"], f["p"], f["lh"], f["yref"], f["yref_e"])
+    stat = f[f"{tag}_stat"]
+    np.testing.assert_array_equal(r["status"], stat[:, 0])
+    assert (np.abs(r["sqp_iter"] - stat[:, 1]) <= 1).all()
+    if tag == "rti":
+        np.testing.assert_array_equal(r["qp_iter"], stat[:, 2])
+    every = np.ones(n, dtype=bool)
+    for k in ("x", "u", "sl", "su"):
+        good, worst = _close(r[k], f[f"{tag}_{k}"], every)
+        assert good, (tag, k, worst)
+    if tag == "sqp":
+        assert (r["res"] < 1e-6).all()
+    # multipliers of a path stage in the reference's order [lbu lh | ubu uh | lsh | ush] (no state boxes in this OCP)
+    lam = s.get(50, "lam")
+    assert lam.shape == (n, 2 * (1 + 8) + 16)
+    np.testing.assert_allclose(lam, f[f"{tag}_lam"][:, 50, :lam.shape[1]], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_soft_rows_equal_hard_rows_when_the_slack_is_pinned():
+    # metamorphic (after the reference's soft_constraint_test.py:185-203, which compares two formulations of the same
+    # constraint): with lsh = ush = 0 and a large linear penalty the slacks stay at their bound and the soft OCP must give
+    # the hard OCP's solution -- the slack condensation path against the plain path of the same kernel
+    from mpc_collisionavoidance_b200.workloads import make_guidance_batch
+    b = make_guidance_batch(16, seed=5)
+    hard = _guidance_solve(_guidance_solver(16, "SQP", soft=False), b.x0, b.p, b.lh, b.yref, b.yref_e)
+    soft = _guidance_solve(_guidance_solver(16, "SQP", soft=True, lsh=np.zeros(8), zl=np.full(8, 1e3), zu=np.full(8, 1e3)),
+                           b.x0, b.p, b.lh, b.yref, b.yref_e)
+    ok = (hard["status"] == 0) & (soft["status"] == 0)
+    assert ok.sum() >= 12
+    assert np.abs(soft["sl"][ok]).max() < 1e-5 and np.abs(soft["su"][ok]).max() < 1e-5
+    for k in ("x", "u"):
+        good, worst = _close(soft[k], hard[k], ok, tol=1e-5)
+        assert good, (k, worst)
+
+
+@pytest.mark.gpu
+def test_json_written_by_the_reference_configures_the_engine(golden_dir):
+    # tests/golden/acados_ocp_*.json were written by the reference's own
+    # ocp_formulation_json_dump (tests/make_reference_json.py).  Loading them must give a working solver:
+    # the benchmark OCP reproduces the known answer, the deployed CA OCP the guidance fixture.
+    from mpc_collisionavoidance_b200 import BatchedAcadosOcpSolver
+    from mpc_collisionavoidance_b200.ocp import ocp_formulation_json_load
+    ocp = ocp_formulation_json_load(os.path.join(golden_dir, "acados_ocp_usv3_cfg1.json"))
+    f = np.load(os.path.join(golden_dir, "usv_cfg1_known_answer.npz"))
+    s = BatchedAcadosOcpSolver(ocp, batch=None)          # unbatched drop-in; x0, yref, p, lh come from the JSON
+    assert s.solve() == 0
+    assert [int(s.get_stats("sqp_iter")[0]), int(s.get_stats("qp_iter")[0])] == list(f["sqp_stat"][1:])
+    np.testing.assert_allclose(s.get_all("x"), f["sqp_x"], rtol=1e-6, atol=1e-6)
+    ocp2 = ocp_formulation_json_load(os.path.join(golden_dir, "acados_ocp_usv_guidance_ca1.json"))
+    g = np.load(os.path.join(golden_dir, "usv_guidance_ca1.npz"))
+    s2 = BatchedAcadosOcpSolver(ocp2, batch=24)
+    assert (s2.cfg.nsh, s2.nx, s2.nu, s2.N) == (8, 8, 1, 100)
+    r = _guidance_solve(s2, g["x0"], g["p"], g["lh"], g["yref"], g["yref_e"])
+    np.testing.assert_array_equal(r["status"], g["rti_stat"][:, 0])
+    good, worst = _close(r["x"], g["rti_x"], np.ones(24, dtype=bool))
+    assert good, worst

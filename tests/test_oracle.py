@@ -169,3 +169,22 @@ def test_obstacle_frontend_restatement_properties():
     np.testing.assert_allclose(r[0], obs[0, ch[0], 2] + 0.5, rtol=1e-6)
     p2, r2, _ = obstacle_frontend(pose, obs, [3], 8)
     assert (p2[0, 6:] == 1000.0).all() and (r2[0, 3:] == 0).all()
+
+
+def _guidance_problem(nlp_type):
+    return rh.RefProblem(model=2, N=100, K=8, num_steps=1, nlp_type=nlp_type, nsh=8, lsh=-0.2, ush=0.0, zl=1.0, zu=1.0,
+                         uh=1e6, max_iter=30)
+
+
+@pytest.mark.parametrize("nlp_type,tag", [(1, "rti"), (0, "sqp")])
+def test_soft_constrained_guidance_ocp_matches_reference_fixture(golden_dir, nlp_type, tag):
+    # the deployed CA solver (usv_guidance_ca1: nx = 8, nu = 1, N = 100, 8 soft obstacle rows): slack condensation
+    # (x_ocp_qp_kkt.c:220-400), slack terms of cost / constraints (cost_ls.c:826-841, bgh.c:1404-1427)
+    f = np.load(os.path.join(golden_dir, "usv_guidance_ca1.npz"))
+    o = op.OracleSolver(_guidance_problem(nlp_type))
+    for i in range(12):
+        r = o.solve(f["x0"][i], f["p"][i], f["lh"][i], f["yref"][i], f["yref_e"][i])
+        assert [r["status"], r["sqp_iter"], r["qp_iter"]] == list(f[f"{tag}_stat"][i])
+        for k in ("x", "u", "sl", "su"):
+            np.testing.assert_allclose(r[k], f[f"{tag}_{k}"][i], rtol=1e-8, atol=1e-9, err_msg=f"{tag} {k} {i}")
+        np.testing.assert_allclose(r["lam"], f[f"{tag}_lam"][i], rtol=1e-6, atol=1e-9)
