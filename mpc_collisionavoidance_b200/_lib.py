@@ -26,7 +26,13 @@ SYMBOLS = ["usvmpc_last_error", "usvmpc_version", "usvmpc_config_default", "usvm
            "usvmpc_solve", "usvmpc_update_params", "usvmpc_cost_model_set", "usvmpc_constraints_model_set",
            "usvmpc_out_set", "usvmpc_out_get", "usvmpc_dims_get_from_attr", "usvmpc_get_stats",
            "usvmpc_solver_opts_set", "usvmpc_info", "usvmpc_eval_cost", "usvmpc_obstacle_frontend",
-           "usvmpc_set_result_buffer", "usvmpc_qp_solve"]
+           "usvmpc_set_result_buffer", "usvmpc_qp_solve", "usvmpc_acados_configure", "usvmpc_config_guidance_ca1"]
+# include/acados_compat.h: the generated solver's and acados_c's own names for one instance
+ACADOS_SYMBOLS = ["acados_create", "acados_update_params", "acados_solve", "acados_free", "acados_print_stats",
+                  "acados_get_nlp_in", "acados_get_nlp_out", "acados_get_nlp_solver", "acados_get_nlp_config",
+                  "acados_get_nlp_opts", "acados_get_nlp_dims", "acados_get_nlp_plan", "ocp_nlp_cost_model_set",
+                  "ocp_nlp_constraints_model_set", "ocp_nlp_out_set", "ocp_nlp_out_get", "ocp_nlp_dims_get_from_attr",
+                  "ocp_nlp_get", "ocp_nlp_solver_opts_set", "ocp_nlp_eval_residuals"]
 
 _lib = None
 
@@ -43,6 +49,8 @@ def load():
     lib.usvmpc_last_error.restype = cp
     lib.usvmpc_version.restype = cp
     lib.usvmpc_config_default.argtypes = [C.POINTER(Config), ci]
+    lib.usvmpc_config_guidance_ca1.argtypes = [C.POINTER(Config)]
+    lib.usvmpc_acados_configure.argtypes = [C.POINTER(Config)]
     lib.usvmpc_create.argtypes = [C.POINTER(Config), ci, ci, C.POINTER(vp)]
     lib.usvmpc_free.argtypes = [vp]
     lib.usvmpc_solve.argtypes = [vp, vp]

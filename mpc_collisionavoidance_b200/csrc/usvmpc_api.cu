@@ -96,7 +96,7 @@ __global__ void ws_copy_kernel(double* ws, long stride, int off, int fstride, in
     }
 }
 
-// multipliers / slacks of one stage between the engine's NLP row layout (layout.h) and the reference's order
+// multipliers / slacks of one stage between the engine's NLP row layout (cta_layout.h) and the reference's order
 // [lbu lbx lh | ubu ubx uh] with the stage's own counts (acados_template/acados_ocp_solver.py:732-735)
 __global__ void ws_rows_kernel(double* ws, long stride, int off, int ncz, int nbu, int nxslots, int nbxk, int K, int ns, int B,
                                double* buf, int to_ws)
@@ -813,9 +813,19 @@ int usvmpc_obstacle_frontend(const double* pose, const double* obs_body, const i
 {
     if (!pose || !obs_body || !len || !p_out || !r_out) return fail(USVMPC_E_INVALID, "null argument");
     if (batch < 1 || K < 1 || max_obs < 1 || max_obs > 64) return fail(USVMPC_E_INVALID, "need batch >= 1, K >= 1, 1 <= max_obs <= 64");
+    // launch on the device that owns the buffers (the caller may have another device current)
+    cudaPointerAttributes attr;
+    CU(cudaPointerGetAttributes(&attr, pose));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return fail(USVMPC_E_INVALID, "usvmpc_obstacle_frontend: pose must be a device pointer");
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
+    if (prev != attr.device) CU(cudaSetDevice(attr.device));
     obstacle_frontend_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t) stream>>>(pose, obs_body, len, batch, max_obs, K, boat_radius,
                                                                                      init_obs_pos, p_out, r_out);
-    CU(cudaGetLastError());
+    const cudaError_t err = cudaGetLastError();
+    if (prev != attr.device) cudaSetDevice(prev);
+    CU(err);
     return 0;
 }
 
@@ -863,5 +873,173 @@ int usvmpc_info(usvmpc_solver* s, const char* what, double* value)
     else return fail(USVMPC_E_FIELD, "unknown info '%s'", what);
     return 0;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// The exact symbols of the reference's generated solver + acados_c calls for B = 1 (include/acados_compat.h)
+// ------------------------------------------------------------------------------------------------------------------
+#include "../../include/acados_compat.h"
+
+namespace {
+usvmpc_solver* g_acados = nullptr;     // the one solver of the process, like the generated library's globals
+usvmpc_config g_acados_cfg;
+bool g_acados_cfg_set = false;
+double g_acados_stats[NSTAT];
+}  // namespace
+
+extern "C" {
+
+int usvmpc_config_guidance_ca1(usvmpc_config* c)
+{
+    int rc = usvmpc_config_default(c, USVMPC_MODEL_GUIDANCE_CA1);
+    if (rc) return rc;
+    const int nx = 8, nu = 1, ny = nx + nu, K = 8;
+    c->N = 100; c->K = K; c->dt = 5.0 / 100; c->num_steps = 1; c->num_stages = 4; c->nlp_type = USVMPC_SQP_RTI;
+    memset(c->W, 0, sizeof(c->W)); memset(c->W_e, 0, sizeof(c->W_e));
+    c->W[2 + ny * 2] = 0.05; c->W[3 + ny * 3] = 0.01; c->W[8 + ny * 8] = 0.2;      // Q = diag(0,0,.05,.01,0,0,0,0), R = .2
+    c->W_e[2 + nx * 2] = 0.1; c->W_e[3 + nx * 3] = 0.05;
+    c->nbu = 1; c->lbu[0] = -0.5; c->ubu[0] = 0.5; c->nbx = 0;
+    c->uh = 1000000.0;
+    c->nsh = K;
+    for (int i = 0; i < K; i++) { c->lsh[i] = -0.2; c->ush[i] = 0.0; c->zl[i] = 1.0; c->zu[i] = 1.0; c->Zl[i] = 0.0; c->Zu[i] = 0.0; }
+    return 0;
+}
+
+int usvmpc_acados_configure(const usvmpc_config* cfg)
+{
+    g_acados_cfg_set = cfg != nullptr;
+    if (cfg) g_acados_cfg = *cfg;
+    return 0;
+}
+
+int acados_create(void)
+{
+    if (g_acados) return 0;
+    if (!g_acados_cfg_set) { int rc = usvmpc_config_guidance_ca1(&g_acados_cfg); if (rc) return 1; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (usvmpc_create(&g_acados_cfg, 1, dev, &g_acados) != 0) { fprintf(stderr, "acados_create: %s\n", g_err); return 1; }
+    const usvmpc_config& c = g_acados_cfg;
+    // initial values of the generated code (acados_solver.in.c:1028-1449): lh from the description would be baked in; the node
+    // sets lh, p, yref, x0 before every solve, so zeros are as good
+    (void) c;
+    return 0;
+}
+
+int acados_free(void)
+{
+    usvmpc_free(g_acados);
+    g_acados = nullptr;
+    return 0;
+}
+
+int acados_update_params(int stage, double* value, int np)
+{
+    if (!g_acados) return 1;
+    if (usvmpc_update_params(g_acados, stage, value, np, 0, nullptr) != 0)
+    {
+        // the generated code exits on a size mismatch (acados_solver.in.c:1746-1751)
+        fprintf(stderr, "acados_update_params: %s\n", g_err);
+        exit(1);
+    }
+    return 0;
+}
+
+int acados_solve(void)
+{
+    if (!g_acados) return 1;
+    if (usvmpc_solve(g_acados, nullptr) != 0 || usvmpc_get_stats(g_acados, g_acados_stats, 0, nullptr) != 0)
+    {
+        fprintf(stderr, "acados_solve: %s\n", g_err);
+        return 1;   // ACADOS_FAILURE
+    }
+    return (int) g_acados_stats[0];
+}
+
+void acados_print_stats(void)
+{
+    printf("iter\tqp_iter\tres_stat\tres_eq\t\tres_ineq\tres_comp\n%d\t%d\t%e\t%e\t%e\t%e\n", (int) g_acados_stats[1],
+           (int) g_acados_stats[2], g_acados_stats[3], g_acados_stats[4], g_acados_stats[5], g_acados_stats[6]);
+}
+
+void* acados_get_nlp_in(void) { return g_acados; }
+void* acados_get_nlp_out(void) { return g_acados; }
+void* acados_get_nlp_solver(void) { return g_acados; }
+void* acados_get_nlp_config(void) { return g_acados; }
+void* acados_get_nlp_opts(void) { return g_acados; }
+void* acados_get_nlp_dims(void) { return g_acados; }
+void* acados_get_nlp_plan(void) { return g_acados; }
+
+static void acados_die(const char* what)
+{
+    // the reference's C side exits on an unknown field
+    fprintf(stderr, "%s: %s\n", what, g_err);
+    exit(1);
+}
+
+int ocp_nlp_cost_model_set(void* config, void* dims, void* in, int stage, const char* field, void* value)
+{
+    (void) config; (void) dims;
+    if (usvmpc_cost_model_set((usvmpc_solver*) in, stage, field, (const double*) value, 0, nullptr) != 0) acados_die("ocp_nlp_cost_model_set");
+    return 0;   // ACADOS_SUCCESS
+}
+
+int ocp_nlp_constraints_model_set(void* config, void* dims, void* in, int stage, const char* field, void* value)
+{
+    (void) config; (void) dims;
+    if (usvmpc_constraints_model_set((usvmpc_solver*) in, stage, field, (const double*) value, 0, nullptr) != 0)
+        acados_die("ocp_nlp_constraints_model_set");
+    return 0;
+}
+
+void ocp_nlp_out_set(void* config, void* dims, void* out, int stage, const char* field, void* value)
+{
+    (void) config; (void) dims;
+    if (usvmpc_out_set((usvmpc_solver*) out, stage, field, (const double*) value, 0, nullptr) != 0) acados_die("ocp_nlp_out_set");
+}
+
+void ocp_nlp_out_get(void* config, void* dims, void* out, int stage, const char* field, void* value)
+{
+    (void) config; (void) dims;
+    if (usvmpc_out_get((usvmpc_solver*) out, stage, field, (double*) value, 0, nullptr) != 0) acados_die("ocp_nlp_out_get");
+}
+
+int ocp_nlp_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field)
+{
+    (void) config; (void) dims;
+    const int d = usvmpc_dims_get_from_attr((usvmpc_solver*) out, stage, field);
+    if (d < 0) acados_die("ocp_nlp_dims_get_from_attr");
+    return d;
+}
+
+void ocp_nlp_get(void* config, void* solver, const char* field, void* return_value)
+{
+    (void) config;
+    usvmpc_solver* s = (usvmpc_solver*) solver;
+    const double* st = g_acados_stats;
+    if (!strcmp(field, "sqp_iter")) *(int*) return_value = (int) st[1];
+    else if (!strcmp(field, "qp_iter")) *(int*) return_value = (int) st[2];
+    else if (!strcmp(field, "status")) *(int*) return_value = (int) st[0];
+    else if (!strcmp(field, "res_stat")) *(double*) return_value = st[3];
+    else if (!strcmp(field, "res_eq")) *(double*) return_value = st[4];
+    else if (!strcmp(field, "res_ineq")) *(double*) return_value = st[5];
+    else if (!strcmp(field, "res_comp")) *(double*) return_value = st[6];
+    else if (!strcmp(field, "time_tot")) *(double*) return_value = st[12] / s->sm_clock_hz;
+    else if (!strcmp(field, "time_lin")) *(double*) return_value = st[13] / s->sm_clock_hz;
+    else if (!strcmp(field, "time_qp") || !strcmp(field, "time_qp_sol")) *(double*) return_value = st[14] / s->sm_clock_hz;
+    else { fail(USVMPC_E_FIELD, "unknown field '%s'", field); acados_die("ocp_nlp_get"); }
+}
+
+void ocp_nlp_solver_opts_set(void* config, void* opts, const char* field, void* value)
+{
+    (void) config;
+    // integer-valued options arrive as int*, tolerances as double* (ocp_nlp_sqp_rti.c:168-242)
+    const bool is_int = !strcmp(field, "rti_phase") || !strcmp(field, "max_iter") || !strcmp(field, "qp_iter_max") || !strcmp(field, "print_level");
+    const double v = is_int ? (double) *(int*) value : *(double*) value;
+    if (usvmpc_solver_opts_set((usvmpc_solver*) opts, field, v) != 0) acados_die("ocp_nlp_solver_opts_set");
+}
+
+void ocp_nlp_eval_residuals(void* solver, void* in, void* out) { (void) solver; (void) in; (void) out; }
 
 }  // extern "C"

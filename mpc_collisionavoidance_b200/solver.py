@@ -131,6 +131,8 @@ class BatchedAcadosOcpSolver:
             _lib.check(lib.usvmpc_update_params(h, stage, ptr, 2 * self.K, dev, st), "set p")
         elif field_ in _CONSTR_FIELDS + ["lh"]:
             if (stage > 0 and field_ in _CONSTR_FIELDS) or field_ in ("lbu", "ubu"):
+                if hasattr(value_, "detach"):       # a torch tensor (possibly on the device): these few numbers go by the host
+                    value_ = value_.detach().cpu().numpy()
                 v = np.ascontiguousarray(value_, dtype=np.float64).ravel()  # shared by the batch, copied by the call
                 if v.shape[0] != self._dims(stage, field_):
                     raise Exception('mismatching dimension for field "{}" with dimension {} (you have {})'.format(

@@ -9,6 +9,7 @@ Fixtures:
   usv_cfg5_solve.npz        256 Monte-Carlo draws of config 5 (128 base scenes x 2 draws of the x0 disturbance)
   usv_cfg2_lq.npz           the instances of the headline batch on which the reference takes its LQ path
   usv_guidance_ca1.npz      the deployed CA solver (nx = 8, nu = 1, N = 100, 8 soft obstacle rows): RTI step and SQP solve
+  usv_unconstrained.npz     an OCP without inequality rows (HPIPM's nc = 0 path: direct solve, zero IPM iterations)
   usv_cfg1_rti.npz          one SQP_RTI step (known answer 2 of SURVEY.md appendix B)
   usv_cfg2_qp.npz           QPs captured at HPIPM's door (after x0 elimination) with HPIPM's solution and
                             iteration count, for QP-level parity of the IPM/Riccati kernels
@@ -55,6 +56,28 @@ def guidance_fixture():
         out[f"{tag}_stat"] = np.array([[r["status"], r["sqp_iter"], r["qp_iter"]] for r in rs])
         print("guidance", tag, out[f"{tag}_stat"].T)
     np.savez_compressed(os.path.join(G, "usv_guidance_ca1.npz"), **out)
+
+
+def unconstrained_problem():
+    W = np.diag([1, 1, 0.1, 10, 0.1, 0.1, 1e-3, 1e-3])
+    none = np.array([])
+    return rh.RefProblem(N=20, K=0, num_steps=2, max_iter=30, W=W, We=5 * W[:6, :6], lbu=none, ubu=none,
+                         idxbx=np.array([], dtype=np.int32), lbx=none, ubx=none)
+
+
+def unconstrained_fixture():
+    """an OCP without any inequality row (no boxes, K = 0): after the x0 elimination HPIPM sees nc = 0 and takes its
+    direct factorise-and-solve path with iter = 0 (x_ocp_qp_ipm.c:2458-2481)"""
+    B = 6
+    rng = np.random.default_rng(3)
+    x0 = np.array([0, 0, 0.1, 0.7, 0, 0.0]) + 0.1 * rng.standard_normal((B, 6))
+    yref = np.tile(np.array([6, 1, 0, 1, 0, 0, 0, 0.0]), (B, 1))
+    yref[:, 1] += rng.uniform(-1, 1, B)
+    p, lh = np.zeros((B, 0)), np.zeros((B, 0))
+    o = rh.solve_batch(unconstrained_problem(), x0, p, lh, yref, yref[:, :6].copy())
+    np.savez_compressed(os.path.join(G, "usv_unconstrained.npz"), x0=x0, yref=yref, x=o["x"], u=o["u"], status=o["status"],
+                        sqp_iter=o["sqp_iter"], qp_iter=o["qp_iter"], res=o["res"])
+    print("unconstrained: status", o["status"], "sqp_iter", o["sqp_iter"], "qp_iter", o["qp_iter"])
 
 
 def lq_fixture():
@@ -117,3 +140,4 @@ if __name__ == "__main__":
     qp_fixture()
     lq_fixture()
     guidance_fixture()
+    unconstrained_fixture()

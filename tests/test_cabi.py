@@ -23,13 +23,35 @@ def lib():
 
 
 def test_library_exports_every_declared_symbol(lib):
-    hdr = open(os.path.join(ROOT, "include", "usvmpc.h")).read()
+    hdr = ""
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        hdr += open(os.path.join(ROOT, "include", h)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = sorted(set(re.findall(r"\b(usvmpc_[a-z_]+)\s*\(", hdr)))
-    assert len(declared) >= 14
+    declared = sorted(set(re.findall(r"\b(usvmpc_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 21
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_lib.SYMBOLS) == declared
+    # include/acados_compat.h: the reference's own symbol names (acados_solver.in.h:44-56, ocp_nlp_interface.h)
+    theirs = sorted(set(re.findall(r"\b((?:acados|ocp_nlp)_[a-z_]+)\s*\(", hdr)))
+    assert len(theirs) == 20 and theirs == sorted(_lib.ACADOS_SYMBOLS)
+    for name in theirs:
+        assert hasattr(lib, name), name
+
+
+def test_deployed_solver_description(lib):
+    # what acados_create() builds by default == the description of the deployed node (workloads.guidance_ca1_ocp)
+    from mpc_collisionavoidance_b200.ocp import config_from_ocp
+    from mpc_collisionavoidance_b200.workloads import guidance_ca1_ocp
+    a = _lib.Config()
+    assert lib.usvmpc_config_guidance_ca1(C.byref(a)) == 0
+    b = config_from_ocp(guidance_ca1_ocp())[0]
+    for name, _ in _lib.Config._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        if hasattr(va, "__len__"):
+            assert list(va) == list(vb), name
+        else:
+            assert va == vb, name
 
 
 def test_config_struct_matches_header(lib):
@@ -86,3 +108,20 @@ def test_json_description_round_trip(lib, tmp_path):
     import json
     d = json.load(open(f))
     assert d["constraints"]["lbx_0"] == d["constraints"]["ubx_0"] and d["solver_options"]["nlp_solver_type"] == "SQP"
+
+
+def build_node_driver(out_dir):
+    """gcc tests/c/ca_node_step.c against libusvmpc.so alone: the generated solver's symbol names must all resolve"""
+    import subprocess
+    exe = os.path.join(str(out_dir), "ca_node_step")
+    pkg = os.path.join(ROOT, "mpc_collisionavoidance_b200")
+    subprocess.run(["gcc", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "ca_node_step.c"),
+                    "-o", exe, "-L" + pkg, "-lusvmpc", "-Wl,-rpath," + pkg, "-Wl,--no-undefined"], check=True)
+    return exe
+
+
+def test_node_driver_links_with_the_generated_solver_symbols(lib, tmp_path):
+    import subprocess
+    exe = build_node_driver(tmp_path)
+    # no input file: exits before any device call
+    assert subprocess.run([exe]).returncode == 2

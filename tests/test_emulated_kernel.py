@@ -1,5 +1,5 @@
-"""Host-side check of the CUDA kernel SOURCE without a GPU: mpc_collisionavoidance_b200/csrc/nmpc_kernel.cuh is
-compiled for the CPU with a 32-fiber warp emulation (tests/emu/) and must reproduce the reference fixtures and the
+"""Host-side check of the CUDA kernel SOURCE without a GPU: mpc_collisionavoidance_b200/csrc/cta_kernel.cuh is
+compiled for the CPU with a fiber emulation of one thread block (tests/emu/) and must reproduce the reference fixtures and the
 oracle.  This guards indexing / masking / control flow; the numerics on the device are covered by the -m gpu tests."""
 import json
 import os
@@ -127,3 +127,24 @@ def test_soft_constrained_guidance_ocp(golden_dir, nlp_type, tag):
         rows = list(range(1 + nbx)) + [1 + 8 + c for c in range(8)]
         idx = rows + [ncz + j for j in rows] + [2 * ncz + j for j in range(16)]
         np.testing.assert_allclose(r["lam"][:, k][:, idx], f[f"{tag}_lam"][:n, k, :len(idx)], rtol=1e-6, atol=1e-9)
+
+
+def _unconstrained_problem():
+    W = np.diag([1, 1, 0.1, 10, 0.1, 0.1, 1e-3, 1e-3])
+    none = np.array([])
+    return rh.RefProblem(N=20, K=0, num_steps=2, max_iter=30, W=W, We=5 * W[:6, :6], lbu=none, ubu=none,
+                         idxbx=np.array([], dtype=np.int32), lbx=none, ubx=none)
+
+
+def test_ocp_without_inequality_rows(golden_dir):
+    # no boxes, K = 0: HPIPM's nc = 0 path -- one direct factorise-and-solve per QP, zero IPM iterations, status 0
+    # (x_ocp_qp_ipm.c:2458-2481); fixture from the unmodified reference (tests/make_golden.py)
+    f = np.load(os.path.join(golden_dir, "usv_unconstrained.npz"))
+    B = len(f["x0"])
+    none = np.zeros((B, 0))
+    r = ep.solve_batch(_unconstrained_problem(), f["x0"], none, none, f["yref"], f["yref"][:, :6].copy())
+    np.testing.assert_array_equal(r["status"], f["status"])
+    np.testing.assert_array_equal(r["sqp_iter"], f["sqp_iter"])
+    np.testing.assert_array_equal(r["qp_iter"], 0)
+    np.testing.assert_allclose(r["x"], f["x"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r["u"], f["u"], rtol=1e-8, atol=1e-8)

@@ -188,3 +188,24 @@ def test_soft_constrained_guidance_ocp_matches_reference_fixture(golden_dir, nlp
         for k in ("x", "u", "sl", "su"):
             np.testing.assert_allclose(r[k], f[f"{tag}_{k}"][i], rtol=1e-8, atol=1e-9, err_msg=f"{tag} {k} {i}")
         np.testing.assert_allclose(r["lam"], f[f"{tag}_lam"][i], rtol=1e-6, atol=1e-9)
+
+
+def _unconstrained_problem():
+    W = np.diag([1, 1, 0.1, 10, 0.1, 0.1, 1e-3, 1e-3])
+    none = np.array([])
+    return rh.RefProblem(N=20, K=0, num_steps=2, max_iter=30, W=W, We=5 * W[:6, :6], lbu=none, ubu=none,
+                         idxbx=np.array([], dtype=np.int32), lbx=none, ubx=none)
+
+
+def test_ocp_without_inequality_rows(golden_dir):
+    # no boxes, K = 0: HPIPM's nc = 0 path -- one direct factorise-and-solve per QP, zero IPM iterations, status 0
+    # (x_ocp_qp_ipm.c:2458-2481); fixture from the unmodified reference (tests/make_golden.py)
+    f = np.load(os.path.join(golden_dir, "usv_unconstrained.npz"))
+    B = len(f["x0"])
+    none = np.zeros((B, 0))
+    r = op.solve_batch(_unconstrained_problem(), f["x0"], none, none, f["yref"], f["yref"][:, :6].copy())
+    np.testing.assert_array_equal(r["status"], f["status"])
+    np.testing.assert_array_equal(r["sqp_iter"], f["sqp_iter"])
+    np.testing.assert_array_equal(r["qp_iter"], 0)
+    np.testing.assert_allclose(r["x"], f["x"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r["u"], f["u"], rtol=1e-8, atol=1e-8)
