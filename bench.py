@@ -251,6 +251,8 @@ def run_engine(args):
         batch = make_batch(cfg_id, B=B, seed=1234 + cfg_id + 1000 * rank)   # weak scaling: every rank its own batch
     s = BatchedAcadosOcpSolver(benchmark_ocp(cfg_id), batch=B, device=local)
     s.options_set("cold_start", 1)
+    if args.riccati_precision == 32:
+        s.options_set("riccati_precision", 32)     # BASELINE.json config 4: fp32 factorisation, fp64 residuals + refinement
     s.sync_host_sets = False
     names = ("x0", "p", "lh", "yref", "yref_e")
     host = {k: torch.from_numpy(np.ascontiguousarray(getattr(batch, k))).pin_memory() for k in names}
@@ -366,9 +368,11 @@ def run_engine(args):
                 "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": bench_config(cfg_id, B, world, args.strong),
                 "converged_solves_per_s": round(conv_total * args.steps / (total_ms * 1e-3), 1),
+                "riccati_precision": args.riccati_precision,
                 "workload_stats": {"converged_frac": round(float(ok.mean()), 4), "mean_sqp_iter": round(sqp_sum / B, 2),
                                    "mean_qp_iter": round(ipm_sum / B, 2), "max_sqp_iter": int(st[:, 1].max()),
                                    "lq_fact_iterations": int(st[:, 7].sum()), "refinement_solves": int(st[:, 11].sum()),
+                                   "fp32_factorisations": int(st[:, 15].sum()),
                                    "finite_outputs": x_ok,
                                    "l2": "256 MB written between timed steps (L2 flush, outside the timed intervals)",
                                    "hbm_resident_bytes": int(s.info("workspace_bytes")),
@@ -402,6 +406,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config (1-based); 2 = the headline")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--riccati-precision", type=int, default=64, choices=[32, 64],
+                    help="32: Riccati factorisation in fp32 with fp64 residuals and refinement (BASELINE.json config 4's variant)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the config's batch is split over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

@@ -50,11 +50,17 @@ int ocp_nlp_constraints_model_set(void* config, void* dims, void* in, int stage,
 void ocp_nlp_out_set(void* config, void* dims, void* out, int stage, const char* field, void* value);
 void ocp_nlp_out_get(void* config, void* dims, void* out, int stage, const char* field, void* value);
 int ocp_nlp_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field);
-/* fields: "sqp_iter" (int), "time_tot", "time_lin", "time_qp", "res_stat", "res_eq", "res_ineq", "res_comp" (double) */
+/* fields: "sqp_iter" (int), "time_tot", "time_lin", "time_qp", "res_stat", "res_eq", "res_ineq", "res_comp", "cost_value" (double) */
 void ocp_nlp_get(void* config, void* solver, const char* field, void* return_value);
 void ocp_nlp_solver_opts_set(void* config, void* opts, const char* field, void* value);
 /* residuals of the current iterate are part of every solve's statistics: nothing to do (ocp_nlp_interface.c:909) */
 void ocp_nlp_eval_residuals(void* solver, void* in, void* out);
+/* cost of the current iterate; read it with ocp_nlp_get(config, solver, "cost_value", &v)  (ocp_nlp_interface.c:919) */
+void ocp_nlp_eval_cost(void* solver, void* in, void* out);
+/* 2-D size queries of the Python wrapper's cost_set / constraints_set (acados_ocp_solver.py:1022-1030, 1090-1098):
+ * vectors report (n, 0), "W" (ny, ny) */
+void ocp_nlp_cost_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field, int* dims_out);
+void ocp_nlp_constraint_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field, int* dims_out);
 
 #ifdef __cplusplus
 }

@@ -886,6 +886,7 @@ usvmpc_solver* g_acados = nullptr;     // the one solver of the process, like th
 usvmpc_config g_acados_cfg;
 bool g_acados_cfg_set = false;
 double g_acados_stats[NSTAT];
+double g_acados_cost = 0.0;
 }  // namespace
 
 extern "C" {
@@ -1025,6 +1026,7 @@ void ocp_nlp_get(void* config, void* solver, const char* field, void* return_val
     else if (!strcmp(field, "res_eq")) *(double*) return_value = st[4];
     else if (!strcmp(field, "res_ineq")) *(double*) return_value = st[5];
     else if (!strcmp(field, "res_comp")) *(double*) return_value = st[6];
+    else if (!strcmp(field, "cost_value")) *(double*) return_value = g_acados_cost;
     else if (!strcmp(field, "time_tot")) *(double*) return_value = st[12] / s->sm_clock_hz;
     else if (!strcmp(field, "time_lin")) *(double*) return_value = st[13] / s->sm_clock_hz;
     else if (!strcmp(field, "time_qp") || !strcmp(field, "time_qp_sol")) *(double*) return_value = st[14] / s->sm_clock_hz;
@@ -1041,5 +1043,40 @@ void ocp_nlp_solver_opts_set(void* config, void* opts, const char* field, void* 
 }
 
 void ocp_nlp_eval_residuals(void* solver, void* in, void* out) { (void) solver; (void) in; (void) out; }
+
+void ocp_nlp_eval_cost(void* solver, void* in, void* out)
+{
+    (void) in; (void) out;
+    if (usvmpc_eval_cost((usvmpc_solver*) solver, &g_acados_cost, 0, nullptr) != 0) acados_die("ocp_nlp_eval_cost");
+}
+
+// the 2-D size queries of the Python wrapper's cost_set / constraints_set (acados_ocp_solver.py:1022-1030, 1090-1098):
+// vectors report (n, 0), the weight matrix (ny, ny)
+static void dims2(void* out, int stage, const char* field, int* dims_out, const char* who)
+{
+    usvmpc_solver* s = (usvmpc_solver*) out;
+    if (!strcmp(field, "W"))
+    {
+        const int ny = usvmpc_dims_get_from_attr(s, stage, "yref");
+        if (ny < 0) acados_die(who);
+        dims_out[0] = ny; dims_out[1] = ny;
+        return;
+    }
+    const int d = usvmpc_dims_get_from_attr(s, stage, field);
+    if (d < 0) acados_die(who);
+    dims_out[0] = d; dims_out[1] = 0;
+}
+
+void ocp_nlp_cost_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field, int* dims_out)
+{
+    (void) config; (void) dims;
+    dims2(out, stage, field, dims_out, "ocp_nlp_cost_dims_get_from_attr");
+}
+
+void ocp_nlp_constraint_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field, int* dims_out)
+{
+    (void) config; (void) dims;
+    dims2(out, stage, field, dims_out, "ocp_nlp_constraint_dims_get_from_attr");
+}
 
 }  // extern "C"
