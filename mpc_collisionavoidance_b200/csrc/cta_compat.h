@@ -26,6 +26,21 @@ DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+DEV unsigned warp_max_u32(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }   // one REDUX instruction
+DEV unsigned long long double_bits(double v) { return (unsigned long long) __double_as_longlong(v); }
+DEV double bits_double(unsigned long long u) { return __longlong_as_double((long long) u); }
+// one fp64 tensor-core product of the warp: D (8 x 8) += A (8 x 4, row-major fragments) * B (4 x 8).  With g = lane / 4,
+// t = lane % 4 the lane holds A[g][t], B[t][g] and D[g][2t], D[g][2t + 1]   (mma.sync.m8n8k4.f64, SASS DMMA)
+DEV void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// shared-memory accesses by 32-bit shared-window byte address (no address arithmetic left to the compiler)
+typedef unsigned saddr;
+DEV saddr smem_addr(const void* p) { return (saddr) __cvta_generic_to_shared(p); }
+DEV double lds64(saddr a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+DEV void lds128(saddr a, double& x, double& y) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
+DEV void sts64(saddr a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 DEV void syncwarp() { __syncwarp(); }
 DEV void syncthreads() { __syncthreads(); }
 // barrier `id` (1..15) among the first `count` threads of the block (count a multiple of 32)
@@ -71,7 +86,7 @@ struct Block {
     int T, cur;
     Fiber f[MAXT];
     Barrier cta, warp[MAXT / WARP], named[16];
-    double slot_d[MAXT];
+    double slot_d[MAXT], slot_e[MAXT];
     long slot_i[MAXT];
     void* main_sp;
     char* stacks;
@@ -83,6 +98,11 @@ void arrive(Barrier* b);                       // tests/emu/emu_solver.cpp
 void run_block(int T, void (*body)(void*), void* arg);
 }  // namespace emu
 
+typedef uintptr_t saddr;
+DEV saddr smem_addr(const void* p) { return (saddr) p; }
+DEV double lds64(saddr a) { return *(const double*) a; }
+DEV void lds128(saddr a, double& x, double& y) { x = ((const double*) a)[0]; y = ((const double*) a)[1]; }
+DEV void sts64(saddr a, double v) { *(double*) a = v; }
 DEV int thread_id() { return emu::g_blk->cur; }
 DEV int block_threads() { return emu::g_blk->T; }
 DEV int lane_id() { return emu::g_blk->cur & 31; }
@@ -104,6 +124,20 @@ DEV double shfl(double v, int src)
     return r;
 }
 DEV float shfl(float v, int src) { return (float) shfl((double) v, src); }
+DEV void dmma884(double& d0, double& d1, double a, double b)
+{
+    emu::Block* blk = emu::g_blk;
+    const int base = blk->cur & ~31, g = (blk->cur & 31) >> 2, t = blk->cur & 3;
+    blk->slot_d[blk->cur] = a; blk->slot_e[blk->cur] = b;
+    syncwarp();
+    for (int k = 0; k < 4; k++)
+    {
+        const double ak = blk->slot_d[base + 4 * g + k];
+        d0 = std::fma(ak, blk->slot_e[base + 4 * (2 * t) + k], d0);
+        d1 = std::fma(ak, blk->slot_e[base + 4 * (2 * t + 1) + k], d1);
+    }
+    syncwarp();
+}
 DEV int shfl(int v, int src)
 {
     emu::Block* b = emu::g_blk;
@@ -115,6 +149,19 @@ DEV int shfl(int v, int src)
 }
 DEV double shfl_xor(double v, int m) { return shfl(v, lane_id() ^ m); }
 DEV int shfl_xor(int v, int m) { return shfl(v, lane_id() ^ m); }
+DEV unsigned warp_max_u32(unsigned v)
+{
+    emu::Block* b = emu::g_blk;
+    b->slot_i[b->cur] = (long) v;
+    syncwarp();
+    unsigned r = 0;
+    const int base = b->cur & ~31;
+    for (int l = 0; l < 32 && base + l < b->T; l++) { const unsigned o = (unsigned) b->slot_i[base + l]; r = o > r ? o : r; }
+    syncwarp();
+    return r;
+}
+DEV unsigned long long double_bits(double v) { unsigned long long u; std::memcpy(&u, &v, 8); return u; }
+DEV double bits_double(unsigned long long u) { double v; std::memcpy(&v, &u, 8); return v; }
 DEV double dsqrt(double a) { return std::sqrt(a); }
 DEV double drsqrt(double a) { return 1.0 / std::sqrt(a); }
 DEV float drsqrt(float a) { return 1.0f / std::sqrt(a); }
@@ -131,12 +178,21 @@ DEV long long clock_now() { return 0; }
 #endif
 
 namespace usvmpc {
-// butterfly reductions over one warp; every lane ends up with the result
+// reductions over one warp; every lane ends up with the result
+// max: the doubles are mapped to unsigned integers of the same order (sign bit flipped for v >= 0, all bits for v < 0),
+// then two 32-bit warp reductions (high word, low word among the lanes that hold the maximal high word) replace a
+// five-step shuffle butterfly.  The value returned is bit for bit one of the inputs.  Callers never pass NaN (their
+// running maxima are built with `q > m ? q : m`, which drops NaN).
 DEV double warp_max(double v)
 {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) { const double o = shfl_xor(v, m); v = o > v ? o : v; }
-    return v;
+    unsigned long long u = double_bits(v);
+    u ^= (u >> 63) ? ~0ull : 0x8000000000000000ull;
+    const unsigned hi = (unsigned) (u >> 32), lo = (unsigned) u;
+    const unsigned mh = warp_max_u32(hi);
+    const unsigned ml = warp_max_u32(hi == mh ? lo : 0u);
+    u = ((unsigned long long) mh << 32) | ml;
+    u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
+    return bits_double(u);
 }
 DEV double warp_sum(double v)
 {

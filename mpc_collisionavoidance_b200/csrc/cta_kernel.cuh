@@ -50,6 +50,9 @@ struct FastDiv {
 #ifndef USVMPC_CHAIN_WARPS
 #define USVMPC_CHAIN_WARPS 2
 #endif
+#ifndef USVMPC_CHAIN_MMA
+#define USVMPC_CHAIN_MMA 1   // fp64 factorisation on the tensor cores (chainA_mma); 0: chainA_impl<double> on CHAIN_WARPS warps
+#endif
 constexpr int CHAIN_WARPS = USVMPC_CHAIN_WARPS;  // warps that share one stage step of the factorisation
 template <int CT>
 DEV void chain_sync()
@@ -224,6 +227,278 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
             }
         }
         chain_sync<CT>();
+    }
+}
+
+// chainA in fp64 on the tensor cores (the product path; chainA_impl above stays for the fp32 variant and as the
+// readable statement of the step).  ONE warp; per stage two small products as DMMA m8n8k4 tiles and the elimination
+// of the input columns on the accumulator fragments:
+//   1. W (NX x NR) = P_{k+1} [G' | res_b]          A = P from sPp (row stride WS), B = G / res_b straight from the fields
+//   2. S (NV x NR) = M + G W                        A = the G fragments of step 1, B = W through sWt ([column][row], stride WS)
+//      column NV of S is the gradient row of the packed matrix (S[i][NV] = entry (NV, i))
+//   3. Cholesky of the NU x NU input block (redone by every lane) and the Schur complement on the lane's own entries;
+//      columns 0 .. NU-1 and NV of S travel through a small exchange array X[row] = {S[row][0], S[row][1], S[row][NV]}.
+// With g = lane / 4, t = lane % 4 a lane holds S[8 mt + g][8 nt + 2 t + e], e = 0, 1.
+// A lone warp runs at ~4 cycles per instruction whatever the instruction is, so the loop is written for instruction
+// count: every shared-memory address is a per-lane 32-bit register that is only decremented by the stage stride
+// (lds64 / sts64), lanes whose index falls outside a matrix read a clamped in-bounds entry (finite, multiplied by an
+// exact zero or feeding an unused entry) and write to a dump slot, so the loop has no predicated memory access.
+// Padding that must be exact (k-padding of P, rows >= NX of W) reads a zero slot.
+// Same pivot rule and the same outputs as chainA_impl: Mx (factor columns, P_k, p_k), Pb, dinv.
+template <class M>
+MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sWt, double* sPp, int N)
+{
+    constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NE = NV * (NV + 1) / 2 + NV;
+    constexpr int MT = (NV + 7) / 8, NT = (NR + 7) / 8, KS = (NX + 3) / 4, WS = 12, XS = 4;
+    constexpr int NTV = NV / 8, TV = (NV % 8) / 2, EV = NV % 2;  // where column NV sits in the fragment layout
+    static_assert(NX <= 8 && NV <= 16 && NU <= 2 && MT <= NT, "fragment layout of chainA_mma");
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    double* X = sWt + NR * WS;                 // exchange array [8 MT][XS]
+    double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only), [1] = dump (write only)
+    if (lane == 0) slots[0] = 0.0;
+    const saddr zero = smem_addr(slots), dump = zero + 8;
+    // ---- stage-independent addresses
+    saddr aP[KS], aWst[NT][2], aWb[NT][KS], aXst[MT][NU], aXr[MT], aXc[NT][2], aPst[MT][NT][2][2];
+    const saddr aXv = (t == TV && g < NU) ? smem_addr(X + g * XS + 2) : dump;   // S[j][NV], j < NU, lives in tile (0, NTV)
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+    {
+        const int kk = 4 * ks + t;
+        aP[ks] = (g < NX && kk < NX) ? smem_addr(sPp + g * WS + kk) : zero;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+        {
+            const int n = 8 * nt + g;
+            aWb[nt][ks] = smem_addr(sWt + (n < NR ? n : NR - 1) * WS + kk);   // columns beyond NR feed only unused columns of S
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+    {
+        const int row = 8 * mt + g;
+        aXr[mt] = smem_addr(X + row * XS);
+#pragma unroll
+        for (int j = 0; j < NU; j++) aXst[mt][j] = t == 0 ? smem_addr(X + row * XS + j) : dump;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+            const int col = 8 * nt + 2 * t + e;
+            aWst[nt][e] = col < NR ? smem_addr(sWt + col * WS + g) : dump;
+            aXc[nt][e] = smem_addr(X + (col < NV ? col : 0) * XS);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+            {
+                const int row = 8 * mt + g;
+                const bool ok = col >= NU && col <= row && row < NV;
+                aPst[mt][nt][e][0] = ok ? smem_addr(sPp + (row - NU) * WS + (col - NU)) : dump;
+                aPst[mt][nt][e][1] = ok ? smem_addr(sPp + (col - NU) * WS + (row - NU)) : dump;
+            }
+        }
+    // ---- addresses that move with the stage (set for stage N, decremented at the end of every stage)
+    saddr aM[MT][NT][2], aMst[MT][NT][2], aG[NT][KS];
+    int dMst[MT][NT][2], dG[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const int row = 8 * mt + g, col = 8 * nt + 2 * t + e;
+                const int r = row < NV ? row : NV - 1, c = col <= NV ? col : NV;           // clamped: any in-bounds entry
+                const int hi = r > c ? r : c, lo = r > c ? c : r;
+                const saddr a = smem_addr(Mx + N * NE + hi * (hi + 1) / 2 + lo);             // c == NV: the gradient row
+                aM[mt][nt][e] = a;
+                const bool st = row < NV && (col == NV || col <= row);
+                aMst[mt][nt][e] = st ? a : dump;
+                dMst[mt][nt][e] = st ? NE * 8 : 0;
+            }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+    {
+        const int n = 8 * nt + g, nn = n <= NV ? n : NV;       // rows beyond NR: read res_b again (their W columns are dumped)
+        dG[nt] = nn == NV ? NX * 8 : NV * NX * 8;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+        {
+            const int kk = 4 * ks + t, kc = kk < NX ? kk : NX - 1;   // k-padding: P's fragment is an exact zero there
+            aG[nt][ks] = nn == NV ? smem_addr(rb + (N - 1) * NX + kc) : smem_addr(G + (N - 1) * (NV * NX) + nn + NV * kc);
+        }
+    }
+    // column NV of W (lanes t == TV, rows g < NX): P res_b goes out as Pb, p_{k+1} (x part of row NV of stage k+1) comes in
+    const bool pb_lane = t == TV && g < NX, dinv_lane = lane < NU;
+    saddr aPb = pb_lane ? smem_addr(Pb + (N - 1) * NX + g) : dump;
+    saddr aPn = pb_lane ? smem_addr(Mx + N * NE + (NV * (NV + 1)) / 2 + NU + g) : zero;
+    saddr aDi = dinv_lane ? smem_addr(dinv + N * NU + lane) : dump;
+    const int dPb = pb_lane ? NX * 8 : 0, dPn = pb_lane ? NE * 8 : 0, dDi = dinv_lane ? NU * 8 : 0;
+    syncwarp();
+#pragma unroll 1
+    for (int k = N; k >= 0; k--)
+    {
+        double s[MT][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (8 * nt + e <= NV) s[mt][nt][e] = lds64(aM[mt][nt][e]); else s[mt][nt][e] = 0.0;
+        if (k < N)
+        {
+            double pa[KS], gb[NT][KS], w[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) gb[nt][ks] = lds64(aG[nt][ks]);
+            const double pnv = lds64(aPn);
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) pa[ks] = lds64(aP[ks]);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+            {
+                w[nt][0] = 0.0; w[nt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) dmma884(w[nt][0], w[nt][1], pa[ks], gb[nt][ks]);
+            }
+            // column NV of W = P res_b: goes out as Pb, and with p_{k+1} added into the product of step 2
+            sts64(aPb, w[NTV][EV]);
+            w[NTV][EV] += pnv;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (8 * nt + e < NR) sts64(aWst[nt][e], w[nt][e]);
+            syncwarp();
+            double wb[NT][KS];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) wb[nt][ks] = lds64(aWb[nt][ks]);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+                        if (8 * nt <= NV) dmma884(s[mt][nt][0], s[mt][nt][1], gb[mt][ks], wb[nt][ks]);
+        }
+        // ---- exchange: columns 0 .. NU-1 of every row, column NV of the rows of the input block
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int j = 0; j < NU; j++) sts64(aXst[mt][j], s[mt][0][j]);
+        sts64(aXv, s[0][NTV][EV]);
+        syncwarp();
+        double ar[MT][2], ac[NT][2][2], blk[2][2], sp[2];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) lds128(aXr[mt], ar[mt][0], ar[mt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+                if (8 * nt + e < NV) lds128(aXc[nt][e], ac[nt][e][0], ac[nt][e][1]); else { ac[nt][e][0] = 0.0; ac[nt][e][1] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < NU; j++)
+        {
+            lds128(smem_addr(X + j * XS), blk[j][0], blk[j][1]);
+            sp[j] = lds64(smem_addr(X + j * XS + 2));
+        }
+        // ---- Cholesky of the input block, redundantly on every lane (see chainA_impl)
+        double Lt[NU][NU], inv[NU];
+        if (NU == 2)
+        {
+            const double m00 = blk[0][0], m10 = blk[NU - 1][0], m11 = blk[NU - 1][NU - 1];
+            const double det = m00 * m11 - m10 * m10;
+            const double i0 = m00 > 0.0 ? drsqrt(m00) : 0.0;
+            double i1;
+            if (m00 > 0.0) i1 = det > 0.0 ? drsqrt(det) * (m00 * i0) : 0.0;
+            else i1 = m11 > 0.0 ? drsqrt(m11) : 0.0;
+            const double l10 = m10 * i0;
+            inv[0] = i0; inv[NU - 1] = i1;
+            Lt[0][0] = m00 * i0; Lt[NU - 1][0] = l10;
+            Lt[NU - 1][NU - 1] = (m11 - l10 * l10) * i1;
+        }
+        else
+        {
+            const double piv = blk[0][0];
+            inv[0] = piv > 0.0 ? drsqrt(piv) : 0.0;
+            Lt[0][0] = piv * inv[0];
+        }
+        sts64(aDi, lane == 0 ? inv[0] : inv[NU - 1]);
+        // ---- Schur complement on the lane's entries
+        double vr[MT][NU];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int j = 0; j < NU; j++)
+            {
+                double x = ar[mt][j];
+#pragma unroll
+                for (int i = 0; i < j; i++) x -= vr[mt][i] * Lt[j][i];
+                vr[mt][j] = x * inv[j];
+            }
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                if (8 * nt + e > NV) continue;     // no lane holds a column of the matrix there
+                const int col = 8 * nt + 2 * t + e;
+                double uc[NU];
+#pragma unroll
+                for (int j = 0; j < NU; j++)
+                {
+                    double y = col == NV ? sp[j] : ac[nt][e][j];
+#pragma unroll
+                    for (int i = 0; i < j; i++) y -= uc[i] * Lt[j][i];
+                    uc[j] = y * inv[j];
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+                {
+                    const int row = 8 * mt + g;
+                    double out = s[mt][nt][e];
+#pragma unroll
+                    for (int j = 0; j < NU; j++) out -= vr[mt][j] * uc[j];
+#pragma unroll
+                    for (int j = 0; j < NU; j++)
+                    {
+                        out = col == j ? vr[mt][j] : out;                 // factor column j
+                        out = (col == NV && row == j) ? uc[j] : out;      // its entry in the gradient row
+                    }
+                    sts64(aMst[mt][nt][e], out);
+                    if (8 * nt + e < NV + 0 && 8 * nt + 6 + e >= NU)
+                    {
+                        sts64(aPst[mt][nt][e][0], out);
+                        sts64(aPst[mt][nt][e][1], out);
+                    }
+                }
+            }
+        // ---- next stage
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                {
+                    aM[mt][nt][e] -= NE * 8;
+                    aMst[mt][nt][e] -= dMst[mt][nt][e];
+                }
+        if (k < N)
+        {
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) aG[nt][ks] -= dG[nt];
+            aPb -= dPb;
+            aPn -= dPn;
+        }
+        aDi -= dDi;
+        syncwarp();
     }
 }
 
@@ -405,7 +680,7 @@ struct CtaSolver {
         red = sm + P.plan.red_off;
         redbuf = 0;
         double* m = sm + P.plan.misc_off;
-        sA0 = m; m += NV * NX; sW = m; m += NX * NR + NE + (NE & 1); sP = m; m += NX * NX + 2;  // sW = [P G' | scratch matrix]
+        sA0 = m; m += NV * NX; sW = m; m += chain_w_doubles(NX, NU); sP = m; m += chain_p_doubles(NX);  // chain scratch: [P G' | matrix], P
         {
             const int nb1 = (N + BS - 1) / BS + 1;
             Phi = m; m += nb1 * NX * NX; phi = m; m += nb1 * NX; Xb = m; m += nb1 * NX;
@@ -466,12 +741,10 @@ struct CtaSolver {
             for (int i = 0; i < NS; i++) r[wid * 8 + NM + i] = vsum[i];
         }
         syncthreads();
-        for (int q = 0; q < W; q++)
-        {
-            if (q == wid) continue;
+        // every warp reduces the W per-warp maxima again (lane l holds warp l mod W's value)
+        const int src = (lane < W ? lane : lane % W) * 8;
 #pragma unroll
-            for (int i = 0; i < NM; i++) { const double o = r[q * 8 + i]; vmax[i] = o > vmax[i] ? o : vmax[i]; }
-        }
+        for (int i = 0; i < NM; i++) vmax[i] = warp_max(r[src + i]);
         // sums in warp order so that every thread adds the same numbers in the same order
         if (NS > 0)
         {
@@ -1152,7 +1425,11 @@ struct CtaSolver {
     {
         if (wid >= CHAIN_WARPS) return;
         if (use_fp32) chainA_impl<M, float>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
+#if USVMPC_CHAIN_MMA
+        else if (wid == 0) chainA_mma<M>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
+#else
         else chainA_impl<M, double>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
+#endif
     }
     // The two vector recursions dx_{k+1} = Acl_k dx_k + c_k and p_k = Acl_k' p_{k+1} + e_k are affine maps, so BS of them
     // compose into one: Phi_j = Acl_{e-1} ... Acl_s for block j = stages [s, e).  The block products are formed once per

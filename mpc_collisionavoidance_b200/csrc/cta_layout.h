@@ -103,6 +103,20 @@ struct Params {
 };
 
 inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
+// scratch of the Riccati factorisation: [P G' | copy of the matrix] (chainA_impl) or W with column stride 12 (chainA_mma),
+// and P_{k+1} as a full matrix (row stride NX or 12)
+#if defined(__CUDACC__)
+#define USVMPC_HD __host__ __device__
+#else
+#define USVMPC_HD
+#endif
+USVMPC_HD constexpr int chain_w_doubles(int nx, int nu)
+{
+    const int nv = nx + nu, ne = nv * (nv + 1) / 2 + nv;
+    const int a = nx * (nv + 1) + ne + (ne & 1), b = 12 * (nv + 1) + 32 * ((nv + 7) / 8) + 2;   // W + exchange array + zero / dump slots
+    return a > b ? a : b;
+}
+USVMPC_HD constexpr int chain_p_doubles(int nx) { return nx * nx + 2 > 12 * nx ? nx * nx + 2 : 12 * nx; }
 
 inline Layout make_layout(int nx, int nu, int N, int K, int ns = 0)
 {
@@ -149,7 +163,7 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int ns, in
     P.red_off = (int) o;
     o += 2 * warps * 8;                                  // two reduction buffers of 8 values per warp
     P.misc_off = (int) o;
-    o += nv * nx + (nx * (nv + 1) + ne + 1) + (nx * nx + 2) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
+    o += nv * nx + chain_w_doubles(nx, nu) + chain_p_doubles(nx) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
     o += ((N + 3) / 4 + 1) * (nx * nx + 2 * nx);         // block maps of the vector recursions (blocks of 4 stages)
     o = round_up((int) o, 2);
     for (int i = 0; i < F_FIRST_FLEX; i++)
