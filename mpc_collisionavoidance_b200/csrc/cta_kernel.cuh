@@ -647,7 +647,6 @@ struct CtaSolver {
     MDEV double* rg_() const { return fld(F_RG); }
     MDEV double* dpi_() const { return fld(F_DPI); }
     MDEV double* gxy_() const { return fld(F_GXY); }
-    MDEV double* ti_() const { return fld(F_TI); }
     MDEV double* d_() const { return fld(F_D); }
     MDEV double* rq_() const { return fld(F_RQ); }
     MDEV double* b_() const { return fld(F_B); }
@@ -1242,7 +1241,6 @@ struct CtaSolver {
             double q = dabs(m0); n3 = q > n3 ? q : n3; q = dabs(m1); n3 = q > n3 ? q : n3;
             q = dabs(rd0); n2 = q > n2 ? q : n2; q = dabs(rd1); n2 = q > n2 ? q : n2;
             const double ti0 = 1.0 / t0, ti1 = 1.0 / t1;
-            ti_()[r0] = ti0; ti_()[r1] = ti1;
             double G0 = ti0 * l0, G1 = ti1 * l1;
             double g0 = ti0 * ((m0 - tau) - l0 * rd0), g1 = ti1 * ((m1 - tau) - l1 * rd1);
             if (is >= 0)
@@ -1260,7 +1258,6 @@ struct CtaSolver {
                     q = dabs(ms); n3 = q > n3 ? q : n3;
                     q = dabs(rds); n2 = q > n2 ? q : n2;
                     const double tis = 1.0 / ts;
-                    ti_()[rs] = tis;
                     const double Gsl = tis * ls, gsl = tis * ((ms - tau) - ls * rds);
                     const double Z = zquad(is, side);
                     const double rgs = Z * sj + rqs_()[si] - ls - (side ? l1 : l0);
@@ -1373,7 +1370,7 @@ struct CtaSolver {
             {
                 auto row_terms = [&](int r0, double& Gs, double& gd) {
                     const int r1 = r0 + ncq;
-                    const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1], i0 = ti_()[r0], i1 = ti_()[r1];
+                    const double l0 = lam_()[r0], l1 = lam_()[r1], t0 = t_()[r0], t1 = t_()[r1], i0 = 1.0 / t0, i1 = 1.0 / t1;
                     double G[2] = {i0 * l0, i1 * l1};
                     double g[2] = {i0 * ((l0 * t0 - tau) - l0 * rd_()[r0]), i1 * ((l1 * t1 - tau) - l1 * rd_()[r1])};
                     const int is = soft_index(r0 - k * s2);
@@ -1383,7 +1380,7 @@ struct CtaSolver {
                         for (int side = 0; side < 2; side++)
                         {
                             const int rs = k * s2 + 2 * ncq + side * ns + is, si = k * 2 * ns + side * ns + is;
-                            const double ls = lam_()[rs], ts = t_()[rs], tis = ti_()[rs];
+                            const double ls = lam_()[rs], ts = t_()[rs], tis = 1.0 / ts;
                             const double Gsl = tis * ls, gsl = tis * ((ls * ts - tau) - ls * rd_()[rs]);
                             const double zi = zsi_()[si], tmp = (rgs_()[si] + g[side] + gsl) * zi, Gr = G[side];
                             (void) Gsl;
@@ -1641,9 +1638,11 @@ struct CtaSolver {
                 m0 = l0 * t_()[r0]; m1 = l1 * t_()[r1];
                 if (mode == 0) { m0 += dt_()[r0] * dlam_()[r0]; m1 += dt_()[r1] * dlam_()[r1]; }
                 m0 -= sigma_mu; m1 -= sigma_mu;
-                rmc_()[r0] = m0; rmc_()[r1] = m1;
+                rmc_()[r0] = m0; rmc_()[r1] = m1;   // kept for a refinement's residual (rare; the field may live in L2)
+                dt_()[r0] = m0; dt_()[r1] = m1;     // the affine step is dead from here on: expand_pass picks the values up
             }
-            double g0 = ti_()[r0] * (m0 - l0 * rdp[r0]), g1 = ti_()[r1] * (m1 - l1 * rdp[r1]);
+            const double ti0 = 1.0 / t_()[r0], ti1 = 1.0 / t_()[r1];   // 1 / t is recomputed where it is needed (same bits as in passA)
+            double g0 = ti0 * (m0 - l0 * rdp[r0]), g1 = ti1 * (m1 - l1 * rdp[r1]);
             const int is = soft_index(j);
             if (is >= 0)
             {
@@ -1664,9 +1663,10 @@ struct CtaSolver {
                         if (mode == 0) ms += dt_()[rs] * dlam_()[rs];
                         ms -= sigma_mu;
                         rmc_()[rs] = ms;
+                        dt_()[rs] = ms;
                     }
-                    const double gsl = ti_()[rs] * (ms - ls * rdp[rs]);
-                    const double gr = side ? g1 : g0, Gr = side ? ti_()[r1] * l1 : ti_()[r0] * l0;
+                    const double gsl = (1.0 / t_()[rs]) * (ms - ls * rdp[rs]);
+                    const double gr = side ? g1 : g0, Gr = side ? ti1 * l1 : ti0 * l0;
                     const double rhs = rgsp[si] + gr + gsl;
                     dso[si] = rhs;
                     const double tmp = rhs * zsi_()[si];
@@ -1750,8 +1750,11 @@ struct CtaSolver {
         // candidates, mu_aff sums, linear-system residual of the row (`lin` = the part of the row's equation that is not dt)
         auto do_row = [&](int r, double dtr, double lin) -> double {
             const double lam0 = lam_()[r], t0 = t_()[r], e0 = rdp[r];
-            const double m = mode == 0 ? lam0 * t0 - tau : rmp[r];
-            const double dlr = -ti_()[r] * (m + (lam0 * dtr) - (lam0 * e0));
+            double m;
+            if (mode == 0) m = lam0 * t0 - tau;
+            else if (mode == 2) m = rmp[r];
+            else m = dto[r];   // the right-hand side rhs_pass formed, parked in the slot this row's new dt is about to overwrite
+            const double dlr = -(1.0 / t0) * (m + (lam0 * dtr) - (lam0 * e0));
             dtr -= e0;
             dlo[r] = dlr; dto[r] = dtr;
             // COMPUTE_ALPHA_QP keeps the ratio closest to zero among rows with a negative step; the running best is
@@ -1787,8 +1790,8 @@ struct CtaSolver {
                 double* dso = mode == 2 ? dsv2_() : dsv_();
                 const double* rgsp = mode == 2 ? rgs2_() : rgs_();
                 const int s0 = k * 2 * ns + is, s1i = s0 + ns, rs0 = k * s2 + 2 * ncq + is, rs1 = rs0 + ns;
-                const double ds0 = -zsi_()[s0] * (dso[s0] + dv * (ti_()[r0] * lam_()[r0]));
-                const double ds1 = -zsi_()[s1i] * (dso[s1i] + (-dv) * (ti_()[r1] * lam_()[r1]));
+                const double ds0 = -zsi_()[s0] * (dso[s0] + dv * ((1.0 / t_()[r0]) * lam_()[r0]));
+                const double ds1 = -zsi_()[s1i] * (dso[s1i] + (-dv) * ((1.0 / t_()[r1]) * lam_()[r1]));
                 dso[s0] = ds0; dso[s1i] = ds1;
                 const double dl0 = do_row(r0, dv + ds0, dv + ds0);
                 const double dl1 = do_row(r1, -dv + ds1, -dv + ds1);

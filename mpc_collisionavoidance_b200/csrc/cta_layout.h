@@ -41,7 +41,7 @@ struct Layout {
 // always in shared memory, the second group in order of decreasing priority for the shared-memory budget
 enum FieldId {
     F_G, F_M, F_ACL, F_KG, F_CC, F_EE, F_PB, F_RB, F_ZV, F_DUX, F_KK, F_DINV,
-    F_UX, F_PI, F_LAM, F_T, F_DLAM, F_DT, F_RD, F_RMC, F_RG, F_DPI, F_GXY, F_TI, F_D, F_RQ, F_B,
+    F_UX, F_PI, F_LAM, F_T, F_DLAM, F_DT, F_RD, F_GXY, F_RG, F_DPI, F_D, F_RQ, F_B, F_RMC,
     F_SV, F_DSV, F_RGS, F_ZSI, F_RQS,   // slack variables: values, step (/ condensation right-hand side), res_g, 1/(Z+Gamma..), gradient
     F_RG2, F_RB2, F_RD2, F_RM2, F_DUX2, F_DPI2, F_DLAM2, F_DT2, F_DSV2, F_RGS2,
     F_COUNT
@@ -139,7 +139,7 @@ inline void field_dims(int nx, int nu, int K, int nbx, int nbu, int ns, int* dim
     dim[F_G] = nv * nx; dim[F_M] = ne; dim[F_ACL] = nx * nx; dim[F_KG] = nu * nx; dim[F_CC] = nx; dim[F_EE] = nx;
     dim[F_PB] = nx; dim[F_RB] = nx; dim[F_ZV] = nv; dim[F_DUX] = nv; dim[F_KK] = nu; dim[F_DINV] = nu;
     dim[F_UX] = nv; dim[F_PI] = nx; dim[F_LAM] = r2; dim[F_T] = r2; dim[F_DLAM] = r2; dim[F_DT] = r2; dim[F_RD] = r2;
-    dim[F_RMC] = r2; dim[F_RG] = nv; dim[F_DPI] = nx; dim[F_GXY] = 2 * K; dim[F_TI] = r2; dim[F_D] = r2; dim[F_RQ] = nv;
+    dim[F_RMC] = r2; dim[F_RG] = nv; dim[F_DPI] = nx; dim[F_GXY] = 2 * K; dim[F_D] = r2; dim[F_RQ] = nv;
     dim[F_B] = nx;
     dim[F_SV] = 2 * ns; dim[F_DSV] = 2 * ns; dim[F_RGS] = 2 * ns; dim[F_ZSI] = 2 * ns; dim[F_RQS] = 2 * ns;
     dim[F_DSV2] = 2 * ns; dim[F_RGS2] = 2 * ns;
