@@ -1219,6 +1219,7 @@ struct CtaSolver {
             t_()[e] = x <= t_min ? t_min : x;
         }
         syncthreads();
+        PROF(18)
         // ---- A2: inequality rows, one (stage, row pair) per thread: res_d, res_m norms, mu, 1/t, and the row's
         // contributions (lam_u - lam_l, Gamma_l + Gamma_u, gamma_l - gamma_u) for A3, parked in the (dead) step arrays
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0, musum = 0;
@@ -1276,6 +1277,7 @@ struct CtaSolver {
             dlam_()[r1] = G0 + G1;
             dt_()[r0] = g0 - g1;
         }
+        PROF(19)
         // ---- res_b = b + [B A] ux - x_{k+1}, one (stage, state) per thread
         for (int it = tid; it < N * NX; it += T)
         {
@@ -1296,6 +1298,7 @@ struct CtaSolver {
             Mx_()[it] = Tp[stage_class(k) * NE + e];
         }
         syncthreads();
+        PROF(20)
         // ---- A3: stationarity residual, diagonal and gradient row, one (stage, variable) per thread
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
@@ -1345,7 +1348,9 @@ struct CtaSolver {
             n0 = q > n0 ? q : n0;
         }
         double vm[4] = {n0, n1, n2, n3}, vs[1] = {musum};
+        PROF(21)
         block_reduce<4, 1>(vm, vs);
+        PROF(22)
         n4[0] = vm[0]; n4[1] = vm[1]; n4[2] = vm[2]; n4[3] = vm[3];
         mu = nct > 0 ? vs[0] / nct : 0.0;
     }
@@ -1861,6 +1866,7 @@ struct CtaSolver {
             const double q = dabs(gi);
             n0 = q > n0 ? q : n0;
         }
+        PROF(14)
         for (int it = tid; it < N * NX; it += T)
         {
             const int k = dnx.div(it), j = it - k * NX;
@@ -1873,6 +1879,7 @@ struct CtaSolver {
             const double q = dabs(acc);
             n1 = q > n1 ? q : n1;
         }
+        PROF(15)
         if (WRITE)
         {
             for (int it = tid; it < N * ncq; it += T)
@@ -1915,7 +1922,9 @@ struct CtaSolver {
             }
         }
         double vm[4] = {n0, n1, n2, n3};
+        PROF(16)
         block_reduce<4, 0>(vm, nullptr);
+        PROF(17)
         out4[0] = (WRITE || !SOFT) ? vm[0] : (vm[0] > lin_g ? vm[0] : lin_g);
         out4[1] = vm[1]; out4[2] = WRITE ? vm[2] : lin_d; out4[3] = WRITE ? vm[3] : lin_m;
     }
@@ -2277,6 +2286,9 @@ struct CtaSolver {
                        "chainC %lld - %lld res %lld init %lld alpha %lld lin %lld upd %lld\n", inst, sqp_iter, qp_total,
                        prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11],
                        prof[12], prof[13]);
+            if (qp_total >= USVMPC_PROFILE)
+                printf("PROF2 res: var %lld state %lld write %lld reduce %lld | passA: A1 %lld A2 %lld resb+tmpl %lld A3 %lld reduce %lld\n",
+                       prof[14], prof[15], prof[16], prof[17], prof[18], prof[19], prof[20], prof[21], prof[22]);
 #endif
         }
         if (P.packed)
