@@ -50,6 +50,8 @@ int ocp_nlp_constraints_model_set(void* config, void* dims, void* in, int stage,
 void ocp_nlp_out_set(void* config, void* dims, void* out, int stage, const char* field, void* value);
 void ocp_nlp_out_get(void* config, void* dims, void* out, int stage, const char* field, void* value);
 int ocp_nlp_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field);
+/* fields "sl", "su" (the slack values, as the Python wrapper reads them: acados_ocp_solver.py:774-782) */
+void ocp_nlp_get_at_stage(void* config, void* dims, void* solver, int stage, const char* field, void* value);
 /* fields: "sqp_iter" (int), "time_tot", "time_lin", "time_qp", "res_stat", "res_eq", "res_ineq", "res_comp", "cost_value" (double) */
 void ocp_nlp_get(void* config, void* solver, const char* field, void* return_value);
 void ocp_nlp_solver_opts_set(void* config, void* opts, const char* field, void* value);

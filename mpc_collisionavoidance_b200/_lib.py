@@ -33,7 +33,7 @@ ACADOS_SYMBOLS = ["acados_create", "acados_update_params", "acados_solve", "acad
                   "acados_get_nlp_opts", "acados_get_nlp_dims", "acados_get_nlp_plan", "ocp_nlp_cost_model_set",
                   "ocp_nlp_constraints_model_set", "ocp_nlp_out_set", "ocp_nlp_out_get", "ocp_nlp_dims_get_from_attr",
                   "ocp_nlp_get", "ocp_nlp_solver_opts_set", "ocp_nlp_eval_residuals", "ocp_nlp_eval_cost",
-                  "ocp_nlp_cost_dims_get_from_attr", "ocp_nlp_constraint_dims_get_from_attr"]
+                  "ocp_nlp_cost_dims_get_from_attr", "ocp_nlp_constraint_dims_get_from_attr", "ocp_nlp_get_at_stage"]
 
 _lib = None
 

@@ -1006,6 +1006,15 @@ void ocp_nlp_out_get(void* config, void* dims, void* out, int stage, const char*
     if (usvmpc_out_get((usvmpc_solver*) out, stage, field, (double*) value, 0, nullptr) != 0) acados_die("ocp_nlp_out_get");
 }
 
+void ocp_nlp_get_at_stage(void* config, void* dims, void* solver, int stage, const char* field, void* value)
+{
+    (void) config; (void) dims;
+    // the slack values are the fields the wrapper reads this way (acados_ocp_solver.py:774-782); the dynamics matrices
+    // ("A", "B") are not kept per instance after a solve
+    if (strcmp(field, "sl") && strcmp(field, "su")) { fail(USVMPC_E_FIELD, "unknown field '%s'", field); acados_die("ocp_nlp_get_at_stage"); }
+    if (usvmpc_out_get((usvmpc_solver*) solver, stage, field, (double*) value, 0, nullptr) != 0) acados_die("ocp_nlp_get_at_stage");
+}
+
 int ocp_nlp_dims_get_from_attr(void* config, void* dims, void* out, int stage, const char* field)
 {
     (void) config; (void) dims;

@@ -37,11 +37,41 @@ def raw_rows(rep):
     return head, units, rows[2:]
 
 
+def metrics_log(path, cfg, batch, traffic):
+    """a `ncu --metrics ... --csv --log-file` capture (one row per metric) of the solve kernel"""
+    name = os.path.splitext(os.path.basename(path))[0]
+    text = open(path).read()
+    text = text[text.index('"ID"'):]
+    rows = list(csv.DictReader(io.StringIO(text)))
+    lines = [f"# {name}: ncu --metrics (traffic / issue) --clock-control none, config {cfg}, batch {batch}"]
+    val = {}
+    for r in rows:
+        if "nmpc_solve_kernel" not in r["Kernel Name"]:
+            continue
+        u = r["Metric Unit"]
+        lines.append(f"  {r['Metric Name']:70s} {r['Metric Value']:>20s} {u}")
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        val[r["Metric Name"]] = v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    dram = val["dram__bytes_read.sum"] + val["dram__bytes_write.sum"]
+    lines.append(f"  -> dram bytes per launch: {dram:.0f}")
+    entry = {"config": int(cfg), "batch": int(batch), "dram_bytes_per_launch": int(dram),
+             "source": f"profiles/{name}_summary.txt (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum)"}
+    traffic[:] = [e for e in traffic if not (e["config"] == entry["config"] and e["batch"] == entry["batch"])] + [entry]
+    open(os.path.join(ROOT, "profiles", name + "_summary.txt"), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
 def main():
     traffic_path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else []
     for spec in sys.argv[1:]:
         rep, cfg, batch = spec.split(":")
+        if rep.endswith(".csv"):
+            metrics_log(rep, cfg, batch, traffic)
+            continue
         name = os.path.splitext(os.path.basename(rep))[0]
         head, units, rows = raw_rows(rep)
         col = {h: i for i, h in enumerate(head)}

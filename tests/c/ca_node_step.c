@@ -65,7 +65,10 @@ int main(int argc, char** argv)
         ocp_nlp_out_get(nlp_config, nlp_dims, nlp_out, k, "x", x);
         for (int i = 0; i < NX; i++) printf("%.17g\n", x[i]);
     }
-    fprintf(stderr, "time_tot %.6f s\n", time_tot);
+    /* the slack of the first soft row at stage 1, read the way the Python wrapper does */
+    double sl[NH];
+    ocp_nlp_get_at_stage(nlp_config, nlp_dims, nlp_solver, 1, "sl", sl);
+    fprintf(stderr, "time_tot %.6f s, sl[0] at stage 1 %.3e\n", time_tot, sl[0]);
     if (!(time_tot > 0.0)) return 4;
     return acados_free();
 }
