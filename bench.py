@@ -1,18 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- NMPC solves/sec of the batched engine on BASELINE.json's headline configuration.
+"""bench.py -- NMPC solves/sec of the batched engine on BASELINE.json's configurations (default: the headline, config 2).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1..5] [--batch B]
+                    [--riccati-precision 32|64] [--strong] [--no-cpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one full solve (SQP to the 1e-6 KKT tolerance, cold start x_k = x0, u = 0, pi = 0, max 100 iterations --
-the reference's semantics) of one synthetic batch of `batch` independent instances per GPU.
-  value     instances / s over all ranks, inputs resident in HBM, CUDA-event time of K steps, max over ranks
+the reference's semantics) of one synthetic batch of `batch` independent instances per GPU
+(weak scaling; --strong splits the config's batch over the GPUs; config 5 is 131072 instances over 8 GPUs = 16384 per GPU).
+  value     instances / s over all ranks, inputs resident in HBM, CUDA events around every one of the K steps on the
+            launching stream, 256 MB written between steps (L2 flush, outside the timed intervals), max over ranks;
+            for N > 1 each step includes the in-place all-gather of the packed results
+  converged_solves_per_s   the same counting only instances that return status 0
   e2e       the same through the public API with pinned HOST buffers: H2D of the step's inputs, solve, D2H of the
-            trajectories + statistics inside the timed region
+            packed trajectories + statistics inside the timed region (phases event-timed: h2d_ms, solve_ms, d2h_ms)
   roofline  algorithmic HBM bytes of the solve kernel (SURVEY.md 8d streaming model x iteration counts the kernel
-            actually executed) / its CUDA-event duration, against MEASURED_PEAKS.json
-  cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on a bounded sample, rank 0, N=1
-`--impl reference` times that CPU implementation alone on the same workload definition.
+            actually executed) / its CUDA-event duration, against MEASURED_PEAKS.json; `traffic` = measured DRAM bytes
+            per launch of the same (config, batch) from the committed ncu capture (profiles/r2_ncu_traffic.json)
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on a bounded sample, rank 0, N=1;
+            value = sample / seconds inside the solves of the busiest thread (solver construction excluded)
+`--impl reference` times that CPU implementation alone on the same workload definition (same `config` object).
 """
 import argparse
 import json

@@ -254,9 +254,9 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
     static_assert(NX <= 8 && NV <= 16 && NU <= 2 && MT <= NT, "fragment layout of chainA_mma");
     const int lane = lane_id(), g = lane >> 2, t = lane & 3;
     double* X = sWt + NR * WS;                 // exchange array [8 MT][XS]
-    double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only), [1] = dump (write only)
+    double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only), [1 + lane] = this lane's dump slot (write only)
     if (lane == 0) slots[0] = 0.0;
-    const saddr zero = smem_addr(slots), dump = zero + 8;
+    const saddr zero = smem_addr(slots), dump = zero + 8 + 8 * lane;
     // ---- stage-independent addresses
     saddr aP[KS], aWst[NT][2], aWb[NT][KS], aXst[MT][NU], aXr[MT], aXc[NT][2], aPst[MT][NT][2][2];
     const saddr aXv = (t == TV && g < NU) ? smem_addr(X + g * XS + 2) : dump;   // S[j][NV], j < NU, lives in tile (0, NTV)
@@ -1209,10 +1209,9 @@ struct CtaSolver {
         for (int e = tid; e < (N + 1) * NV; e += T) ux_()[e] += a * dux_()[e];
         for (int e = tid; e < N * NX; e += T) pi_()[e] += a * dpi_()[e];
         if (SOFT) for (int e = tid; e < N * 2 * ns; e += T) sv_()[e] += a * dsv_()[e];
+        // (rows that do not exist -- the x boxes of stage 0 -- hold lam = 0, t = 1 and a zero step since ipm_init: no test)
         for (int e = tid; e < N * s2; e += T)
         {
-            int k;
-            if (!elem_active(e, k)) continue;
             double x = lam_()[e] + a * dlam_()[e];
             lam_()[e] = x <= lam_min ? lam_min : x;
             x = t_()[e] + a * dt_()[e];
@@ -1469,7 +1468,11 @@ struct CtaSolver {
             if (live)
             {
                 vr = nv_;
-                if (out && r < NX) out[(FWD ? kc + 1 : kc) * NV + NU + r] = vr;
+                // the vector at a block boundary is written by the block that STARTS there (from the block recursion): two
+                // groups must not store two roundings of the same quantity to one address.  Only the ends of the horizon
+                // (stage N forward, stage 0 backward) belong to the last step of a block.
+                const bool mine = FWD ? (kc + 1 < e || e == N) : (kc > s || s == 0);
+                if (out && r < NX && mine) out[(FWD ? kc + 1 : kc) * NV + NU + r] = vr;
             }
         }
         return vr;

@@ -113,7 +113,7 @@ inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
 USVMPC_HD constexpr int chain_w_doubles(int nx, int nu)
 {
     const int nv = nx + nu, ne = nv * (nv + 1) / 2 + nv;
-    const int a = nx * (nv + 1) + ne + (ne & 1), b = 12 * (nv + 1) + 32 * ((nv + 7) / 8) + 2;   // W + exchange array + zero / dump slots
+    const int a = nx * (nv + 1) + ne + (ne & 1), b = 12 * (nv + 1) + 32 * ((nv + 7) / 8) + 34;   // W + exchange array + zero slot + 32 dump slots
     return a > b ? a : b;
 }
 USVMPC_HD constexpr int chain_p_doubles(int nx) { return nx * nx + 2 > 12 * nx ? nx * nx + 2 : 12 * nx; }
