@@ -194,6 +194,15 @@ DEV double warp_max(double v)
     u ^= (u >> 63) ? 0x8000000000000000ull : ~0ull;
     return bits_double(u);
 }
+// the same for values that are known to be >= 0 (not -0, not NaN): their bit patterns already order like the values
+DEV double warp_max_nonneg(double v)
+{
+    const unsigned long long u = double_bits(v);
+    const unsigned hi = (unsigned) (u >> 32), lo = (unsigned) u;
+    const unsigned mh = warp_max_u32(hi);
+    const unsigned ml = warp_max_u32(hi == mh ? lo : 0u);
+    return bits_double(((unsigned long long) mh << 32) | ml);
+}
 DEV double warp_sum(double v)
 {
 #pragma unroll

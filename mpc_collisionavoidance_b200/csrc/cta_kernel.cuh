@@ -723,11 +723,12 @@ struct CtaSolver {
     MDEV const double* Hk(int k) const { return k < N ? Hs : Hes; }
 
     // ---------------------------------------------------------------- block-wide reductions (every thread gets the result)
-    template <int NM, int NS>
+    // The first NSG entries of vmax may have either sign (step-length ratios), the others are norms (>= 0, never -0 or NaN).
+    template <int NM, int NS, int NSG = 0>
     MDEV void block_reduce(double* vmax, double* vsum)
     {
 #pragma unroll
-        for (int i = 0; i < NM; i++) vmax[i] = warp_max(vmax[i]);
+        for (int i = 0; i < NM; i++) vmax[i] = i < NSG ? warp_max(vmax[i]) : warp_max_nonneg(vmax[i]);
 #pragma unroll
         for (int i = 0; i < NS; i++) vsum[i] = warp_sum(vsum[i]);
         double* r = red + redbuf * W * 8;
@@ -743,7 +744,7 @@ struct CtaSolver {
         // every warp reduces the W per-warp maxima again (lane l holds warp l mod W's value)
         const int src = (lane < W ? lane : lane % W) * 8;
 #pragma unroll
-        for (int i = 0; i < NM; i++) vmax[i] = warp_max(r[src + i]);
+        for (int i = 0; i < NM; i++) vmax[i] = i < NSG ? warp_max(r[src + i]) : warp_max_nonneg(r[src + i]);
         // sums in warp order so that every thread adds the same numbers in the same order
         if (NS > 0)
         {
@@ -1499,6 +1500,7 @@ struct CtaSolver {
         const int nb = num_blocks(), ngrp = T / GS;
         for (int j0 = 0; j0 < nb; j0 += ngrp)
         {
+            if (j0 + (tid - lane) / GS >= nb) continue;   // no live group in this warp (warp-uniform)
             const int j = j0 + tid / GS, r = lane % GS;
             const bool act = j < nb;
             const double v = group_steps<true, true>(act ? j : nb - 1, 0.0, cc_(), nullptr);
@@ -1509,6 +1511,7 @@ struct CtaSolver {
         syncthreads();
         for (int j0 = 0; j0 < nb; j0 += ngrp)
         {
+            if (j0 + (tid - lane) / GS >= nb) continue;
             const int j = j0 + tid / GS, r = lane % GS;
             const bool act = j < nb;
             const int jc = act ? j : nb - 1;
@@ -1523,6 +1526,7 @@ struct CtaSolver {
         const int nb = num_blocks(), ngrp = T / GS;
         for (int j0 = 0; j0 < nb; j0 += ngrp)
         {
+            if (j0 + (tid - lane) / GS >= nb) continue;
             const int j = j0 + tid / GS, r = lane % GS;
             const bool act = j < nb;
             const double v = group_steps<false, true>(act ? j : nb - 1, 0.0, ee_(), nullptr);
@@ -1535,6 +1539,7 @@ struct CtaSolver {
         double* z = zv_();
         for (int j0 = 0; j0 < nb; j0 += ngrp)
         {
+            if (j0 + (tid - lane) / GS >= nb) continue;
             const int j = j0 + tid / GS, r = lane % GS;
             const bool act = j < nb;
             const int jc = act ? j : nb - 1;
@@ -1824,7 +1829,7 @@ struct CtaSolver {
         if (mode != 2)
         {
             double vm[5] = {bpn / bpd, bdn / bdd, nd, nm, ng}, vs[2] = {s1, s2s};
-            block_reduce<5, 2>(vm, vs);
+            block_reduce<5, 2, 2>(vm, vs);
             alpha = -(vm[0] > vm[1] ? vm[0] : vm[1]);
             lin_d = vm[2]; lin_m = vm[3]; lin_g = vm[4];
             S1 = vs[0]; S2 = vs[1];
@@ -1944,7 +1949,7 @@ struct CtaSolver {
             if (a_prim * dt_()[it] > t_()[it]) a_prim = t_()[it] / dt_()[it];
         }
         double vm[2] = {a_prim, a_dual};
-        block_reduce<2, 0>(vm, nullptr);
+        block_reduce<2, 0, 2>(vm, nullptr);
         alpha = -(vm[0] > vm[1] ? vm[0] : vm[1]);
     }
 
