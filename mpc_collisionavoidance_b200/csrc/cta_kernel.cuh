@@ -246,7 +246,8 @@ MDEVNI void chainA_impl(const double* G, double* Mx, const double* rb, double* P
 // Padding that must be exact (k-padding of P, rows >= NX of W) reads a zero slot.
 // Same pivot rule and the same outputs as chainA_impl: Mx (factor columns, P_k, p_k), Pb, dinv.
 template <class M>
-MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sWt, double* sPp, int N)
+MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb, double* dinv, double* sWt, double* sPp,
+                       double* dumps, int N)
 {
     constexpr int NX = M::NX, NU = M::NU, NV = NX + NU, NR = NV + 1, NE = NV * (NV + 1) / 2 + NV;
     constexpr int MT = (NV + 7) / 8, NT = (NR + 7) / 8, KS = (NX + 3) / 4, WS = 12, XS = 4;
@@ -254,9 +255,12 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
     static_assert(NX <= 8 && NV <= 16 && NU <= 2 && MT <= NT, "fragment layout of chainA_mma");
     const int lane = lane_id(), g = lane >> 2, t = lane & 3;
     double* X = sWt + NR * WS;                 // exchange array [8 MT][XS]
-    double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only), [1 + lane] = this lane's dump slot (write only)
+    double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only)
     if (lane == 0) slots[0] = 0.0;
-    const saddr zero = smem_addr(slots), dump = zero + 8 + 8 * lane;
+    // dumps: one write-only slot per lane (the block maps of the vector recursions: >= 32 doubles, rebuilt after every
+    // factorisation and separated from this function by block-wide barriers on both sides)
+    ASSUME_SHARED(dumps);
+    const saddr zero = smem_addr(slots), dump = smem_addr(dumps + lane);
     // ---- stage-independent addresses
     saddr aP[KS], aWst[NT][2], aWb[NT][KS], aXst[MT][NU], aXr[MT], aXc[NT][2], aPst[MT][NT][2][2];
     const saddr aXv = (t == TV && g < NU) ? smem_addr(X + g * XS + 2) : dump;   // S[j][NV], j < NU, lives in tile (0, NTV)
@@ -595,7 +599,7 @@ struct CtaSolver {
     FastDiv dq, dnv, dnx, ds2;
     double *sm, *gs, *w;
     // constants in shared memory
-    double *Hs, *Hes, *Ws, *Wes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
+    double *Hs, *Hes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
     int *sxrow, *srvar;
     int redbuf;
     // working-set fields: no pointer is kept in registers; every access forms the address from the block's shared-memory
@@ -675,7 +679,7 @@ struct CtaSolver {
         nct = N >= 1 ? 2 * ((nbu + K + ns) + (N - 1) * (nbu + nbx + K + ns)) : 0;
         dq.set(ncq); dnv.set(NV); dnx.set(NX); ds2.set(s2);
         double* c = sm + P.plan.const_off;
-        Hs = c; c += NV * NV; Hes = c; c += NV * NV; Ws = c; c += NV * NV; Wes = c; c += NX * NX; Tp = c;
+        Hs = c; c += NV * NV; Hes = c; c += NV * NV; Tp = c;
         red = sm + P.plan.red_off;
         redbuf = 0;
         double* m = sm + P.plan.misc_off;
@@ -686,7 +690,7 @@ struct CtaSolver {
         }
         sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
         // address-space hints: these always point into shared memory
-        ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Ws); ASSUME_SHARED(Wes); ASSUME_SHARED(Tp);
+        ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Tp);
         ASSUME_SHARED(red); ASSUME_SHARED(sA0); ASSUME_SHARED(sW); ASSUME_SHARED(sP); ASSUME_SHARED(sxrow); ASSUME_SHARED(srvar);
         ASSUME_SHARED(Phi); ASSUME_SHARED(phi); ASSUME_SHARED(Xb);
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
@@ -771,15 +775,9 @@ struct CtaSolver {
         for (int e = tid; e < NV * NV; e += T)
         {
             const int i = e % NV, j = e / NV;
-            Ws[e] = i >= j ? Wg[i + NY * j] : Wg[j + NY * i];
             const int yi = i < NU ? NX + i : i - NU, yj = j < NU ? NX + j : j - NU;
             Hs[e] = P.dt * (yi >= yj ? Wg[yi + NY * yj] : Wg[yj + NY * yi]);
             Hes[e] = (i >= NU && j >= NU) ? ((i >= j) ? Weg[(i - NU) + NX * (j - NU)] : Weg[(j - NU) + NX * (i - NU)]) : 0.0;
-        }
-        for (int e = tid; e < NX * NX; e += T)
-        {
-            const int i = e % NX, j = e / NX;
-            Wes[e] = i >= j ? Weg[i + NX * j] : Weg[j + NX * i];
         }
         if (tid < NX)
         {
@@ -927,6 +925,8 @@ struct CtaSolver {
                        double* res4)
     {
         if (P.nlp_type == 1 && P.rti_phase == 2) prep_load(inst); else integrate_all();
+        const double* Wg = P.cst;                 // cost weights: read from global (L2) once per SQP iteration
+        const double* Weg = P.cst + NY * NY;
         double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
         for (int k = tid; k <= N; k += T)
         {
@@ -951,7 +951,7 @@ struct CtaSolver {
                 {
                     double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NY; j++) acc += Ws[i + NY * j] * r[j];
+                    for (int j = 0; j < NY; j++) acc += (i >= j ? Wg[i + NY * j] : Wg[j + NY * i]) * r[j];   // lower triangle of W (global, L2)
                     if (i < NX) cg[NU + i] = P.dt * acc; else cg[i - NX] = P.dt * acc;
                 }
             }
@@ -967,7 +967,7 @@ struct CtaSolver {
                 {
                     double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NX; j++) acc += Wes[i + NX * j] * r[j];
+                    for (int j = 0; j < NX; j++) acc += (i >= j ? Weg[i + NX * j] : Weg[j + NX * i]) * r[j];
                     cg[NU + i] = acc;
                 }
             }
@@ -1428,7 +1428,7 @@ struct CtaSolver {
         if (wid >= CHAIN_WARPS) return;
         if (use_fp32) chainA_impl<M, float>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
 #if USVMPC_CHAIN_MMA
-        else if (wid == 0) chainA_mma<M>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
+        else if (wid == 0) chainA_mma<M>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, Phi, N);
 #else
         else chainA_impl<M, double>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
 #endif

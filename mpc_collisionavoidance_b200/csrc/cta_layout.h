@@ -41,7 +41,7 @@ struct Layout {
 // always in shared memory, the second group in order of decreasing priority for the shared-memory budget
 enum FieldId {
     F_G, F_M, F_ACL, F_KG, F_CC, F_EE, F_PB, F_RB, F_ZV, F_DUX, F_KK, F_DINV,
-    F_UX, F_PI, F_LAM, F_T, F_DLAM, F_DT, F_RD, F_GXY, F_RG, F_DPI, F_D, F_RQ, F_B, F_RMC,
+    F_UX, F_PI, F_LAM, F_T, F_DLAM, F_DT, F_RD, F_GXY, F_DPI, F_RG, F_D, F_RQ, F_B, F_RMC,
     F_SV, F_DSV, F_RGS, F_ZSI, F_RQS,   // slack variables: values, step (/ condensation right-hand side), res_g, 1/(Z+Gamma..), gradient
     F_RG2, F_RB2, F_RD2, F_RM2, F_DUX2, F_DPI2, F_DLAM2, F_DT2, F_DSV2, F_RGS2,
     F_COUNT
@@ -113,7 +113,7 @@ inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
 USVMPC_HD constexpr int chain_w_doubles(int nx, int nu)
 {
     const int nv = nx + nu, ne = nv * (nv + 1) / 2 + nv;
-    const int a = nx * (nv + 1) + ne + (ne & 1), b = 12 * (nv + 1) + 32 * ((nv + 7) / 8) + 34;   // W + exchange array + zero slot + 32 dump slots
+    const int a = nx * (nv + 1) + ne + (ne & 1), b = 12 * (nv + 1) + 32 * ((nv + 7) / 8) + 2;   // W + exchange array + zero slot
     return a > b ? a : b;
 }
 USVMPC_HD constexpr int chain_p_doubles(int nx) { return nx * nx + 2 > 12 * nx ? nx * nx + 2 : 12 * nx; }
@@ -158,7 +158,7 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int ns, in
     field_dims(nx, nu, K, nbx, nbu, ns, dim);
     long o = 0;
     P.const_off = (int) o;
-    o += 2 * nv * nv + nv * nv + nx * nx + 3 * ne;      // Hs, Hes, Ws, Wes, Tp
+    o += 2 * nv * nv + 3 * ne;                          // Hs, Hes, Tp
     o = round_up((int) o, 2);
     P.red_off = (int) o;
     o += 2 * warps * 8;                                  // two reduction buffers of 8 values per warp
@@ -166,10 +166,12 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int ns, in
     o += nv * nx + chain_w_doubles(nx, nu) + chain_p_doubles(nx) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
     o += ((N + 3) / 4 + 1) * (nx * nx + 2 * nx);         // block maps of the vector recursions (blocks of 4 stages)
     o = round_up((int) o, 2);
+    // [B';A'] and the closed-loop matrices exist for stages 0 .. N-1 only
+    auto stages = [&](int i) { return (i == F_G || i == F_ACL) ? N : N1; };
     for (int i = 0; i < F_FIRST_FLEX; i++)
     {
         P.f[i].off = (int) o; P.f[i].stride = dim[i]; P.f[i].space = 0;
-        o += (long) dim[i] * N1;
+        o += (long) dim[i] * stages(i);
     }
     if (o * 8 > smem_budget) return false;
     long g = 0;
