@@ -596,7 +596,7 @@ struct CtaSolver {
     const Params& P;
     int tid, lane, wid, T, W;
     int N, K, nbu, nbx, ncq, ncz, nbq, nct, s2, ns;  // ns: soft rows (the first ns rows of h); 0 unless SOFT
-    FastDiv dq, dnv, dnx, ds2;
+    FastDiv dq, ds2;
     double *sm, *gs, *w;
     // constants in shared memory
     double *Hs, *Hes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
@@ -677,7 +677,7 @@ struct CtaSolver {
         ns = SOFT ? P.ns : 0;
         s2 = 2 * ncq + 2 * ns;
         nct = N >= 1 ? 2 * ((nbu + K + ns) + (N - 1) * (nbu + nbx + K + ns)) : 0;
-        dq.set(ncq); dnv.set(NV); dnx.set(NX); ds2.set(s2);
+        dq.set(ncq); ds2.set(s2);
         double* c = sm + P.plan.const_off;
         Hs = c; c += NV * NV; Hes = c; c += NV * NV; Tp = c;
         red = sm + P.plan.red_off;
@@ -1281,7 +1281,7 @@ struct CtaSolver {
         // ---- res_b = b + [B A] ux - x_{k+1}, one (stage, state) per thread
         for (int it = tid; it < N * NX; it += T)
         {
-            const int k = dnx.div(it), j = it - k * NX;
+            const int k = (it / NX), j = it - k * NX;
             const double* v = ux_() + k * NV;
             const double* Gk = G_() + k * (NV * NX) + NV * j;
             double acc = b_()[it] - ux_()[(k + 1) * NV + NU + j];
@@ -1302,7 +1302,7 @@ struct CtaSolver {
         // ---- A3: stationarity residual, diagonal and gradient row, one (stage, variable) per thread
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
-            const int k = dnv.div(it), i = it - k * NV;
+            const int k = (it / NV), i = it - k * NV;
             const double* v = ux_() + k * NV;
             const double* H = Hk(k);
             double g = rq_()[it], dg = 0.0, gg = 0.0;
@@ -1328,14 +1328,18 @@ struct CtaSolver {
                     const double* gk = gxy_() + k * 2 * K;
                     const double* gi = i == HXV ? gk : gk + K;
                     double aYX = 0.0;
+                    const double* pl = dlam_() + k * s2 + nbq;   // parked by A2: lam_u - lam_l | Gamma_l + Gamma_u | gamma_l - gamma_u
+                    const double* pG = pl + ncq;
+                    const double* pg = dt_() + k * s2 + nbq;
+                    const bool isy = i == HYV;
+#pragma unroll 5
                     for (int c = 0; c < K; c++)
                     {
-                        const int r0 = k * s2 + nbq + c;
-                        const double Gs = dlam_()[r0 + ncq];
-                        g += gi[c] * dlam_()[r0];
-                        dg += (gi[c] * Gs) * gi[c];
-                        gg += dt_()[r0] * gi[c];
-                        if (i == HYV) aYX += (gk[K + c] * Gs) * gk[c];
+                        const double Gs = pG[c], gc = gi[c];
+                        g += gc * pl[c];
+                        dg += (gc * Gs) * gc;
+                        gg += pg[c] * gc;
+                        if (isy) aYX += (gc * Gs) * gk[c];
                     }
                     if (i == HYV) Mx_()[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
                 }
@@ -1369,7 +1373,7 @@ struct CtaSolver {
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
-            const int k = dnv.div(it), i = it - k * NV;
+            const int k = (it / NV), i = it - k * NV;
             double dg = 0.0, gg = 0.0;
             if (k < N)
             {
@@ -1556,7 +1560,7 @@ struct CtaSolver {
     {
         for (int it = tid; it < (N + 1) * NX; it += T)
         {
-            const int k = dnx.div(it), j = it - k * NX;
+            const int k = (it / NX), j = it - k * NX;
             const double* Mk = Mx_() + k * NE;
             double kg[NU];
 #pragma unroll
@@ -1589,7 +1593,7 @@ struct CtaSolver {
     {
         for (int it = tid; it < N * NX; it += T)
         {
-            const int k = dnx.div(it), mm = it - k * NX;
+            const int k = (it / NX), mm = it - k * NX;
             const double* Mk = Mx_() + k * NE;
             const double* Gk = G_() + k * (NV * NX);
             double lu[NU], kv[NU];
@@ -1691,14 +1695,16 @@ struct CtaSolver {
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
-            const int k = dnv.div(it), i = it - k * NV;
+            const int k = (it / NV), i = it - k * NV;
             double z = rgp[it];
             const int row = vrow(k, i);
             if (row >= 0) z += gsc[k * s2 + row];
             if ((i == HXV || i == HYV) && k >= 1 && k < N)
             {
                 const double* gi = gxy_() + k * 2 * K + (i == HXV ? 0 : K);
-                for (int c = 0; c < K; c++) z += gi[c] * gsc[k * s2 + nbq + c];
+                const double* gs_ = gsc + k * s2 + nbq;
+#pragma unroll 5
+                for (int c = 0; c < K; c++) z += gi[c] * gs_[c];
             }
             zv_()[it] = var_active(k, i) ? z : 0.0;
         }
@@ -1707,7 +1713,7 @@ struct CtaSolver {
             // Pb = P_{k+1} rhs_b for the new right-hand side (the factor's Pb belongs to res_b)
             for (int it = tid; it < N * NX; it += T)
             {
-                const int k = dnx.div(it), m = it - k * NX;
+                const int k = (it / NX), m = it - k * NX;
                 const double* Mn = Mx_() + (k + 1) * NE;
                 double acc = 0.0;
 #pragma unroll
@@ -1719,7 +1725,7 @@ struct CtaSolver {
         // e_k = Acl_k' Pb_k + z0_x + K_k' z0_u   (e_N = z0_x)
         for (int it = tid; it < (N + 1) * NX; it += T)
         {
-            const int k = dnx.div(it), j = it - k * NX;
+            const int k = (it / NX), j = it - k * NX;
             double acc = zv_()[k * NV + NU + j];
 #pragma unroll
             for (int m = 0; m < NU; m++) acc += Kg_()[k * (NU * NX) + m * NX + j] * zv_()[k * NV + m];
@@ -1818,7 +1824,7 @@ struct CtaSolver {
         // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
         for (int it = tid; it < N * NX; it += T)
         {
-            const int k = dnx.div(it), i = it - k * NX;
+            const int k = (it / NX), i = it - k * NX;
             const double* Mn = Mx_() + (k + 1) * NE;
             const double* xn = vo + (k + 1) * NV + NU;
             double acc = mode == 0 ? Mn[MI(NV, NU + i)] : zv_()[(k + 1) * NV + NU + i];
@@ -1846,7 +1852,7 @@ struct CtaSolver {
         double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         for (int it = tid; it < (N + 1) * NV; it += T)
         {
-            const int k = dnv.div(it), i = it - k * NV;
+            const int k = (it / NV), i = it - k * NV;
             const double* v = dux_() + k * NV;
             const double* H = Hk(k);
             double g = rg_()[it];
@@ -1866,7 +1872,10 @@ struct CtaSolver {
                 if ((i == HXV || i == HYV) && k >= 1)
                 {
                     const double* gi = gxy_() + k * 2 * K + (i == HXV ? 0 : K);
-                    for (int c = 0; c < K; c++) g += gi[c] * (dlam_()[k * s2 + ncq + nbq + c] - dlam_()[k * s2 + nbq + c]);
+                    const double* dl_ = dlam_() + k * s2 + nbq;
+                    const double* du_ = dl_ + ncq;
+#pragma unroll 5
+                    for (int c = 0; c < K; c++) g += gi[c] * (du_[c] - dl_[c]);
                 }
             }
             const double gi = var_active(k, i) ? g : 0.0;
@@ -1877,7 +1886,7 @@ struct CtaSolver {
         PROF(14)
         for (int it = tid; it < N * NX; it += T)
         {
-            const int k = dnx.div(it), j = it - k * NX;
+            const int k = (it / NX), j = it - k * NX;
             const double* v = dux_() + k * NV;
             const double* Gk = G_() + k * (NV * NX) + NV * j;
             double acc = rb_()[it] - dux_()[(k + 1) * NV + NU + j];
