@@ -148,3 +148,24 @@ def test_ocp_without_inequality_rows(golden_dir):
     np.testing.assert_array_equal(r["qp_iter"], 0)
     np.testing.assert_allclose(r["x"], f["x"], rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(r["u"], f["u"], rtol=1e-8, atol=1e-8)
+
+
+def _edge_case(N, K):
+    b = make_batch(1, B=3, seed=11)
+    rng = np.random.default_rng(5)
+    p = np.concatenate([rng.uniform(1.5, 4, (3, K, 1)), rng.uniform(-2, 2, (3, K, 1))], 2).reshape(3, 2 * K)
+    return rh.RefProblem(N=N, K=K, num_steps=1), b, p, np.full((3, K), 0.5)
+
+
+@pytest.mark.parametrize("N,K", [(1, 1), (2, 1), (3, 32)])
+def test_smallest_horizons_and_maximum_obstacle_count(N, K):
+    # edge sizes: one- and two-stage horizons (stage 0 after the x0 elimination + the terminal stage only), and KMAX = 32
+    # obstacle rows per stage; checker = the C restatement (agrees with the unmodified reference on these to 1e-14)
+    P, b, p, lh = _edge_case(N, K)
+    a = op.solve_batch(P, b.x0, p, lh, b.yref, b.yref_e)
+    r = ep.solve_batch(P, b.x0, p, lh, b.yref, b.yref_e)
+    np.testing.assert_array_equal(r["status"], a["status"])
+    np.testing.assert_array_equal(r["sqp_iter"], a["sqp_iter"])
+    assert (a["status"] == 0).all()
+    np.testing.assert_allclose(r["x"], a["x"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r["u"], a["u"], rtol=1e-8, atol=1e-8)
