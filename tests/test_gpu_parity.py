@@ -217,6 +217,16 @@ def test_closed_loop_rti_against_oracle():
     s.set("all", "x", np.repeat(b.x0[:, None, :], N + 1, axis=1))
     X, U, S = simulate_closed_loop(s, b.x0, steps)
     assert (S == 0).all()
+    # the same loop on the real-time-iteration schedule (preparation before the measurement, feedback after it)
+    s2 = BatchedAcadosOcpSolver(ocp_from_problem(P), batch=B)
+    s2.set("every", "yref", b.yref); s2.set(N, "yref", b.yref_e)
+    s2.set("every", "p", b.p); s2.constraints_set("every", "lh", b.lh)
+    s2.set("all", "x", np.repeat(b.x0[:, None, :], N + 1, axis=1))
+    s2.set(0, "lbx", b.x0); s2.set(0, "ubx", b.x0)
+    X2, U2, S2 = simulate_closed_loop(s2, b.x0, steps, split_phases=True)
+    assert (S2 == 0).all()
+    np.testing.assert_allclose(X2, X, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(U2, U, rtol=0, atol=1e-10)
     for i in range(B):
         o = op.OracleSolver(P)
         x = b.x0[i].copy()
