@@ -257,8 +257,7 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
     double* X = sWt + NR * WS;                 // exchange array [8 MT][XS]
     double* slots = X + 8 * MT * XS;           // [0] = 0.0 (read only)
     if (lane == 0) slots[0] = 0.0;
-    // dumps: one write-only slot per lane (the block maps of the vector recursions: >= 32 doubles, rebuilt after every
-    // factorisation and separated from this function by block-wide barriers on both sides)
+    // dumps: one write-only slot per lane
     ASSUME_SHARED(dumps);
     const saddr zero = smem_addr(slots), dump = smem_addr(dumps + lane);
     // ---- stage-independent addresses
@@ -506,83 +505,76 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
     }
 }
 
-// chainF: dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k  -> out[(k+1) * NV + NU + i]                  (x_ocp_qp_kkt.c:537-575)
-// (used on the BLOCK maps of the horizon, see CtaSolver::chainF: N = number of blocks, NV = NX, NU = 0)
-template <class M>
-MDEVNI void chainF_impl(const double* Acl, const double* cc, double* out, int N, int NV, int NU)
+// The two vector recursions of a solve with the factor, on the fp64 tensor cores:
+//   FWD : dx_0 = 0,   dx_{k+1} = Acl_k  dx_k    + c_k  -> out[(k+1) * NV + NU + i]               (x_ocp_qp_kkt.c:537-575)
+//   !FWD: p_N = e_N,  p_k      = Acl_k' p_{k+1} + e_k  -> out[k * NV + NU + i]                   (x_ocp_qp_kkt.c:1096-1242)
+// One warp.  A step is ONE 8 x 8 x 8 product: A = Acl_k (or its transpose) from the field, B = the vector in column 0 (lanes
+// g = 0), C = the affine term in column 0; the result's column 0 sits in the accumulators of the lanes t = 0 and travels to
+// the next step's B fragment with two shuffles.  ~20 instructions and ~90 cycles per stage -- a mat-vec with FMAs,
+// shuffles for the broadcast and its own index arithmetic took 40 / 180 (and a blocked variant of the recursion, 19
+// dependent steps instead of N, three times the instructions).  The next stage's operands are loaded before the current
+// product (they do not depend on the recursion); the load one stage past the end reads the neighbouring field and is unused.
+// slots: [0] = 0.0, [1 + lane] = the lane's dump slot.
+template <class M, bool FWD>
+MDEVNI void chain_vec_mma(const double* Acl, const double* aff, double* out, double* slots, int N, int NV, int NU)
 {
-    constexpr int NX = M::NX;
-    ASSUME_SHARED(Acl); ASSUME_SHARED(cc);
-    const int lane = lane_id();
-    const int l = lane < NX ? lane : 0;
-    double xc[NX];
+    constexpr int NX = M::NX, KS = (NX + 3) / 4;
+    static_assert(NX <= 8, "fragment layout of chain_vec_mma");
+    ASSUME_SHARED(Acl); ASSUME_SHARED(aff); ASSUME_SHARED(out); ASSUME_SHARED(slots);
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    if (lane == 0) slots[0] = 0.0;
+    syncwarp();
+    const saddr zero = smem_addr(slots), dump = smem_addr(slots + 1 + lane);
+    const int k0 = FWD ? 0 : N - 1, sgn = FWD ? 1 : -1;
+    const bool col0 = t == 0 && g < NX;     // the lanes that hold column 0 of the result
+    saddr aA[KS], aC, aO;
+    int dA[KS];
 #pragma unroll
-    for (int i = 0; i < NX; i++) xc[i] = 0.0;
-    if (lane < NX) out[NU + lane] = 0.0;
-    // the rows of Acl_k and c_k do not depend on the recursion: fetch stage k+1 while stage k is being multiplied
-    double ar[NX], cv;
+    for (int ks = 0; ks < KS; ks++)
+    {
+        const int c = 4 * ks + t;
+        const bool ok = g < NX && c < NX;
+        aA[ks] = ok ? smem_addr(Acl + k0 * (NX * NX) + (FWD ? g * NX + c : c * NX + g)) : zero;
+        dA[ks] = ok ? sgn * NX * NX * 8 : 0;
+    }
+    aC = col0 ? smem_addr(aff + k0 * NX + g) : zero;
+    aO = col0 ? smem_addr(out + (FWD ? 1 : N - 1) * NV + NU + g) : dump;
+    const int dC = col0 ? sgn * NX * 8 : 0, dO = col0 ? sgn * NV * 8 : 0;
+    // the start vector: B fragments (lanes g = 0 hold component 4 ks + t) and its place in `out`
+    double b[KS];
 #pragma unroll
-    for (int j = 0; j < NX; j++) ar[j] = N > 0 ? Acl[l * NX + j] : 0.0;
-    cv = N > 0 ? cc[l] : 0.0;
+    for (int ks = 0; ks < KS; ks++)
+    {
+        const int c = 4 * ks + t;
+        b[ks] = (!FWD && g == 0 && c < NX) ? aff[N * NX + c] : 0.0;
+    }
+    double an[KS], cn;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) an[ks] = lds64(aA[ks]);
+    cn = lds64(aC);
+    const double v0 = (!FWD && col0) ? aff[N * NX + g] : 0.0;
+    if (col0) out[(FWD ? 0 : N) * NV + NU + g] = v0;   // after the first affine term is in a register: `out` may be `aff`
 #pragma unroll 1
     for (int k = 0; k < N; k++)
     {
-        double an[NX], cn = 0.0;
-        const int kn = k + 1 < N ? k + 1 : k;
+        double a[KS], d0[KS], d1[KS];
 #pragma unroll
-        for (int j = 0; j < NX; j++) an[j] = Acl[kn * (NX * NX) + l * NX + j];
-        cn = cc[kn * NX + l];
-        double a0 = cv, a1 = 0.0;
+        for (int ks = 0; ks < KS; ks++) { a[ks] = an[ks]; aA[ks] += dA[ks]; d0[ks] = ks == 0 ? cn : 0.0; d1[ks] = 0.0; }
+        aC += dC;
 #pragma unroll
-        for (int j = 0; j < NX; j += 2) { a0 += ar[j] * xc[j]; if (j + 1 < NX) a1 += ar[j + 1] * xc[j + 1]; }
-        const double x1 = a0 + a1;
-        if (lane < NX) out[(k + 1) * NV + NU + lane] = x1;
+        for (int ks = 0; ks < KS; ks++) an[ks] = lds64(aA[ks]);
+        cn = lds64(aC);
+        // the two halves of the inner dimension as independent products (they pipeline), summed afterwards
 #pragma unroll
-        for (int m = 0; m < NX; m++) xc[m] = shfl(x1, m);
+        for (int ks = 0; ks < KS; ks++) dmma884(d0[ks], d1[ks], a[ks], b[ks]);
+        const double y = KS == 2 ? d0[0] + d0[KS - 1] : d0[0];
+        sts64(aO, y);
+        aO += dO;
+        // every column of the next B fragment becomes a copy of the vector: only column 0 is used, the others stay finite
 #pragma unroll
-        for (int j = 0; j < NX; j++) ar[j] = an[j];
-        cv = cn;
+        for (int ks = 0; ks < KS; ks++) b[ks] = shfl(y, 4 * (4 * ks + t));
     }
-}
-
-// chainC: p_N = e_N, p_k = Acl_k' p_{k+1} + e_k  -> zv[k * NV + NU + i]                          (x_ocp_qp_kkt.c:1096-1242)
-template <class M>
-MDEVNI void chainC_impl(const double* Acl, const double* ee, double* zv, int N, int NV, int NU)
-{
-    constexpr int NX = M::NX;
-    ASSUME_SHARED(Acl); ASSUME_SHARED(ee); ASSUME_SHARED(zv);
-    const int lane = lane_id();
-    const int l = lane < NX ? lane : 0;
-    double pn[NX];
-    {
-        const double e = ee[N * NX + l];
-        if (lane < NX) zv[N * NV + NU + lane] = e;
-#pragma unroll
-        for (int m = 0; m < NX; m++) pn[m] = shfl(e, m);
-    }
-    double ac[NX], ev;
-#pragma unroll
-    for (int m = 0; m < NX; m++) ac[m] = N > 0 ? Acl[(N - 1) * (NX * NX) + m * NX + l] : 0.0;
-    ev = N > 0 ? ee[(N - 1) * NX + l] : 0.0;
-#pragma unroll 1
-    for (int k = N - 1; k >= 0; k--)
-    {
-        double an[NX], en;
-        const int kn = k > 0 ? k - 1 : 0;
-#pragma unroll
-        for (int m = 0; m < NX; m++) an[m] = Acl[kn * (NX * NX) + m * NX + l];
-        en = ee[kn * NX + l];
-        double a0 = ev, a1 = 0.0;
-#pragma unroll
-        for (int m = 0; m < NX; m += 2) { a0 += ac[m] * pn[m]; if (m + 1 < NX) a1 += ac[m + 1] * pn[m + 1]; }
-        const double p1 = a0 + a1;
-        if (lane < NX) zv[k * NV + NU + lane] = p1;
-#pragma unroll
-        for (int m = 0; m < NX; m++) pn[m] = shfl(p1, m);
-#pragma unroll
-        for (int m = 0; m < NX; m++) ac[m] = an[m];
-        ev = en;
-    }
+    syncwarp();
 }
 
 template <class M, bool SOFT>
@@ -599,7 +591,7 @@ struct CtaSolver {
     FastDiv dq, ds2;
     double *sm, *gs, *w;
     // constants in shared memory
-    double *Hs, *Hes, *Tp, *red, *sA0, *sW, *sP, *Phi, *phi, *Xb;
+    double *Hs, *Hes, *Tp, *red, *sA0, *sW, *sP, *slots;
     int *sxrow, *srvar;
     int redbuf;
     // working-set fields: no pointer is kept in registers; every access forms the address from the block's shared-memory
@@ -684,15 +676,12 @@ struct CtaSolver {
         redbuf = 0;
         double* m = sm + P.plan.misc_off;
         sA0 = m; m += NV * NX; sW = m; m += chain_w_doubles(NX, NU); sP = m; m += chain_p_doubles(NX);  // chain scratch: [P G' | matrix], P
-        {
-            const int nb1 = (N + BS - 1) / BS + 1;
-            Phi = m; m += nb1 * NX * NX; phi = m; m += nb1 * NX; Xb = m; m += nb1 * NX;
-        }
+        slots = m; m += 34;   // [0] = 0.0 and one dump slot per lane for the recursions' unpredicated stores
         sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
         // address-space hints: these always point into shared memory
         ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Tp);
         ASSUME_SHARED(red); ASSUME_SHARED(sA0); ASSUME_SHARED(sW); ASSUME_SHARED(sP); ASSUME_SHARED(sxrow); ASSUME_SHARED(srvar);
-        ASSUME_SHARED(Phi); ASSUME_SHARED(phi); ASSUME_SHARED(Xb);
+        ASSUME_SHARED(slots);
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;
@@ -1432,126 +1421,33 @@ struct CtaSolver {
         if (wid >= CHAIN_WARPS) return;
         if (use_fp32) chainA_impl<M, float>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
 #if USVMPC_CHAIN_MMA
-        else if (wid == 0) chainA_mma<M>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, Phi, N);
+        else if (wid == 0) chainA_mma<M>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, slots + 1, N);
 #else
         else chainA_impl<M, double>(G_(), Mx_(), rb_(), Pb_(), dinv_(), sW, sP, N);
 #endif
     }
-    // The two vector recursions dx_{k+1} = Acl_k dx_k + c_k and p_k = Acl_k' p_{k+1} + e_k are affine maps, so BS of them
-    // compose into one: Phi_j = Acl_{e-1} ... Acl_s for block j = stages [s, e).  The block products are formed once per
-    // factorisation (block_products), then every solve runs
-    //   1. the affine term of every block map          (all blocks in parallel, BS dependent mat-vecs)
-    //   2. the recursion over the nb = N / BS blocks    (warp 0, nb dependent mat-vecs instead of N)
-    //   3. the stages inside every block                (all blocks in parallel, BS - 1 dependent mat-vecs)
-    // i.e. 2 BS + N / BS dependent mat-vecs instead of N.  A block is handled by a group of GS lanes (lane r = row r of the
-    // mat-vec, the vector travels by shuffle).
-    static constexpr int BS = 4, GS = NX <= 8 ? 8 : 16;
-    // steps of block j applied to the vector whose component r this lane holds.  FWD: k = s .. e-1, v <- Acl_k v + aff_k,
-    // else k = e-1 .. s, v <- Acl_k' v + aff_k.  out != nullptr: every intermediate vector is stored (stage stride NV,
-    // offset NU; FWD: at stage k+1, else at stage k).
-    template <bool FWD, bool AFFINE>
-    MDEV double group_steps(int j, double vr, const double* aff, double* out) const
-    {
-        const int r = lane % GS, base = lane - r, rr = r < NX ? r : NX - 1;
-        const int s = j * BS, e = s + BS < N ? s + BS : N;
-        const double* A = Acl_();
-#pragma unroll 1
-        for (int q = 0; q < BS; q++)
-        {
-            const int k = FWD ? s + q : e - 1 - q;
-            const bool live = FWD ? k < e : k >= s;
-            const int kc = live ? k : (FWD ? e - 1 : s);
-            const double* Ak = A + kc * (NX * NX);
-            double a0 = AFFINE ? aff[kc * NX + rr] : 0.0, a1 = 0.0;
-#pragma unroll
-            for (int m = 0; m < NX; m += 2)
-            {
-                a0 += (FWD ? Ak[rr * NX + m] : Ak[m * NX + rr]) * shfl(vr, base + m);
-                if (m + 1 < NX) a1 += (FWD ? Ak[rr * NX + m + 1] : Ak[(m + 1) * NX + rr]) * shfl(vr, base + m + 1);
-            }
-            const double nv_ = a0 + a1;
-            if (live)
-            {
-                vr = nv_;
-                // the vector at a block boundary is written by the block that STARTS there (from the block recursion): two
-                // groups must not store two roundings of the same quantity to one address.  Only the ends of the horizon
-                // (stage N forward, stage 0 backward) belong to the last step of a block.
-                const bool mine = FWD ? (kc + 1 < e || e == N) : (kc > s || s == 0);
-                if (out && r < NX && mine) out[(FWD ? kc + 1 : kc) * NV + NU + r] = vr;
-            }
-        }
-        return vr;
-    }
-    MDEV int num_blocks() const { return (N + BS - 1) / BS; }
-    // Phi_j, column by column: the block's steps applied to the unit vectors
-    MDEV void block_products()
-    {
-        const int nb = num_blocks(), ngrp = T / GS;
-        for (int it0 = 0; it0 < nb * NX; it0 += ngrp)
-        {
-            const int it = it0 + tid / GS, r = lane % GS;
-            const bool act = it < nb * NX;
-            const int itc = act ? it : nb * NX - 1;
-            const int j = itc / NX, c = itc - j * NX;
-            const double v = group_steps<true, false>(j, r == c ? 1.0 : 0.0, nullptr, nullptr);
-            if (act && r < NX) Phi[j * (NX * NX) + r * NX + c] = v;
-        }
-        syncthreads();
-    }
     // dx_0 = 0, dx_{k+1} = Acl_k dx_k + c_k -> x part of `out` (stage stride NV)
-    MDEV void chainF(double* out)
+    // `out` in the block's global scratch (the refinement step on a long horizon): the recursion runs in place on the
+    // affine terms (every c_k is in a register before x_k lands on it) and the block copies the result out.
+    MDEV void chainF(double* out, bool out_shared)
     {
-        const int nb = num_blocks(), ngrp = T / GS;
-        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        if (out_shared)
         {
-            if (j0 + (tid - lane) / GS >= nb) continue;   // no live group in this warp (warp-uniform)
-            const int j = j0 + tid / GS, r = lane % GS;
-            const bool act = j < nb;
-            const double v = group_steps<true, true>(act ? j : nb - 1, 0.0, cc_(), nullptr);
-            if (act && r < NX) phi[j * NX + r] = v;
+            if (wid == 0) chain_vec_mma<M, true>(Acl_(), cc_(), out, slots, N, NV, NU);
+            return;
         }
+        if (wid == 0) chain_vec_mma<M, true>(Acl_(), cc_(), cc_(), slots, N, NX, 0);
         syncthreads();
-        if (wid == 0) chainF_impl<M>(Phi, phi, Xb, nb, NX, 0);
-        syncthreads();
-        for (int j0 = 0; j0 < nb; j0 += ngrp)
+        for (int it = tid; it < (N + 1) * NX; it += T)
         {
-            if (j0 + (tid - lane) / GS >= nb) continue;
-            const int j = j0 + tid / GS, r = lane % GS;
-            const bool act = j < nb;
-            const int jc = act ? j : nb - 1;
-            const double x0 = Xb[jc * NX + (r < NX ? r : NX - 1)];
-            if (act && r < NX) out[jc * BS * NV + NU + r] = x0;
-            group_steps<true, true>(jc, x0, cc_(), act ? out : nullptr);
+            const int k = it / NX, i = it - k * NX;
+            out[k * NV + NU + i] = cc_()[it];
         }
     }
     // p_N = e_N, p_k = Acl_k' p_{k+1} + e_k -> x part of zv
     MDEV void chainC()
     {
-        const int nb = num_blocks(), ngrp = T / GS;
-        for (int j0 = 0; j0 < nb; j0 += ngrp)
-        {
-            if (j0 + (tid - lane) / GS >= nb) continue;
-            const int j = j0 + tid / GS, r = lane % GS;
-            const bool act = j < nb;
-            const double v = group_steps<false, true>(act ? j : nb - 1, 0.0, ee_(), nullptr);
-            if (act && r < NX) phi[j * NX + r] = v;
-        }
-        if (tid < NX) phi[nb * NX + tid] = ee_()[N * NX + tid];
-        syncthreads();
-        if (wid == 0) chainC_impl<M>(Phi, phi, Xb, nb, NX, 0);
-        syncthreads();
-        double* z = zv_();
-        for (int j0 = 0; j0 < nb; j0 += ngrp)
-        {
-            if (j0 + (tid - lane) / GS >= nb) continue;
-            const int j = j0 + tid / GS, r = lane % GS;
-            const bool act = j < nb;
-            const int jc = act ? j : nb - 1;
-            const int e = jc * BS + BS < N ? jc * BS + BS : N;
-            const double p0 = Xb[(jc + 1) * NX + (r < NX ? r : NX - 1)];
-            if (act && r < NX) z[e * NV + NU + r] = p0;
-            group_steps<false, true>(jc, p0, ee_(), act ? z : nullptr);
-        }
+        if (wid == 0) chain_vec_mma<M, false>(Acl_(), ee_(), zv_(), slots, N, NV, NU);
     }
 
     // ---------------------------------------------------------------- IPM: passes around the chains
@@ -2021,7 +1917,6 @@ struct CtaSolver {
                     PROF(1)
                     gains_pass();
                     syncthreads();
-                    block_products();
                 }
                 else
                 {
@@ -2034,7 +1929,7 @@ struct CtaSolver {
                 }
                 feedforward_pass(kind == AFF, kind == REF ? rb2_() : rb_());
                 PROF(2)
-                chainF(kind == REF ? dux2_() : dux_());
+                chainF(kind == REF ? dux2_() : dux_(), kind != REF || P.plan.f[F_DUX2].space == 0);
                 syncthreads();
                 PROF(3)
                 expand_pass(kind == AFF ? 0 : (kind == REF ? 2 : 1), tau_min);
