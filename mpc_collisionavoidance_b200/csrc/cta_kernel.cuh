@@ -1281,10 +1281,20 @@ struct CtaSolver {
             n1 = q > n1 ? q : n1;
         }
         // ---- template of the matrix to factorise (off-diagonal entries), four-entry chunks
-        for (int it = tid; it < (N + 1) * NE; it += T)
+        if (T < NE)
         {
-            const int k = it / NE, e = it - k * NE;
-            Mx_()[it] = Tp[stage_class(k) * NE + e];
+            for (int it = tid; it < (N + 1) * NE; it += T) Mx_()[it] = Tp[stage_class(it / NE) * NE + it % NE];
+        }
+        else
+        {
+            // thread -> (stage k0 + q * SPR, entry e): the path-stage template value stays in a register
+            const int SPR = T / NE, k0 = tid / NE, e = tid - k0 * NE;
+            if (k0 < SPR)
+            {
+                const double tv = Tp[NE + e];
+                double* dst = Mx_() + e;
+                for (int k = k0; k <= N; k += SPR) dst[k * NE] = (k == 0 || k == N) ? Tp[(k == 0 ? 0 : 2) * NE + e] : tv;
+            }
         }
         syncthreads();
         PROF(20)
@@ -1320,7 +1330,6 @@ struct CtaSolver {
                     const double* pl = dlam_() + k * s2 + nbq;   // parked by A2: lam_u - lam_l | Gamma_l + Gamma_u | gamma_l - gamma_u
                     const double* pG = pl + ncq;
                     const double* pg = dt_() + k * s2 + nbq;
-                    const bool isy = i == HYV;
 #pragma unroll 5
                     for (int c = 0; c < K; c++)
                     {
@@ -1328,7 +1337,7 @@ struct CtaSolver {
                         g += gc * pl[c];
                         dg += (gc * Gs) * gc;
                         gg += pg[c] * gc;
-                        if (isy) aYX += (gc * Gs) * gk[c];
+                        aYX += (gc * Gs) * gk[c];   // used by the HY lane only (for it gc = gy[c], gk[c] = gx[c]); no branch in the loop
                     }
                     if (i == HYV) Mx_()[k * NE + MI(HYV > HXV ? HYV : HXV, HYV > HXV ? HXV : HYV)] += aYX;
                 }
@@ -1354,10 +1363,20 @@ struct CtaSolver {
     MDEV void passM()
     {
         const double tau = 1e-16;
-        for (int it = tid; it < (N + 1) * NE; it += T)
+        if (T < NE)
         {
-            const int k = it / NE, e = it - k * NE;
-            Mx_()[it] = Tp[stage_class(k) * NE + e];
+            for (int it = tid; it < (N + 1) * NE; it += T) Mx_()[it] = Tp[stage_class(it / NE) * NE + it % NE];
+        }
+        else
+        {
+            // thread -> (stage k0 + q * SPR, entry e): the path-stage template value stays in a register
+            const int SPR = T / NE, k0 = tid / NE, e = tid - k0 * NE;
+            if (k0 < SPR)
+            {
+                const double tv = Tp[NE + e];
+                double* dst = Mx_() + e;
+                for (int k = k0; k <= N; k += SPR) dst[k * NE] = (k == 0 || k == N) ? Tp[(k == 0 ? 0 : 2) * NE + e] : tv;
+            }
         }
         syncthreads();
         for (int it = tid; it < (N + 1) * NV; it += T)
