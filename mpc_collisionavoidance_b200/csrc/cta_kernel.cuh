@@ -592,6 +592,7 @@ struct CtaSolver {
     double *sm, *gs, *w;
     // constants in shared memory
     double *Hs, *Hes, *Tp, *red, *sA0, *sW, *sP, *slots;
+    double** ftab;
     int *sxrow, *srvar;
     int redbuf;
     // working-set fields: no pointer is kept in registers; every access forms the address from the block's shared-memory
@@ -618,7 +619,7 @@ struct CtaSolver {
     {
         const SField& f = P.plan.f[id];
         if (id < F_FIRST_FLEX) return sm + f.off;  // the chain fields are always in shared memory
-        return (f.space ? gs : sm) + f.off;
+        return ftab[id];                            // resolved once per block (shared memory or the block's scratch)
     }
     MDEV double* G_() const { double* p_ = sm + P.plan.f[F_G].off; ASSUME_SHARED(p_); return p_; }
     MDEV double* Mx_() const { double* p_ = sm + P.plan.f[F_M].off; ASSUME_SHARED(p_); return p_; }
@@ -677,11 +678,13 @@ struct CtaSolver {
         double* m = sm + P.plan.misc_off;
         sA0 = m; m += NV * NX; sW = m; m += chain_w_doubles(NX, NU); sP = m; m += chain_p_doubles(NX);  // chain scratch: [P G' | matrix], P
         slots = m; m += 34;   // [0] = 0.0 and one dump slot per lane for the recursions' unpredicated stores
+        ftab = (double**) m; m += F_COUNT;   // field id -> address; filled here, first read after load_constants' barrier
+        for (int id = tid; id < F_COUNT; id += T) ftab[id] = (P.plan.f[id].space ? gs : sm) + P.plan.f[id].off;
         sxrow = (int*) m; srvar = sxrow + NX + (NX & 1);
         // address-space hints: these always point into shared memory
         ASSUME_SHARED(sm); ASSUME_SHARED(Hs); ASSUME_SHARED(Hes); ASSUME_SHARED(Tp);
         ASSUME_SHARED(red); ASSUME_SHARED(sA0); ASSUME_SHARED(sW); ASSUME_SHARED(sP); ASSUME_SHARED(sxrow); ASSUME_SHARED(srvar);
-        ASSUME_SHARED(slots);
+        ASSUME_SHARED(slots); ASSUME_SHARED(ftab);
         tol_stat = 1e-6; tol_eq = 1e-8; tol_ineq = 1e-8; tol_comp = 1e-8;
         if (P.nlp_type == 0) { tol_stat = P.tol[0]; tol_eq = P.tol[1]; tol_ineq = P.tol[2]; tol_comp = P.tol[3]; }
         iter_max = P.qp_iter_max > 0 ? P.qp_iter_max : 50;

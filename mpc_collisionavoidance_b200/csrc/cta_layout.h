@@ -165,6 +165,7 @@ inline bool make_plan(int nx, int nu, int N, int K, int nbx, int nbu, int ns, in
     P.misc_off = (int) o;
     o += nv * nx + chain_w_doubles(nx, nu) + chain_p_doubles(nx) + (nx + 2 * (nu + nx + K) + 8) / 2 + 8;  // A0, chain scratch, int tables
     o += 34;                                             // zero slot + one dump slot per lane of the recursions
+    o += F_COUNT;                                        // field id -> address table
     o = round_up((int) o, 2);
     // [B';A'] and the closed-loop matrices exist for stages 0 .. N-1 only
     auto stages = [&](int i) { return (i == F_G || i == F_ACL) ? N : N1; };
