@@ -415,10 +415,10 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
         {
             const double m00 = blk[0][0], m10 = blk[NU - 1][0], m11 = blk[NU - 1][NU - 1];
             const double det = m00 * m11 - m10 * m10;
-            const double i0 = m00 > 0.0 ? drsqrt(m00) : 0.0;
+            const double i0 = m00 > 0.0 ? drsqrt_pos(m00) : 0.0;
             double i1;
-            if (m00 > 0.0) i1 = det > 0.0 ? drsqrt(det) * (m00 * i0) : 0.0;
-            else i1 = m11 > 0.0 ? drsqrt(m11) : 0.0;
+            if (m00 > 0.0) i1 = det > 0.0 ? drsqrt_pos(det) * (m00 * i0) : 0.0;
+            else i1 = m11 > 0.0 ? drsqrt_pos(m11) : 0.0;
             const double l10 = m10 * i0;
             inv[0] = i0; inv[NU - 1] = i1;
             Lt[0][0] = m00 * i0; Lt[NU - 1][0] = l10;
@@ -427,7 +427,7 @@ MDEVNI void chainA_mma(const double* G, double* Mx, const double* rb, double* Pb
         else
         {
             const double piv = blk[0][0];
-            inv[0] = piv > 0.0 ? drsqrt(piv) : 0.0;
+            inv[0] = piv > 0.0 ? drsqrt_pos(piv) : 0.0;
             Lt[0][0] = piv * inv[0];
         }
         sts64(aDi, lane == 0 ? inv[0] : inv[NU - 1]);
