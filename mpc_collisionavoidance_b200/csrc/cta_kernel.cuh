@@ -19,7 +19,7 @@
 //     of the matrices to factorise, gains, dt/dlam, step lengths, right-hand sides -- is a PASS: the (stage, row) or
 //     (stage, variable) items are spread over all T threads, block-wide reductions give norms / step lengths;
 //   * only the Riccati recursions are serial in the stage index.  They run as CHAINS on warp 0, straight out of shared
-//     memory, and are cut down to what really is serial:
+//     memory, on the fp64 tensor cores (mma.sync.m8n8k4.f64), and are cut down to what really is serial:
 //       chainA  backward: P_k, p_k from P_{k+1}, p_{k+1}: M = (H + Gamma terms) + G' P_{k+1} G, eliminate the NU input
 //               columns (Cholesky with HPIPM's pivot rule); the Schur complement IS P_k, so the x block is never
 //               factorised (the reference factorises it only to form G' P G as a product of triangular factors);
@@ -28,6 +28,8 @@
 //     with the closed-loop matrices Acl_k = A_k + B_k K_k, the gains K_k and the affine terms c_k, e_k computed by
 //     passes between the chains.  Mathematically this is the reference's recursion (x_ocp_qp_kkt.c:455-575,
 //     1096-1290); iteration counts, status and converged trajectories are the reference's (tests/).
+//     A lone warp issues about one instruction per four cycles whatever the instruction, so the chains are written for
+//     instruction count: per-lane shared addresses held in registers, no predicated accesses, DMMA for the products.
 // Inactive variables (x at stage 0 after x0 elimination, u at stage N) and inactive inequality rows are kept in
 // the uniform per-stage layout and masked (identity rows in the matrix, zero rows in [B';A']), so every stage runs
 // the same code.
