@@ -169,3 +169,26 @@ def test_smallest_horizons_and_maximum_obstacle_count(N, K):
     assert (a["status"] == 0).all()
     np.testing.assert_allclose(r["x"], a["x"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(r["u"], a["u"], rtol=1e-8, atol=1e-8)
+
+
+def test_placement_plan_block_geometry_and_fp32_factorisation(golden_dir):
+    # One instance that needs iterative refinement and fails the factorisation accuracy test once (the reference's LQ
+    # instance 1252 of the headline batch), solved with (1) the GPU's shared-memory budget of two blocks per SM -- fields and
+    # the refinement copies move to the block scratch, the refinement's forward recursion runs in place and is copied out --
+    # (2) 128-thread blocks (every item-to-thread mapping and reduction tree changes), (3) the fp32 factorisation with its
+    # fp64 accuracy test and fallback: same status and iteration counts, same trajectory.
+    f = np.load(os.path.join(golden_dir, "usv_cfg2_lq.npz"))
+    i = int(np.flatnonzero(f["index"] == 1252)[0])
+    P = rh.RefProblem(N=40, K=5, num_steps=4)
+    args = [f[k][i:i + 1] for k in ("x0", "p", "lh", "yref", "yref_e")]
+    r = ep.solve_batch(P, *args)
+    assert r["status"][0] == 0 == f["status"][i] and r["itref"][0] > 0 and r["lq_calls"][0] > 0
+    assert abs(int(r["sqp_iter"][0]) - int(f["sqp_iter"][i])) <= 1
+    np.testing.assert_allclose(r["x"][0], f["x"][i], rtol=0, atol=1e-6)
+    for kw, tol in ((dict(smem_budget=115200), 0.0), (dict(block_threads=128), 1e-10), (dict(smem_budget=115200, block_threads=128), 1e-10),
+                    (dict(chain_fp32=True), 1e-7)):
+        q = ep.solve_batch(P, *args, **kw)
+        assert (q["status"][0], q["sqp_iter"][0]) == (r["status"][0], r["sqp_iter"][0]), kw
+        if "chain_fp32" not in kw:
+            assert q["qp_iter"][0] == r["qp_iter"][0] and q["itref"][0] == r["itref"][0], kw
+        assert np.abs(q["x"] - r["x"]).max() <= tol and np.abs(q["u"] - r["u"]).max() <= tol * 1e3, kw
